@@ -1,0 +1,90 @@
+// Shared helpers for libdmpnn_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dmpnn.h"
+
+namespace dmpnn {
+
+void set_error(const char* fmt, ...);
+void count_launches(int n);  // bookkeeping for dmpnn_launch_count()
+
+#define DMPNN_CHECK_ARG(cond, ...)        \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::dmpnn::set_error(__VA_ARGS__);    \
+      return -1;                          \
+    }                                     \
+  } while (0)
+
+#define DMPNN_CHECK_LAUNCH(name, n_kernels)                                           \
+  do {                                                                                \
+    ::dmpnn::count_launches(n_kernels);                                               \
+    cudaError_t e__ = cudaGetLastError();                                             \
+    if (e__ != cudaSuccess) {                                                         \
+      ::dmpnn::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));     \
+      return -2;                                                                      \
+    }                                                                                 \
+  } while (0)
+
+// ---- element access ------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p);
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+template <typename T>
+__device__ __forceinline__ void st_from_float(T* p, float v);
+template <>
+__device__ __forceinline__ void st_from_float<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+  *p = __float2bfloat16_rn(v);
+}
+
+// ---- activations (chemprop/nn/utils.py:43-55) ------------------------------------------
+__device__ __forceinline__ float act_apply(int act, float p, float z) {
+  switch (act) {
+    case DMPNN_ACT_RELU: return fmaxf(z, 0.f);
+    case DMPNN_ACT_LEAKYRELU: return z > 0.f ? z : p * z;
+    case DMPNN_ACT_TANH: return tanhf(z);
+    case DMPNN_ACT_ELU: return z > 0.f ? z : p * expm1f(z);
+    default: return z;
+  }
+}
+// derivative expressed through the OUTPUT y = tau(z)
+__device__ __forceinline__ float act_grad_from_out(int act, float p, float y) {
+  switch (act) {
+    case DMPNN_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case DMPNN_ACT_LEAKYRELU: return y > 0.f ? 1.f : p;
+    case DMPNN_ACT_TANH: return 1.f - y * y;
+    case DMPNN_ACT_ELU: return y > 0.f ? 1.f : y + p;
+    default: return 1.f;
+  }
+}
+// derivative expressed through the PRE-activation z
+__device__ __forceinline__ float act_grad_from_pre(int act, float p, float z) {
+  switch (act) {
+    case DMPNN_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+    case DMPNN_ACT_LEAKYRELU: return z > 0.f ? 1.f : p;
+    case DMPNN_ACT_TANH: { float t = tanhf(z); return 1.f - t * t; }
+    case DMPNN_ACT_ELU: return z > 0.f ? 1.f : p * expf(z);
+    default: return 1.f;
+  }
+}
+
+// dtype dispatch over {f32, bf16}
+#define DMPNN_DISPATCH_DTYPE(dt, T, ...)                              \
+  if ((dt) == DMPNN_F32) { using T = float; __VA_ARGS__ }             \
+  else if ((dt) == DMPNN_BF16) { using T = __nv_bfloat16; __VA_ARGS__ } \
+  else { ::dmpnn::set_error("bad dtype %d", (int)(dt)); return -1; }
+
+static inline int ceil_div_i64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace dmpnn

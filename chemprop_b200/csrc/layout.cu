@@ -1,0 +1,308 @@
+// Device layout build: reference BatchMolGraph index tensors -> dst-sorted CSR + tile table.
+// Replaces the per-call index materialisation of chemprop/nn/message_passing/mixins.py:12-15
+// and chemprop/nn/agg.py:74-75 with a one-off integer preprocessing pass per batch.
+// All outputs are deterministic (stable sort by destination) and bit-exact w.r.t.
+// oracle/layout_np.py.
+#include "common.cuh"
+
+namespace dmpnn {
+
+constexpr int kTileRows = 128;
+constexpr int kTileAtoms = 128;
+
+struct LayoutWs {
+  int32_t* deg;     // V+1
+  int32_t* cursor;  // V
+  int32_t* tmp;     // E
+  int32_t* bsum;    // nblk_scan + 1
+  int32_t* viol;    // 4 words: [0]=violation bits, [1]=max indeg
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static size_t carve(LayoutWs* ws, void* base, int64_t V, int64_t E) {
+  size_t off = 0;
+  char* b = (char*)base;
+  auto take = [&](size_t bytes) { char* p = b ? b + off : nullptr; off += align_up(bytes, 256); return p; };
+  int32_t* deg = (int32_t*)take(sizeof(int32_t) * (V + 1));
+  int32_t* cursor = (int32_t*)take(sizeof(int32_t) * (V + 1));
+  int32_t* tmp = (int32_t*)take(sizeof(int32_t) * (E + 1));
+  int64_t nblk = (V + 1 + 2047) / 2048;
+  int32_t* bsum = (int32_t*)take(sizeof(int32_t) * (nblk + 1));
+  int32_t* viol = (int32_t*)take(sizeof(int32_t) * 4);
+  if (ws) { ws->deg = deg; ws->cursor = cursor; ws->tmp = tmp; ws->bsum = bsum; ws->viol = viol; }
+  return off;
+}
+
+// bits in viol[0]
+enum { V_RANGE = 1, V_INVOL = 2, V_BATCH = 4 };
+
+__global__ void k_count(const int64_t* __restrict__ ei, const int64_t* __restrict__ rev,
+                        const int64_t* __restrict__ batch, int64_t V, int64_t E, int64_t B,
+                        int32_t* deg, int32_t* viol) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t s = ei[e], d = ei[E + e], r = rev[e];
+  int bad = 0;
+  if (s < 0 || s >= V || d < 0 || d >= V || r < 0 || r >= E) {
+    bad |= V_RANGE;
+  } else {
+    int64_t rs = ei[r], rd = ei[E + r], rr = rev[r];
+    if (rr != e || rs != d || rd != s) bad |= V_INVOL;
+    int64_t bs = batch[s], bd = batch[d];
+    if (bs != bd) bad |= V_BATCH;
+    atomicAdd(&deg[d], 1);
+  }
+  if (bad) atomicOr(&viol[0], bad);
+}
+
+__global__ void k_batch_check(const int64_t* __restrict__ batch, int64_t V, int64_t B, int32_t* viol) {
+  int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  int64_t b = batch[v];
+  int bad = 0;
+  if (b < 0 || b >= B) bad |= V_RANGE;
+  if (v + 1 < V && batch[v + 1] < b) bad |= V_BATCH;
+  if (bad) atomicOr(&viol[0], bad);
+}
+
+// ---- exclusive scan (n elements, int32), 2048 per block ------------------------------
+__global__ void k_scan_block(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                             int32_t* __restrict__ bsum, int64_t n) {
+  __shared__ int32_t warp_tot[8];
+  const int tid = threadIdx.x;  // 256 threads x 8 items
+  const int64_t base = blockIdx.x * 2048LL + tid * 8;
+  int32_t v[8];
+  int32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = (base + i < n) ? in[base + i] : 0;
+    s += v[i];
+  }
+  // warp inclusive scan of s
+  int32_t inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((tid & 31) >= o) inc += t;
+  }
+  if ((tid & 31) == 31) warp_tot[tid >> 5] = inc;
+  __syncthreads();
+  int32_t woff = 0;
+  for (int w = 0; w < (tid >> 5); ++w) woff += warp_tot[w];
+  int32_t run = woff + inc - s;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (base + i < n) out[base + i] = run;
+    run += v[i];
+  }
+  if (tid == 255) bsum[blockIdx.x] = woff + inc;
+}
+
+__global__ void k_scan_bsums(int32_t* bsum, int64_t nblk) {
+  // single block: sequential chunks of 1024 with a running carry
+  __shared__ int32_t sh[1024];
+  __shared__ int32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < nblk; base += 1024) {
+    int64_t i = base + threadIdx.x;
+    int32_t x = (i < nblk) ? bsum[i] : 0;
+    sh[threadIdx.x] = x;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int32_t t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    int32_t c = carry;
+    if (i < nblk) bsum[i] = c + sh[threadIdx.x] - x;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c + sh[1023];
+    __syncthreads();
+  }
+}
+
+__global__ void k_scan_add(int32_t* out, const int32_t* __restrict__ bsum, int64_t n) {
+  int64_t i = blockIdx.x * 2048LL + threadIdx.x;
+  int32_t add = bsum[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int64_t j = i + k * 256;
+    if (j < n) out[j] += add;
+  }
+}
+
+__global__ void k_place(const int64_t* __restrict__ ei, int64_t V, int64_t E,
+                        const int32_t* __restrict__ rowptr, int32_t* cursor, int32_t* tmp) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t d = ei[E + e];
+  if (d < 0 || d >= V) return;
+  int32_t p = atomicAdd(&cursor[d], 1);
+  tmp[rowptr[d] + p] = (int32_t)e;
+}
+
+// one thread per atom: sort the bucket by edge id (stable order), emit per-row arrays
+__global__ void k_bucket_sort(const int64_t* __restrict__ ei, int64_t V, int64_t E,
+                              const int32_t* __restrict__ rowptr, int32_t* tmp,
+                              int32_t* perm, int32_t* inv_perm, int32_t* src_row, int32_t* dst_row,
+                              int32_t* viol) {
+  int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  int32_t a = rowptr[v], b = rowptr[v + 1];
+  for (int32_t i = a + 1; i < b; ++i) {  // insertion sort (in-degree is tiny for molecules)
+    int32_t x = tmp[i];
+    int32_t j = i - 1;
+    while (j >= a && tmp[j] > x) { tmp[j + 1] = tmp[j]; --j; }
+    tmp[j + 1] = x;
+  }
+  for (int32_t i = a; i < b; ++i) {
+    int32_t e = tmp[i];
+    perm[i] = e;
+    inv_perm[e] = i;
+    dst_row[i] = (int32_t)v;
+    src_row[i] = (int32_t)ei[e];
+  }
+  if (b - a > 0) atomicMax(&viol[1], b - a);
+}
+
+__global__ void k_rev_rows(const int64_t* __restrict__ rev, int64_t E, const int32_t* __restrict__ perm,
+                           const int32_t* __restrict__ inv_perm, int32_t* rev_row) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= E) return;
+  int64_t q = rev[perm[r]];
+  rev_row[r] = (q >= 0 && q < E) ? inv_perm[q] : 0;
+}
+
+// mol_atom_ptr[b] = first atom v with batch[v] >= b  (batch non-decreasing)
+__global__ void k_mol_ptr(const int64_t* __restrict__ batch, int64_t V, int64_t B,
+                          const int32_t* __restrict__ rowptr, int32_t* mol_atom_ptr, int32_t* mol_row_ptr) {
+  int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // v in [0, V]
+  if (v > V) return;
+  int64_t lo = (v == 0) ? 0 : batch[v - 1] + 1;
+  int64_t hi = (v == V) ? B : batch[v];
+  if (lo < 0) lo = 0;
+  if (hi > B) hi = B;
+  if (v == V) hi = B;  // ptr[B] included below
+  for (int64_t b = lo; b <= hi && b <= B; ++b) {
+    if (v < V && b > batch[v]) break;
+    mol_atom_ptr[b] = (int32_t)v;
+    if (mol_row_ptr) mol_row_ptr[b] = rowptr[v];
+  }
+}
+
+// Greedy molecule-aligned packing into tiles of <= kTileRows rows and <= kTileAtoms atoms.
+// Sequential by nature; one thread walks the molecule offsets staged through shared memory.
+__global__ void k_tiles(const int32_t* __restrict__ mol_atom_ptr, const int32_t* __restrict__ mol_row_ptr,
+                        int64_t B, int32_t* tile_mol_ptr, int32_t* meta, const int32_t* viol) {
+  constexpr int CH = 4096;
+  __shared__ int32_t s_at[CH + 1];
+  __shared__ int32_t s_rw[CH + 1];
+  int32_t n_tiles = 0, max_rows = 0, max_atoms = 0;
+  int32_t t_mol = 0, t_row = 0, t_atom = 0;  // start of the open tile
+  for (int64_t base = 0; base < B; base += CH) {
+    int64_t n = (B - base < CH) ? (B - base) : CH;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i <= n; i += blockDim.x) {
+      s_at[i] = mol_atom_ptr[base + i];
+      s_rw[i] = mol_row_ptr[base + i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int64_t i = 0; i < n; ++i) {
+        int32_t m = (int32_t)(base + i);
+        int32_t end_row = s_rw[i + 1], end_atom = s_at[i + 1];
+        if (m > t_mol && (end_row - t_row > kTileRows || end_atom - t_atom > kTileAtoms)) {
+          // close the open tile [t_mol, m)
+          tile_mol_ptr[n_tiles++] = t_mol;
+          int32_t rows = s_rw[i] - t_row, atoms = s_at[i] - t_atom;
+          max_rows = rows > max_rows ? rows : max_rows;
+          max_atoms = atoms > max_atoms ? atoms : max_atoms;
+          t_mol = m; t_row = s_rw[i]; t_atom = s_at[i];
+        }
+      }
+      if (base + n == B) {
+        int32_t rows = s_rw[n] - t_row, atoms = s_at[n] - t_atom;
+        tile_mol_ptr[n_tiles++] = t_mol;
+        max_rows = rows > max_rows ? rows : max_rows;
+        max_atoms = atoms > max_atoms ? atoms : max_atoms;
+        tile_mol_ptr[n_tiles] = (int32_t)B;
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (B == 0) { tile_mol_ptr[0] = 0; n_tiles = 0; }
+    int32_t vb = viol[0];
+    int32_t flags = 0;
+    if (!(vb & V_RANGE)) flags |= DMPNN_FLAG_INDEX_IN_RANGE;
+    if (!(vb & (V_INVOL | V_RANGE))) flags |= DMPNN_FLAG_REV_INVOLUTION;
+    if (!(vb & (V_BATCH | V_RANGE))) flags |= DMPNN_FLAG_BATCH_SORTED;
+    meta[DMPNN_META_N_TILES] = n_tiles;
+    meta[DMPNN_META_FLAGS] = flags;
+    meta[DMPNN_META_MAX_INDEG] = viol[1];
+    meta[DMPNN_META_MAX_TILE_ROWS] = max_rows;
+    meta[DMPNN_META_MAX_TILE_ATOMS] = max_atoms;
+    meta[5] = 0; meta[6] = 0; meta[7] = 0;
+  }
+}
+
+}  // namespace dmpnn
+
+using namespace dmpnn;
+
+extern "C" int dmpnn_layout_workspace_bytes(int64_t V, int64_t E, int64_t B, size_t* bytes) {
+  DMPNN_CHECK_ARG(V >= 0 && E >= 0 && B >= 0 && bytes, "layout_workspace_bytes: bad args");
+  *bytes = carve(nullptr, nullptr, V, E);
+  return 0;
+}
+
+extern "C" int dmpnn_layout_build(const int64_t* edge_index, const int64_t* rev_edge_index,
+                                  const int64_t* batch, int64_t V, int64_t E, int64_t B,
+                                  int32_t* perm, int32_t* inv_perm, int32_t* rowptr, int32_t* src_row,
+                                  int32_t* dst_row, int32_t* rev_row, int32_t* mol_atom_ptr,
+                                  int32_t* mol_row_ptr, int32_t* tile_mol_ptr, int32_t* meta,
+                                  void* workspace, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DMPNN_CHECK_ARG(V >= 0 && E >= 0 && B >= 0, "layout_build: negative size");
+  DMPNN_CHECK_ARG(V < (1LL << 31) - 4096 && E < (1LL << 31) - 4096, "layout_build: V/E exceed int32");
+  DMPNN_CHECK_ARG(workspace && rowptr && mol_atom_ptr && mol_row_ptr && tile_mol_ptr && meta,
+                  "layout_build: null pointer");
+  LayoutWs ws;
+  size_t total = carve(&ws, workspace, V, E);
+  cudaMemsetAsync(workspace, 0, total, st);
+  const int T = 256;
+  if (E > 0) {
+    k_count<<<ceil_div_i64(E, T), T, 0, st>>>(edge_index, rev_edge_index, batch, V, E, B, ws.deg, ws.viol);
+  }
+  if (V > 0) k_batch_check<<<ceil_div_i64(V, T), T, 0, st>>>(batch, V, B, ws.viol);
+  // exclusive scan of deg[0..V] -> rowptr[0..V]
+  int64_t n = V + 1;
+  int nblk = ceil_div_i64(n, 2048);
+  k_scan_block<<<nblk, 256, 0, st>>>(ws.deg, rowptr, ws.bsum, n);
+  k_scan_bsums<<<1, 1024, 0, st>>>(ws.bsum, nblk);
+  k_scan_add<<<nblk, 256, 0, st>>>(rowptr, ws.bsum, n);
+  if (E > 0) k_place<<<ceil_div_i64(E, T), T, 0, st>>>(edge_index, V, E, rowptr, ws.cursor, ws.tmp);
+  if (V > 0)
+    k_bucket_sort<<<ceil_div_i64(V, T), T, 0, st>>>(edge_index, V, E, rowptr, ws.tmp, perm, inv_perm,
+                                                    src_row, dst_row, ws.viol);
+  if (E > 0) k_rev_rows<<<ceil_div_i64(E, T), T, 0, st>>>(rev_edge_index, E, perm, inv_perm, rev_row);
+  k_mol_ptr<<<ceil_div_i64(V + 1, T), T, 0, st>>>(batch, V, B, rowptr, mol_atom_ptr, mol_row_ptr);
+  k_tiles<<<1, 1024, 0, st>>>(mol_atom_ptr, mol_row_ptr, B, tile_mol_ptr, meta, ws.viol);
+  DMPNN_CHECK_LAUNCH("layout_build", 10);
+  return 0;
+}
+
+extern "C" int dmpnn_sorted_index_to_ptr(const int64_t* index, int64_t n, int64_t n_seg, int32_t* ptr,
+                                         int32_t* status, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DMPNN_CHECK_ARG(n >= 0 && n_seg >= 0 && ptr && status, "sorted_index_to_ptr: bad args");
+  DMPNN_CHECK_ARG(n < (1LL << 31) - 4096, "sorted_index_to_ptr: n exceeds int32");
+  cudaMemsetAsync(status, 0, sizeof(int32_t), st);
+  const int T = 256;
+  if (n > 0) k_batch_check<<<ceil_div_i64(n, T), T, 0, st>>>(index, n, n_seg, status);
+  k_mol_ptr<<<ceil_div_i64(n + 1, T), T, 0, st>>>(index, n, n_seg, nullptr, ptr, nullptr);
+  DMPNN_CHECK_LAUNCH("sorted_index_to_ptr", 2);
+  return 0;
+}

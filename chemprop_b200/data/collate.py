@@ -1,0 +1,130 @@
+"""`BatchMolGraph` / `collate_batch` with the public surface of chemprop/data/collate.py:13-97.
+
+Public view (unchanged): ``V`` f32 (V x d_v), ``E`` f32 (E x d_e), ``edge_index`` int64 (2 x E),
+``rev_edge_index`` int64 (E), ``batch`` int64 (V), ``len(bmg)`` = number of molecules,
+in-place ``.to(device)`` returning None.
+
+What differs from the reference: concatenation is done by one C call
+(`dmpnn_collate_host`, replacing the per-molecule Python loop at collate.py:48-62), host tensors
+can be pinned, and the engine's device layout (dst-sorted CSR + tile table, built by
+`dmpnn_layout_build`) is cached on the object after first use so the depth loop, the readout and
+the backward pass all share it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, NamedTuple, Sequence
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from .. import _lib
+from .molgraph import MolGraph
+
+
+class BatchMolGraph:
+    __slots__ = ("V", "E", "edge_index", "rev_edge_index", "batch", "_size", "_layout")
+
+    def __init__(self, mgs: Sequence[MolGraph], pin_memory: bool = False):
+        self._size = len(mgs)
+        self._layout = None
+        n = len(mgs)
+        n_atoms = np.fromiter((mg.V.shape[0] for mg in mgs), dtype=np.int64, count=n)
+        n_edges = np.fromiter((mg.edge_index.shape[1] for mg in mgs), dtype=np.int64, count=n)
+        d_v = int(mgs[0].V.shape[1]) if n else 0
+        d_e = int(mgs[0].E.shape[1]) if n else 0
+        Vt, Et = int(n_atoms.sum()), int(n_edges.sum())
+        # keep converted arrays alive for the duration of the C call
+        Vs = [np.ascontiguousarray(mg.V, dtype=np.float32) for mg in mgs]
+        Es = [np.ascontiguousarray(mg.E, dtype=np.float32) for mg in mgs]
+        EIs = [np.ascontiguousarray(mg.edge_index, dtype=np.int64) for mg in mgs]
+        RVs = [np.ascontiguousarray(mg.rev_edge_index, dtype=np.int64) for mg in mgs]
+        for mg, e, ne in zip(mgs, Es, n_edges):
+            if e.shape[0] != ne:
+                raise ValueError(f"MolGraph.E has {e.shape[0]} rows but edge_index has {ne} edges")
+
+        def ptrs(arrs):
+            return np.fromiter((a.ctypes.data for a in arrs), dtype=np.uint64, count=n)
+
+        pV, pE, pEI, pRV = ptrs(Vs), ptrs(Es), ptrs(EIs), ptrs(RVs)
+        kw = dict(pin_memory=True) if pin_memory else {}
+        self.V = torch.empty((Vt, d_v), dtype=torch.float32, **kw)
+        self.E = torch.empty((Et, d_e), dtype=torch.float32, **kw)
+        self.edge_index = torch.empty((2, Et), dtype=torch.int64, **kw)
+        self.rev_edge_index = torch.empty((Et,), dtype=torch.int64, **kw)
+        self.batch = torch.empty((Vt,), dtype=torch.int64, **kw)
+        lib = _lib.load()
+        rc = lib.dmpnn_collate_host(
+            n, n_atoms.ctypes.data, n_edges.ctypes.data, pV.ctypes.data, pE.ctypes.data, pEI.ctypes.data,
+            pRV.ctypes.data, d_v, d_e, self.V.data_ptr(), self.E.data_ptr(), self.edge_index.data_ptr(),
+            self.rev_edge_index.data_ptr(), self.batch.data_ptr(),
+        )
+        _lib.check(rc, "dmpnn_collate_host")
+
+    @classmethod
+    def from_tensors(cls, V: Tensor, E: Tensor, edge_index: Tensor, rev_edge_index: Tensor, batch: Tensor,
+                     size: int) -> "BatchMolGraph":
+        """Wrap already-batched tensors (e.g. the five leaves of a reference BatchMolGraph)."""
+        bmg = object.__new__(cls)
+        bmg.V, bmg.E, bmg.edge_index, bmg.rev_edge_index, bmg.batch = V, E, edge_index, rev_edge_index, batch
+        bmg._size = int(size)
+        bmg._layout = None
+        return bmg
+
+    def __len__(self) -> int:
+        return self._size
+
+    def to(self, device, non_blocking: bool = False):
+        """In place, returns None (chemprop/data/collate.py:68-73)."""
+        dev = torch.device(device)
+        if self.V.device != dev:
+            self._layout = None
+        self.V = self.V.to(dev, non_blocking=non_blocking)
+        self.E = self.E.to(dev, non_blocking=non_blocking)
+        self.edge_index = self.edge_index.to(dev, non_blocking=non_blocking)
+        self.rev_edge_index = self.rev_edge_index.to(dev, non_blocking=non_blocking)
+        self.batch = self.batch.to(dev, non_blocking=non_blocking)
+
+    def __copy__(self):
+        # GraphTransform makes a shallow copy and replaces V / E (chemprop/nn/transforms.py:69-72);
+        # the index layout stays valid for the copy.
+        new = object.__new__(type(self))
+        for s in self.__slots__:
+            setattr(new, s, getattr(self, s))
+        return new
+
+
+class Datum(NamedTuple):
+    """chemprop/data/datasets.py `Datum` (fields in the same order)."""
+    mg: MolGraph
+    V_d: np.ndarray | None
+    x_d: np.ndarray | None
+    y: np.ndarray | None
+    weight: float
+    lt_mask: np.ndarray | None
+    gt_mask: np.ndarray | None
+
+
+class TrainingBatch(NamedTuple):
+    bmg: BatchMolGraph
+    V_d: Tensor | None
+    X_d: Tensor | None
+    Y: Tensor | None
+    w: Tensor
+    lt_mask: Tensor | None
+    gt_mask: Tensor | None
+
+
+def collate_batch(batch: Iterable[Datum]) -> TrainingBatch:
+    """Same contract as chemprop/data/collate.py:86-97."""
+    mgs, V_ds, x_ds, ys, weights, lt_masks, gt_masks = zip(*batch)
+    return TrainingBatch(
+        BatchMolGraph(mgs),
+        None if V_ds[0] is None else torch.from_numpy(np.concatenate(V_ds)).float(),
+        None if x_ds[0] is None else torch.from_numpy(np.array(x_ds)).float(),
+        None if ys[0] is None else torch.from_numpy(np.array(ys)).float(),
+        torch.tensor(weights, dtype=torch.float).unsqueeze(1),
+        None if lt_masks[0] is None else torch.from_numpy(np.array(lt_masks)),
+        None if gt_masks[0] is None else torch.from_numpy(np.array(gt_masks)),
+    )

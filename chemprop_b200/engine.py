@@ -1,0 +1,636 @@
+"""Host side of the engine: device layout, thin wrappers over the C ABI (raw pointers in, nothing
+allocated inside the library) and the autograd functions the nn modules call.
+
+PyTorch here is plumbing only: it owns device memory (caching allocator), streams and the
+autograd graph; every arithmetic step on the path is a kernel of libdmpnn_sm100.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import (ACT_ELU, ACT_LEAKYRELU, ACT_NONE, ACT_RELU, ACT_TANH, BF16, F32, SCALE_DIV_CONST,
+                   SCALE_INV_COUNT, SCALE_NONE, DmpnnError)
+
+HIDDEN_ALIGN = 16  # hidden row stride is padded to a multiple of 16 elements (UMMA K granularity)
+
+# Optional device-side timing of the depth step (bench.py's roofline): when a list, every depth step
+# appends (tag, start_event, end_event) recorded on the launching stream.
+STEP_EVENTS: list | None = None
+
+
+class _StepTimer:
+    def __init__(self, tag: str):
+        self.tag = tag
+
+    def __enter__(self):
+        if STEP_EVENTS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream())
+        return self
+
+    def __exit__(self, *exc):
+        if STEP_EVENTS is not None:
+            self.e1.record(torch.cuda.current_stream())
+            STEP_EVENTS.append((self.tag, self.e0, self.e1))
+        return False
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise DmpnnError(f"unsupported dtype {t.dtype}")
+
+
+def _ptr(t: Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _ld(t: Tensor) -> int:
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] <= 1), "rows must be contiguous"
+    return max(int(t.stride(0)), int(t.shape[1]))
+
+
+def _require_cuda(*ts: Tensor):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise DmpnnError(
+                "chemprop_b200 runs on CUDA (sm_100a) only; got a CPU tensor. There is no CPU fallback: "
+                "move the BatchMolGraph and the module to the GPU."
+            )
+
+
+def pad_hidden(h: int) -> int:
+    return (h + HIDDEN_ALIGN - 1) // HIDDEN_ALIGN * HIDDEN_ALIGN
+
+
+# ----------------------------------------------------------------------------------------------
+# layout
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class Layout:
+    V: int
+    E: int
+    B: int
+    perm: Tensor
+    inv_perm: Tensor
+    rowptr: Tensor
+    src_row: Tensor
+    dst_row: Tensor
+    rev_row: Tensor
+    mol_atom_ptr: Tensor
+    mol_row_ptr: Tensor
+    tile_mol_ptr: Tensor
+    meta: Tensor
+    _meta_host: list | None = None
+
+    def _host(self):
+        if self._meta_host is None:
+            self._meta_host = self.meta.tolist()  # one small D2H sync per batch
+        return self._meta_host
+
+    @property
+    def n_tiles(self) -> int:
+        return self._host()[_lib.META_N_TILES]
+
+    @property
+    def flags(self) -> int:
+        return self._host()[_lib.META_FLAGS]
+
+    @property
+    def max_indeg(self) -> int:
+        return self._host()[_lib.META_MAX_INDEG]
+
+    @property
+    def max_tile_rows(self) -> int:
+        return self._host()[_lib.META_MAX_TILE_ROWS]
+
+    @property
+    def max_tile_atoms(self) -> int:
+        return self._host()[_lib.META_MAX_TILE_ATOMS]
+
+    def validate(self):
+        f = self.flags
+        if not f & _lib.FLAG_INDEX_IN_RANGE:
+            raise DmpnnError("BatchMolGraph indices out of range (edge_index / rev_edge_index / batch)")
+        if not f & _lib.FLAG_BATCH_SORTED:
+            raise DmpnnError("BatchMolGraph.batch must be non-decreasing and edges must stay inside a molecule")
+        if not f & _lib.FLAG_REV_INVOLUTION:
+            raise DmpnnError(
+                "rev_edge_index is not a proper reverse-edge map (rev[rev[e]]==e with swapped endpoints); "
+                "the engine requires it (every featuriser-made graph satisfies it)"
+            )
+
+
+def build_layout(edge_index: Tensor, rev_edge_index: Tensor, batch: Tensor, n_mols: int) -> Layout:
+    """dmpnn_layout_build on the current stream.  Inputs are the reference's int64 index tensors."""
+    _require_cuda(edge_index, rev_edge_index, batch)
+    lib = _lib.load()
+    dev = edge_index.device
+    edge_index = edge_index.contiguous()
+    rev_edge_index = rev_edge_index.contiguous()
+    batch = batch.contiguous()
+    if edge_index.dtype != torch.int64 or rev_edge_index.dtype != torch.int64 or batch.dtype != torch.int64:
+        raise DmpnnError("edge_index / rev_edge_index / batch must be int64 (as in the reference BatchMolGraph)")
+    E = int(edge_index.shape[1])
+    V = int(batch.shape[0])
+    B = int(n_mols)
+    i32 = dict(dtype=torch.int32, device=dev)
+    perm = torch.empty(max(E, 1), **i32)
+    inv_perm = torch.empty(max(E, 1), **i32)
+    rowptr = torch.empty(V + 1, **i32)
+    src_row = torch.empty(max(E, 1), **i32)
+    dst_row = torch.empty(max(E, 1), **i32)
+    rev_row = torch.empty(max(E, 1), **i32)
+    mol_atom_ptr = torch.zeros(B + 1, **i32)
+    mol_row_ptr = torch.zeros(B + 1, **i32)
+    tile_mol_ptr = torch.zeros(B + 2, **i32)
+    meta = torch.zeros(_lib.META_WORDS, **i32)
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.dmpnn_layout_workspace_bytes(V, E, B, C.byref(nbytes)), "dmpnn_layout_workspace_bytes")
+    ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=dev)
+    rc = lib.dmpnn_layout_build(
+        edge_index.data_ptr(), rev_edge_index.data_ptr(), batch.data_ptr(), V, E, B,
+        perm.data_ptr(), inv_perm.data_ptr(), rowptr.data_ptr(), src_row.data_ptr(), dst_row.data_ptr(),
+        rev_row.data_ptr(), mol_atom_ptr.data_ptr(), mol_row_ptr.data_ptr(), tile_mol_ptr.data_ptr(),
+        meta.data_ptr(), ws.data_ptr(), _stream(),
+    )
+    _lib.check(rc, "dmpnn_layout_build")
+    return Layout(V, E, B, perm[:E], inv_perm[:E], rowptr, src_row[:E], dst_row[:E], rev_row[:E], mol_atom_ptr,
+                  mol_row_ptr, tile_mol_ptr, meta)
+
+
+def get_layout(bmg) -> Layout:
+    """Layout of a BatchMolGraph (ours or the reference's), cached on the object when it allows it."""
+    lay = getattr(bmg, "_layout", None)
+    if lay is not None and lay.rowptr.device == bmg.edge_index.device:
+        return lay
+    lay = build_layout(bmg.edge_index, bmg.rev_edge_index, bmg.batch, len(bmg))
+    lay.validate()
+    try:
+        bmg._layout = lay
+    except AttributeError:  # reference BatchMolGraph is a slots dataclass: rebuild per call
+        pass
+    # let Aggregation.forward(H, bmg.batch) find the molecule offsets without a device sync
+    try:
+        bmg.batch._dmpnn_seg = (lay.mol_atom_ptr, bmg.batch.to(torch.int32), lay.B)
+    except Exception:
+        pass
+    return lay
+
+
+def segments_of(batch: Tensor):
+    """(ptr int32 [B+1], seg_of_row int32 [V], B) for a sorted int64 `batch` (agg.py:74-75)."""
+    seg = getattr(batch, "_dmpnn_seg", None)
+    if seg is not None and seg[0].device == batch.device:
+        return seg
+    _require_cuda(batch)
+    lib = _lib.load()
+    n = int(batch.shape[0])
+    B = int(batch.max().item()) + 1 if n > 0 else 0   # same device sync as the reference (agg.py:75)
+    ptr = torch.zeros(B + 1, dtype=torch.int32, device=batch.device)
+    status = torch.zeros(1, dtype=torch.int32, device=batch.device)
+    bc = batch.contiguous()
+    _lib.check(lib.dmpnn_sorted_index_to_ptr(bc.data_ptr(), n, B, ptr.data_ptr(), status.data_ptr(), _stream()),
+               "dmpnn_sorted_index_to_ptr")
+    if int(status.item()) != 0:
+        raise DmpnnError("Aggregation: `batch` must be non-decreasing (atoms of a molecule contiguous)")
+    seg = (ptr, bc.to(torch.int32), B)
+    try:
+        batch._dmpnn_seg = seg
+    except Exception:
+        pass
+    return seg
+
+
+# ----------------------------------------------------------------------------------------------
+# op wrappers (tensors in, launches on the current stream)
+# ----------------------------------------------------------------------------------------------
+def linear_fwd(X1: Tensor, K1: int, W: Tensor, out: Tensor, N: int, *, idx1: Tensor | None = None,
+               X2: Tensor | None = None, K2: int = 0, idx2: Tensor | None = None, bias: Tensor | None = None,
+               res: Tensor | None = None, act: int = ACT_NONE, act_param: float = 0.0, R: int | None = None,
+               pad_to: int | None = None):
+    lib = _lib.load()
+    R = out.shape[0] if R is None else R
+    assert W.dtype == torch.float32 and W.stride(1) == 1 and W.shape[0] == N and W.shape[1] == K1 + K2
+    rc = lib.dmpnn_linear_fwd(
+        X1.data_ptr(), _dt(X1), _ld(X1), _ptr(idx1), K1,
+        _ptr(X2), _dt(X2) if X2 is not None else F32, _ld(X2) if X2 is not None else 0, _ptr(idx2), K2,
+        W.data_ptr(), W.stride(0), _ptr(bias),
+        _ptr(res), _dt(res) if res is not None else F32, _ld(res) if res is not None else 0,
+        act, float(act_param), out.data_ptr(), _dt(out), _ld(out), pad_to if pad_to is not None else min(_ld(out), out.shape[1]),
+        R, N, _stream(),
+    )
+    _lib.check(rc, "dmpnn_linear_fwd")
+
+
+def linear_wgrad(dY: Tensor, X1: Tensor, K1: int, dW: Tensor, N: int, *, idx1: Tensor | None = None,
+                 X2: Tensor | None = None, K2: int = 0, idx2: Tensor | None = None, dbias: Tensor | None = None,
+                 accumulate: bool = False, R: int | None = None):
+    lib = _lib.load()
+    R = dY.shape[0] if R is None else R
+    assert dW.dtype == torch.float32 and dW.stride(1) == 1
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.dmpnn_linear_wgrad_workspace_bytes(R, N, K1 + K2, C.byref(nbytes)), "wgrad_workspace_bytes")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dY.device)
+    rc = lib.dmpnn_linear_wgrad(
+        dY.data_ptr(), _dt(dY), _ld(dY), X1.data_ptr(), _dt(X1), _ld(X1), _ptr(idx1), K1,
+        _ptr(X2), _dt(X2) if X2 is not None else F32, _ld(X2) if X2 is not None else 0, _ptr(idx2), K2,
+        dW.data_ptr(), dW.stride(0), _ptr(dbias), 1 if accumulate else 0, R, N, ws.data_ptr(), _stream(),
+    )
+    _lib.check(rc, "dmpnn_linear_wgrad")
+
+
+def segment_sum(X: Tensor, ptr: Tensor, n_seg: int, Ccols: int, out: Tensor, *, idx: Tensor | None = None,
+                act: int = ACT_NONE, act_param: float = 0.0, scale_mode: int = SCALE_NONE, scale: float = 1.0,
+                pad_to: int | None = None):
+    lib = _lib.load()
+    rc = lib.dmpnn_segment_sum(
+        X.data_ptr(), _dt(X), _ld(X), _ptr(idx), ptr.data_ptr(), n_seg, Ccols, act, float(act_param),
+        scale_mode, float(scale), out.data_ptr(), _dt(out), _ld(out),
+        pad_to if pad_to is not None else min(_ld(out), out.shape[1]), _stream(),
+    )
+    _lib.check(rc, "dmpnn_segment_sum")
+
+
+def segment_bcast(G: Tensor, seg_of_row: Tensor, ptr: Tensor | None, R: int, Ccols: int, out: Tensor, *,
+                  scale_mode: int = SCALE_NONE, scale: float = 1.0):
+    lib = _lib.load()
+    rc = lib.dmpnn_segment_bcast(G.data_ptr(), _dt(G), _ld(G), seg_of_row.data_ptr(), _ptr(ptr), R, Ccols,
+                                 scale_mode, float(scale), out.data_ptr(), _dt(out), _ld(out), _stream())
+    _lib.check(rc, "dmpnn_segment_bcast")
+
+
+def bond_message(X: Tensor, lay: Layout, Ccols: int, out: Tensor, *, act: int = ACT_NONE, act_param: float = 0.0,
+                 permute_on_read: bool = False):
+    lib = _lib.load()
+    rc = lib.dmpnn_bond_message(X.data_ptr(), _dt(X), _ld(X), lay.rowptr.data_ptr(), lay.rev_row.data_ptr(),
+                                lay.V, Ccols, act, float(act_param), 1 if permute_on_read else 0,
+                                out.data_ptr(), _dt(out), _ld(out), _stream())
+    _lib.check(rc, "dmpnn_bond_message")
+
+
+def rev_average(X: Tensor, lay: Layout, Ccols: int, out: Tensor, *, act: int = ACT_NONE, act_param: float = 0.0):
+    lib = _lib.load()
+    rc = lib.dmpnn_rev_average(X.data_ptr(), _dt(X), _ld(X), lay.rev_row.data_ptr(), lay.E, Ccols, act,
+                               float(act_param), out.data_ptr(), _dt(out), _ld(out), _stream())
+    _lib.check(rc, "dmpnn_rev_average")
+
+
+def act_bwd(G: Tensor, Yact: Tensor, R: int, Ccols: int, *, act: int, act_param: float = 0.0,
+            gidx: Tensor | None = None, from_preact: bool = False, dZ: Tensor | None = None,
+            acc: Tensor | None = None):
+    lib = _lib.load()
+    rc = lib.dmpnn_act_bwd(
+        G.data_ptr(), _dt(G), _ld(G), _ptr(gidx), Yact.data_ptr(), _dt(Yact), _ld(Yact),
+        1 if from_preact else 0, act, float(act_param),
+        _ptr(dZ), _dt(dZ) if dZ is not None else F32, _ld(dZ) if dZ is not None else 0,
+        _ptr(acc), _dt(acc) if acc is not None else F32, _ld(acc) if acc is not None else 0,
+        R, Ccols, _stream(),
+    )
+    _lib.check(rc, "dmpnn_act_bwd")
+
+
+# ----------------------------------------------------------------------------------------------
+# message passing: forward / backward drivers
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class MPConfig:
+    depth: int
+    act: int
+    act_param: float
+    undirected: bool
+    hidden_dtype: torch.dtype  # torch.float32 (<=1e-5 tier) or torch.bfloat16 (<=1e-2 tier)
+    fused: bool = True         # use the tcgen05 fused depth-step kernel when applicable
+
+
+def _hidden(rows: int, hp: int, dtype, dev) -> Tensor:
+    return torch.zeros((max(rows, 1), hp), dtype=dtype, device=dev)
+
+
+def _fused_step_ok(cfg: MPConfig, lay: Layout, h: int) -> bool:
+    return (cfg.fused and cfg.hidden_dtype == torch.bfloat16 and not cfg.undirected and h <= 304
+            and lay.E > 0 and lay.max_tile_rows <= 128 and _fused_available())
+
+
+_FUSED_STATE: dict = {}
+
+
+def _fused_available() -> bool:
+    if "ok" not in _FUSED_STATE:
+        lib = _lib.load()
+        n = C.c_size_t(0)
+        _FUSED_STATE["ok"] = lib.dmpnn_pack_weight_bf16_bytes(304, 304, C.byref(n)) == 0
+    return _FUSED_STATE["ok"]
+
+
+def pack_weight_bf16(W: Tensor) -> Tensor:
+    lib = _lib.load()
+    N, K = W.shape
+    n = C.c_size_t(0)
+    _lib.check(lib.dmpnn_pack_weight_bf16_bytes(N, K, C.byref(n)), "dmpnn_pack_weight_bf16_bytes")
+    out = torch.empty(n.value, dtype=torch.uint8, device=W.device)
+    Wc = W.detach().contiguous().float()
+    _lib.check(lib.dmpnn_pack_weight_bf16(Wc.data_ptr(), Wc.stride(0), N, K, out.data_ptr(), _stream()),
+               "dmpnn_pack_weight_bf16")
+    return out
+
+
+def bond_step_fused(H_prev: Tensor, H0: Tensor, H_next: Tensor, h: int, Wpk: Tensor, bias: Tensor | None,
+                    lay: Layout, act: int, act_param: float, first_step: bool):
+    lib = _lib.load()
+    rc = lib.dmpnn_bond_step_fused_bf16(
+        H_prev.data_ptr(), H0.data_ptr(), H_next.data_ptr(), _ld(H0), H0.shape[0], h, Wpk.data_ptr(), _ptr(bias),
+        lay.rowptr.data_ptr(), lay.rev_row.data_ptr(), lay.mol_atom_ptr.data_ptr(), lay.mol_row_ptr.data_ptr(),
+        lay.tile_mol_ptr.data_ptr(), lay.n_tiles, act, float(act_param), 1 if first_step else 0, _stream(),
+    )
+    _lib.check(rc, "dmpnn_bond_step_fused_bf16")
+
+
+def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, bh, Wo: Tensor, bo,
+                 cfg: MPConfig):
+    """BondMessagePassing.forward up to W_o (chemprop/nn/message_passing/base.py:196-212 with
+    mixins.py:8-18 and base.py:135-141, 180-182).  Returns (H_v, saved-for-backward)."""
+    dev = V.device
+    h = Wh.shape[0]
+    hp = pad_hidden(h)
+    d_v, d_e = V.shape[1], E.shape[1]
+    T = cfg.hidden_dtype
+    nE, nV = lay.E, lay.V
+    a, ap = cfg.act, cfg.act_param
+    # H_0 = W_i([V[src] || E])   (mixins.py:8-9); rows in dst-sorted order
+    H0 = _hidden(nE, hp, T, dev)
+    linear_fwd(V, d_v, Wi, H0, h, idx1=lay.src_row, X2=E, K2=d_e, idx2=lay.perm, bias=bi, R=nE, pad_to=hp)
+    Hs, Ms, Hbars = [], [], []
+    Hprev, first = H0, True  # H^0 = tau(H_0) is applied on load (base.py:200)
+    use_fused = cfg.depth > 1 and _fused_step_ok(cfg, lay, h)
+    Wpk = pack_weight_bf16(Wh) if use_fused else None
+    for _ in range(1, cfg.depth):
+        if use_fused:
+            Hn = _hidden(nE, hp, T, dev)
+            with _StepTimer("fused_first" if first else "fused"):
+                bond_step_fused(Hprev, H0, Hn, h, Wpk, bh, lay, a, ap, first)
+            Ms.append(None)
+        else:
+            src_in, fa = Hprev, (a if first else ACT_NONE)
+            if cfg.undirected:  # H = (H + H[rev]) / 2   (base.py:202-203)
+                Hbar = _hidden(nE, hp, T, dev)
+                rev_average(src_in, lay, h, Hbar, act=fa, act_param=ap)
+                Hbars.append(Hbar)
+                src_in, fa = Hbar, ACT_NONE
+            M = _hidden(nE, hp, T, dev)
+            Hn = _hidden(nE, hp, T, dev)
+            with _StepTimer("unfused_first" if first else "unfused"):
+                bond_message(src_in, lay, h, M, act=fa, act_param=ap)           # mixins.py:11-18
+                linear_fwd(M, h, Wh, Hn, h, bias=bh, res=H0, act=a, act_param=ap, R=nE, pad_to=hp)  # base.py:135-141
+            Ms.append(M)
+        Hs.append(Hn)
+        Hprev, first = Hn, False
+    # M_v = sum_{dst(e)=v} H[e]   (base.py:208-211)
+    Mv = _hidden(nV, hp, T, dev)
+    segment_sum(Hprev, lay.rowptr, nV, h, Mv, act=(a if first else ACT_NONE), act_param=ap, pad_to=hp)
+    # H_v = tau(W_o([V || M_v]))   (base.py:180-182)
+    Hv = torch.empty((nV, h), dtype=T, device=dev)
+    linear_fwd(V, d_v, Wo, Hv, h, X2=Mv, K2=h, bias=bo, act=a, act_param=ap, R=nV, pad_to=h)
+    saved = dict(H0=H0, Hs=Hs, Ms=Ms, Hbars=Hbars, Mv=Mv, Hv=Hv)
+    return Hv, saved
+
+
+def bond_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo: Tensor, cfg: MPConfig,
+                  saved: dict, gHv: Tensor, need_bias: tuple[bool, bool, bool]):
+    """Hand-written autograd mirror of bond_forward.  Returns
+    (dWi, dbi, dWh, dbh, dWo, dbo)."""
+    dev = V.device
+    h = Wh.shape[0]
+    hp = pad_hidden(h)
+    d_v, d_e = V.shape[1], E.shape[1]
+    T = cfg.hidden_dtype
+    nE, nV = lay.E, lay.V
+    a, ap = cfg.act, cfg.act_param
+    H0, Hs, Ms, Hbars, Mv, Hv = saved["H0"], saved["Hs"], saved["Ms"], saved["Hbars"], saved["Mv"], saved["Hv"]
+    f32 = dict(dtype=torch.float32, device=dev)
+    dWi = torch.zeros_like(Wi, dtype=torch.float32)
+    dWh = torch.zeros_like(Wh, dtype=torch.float32)
+    dWo = torch.zeros_like(Wo, dtype=torch.float32)
+    dbi = torch.zeros(h, **f32) if need_bias[0] else None
+    dbh = torch.zeros(h, **f32) if need_bias[1] else None
+    dbo = torch.zeros(h, **f32) if need_bias[2] else None
+    gHv = gHv.contiguous()
+    # readout: dY = g * tau'(Y); dW_o = dY^T [V || M_v]; dM_v = dY . W_o[:, d_v:]
+    dY = _hidden(nV, hp, T, dev)
+    act_bwd(gHv, Hv, nV, h, act=a, act_param=ap, dZ=dY)
+    linear_wgrad(dY, V, d_v, dWo, h, X2=Mv, K2=h, dbias=dbo, R=nV)
+    WoT = Wo[:, d_v:].t().contiguous()
+    dMv = _hidden(nV, hp, T, dev)
+    linear_fwd(dY, h, WoT, dMv, h, R=nV, pad_to=hp)
+    dH0 = torch.zeros((max(nE, 1), hp), **f32)  # f32 accumulator of dH_0 over all depth steps
+    if nE > 0:
+        if cfg.depth == 1:
+            # dH^0[e] = dM_v[dst(e)];  dH_0 = dH^0 * tau'(H_0)
+            act_bwd(dMv, H0, nE, h, act=a, act_param=ap, gidx=lay.dst_row, from_preact=True, acc=dH0)
+        else:
+            WhT = Wh.t().contiguous()
+            dZ = _hidden(nE, hp, T, dev)
+            act_bwd(dMv, Hs[-1], nE, h, act=a, act_param=ap, gidx=lay.dst_row, dZ=dZ, acc=dH0)
+            for t in range(cfg.depth - 1, 0, -1):
+                # inputs of step t: Hin = H^{t-1} (or tau(H_0) when t == 1)
+                first = t == 1
+                Hin = H0 if first else Hs[t - 2]
+                M = Ms[t - 1]
+                if M is None:  # fused forward did not materialise M^t: recompute it
+                    M = _hidden(nE, hp, T, dev)
+                    bond_message(Hin, lay, h, M, act=(a if first else ACT_NONE), act_param=ap)
+                linear_wgrad(dZ, M, h, dWh, h, dbias=dbh, accumulate=True, R=nE)
+                dM = _hidden(nE, hp, T, dev)
+                linear_fwd(dZ, h, WhT, dM, h, R=nE, pad_to=hp)
+                dHin = _hidden(nE, hp, T, dev)
+                bond_message(dM, lay, h, dHin, permute_on_read=True)
+                if cfg.undirected:
+                    tmp = _hidden(nE, hp, T, dev)
+                    rev_average(dHin, lay, h, tmp)
+                    dHin = tmp
+                if first:
+                    act_bwd(dHin, H0, nE, h, act=a, act_param=ap, from_preact=True, acc=dH0)
+                else:
+                    dZ = _hidden(nE, hp, T, dev)
+                    act_bwd(dHin, Hin, nE, h, act=a, act_param=ap, dZ=dZ, acc=dH0)
+        linear_wgrad(dH0, V, d_v, dWi, h, idx1=lay.src_row, X2=E, K2=d_e, idx2=lay.perm, dbias=dbi, R=nE)
+    return dWi, dbi, dWh, dbh, dWo, dbo
+
+
+class BondMPFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, V, E, Wi, bi, Wh, bh, Wo, bo, lay, cfg):
+        _require_cuda(V, E, Wi, Wh, Wo)
+        V = V.contiguous().float()
+        E = E.contiguous().float()
+        Wi_, Wh_, Wo_ = Wi.detach().contiguous().float(), Wh.detach().contiguous().float(), Wo.detach().contiguous().float()
+        bi_ = None if bi is None else bi.detach().contiguous().float()
+        bh_ = None if bh is None else bh.detach().contiguous().float()
+        bo_ = None if bo is None else bo.detach().contiguous().float()
+        Hv, saved = bond_forward(lay, V, E, Wi_, bi_, Wh_, bh_, Wo_, bo_, cfg)
+        ctx.lay, ctx.cfg, ctx.saved = lay, cfg, saved
+        ctx.VE = (V, E)
+        ctx.W = (Wi_, Wh_, Wo_)
+        ctx.has_bias = (bi is not None, bh is not None, bo is not None)
+        ctx.wdtypes = (Wi.dtype, Wh.dtype, Wo.dtype)
+        return Hv
+
+    @staticmethod
+    def backward(ctx, gHv):
+        V, E = ctx.VE
+        Wi, Wh, Wo = ctx.W
+        dWi, dbi, dWh, dbh, dWo, dbo = bond_backward(ctx.lay, V, E, Wi, Wh, Wo, ctx.cfg, ctx.saved, gHv, ctx.has_bias)
+        ctx.saved = None
+        d0, d1, d2 = ctx.wdtypes
+        cast = lambda g, d: None if g is None else g.to(d)
+        return (None, None, cast(dWi, d0), cast(dbi, d0), cast(dWh, d1), cast(dbh, d1), cast(dWo, d2),
+                cast(dbo, d2), None, None)
+
+
+# ----------------------------------------------------------------------------------------------
+# atom message passing (atom-granular: every edge row depends only on its source atom)
+# ----------------------------------------------------------------------------------------------
+def atom_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, bh, Wo: Tensor, bo,
+                 cfg: MPConfig):
+    """AtomMessagePassing.forward up to W_o (base.py:196-212 with mixins.py:22-30), restated on atoms:
+    the reference's H[e] equals Ha[src(e)], so M[e] = [sum_{u in N(src e)} Ha[u] || sum_in E]."""
+    dev = V.device
+    h = Wi.shape[0]
+    hp = pad_hidden(h)
+    d_v, d_e = V.shape[1], E.shape[1]
+    T = cfg.hidden_dtype
+    nV = lay.V
+    a, ap = cfg.act, cfg.act_param
+    H0 = _hidden(nV, hp, T, dev)
+    linear_fwd(V, d_v, Wi, H0, h, bias=bi, R=nV, pad_to=hp)                       # mixins.py:22-23
+    SE = torch.zeros((max(nV, 1), max(d_e, 1)), dtype=torch.float32, device=dev)   # sum of in-edge bond features
+    if d_e > 0:
+        segment_sum(E, lay.rowptr, nV, d_e, SE, idx=lay.perm)
+    Hs, Ns = [], []
+    Hprev, first = H0, True
+    for _ in range(1, cfg.depth):
+        Nb = _hidden(nV, hp, T, dev)  # sum over in-neighbours u of Ha[u]   (mixins.py:25-30)
+        segment_sum(Hprev, lay.rowptr, nV, h, Nb, idx=lay.src_row, act=(a if first else ACT_NONE), act_param=ap,
+                    pad_to=hp)
+        Hn = _hidden(nV, hp, T, dev)
+        linear_fwd(Nb, h, Wh, Hn, h, X2=SE if d_e > 0 else None, K2=d_e, bias=bh, res=H0, act=a, act_param=ap,
+                   R=nV, pad_to=hp)                                                  # base.py:135-141
+        Hs.append(Hn)
+        Ns.append(Nb)
+        Hprev, first = Hn, False
+    Mv = _hidden(nV, hp, T, dev)
+    segment_sum(Hprev, lay.rowptr, nV, h, Mv, idx=lay.src_row, act=(a if first else ACT_NONE), act_param=ap,
+                pad_to=hp)                                                           # base.py:208-211
+    Hv = torch.empty((nV, h), dtype=T, device=dev)
+    linear_fwd(V, d_v, Wo, Hv, h, X2=Mv, K2=h, bias=bo, act=a, act_param=ap, R=nV, pad_to=h)
+    return Hv, dict(H0=H0, Hs=Hs, Ns=Ns, SE=SE, Mv=Mv, Hv=Hv)
+
+
+def atom_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo: Tensor, cfg: MPConfig,
+                  saved: dict, gHv: Tensor, need_bias):
+    dev = V.device
+    h = Wi.shape[0]
+    hp = pad_hidden(h)
+    d_v, d_e = V.shape[1], E.shape[1]
+    T = cfg.hidden_dtype
+    nV = lay.V
+    a, ap = cfg.act, cfg.act_param
+    H0, Hs, Ns, SE, Mv, Hv = saved["H0"], saved["Hs"], saved["Ns"], saved["SE"], saved["Mv"], saved["Hv"]
+    f32 = dict(dtype=torch.float32, device=dev)
+    dWi = torch.zeros_like(Wi, dtype=torch.float32)
+    dWh = torch.zeros_like(Wh, dtype=torch.float32)
+    dWo = torch.zeros_like(Wo, dtype=torch.float32)
+    dbi = torch.zeros(h, **f32) if need_bias[0] else None
+    dbh = torch.zeros(h, **f32) if need_bias[1] else None
+    dbo = torch.zeros(h, **f32) if need_bias[2] else None
+    gHv = gHv.contiguous()
+    dY = _hidden(nV, hp, T, dev)
+    act_bwd(gHv, Hv, nV, h, act=a, act_param=ap, dZ=dY)
+    linear_wgrad(dY, V, d_v, dWo, h, X2=Mv, K2=h, dbias=dbo, R=nV)
+    WoT = Wo[:, d_v:].t().contiguous()
+    dMv = _hidden(nV, hp, T, dev)
+    linear_fwd(dY, h, WoT, dMv, h, R=nV, pad_to=hp)
+    # d(Ha^{T-1})[u] = sum_{e: src(e)=u} dM_v[dst(e)] = sum_{e' in in(u)} dM_v[src(e')]  (rev is an involution)
+    dH0 = torch.zeros((max(nV, 1), hp), **f32)
+    dHa = _hidden(nV, hp, T, dev)
+    segment_sum(dMv, lay.rowptr, nV, h, dHa, idx=lay.src_row, pad_to=hp)
+    WhT = Wh[:, :h].t().contiguous() if cfg.depth > 1 else None
+    for t in range(cfg.depth - 1, 0, -1):
+        first = t == 1
+        dZ = _hidden(nV, hp, T, dev)
+        act_bwd(dHa, Hs[t - 1], nV, h, act=a, act_param=ap, dZ=dZ, acc=dH0)
+        linear_wgrad(dZ, Ns[t - 1], h, dWh, h, X2=SE if d_e > 0 else None, K2=d_e, dbias=dbh, accumulate=True, R=nV)
+        dN = _hidden(nV, hp, T, dev)
+        linear_fwd(dZ, h, WhT, dN, h, R=nV, pad_to=hp)
+        dHa = _hidden(nV, hp, T, dev)
+        segment_sum(dN, lay.rowptr, nV, h, dHa, idx=lay.src_row, pad_to=hp)
+    act_bwd(dHa, H0, nV, h, act=a, act_param=ap, from_preact=True, acc=dH0)
+    linear_wgrad(dH0, V, d_v, dWi, h, dbias=dbi, R=nV)
+    return dWi, dbi, dWh, dbh, dWo, dbo
+
+
+class AtomMPFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, V, E, Wi, bi, Wh, bh, Wo, bo, lay, cfg):
+        _require_cuda(V, E, Wi, Wh, Wo)
+        V = V.contiguous().float()
+        E = E.contiguous().float()
+        Wi_, Wh_, Wo_ = Wi.detach().contiguous().float(), Wh.detach().contiguous().float(), Wo.detach().contiguous().float()
+        bi_ = None if bi is None else bi.detach().contiguous().float()
+        bh_ = None if bh is None else bh.detach().contiguous().float()
+        bo_ = None if bo is None else bo.detach().contiguous().float()
+        Hv, saved = atom_forward(lay, V, E, Wi_, bi_, Wh_, bh_, Wo_, bo_, cfg)
+        ctx.lay, ctx.cfg, ctx.saved = lay, cfg, saved
+        ctx.VE = (V, E)
+        ctx.W = (Wi_, Wh_, Wo_)
+        ctx.has_bias = (bi is not None, bh is not None, bo is not None)
+        ctx.wdtypes = (Wi.dtype, Wh.dtype, Wo.dtype)
+        return Hv
+
+    @staticmethod
+    def backward(ctx, gHv):
+        V, E = ctx.VE
+        Wi, Wh, Wo = ctx.W
+        dWi, dbi, dWh, dbh, dWo, dbo = atom_backward(ctx.lay, V, E, Wi, Wh, Wo, ctx.cfg, ctx.saved, gHv, ctx.has_bias)
+        ctx.saved = None
+        d0, d1, d2 = ctx.wdtypes
+        cast = lambda g, d: None if g is None else g.to(d)
+        return (None, None, cast(dWi, d0), cast(dbi, d0), cast(dWh, d1), cast(dbh, d1), cast(dWo, d2),
+                cast(dbo, d2), None, None)
+
+
+# ----------------------------------------------------------------------------------------------
+# aggregation
+# ----------------------------------------------------------------------------------------------
+class SegmentAggFunction(torch.autograd.Function):
+    """Mean / Sum / Norm aggregation over molecules (chemprop/nn/agg.py:73-78, 90-95, 112-113)."""
+
+    @staticmethod
+    def forward(ctx, H, mol_atom_ptr, atom_mol, n_mols, scale_mode, scale):
+        _require_cuda(H)
+        Hc = H.contiguous()
+        out = torch.empty((n_mols, H.shape[1]), dtype=H.dtype, device=H.device)
+        segment_sum(Hc, mol_atom_ptr, n_mols, H.shape[1], out, scale_mode=scale_mode, scale=scale,
+                    pad_to=H.shape[1])
+        ctx.ptr, ctx.atom_mol, ctx.mode, ctx.scale = mol_atom_ptr, atom_mol, scale_mode, scale
+        ctx.nV = H.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        dH = torch.empty((ctx.nV, g.shape[1]), dtype=g.dtype, device=g.device)
+        segment_bcast(g, ctx.atom_mol, ctx.ptr, ctx.nV, g.shape[1], dH, scale_mode=ctx.mode, scale=ctx.scale)
+        return dH, None, None, None, None, None

@@ -1,0 +1,143 @@
+"""`BondMessagePassing` / `AtomMessagePassing` with the module API of
+chemprop/nn/message_passing/base.py:16-289 (same constructor arguments, `hparams`, parameter names
+W_i / W_h / W_o / W_d, `output_dim`, `forward(bmg, V_d=None)`), executed by the sm_100a engine.
+
+Differences a user can see: the module must live on a CUDA device (there is no CPU fallback), and a
+`precision` keyword selects the hidden-state storage type: "fp32" (default; matches the reference
+within 1e-5) or "bf16" (bf16 hidden states + tensor-core depth step; within 1e-2).
+"""
+from __future__ import annotations
+
+import torch
+from torch import Tensor, nn
+
+from .. import _lib
+from ..engine import AtomMPFunction, BondMPFunction, MPConfig, get_layout
+from ..exceptions import InvalidShapeError
+
+DEFAULT_ATOM_FDIM, DEFAULT_BOND_FDIM, DEFAULT_HIDDEN_DIM = 72, 14, 300  # chemprop/conf.py
+
+_ACT_NAMES = {"relu": nn.ReLU, "leakyrelu": lambda: nn.LeakyReLU(0.1), "prelu": nn.PReLU, "tanh": nn.Tanh,
+              "elu": nn.ELU}
+
+
+def get_activation_function(activation) -> nn.Module:
+    """chemprop/nn/utils.py:19-55 (string / enum-like / module -> module)."""
+    if isinstance(activation, nn.Module):
+        return activation
+    name = getattr(activation, "name", activation)
+    key = str(name).lower()
+    if key == "selu":
+        return nn.SELU()
+    if key not in _ACT_NAMES:
+        raise KeyError(f"Unsupported activation: {activation!r}; one of {sorted(_ACT_NAMES)}")
+    return _ACT_NAMES[key]()
+
+
+def engine_activation(tau: nn.Module) -> tuple[int, float]:
+    """Map a torch activation module to the engine's fused activation code."""
+    if isinstance(tau, nn.ReLU):
+        return _lib.ACT_RELU, 0.0
+    if isinstance(tau, nn.LeakyReLU):
+        return _lib.ACT_LEAKYRELU, float(tau.negative_slope)
+    if isinstance(tau, nn.Tanh):
+        return _lib.ACT_TANH, 0.0
+    if isinstance(tau, nn.ELU):
+        return _lib.ACT_ELU, float(tau.alpha)
+    if isinstance(tau, nn.Identity):
+        return _lib.ACT_NONE, 0.0
+    raise NotImplementedError(
+        f"activation {type(tau).__name__} is not fused by the sm_100a engine "
+        "(supported: ReLU, LeakyReLU, Tanh, ELU)"
+    )
+
+
+class _MessagePassingBase(nn.Module):
+    _function = None
+
+    def __init__(self, d_v: int = DEFAULT_ATOM_FDIM, d_e: int = DEFAULT_BOND_FDIM, d_h: int = DEFAULT_HIDDEN_DIM,
+                 bias: bool = False, depth: int = 3, dropout: float = 0.0, activation="relu",
+                 undirected: bool = False, d_vd: int | None = None, V_d_transform: nn.Module | None = None,
+                 graph_transform: nn.Module | None = None, precision: str = "fp32"):
+        super().__init__()
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        # same keys as the reference's save_hyperparameters() result (base.py:70-80)
+        self.hparams = dict(d_v=d_v, d_e=d_e, d_h=d_h, bias=bias, depth=depth, dropout=dropout,
+                            activation=activation, undirected=undirected, d_vd=d_vd,
+                            V_d_transform=V_d_transform, graph_transform=graph_transform,
+                            precision=precision, cls=self.__class__)
+        self.W_i, self.W_h, self.W_o, self.W_d = self.setup(d_v, d_e, d_h, d_vd, bias)
+        self.depth = depth
+        self.undirected = undirected
+        self.dropout = nn.Dropout(dropout)
+        self.tau = get_activation_function(activation)
+        self.V_d_transform = V_d_transform if V_d_transform is not None else nn.Identity()
+        self.graph_transform = graph_transform if graph_transform is not None else nn.Identity()
+        self.precision = precision
+        self.fused = True
+
+    @property
+    def output_dim(self) -> int:
+        return self.W_d.out_features if self.W_d is not None else self.W_o.out_features
+
+    def setup(self, d_v, d_e, d_h, d_vd, bias):
+        raise NotImplementedError
+
+    def _config(self) -> MPConfig:
+        act, ap = engine_activation(self.tau)
+        return MPConfig(depth=int(self.depth), act=act, act_param=ap, undirected=bool(self.undirected),
+                        hidden_dtype=torch.bfloat16 if self.precision == "bf16" else torch.float32,
+                        fused=bool(self.fused))
+
+    def forward(self, bmg, V_d: Tensor | None = None) -> Tensor:
+        if self.training and self.dropout.p > 0:
+            raise NotImplementedError("dropout > 0 inside the fused depth loop is not implemented yet")
+        bmg = self.graph_transform(bmg)
+        lay = get_layout(bmg)
+        H = type(self)._function.apply(
+            bmg.V, bmg.E, self.W_i.weight, self.W_i.bias, self.W_h.weight, self.W_h.bias,
+            self.W_o.weight, self.W_o.bias, lay, self._config(),
+        )
+        return self.finalize_descriptors(H, V_d)
+
+    def finalize_descriptors(self, H: Tensor, V_d: Tensor | None) -> Tensor:
+        """Second half of `finalize` (base.py:184-194): optional W_d on [H || V_d]; no activation."""
+        if V_d is None:
+            return H
+        V_d = self.V_d_transform(V_d)
+        try:
+            H = self.W_d(torch.cat((H.to(self.W_d.weight.dtype), V_d), dim=1))
+            H = self.dropout(H)
+        except RuntimeError:
+            raise InvalidShapeError("V_d", V_d.shape, [len(H), self.W_d.in_features - self.W_o.out_features])
+        return H
+
+
+class BondMessagePassing(_MessagePassingBase):
+    """Directed-bond message passing (chemprop/nn/message_passing/base.py:215-251)."""
+    _function = BondMPFunction
+
+    def setup(self, d_v=DEFAULT_ATOM_FDIM, d_e=DEFAULT_BOND_FDIM, d_h=DEFAULT_HIDDEN_DIM, d_vd=None, bias=False):
+        W_i = nn.Linear(d_v + d_e, d_h, bias)
+        W_h = nn.Linear(d_h, d_h, bias)
+        W_o = nn.Linear(d_v + d_h, d_h)
+        W_d = nn.Linear(d_h + d_vd, d_h + d_vd) if d_vd else None
+        return W_i, W_h, W_o, W_d
+
+
+class AtomMessagePassing(_MessagePassingBase):
+    """Atom message passing (chemprop/nn/message_passing/base.py:254-289)."""
+    _function = AtomMPFunction
+
+    def setup(self, d_v=DEFAULT_ATOM_FDIM, d_e=DEFAULT_BOND_FDIM, d_h=DEFAULT_HIDDEN_DIM, d_vd=None, bias=False):
+        W_i = nn.Linear(d_v, d_h, bias)
+        W_h = nn.Linear(d_e + d_h, d_h, bias)
+        W_o = nn.Linear(d_v + d_h, d_h)
+        W_d = nn.Linear(d_h + d_vd, d_h + d_vd) if d_vd else None
+        return W_i, W_h, W_o, W_d
+
+    def forward(self, bmg, V_d: Tensor | None = None) -> Tensor:
+        if self.undirected:
+            raise NotImplementedError("AtomMessagePassing(undirected=True) is not supported by the engine yet")
+        return super().forward(bmg, V_d)

@@ -1,0 +1,219 @@
+/*
+ * dmpnn.h -- C ABI of libdmpnn_sm100.so, the B200 (sm_100a) D-MPNN message-passing engine.
+ *
+ * The reference (chemprop v2.3.1) has no FFI on this path: the hot path is ~150 lines of
+ * Python dispatching stock ATen ops.  This header is therefore the boundary a maintainer
+ * would bind (ctypes) from the reference's module layer; each entry point names the
+ * reference code (file:line, relative to the chemprop repo root) it replaces.
+ *
+ * Conventions
+ *  - Plain C symbols; raw device pointers; int64_t sizes; `stream` is a cudaStream_t passed
+ *    as void* (torch.cuda.current_stream().cuda_stream).  No torch types.
+ *  - The library never allocates, frees or synchronises; all buffers (outputs, saved
+ *    activations, workspaces) are owned by the caller.  Launches are asynchronous on `stream`.
+ *  - Every function returns 0 on success, <0 on error; dmpnn_last_error() gives the
+ *    thread-local message.
+ *  - "Hidden" matrices (edge / atom hidden states) are row-major with a row stride `ld`
+ *    given in ELEMENTS; their element type is `dmpnn_dtype_t` (f32 or bf16).  Inputs V, E and
+ *    all weights / weight gradients are f32.
+ *  - Internal edge order: the engine keeps edge hidden states sorted by destination atom
+ *    (stable), so the in-edges of atom v are the contiguous rows [rowptr[v], rowptr[v+1]).
+ *    `perm[row]` is the caller's edge id of an internal row; outputs of the path are atom- or
+ *    molecule-level, so this order never leaks out.
+ */
+#ifndef DMPNN_H_
+#define DMPNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMPNN_VERSION 100 /* 0.1.0 */
+
+typedef enum { DMPNN_F32 = 0, DMPNN_BF16 = 1 } dmpnn_dtype_t;
+
+/* Activations of chemprop/nn/utils.py:11-55 that the engine fuses (PReLU / arbitrary modules
+ * are handled by the Python host as an unfused composition). */
+typedef enum {
+  DMPNN_ACT_NONE = 0,
+  DMPNN_ACT_RELU = 1,
+  DMPNN_ACT_LEAKYRELU = 2, /* slope = act_param (reference: 0.1) */
+  DMPNN_ACT_TANH = 3,
+  DMPNN_ACT_ELU = 4 /* alpha = act_param (reference: 1.0) */
+} dmpnn_act_t;
+
+/* segment scaling: none; divide by the constant `scale` (NormAggregation, agg.py:112-113);
+ * divide by the segment's row count (MeanAggregation, agg.py:73-78; empty segment -> 0). */
+typedef enum { DMPNN_SCALE_NONE = 0, DMPNN_SCALE_DIV_CONST = 1, DMPNN_SCALE_INV_COUNT = 2 } dmpnn_scale_t;
+
+/* Layout meta words written by dmpnn_layout_build (int32 each). */
+enum {
+  DMPNN_META_N_TILES = 0,      /* number of molecule-aligned tiles                              */
+  DMPNN_META_FLAGS = 1,        /* bit set below                                                 */
+  DMPNN_META_MAX_INDEG = 2,    /* max in-degree of any atom                                     */
+  DMPNN_META_MAX_TILE_ROWS = 3,/* largest tile (edge rows); >128 => some molecule is oversized  */
+  DMPNN_META_MAX_TILE_ATOMS = 4,
+  DMPNN_META_WORDS = 8
+};
+enum {
+  DMPNN_FLAG_REV_INVOLUTION = 1, /* rev[rev[e]]==e, src[rev e]==dst[e], dst[rev e]==src[e]      */
+  DMPNN_FLAG_BATCH_SORTED = 2,   /* batch non-decreasing and every edge intra-molecule          */
+  DMPNN_FLAG_INDEX_IN_RANGE = 4  /* all indices within [0,V) / [0,E) / [0,B)                    */
+};
+
+int dmpnn_version(void);
+const char* dmpnn_last_error(void);
+/* 1 if a CUDA device of compute capability 10.x is current, else 0 (never throws). */
+int dmpnn_device_ok(void);
+/* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
+long long dmpnn_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Host-side collate.  Replaces BatchMolGraph.__post_init__ (chemprop/data/collate.py:37-62):
+ * concatenates per-molecule arrays and offsets edge_index / rev_edge_index; produces the same
+ * five public arrays (V, E f32; edge_index 2xE, rev_edge_index E, batch V -- all int64).
+ * CPU code (the reference runs this in DataLoader worker processes).
+ * `n_atoms[i]`, `n_edges[i]` give molecule sizes; `V_ptrs[i]` etc. point at that molecule's
+ * arrays (V: n_atoms x d_v f32; E: n_edges x d_e f32; edge_index: 2 x n_edges int64 row-major;
+ * rev: n_edges int64).
+ * ------------------------------------------------------------------------------------- */
+int dmpnn_collate_host(int64_t n_mols, const int64_t* n_atoms, const int64_t* n_edges,
+                       const float* const* V_ptrs, const float* const* E_ptrs,
+                       const int64_t* const* edge_index_ptrs, const int64_t* const* rev_ptrs,
+                       int64_t d_v, int64_t d_e,
+                       float* V_out, float* E_out, int64_t* edge_index_out /*2 x E_tot*/,
+                       int64_t* rev_out, int64_t* batch_out);
+
+/* ---------------------------------------------------------------------------------------
+ * Device layout build.  Consumes the reference's BatchMolGraph index tensors
+ * (chemprop/data/collate.py:24-33: edge_index int64 2xE, rev_edge_index int64 E, batch int64 V)
+ * and produces the engine's int32 layout: the stable sort of edges by destination atom
+ * (perm / inv_perm / rowptr), per-row src / dst / rev (internal row ids), molecule atom/row
+ * offsets, and a table of molecule-aligned tiles holding <=128 edge rows and <=128 atoms each
+ * (a molecule larger than that gets a tile of its own; see DMPNN_META_MAX_TILE_*).
+ * This replaces the index materialisation in chemprop/nn/message_passing/mixins.py:12
+ * (`edge_index[1].unsqueeze(1).repeat(1, h)`) and chemprop/nn/agg.py:74-75.
+ * Integer outputs are bit-exact w.r.t. oracle/layout_np.py.
+ * ------------------------------------------------------------------------------------- */
+int dmpnn_layout_workspace_bytes(int64_t V, int64_t E, int64_t B, size_t* bytes);
+int dmpnn_layout_build(const int64_t* edge_index, const int64_t* rev_edge_index, const int64_t* batch,
+                       int64_t V, int64_t E, int64_t B,
+                       int32_t* perm /*E*/, int32_t* inv_perm /*E*/, int32_t* rowptr /*V+1*/,
+                       int32_t* src_row /*E*/, int32_t* dst_row /*E*/, int32_t* rev_row /*E*/,
+                       int32_t* mol_atom_ptr /*B+1*/, int32_t* mol_row_ptr /*B+1*/,
+                       int32_t* tile_mol_ptr /*B+1, first n_tiles+1 valid*/,
+                       int32_t* meta /*DMPNN_META_WORDS*/,
+                       void* workspace, void* stream);
+
+/* Segment offsets of a sorted int64 index (the `batch` argument of Aggregation.forward,
+ * chemprop/nn/agg.py:39-59): ptr[b] = first i with index[i] >= b, ptr[n_seg] = n.  `status`
+ * (1 int32, device) is set non-zero if index is not non-decreasing or leaves [0, n_seg). */
+int dmpnn_sorted_index_to_ptr(const int64_t* index, int64_t n, int64_t n_seg, int32_t* ptr,
+                              int32_t* status, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Generic fused linear:  C[cr(r), 0:N] = act( [X1[i1(r)] || X2[i2(r)]] . W^T + bias + R[r] )
+ * for r in [0,R).  W is the nn.Linear weight, f32 row-major N x (K1+K2), row stride ldw.
+ * X1 / X2: f32 or hidden dtype (per *_dtype); idx1 / idx2 optional int32 row gathers (NULL =
+ * identity); K2 may be 0.  bias (f32, N) and residual R (hidden dtype, ldr) optional (NULL).
+ * Columns [N, ldc_pad) of C are zero-filled (ldc_pad <= ldc), keeping row padding clean.
+ * Covers: W_i initialise (mixins.py:8-9, :22-23), W_h update (base.py:135-141), W_o finalize
+ * (base.py:180-182) and the dX = dY.W GEMMs of their autograd mirror.
+ * fp32-accurate SIMT path (no tensor cores): this is the <=1e-5 tier and the fallback.
+ * ------------------------------------------------------------------------------------- */
+int dmpnn_linear_fwd(const void* X1, int x1_dtype, int64_t ld1, const int32_t* idx1, int64_t K1,
+                     const void* X2, int x2_dtype, int64_t ld2, const int32_t* idx2, int64_t K2,
+                     const float* W, int64_t ldw, const float* bias,
+                     const void* Rres, int r_dtype, int64_t ldr,
+                     int act, float act_param,
+                     void* C, int c_dtype, int64_t ldc, int64_t ldc_pad,
+                     int64_t R, int64_t N, void* stream);
+
+/* Weight gradient: dW[n, 0:K1+K2] (+)= sum_r dY[r,n] * [X1[i1(r)] || X2[i2(r)]][k];
+ * optional dbias[n] (+)= sum_r dY[r,n].  Two-pass deterministic reduction through
+ * `workspace` (dmpnn_linear_wgrad_workspace_bytes).  accumulate!=0 adds into dW / dbias. */
+int dmpnn_linear_wgrad_workspace_bytes(int64_t R, int64_t N, int64_t K, size_t* bytes);
+int dmpnn_linear_wgrad(const void* dY, int dy_dtype, int64_t lddy,
+                       const void* X1, int x1_dtype, int64_t ld1, const int32_t* idx1, int64_t K1,
+                       const void* X2, int x2_dtype, int64_t ld2, const int32_t* idx2, int64_t K2,
+                       float* dW, int64_t lddw, float* dbias, int accumulate,
+                       int64_t R, int64_t N, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Segmented row sum:  Y[s, 0:C] = scale(s) * sum_{r in [ptr[s], ptr[s+1])} f(X[idx(r), 0:C]).
+ * f = activation `act` applied on load (ACT_NONE = identity).  Covers the final atom
+ * scatter-sum (base.py:208-211; segments = atoms over dst-sorted rows), the neighbour sum of
+ * the atom-granular AtomMessagePassing (mixins.py:25-30), and Mean/Sum/Norm aggregation
+ * (agg.py:73-78, 90-95, 112-113; segments = molecules; divide by count / nothing / norm).
+ * Empty segments give zero rows (agg.py:44-45).  Accumulates in f32, deterministic order.
+ * ------------------------------------------------------------------------------------- */
+int dmpnn_segment_sum(const void* X, int x_dtype, int64_t ldx, const int32_t* idx,
+                      const int32_t* ptr, int64_t n_seg, int64_t C,
+                      int act, float act_param, int scale_mode, float scale,
+                      void* Y, int y_dtype, int64_t ldy, int64_t ldy_pad, void* stream);
+
+/* Row broadcast (autograd mirror of segment_sum with identity f):
+ * Y[r, 0:C] = scale(seg(r)) * G[seg_of_row[r], 0:C]; for SCALE_INV_COUNT, `ptr` gives counts. */
+int dmpnn_segment_bcast(const void* G, int g_dtype, int64_t ldg, const int32_t* seg_of_row,
+                        const int32_t* ptr, int64_t R, int64_t C, int scale_mode, float scale,
+                        void* Y, int y_dtype, int64_t ldy, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Bond message (mixins.py:11-18):  M[e] = sum_{e': dst(e')=src(e)} H[e'] - H[rev(e)], computed
+ * per atom v over its in-edge rows e'_1..e'_d:  s = sum_i f(X[rd(e'_i)]);
+ * OUT[wr(e'_i)] = s - f(X[rd(e'_i)])  with (rd, wr) = (identity, rev) when permute_on_read==0
+ * (forward: OUT = M) and (rev, identity) when permute_on_read!=0 (autograd mirror:
+ * dH[e] = sum_{src(e'')=dst(e)} dM[e''] - dM[rev(e)]).  Requires DMPNN_FLAG_REV_INVOLUTION.
+ * f = `act` on load (used at depth step 1 where H^0 = tau(H_0), base.py:200).
+ * ------------------------------------------------------------------------------------- */
+int dmpnn_bond_message(const void* X, int x_dtype, int64_t ldx,
+                       const int32_t* rowptr, const int32_t* rev_row, int64_t V, int64_t C,
+                       int act, float act_param, int permute_on_read,
+                       void* OUT, int out_dtype, int64_t ldo, void* stream);
+
+/* Undirected averaging (base.py:202-203): OUT[r] = (f(X[r]) + f(X[rev(r)])) / 2, f = `act` on
+ * load (identity for ACT_NONE).  Self-adjoint when rev is an involution, so with ACT_NONE the
+ * same call is its own autograd mirror. */
+int dmpnn_rev_average(const void* X, int x_dtype, int64_t ldx, const int32_t* rev_row,
+                      int64_t R, int64_t C, int act, float act_param,
+                      void* OUT, int out_dtype, int64_t ldo, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Activation backward:  dZ[r,c] = G[gi(r), c] * tau'(.)  where tau' is evaluated from
+ * Yact (from_preact==0: Yact holds tau(z); from_preact!=0: Yact holds z).  If ACC != NULL,
+ * ACC[r,c] += dZ[r,c] (the dH_0 accumulator of the autograd mirror of base.py:135-141).
+ * dZ may be NULL when only the accumulation is wanted.
+ * ------------------------------------------------------------------------------------- */
+int dmpnn_act_bwd(const void* G, int g_dtype, int64_t ldg, const int32_t* gidx,
+                  const void* Yact, int y_dtype, int64_t ldy, int from_preact,
+                  int act, float act_param,
+                  void* dZ, int dz_dtype, int64_t lddz,
+                  void* ACC, int acc_dtype, int64_t ldacc,
+                  int64_t R, int64_t C, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused Blackwell depth step (bf16 hidden states, tcgen05 + TMEM + TMA):
+ *   H_next[rev(e')] = tau( H_0[rev(e')] + bias + W_h . ( sum_{in(v)} g(H_prev) - g(H_prev[e']) ) )
+ * i.e. message (mixins.py:11-18) + update (base.py:135-141) in ONE launch, one CTA per SM,
+ * molecule-aligned 128-row tiles from dmpnn_layout_build.  g = tau when first_step!=0
+ * (H_prev = H_0 and H^0 = tau(H_0) is recomputed on load), identity otherwise.
+ * Wpk is W_h packed by dmpnn_pack_weight_bf16.  Requires ld % 8 == 0, h <= 304, all tiles
+ * <= 128 rows, DMPNN_FLAG_REV_INVOLUTION.  Returns <0 (and does nothing) otherwise.
+ * ------------------------------------------------------------------------------------- */
+int dmpnn_pack_weight_bf16_bytes(int64_t N, int64_t K, size_t* bytes);
+int dmpnn_pack_weight_bf16(const float* W, int64_t ldw, int64_t N, int64_t K, void* Wpk, void* stream);
+int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, void* H_next, int64_t ld,
+                               int64_t n_rows_alloc, int64_t h,
+                               const void* Wpk, const float* bias,
+                               const int32_t* rowptr, const int32_t* rev_row,
+                               const int32_t* mol_atom_ptr, const int32_t* mol_row_ptr,
+                               const int32_t* tile_mol_ptr, int64_t n_tiles,
+                               int act, float act_param, int first_step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMPNN_H_ */

@@ -1,0 +1,201 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz by running the UNMODIFIED reference
+(chemprop v2.3.1 at /root/reference, imported through oracle/ref_shim.py) on small seeded cases.
+Run here (the reference cannot travel to the GPU box); the outputs are committed.
+
+    python -m oracle.make_golden
+
+Each .npz holds the inputs (V, E, edge_index, rev_edge_index, batch, n_mols, optional V_d), the
+module's state_dict, its config, and the reference results: H_v = mp(bmg[, V_d]), the
+Mean/Sum/Norm aggregations of H_v, and the weight gradients of loss = sum(mean_agg(H_v) * G).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.ref_shim import REFERENCE_ROOT, import_reference  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# name -> config.  graph: how the batch is made (see make_batch)
+CASES = {
+    "bond_d3_relu":        dict(kind="bond", depth=3, d_h=64, graph="mols6"),
+    "bond_d1":             dict(kind="bond", depth=1, d_h=48, graph="mols6"),
+    "bond_d2_bias":        dict(kind="bond", depth=2, d_h=64, bias=True, graph="mols6"),
+    "bond_d6":             dict(kind="bond", depth=6, d_h=40, graph="mols6"),
+    "bond_d3_undirected":  dict(kind="bond", depth=3, d_h=64, undirected=True, graph="mols6"),
+    "bond_d3_leakyrelu":   dict(kind="bond", depth=3, d_h=64, activation="leakyrelu", graph="mols6"),
+    "bond_d3_tanh":        dict(kind="bond", depth=3, d_h=64, activation="tanh", bias=True, graph="mols6"),
+    "bond_d3_elu":         dict(kind="bond", depth=3, d_h=64, activation="elu", graph="mols6"),
+    "bond_d3_shuffled":    dict(kind="bond", depth=3, d_h=64, graph="mols6_shuffled"),
+    "bond_d3_chain":       dict(kind="bond", depth=3, d_h=300, graph="chain5"),
+    "bond_d3_noedges":     dict(kind="bond", depth=3, d_h=32, graph="single_atoms4"),
+    "bond_d3_mixed":       dict(kind="bond", depth=3, d_h=64, graph="mixed"),
+    "bond_d3_vd":          dict(kind="bond", depth=3, d_h=64, d_vd=5, graph="mols6"),
+    "bond_d3_h300":        dict(kind="bond", depth=3, d_h=300, graph="mols6"),
+    "bond_d3_big_mol":     dict(kind="bond", depth=3, d_h=32, graph="bigmol"),
+    "bond_d3_trained":     dict(kind="bond", depth=3, d_h=300, graph="mols6", checkpoint="example_model_v2_regression_mol.pt"),
+    "bond_d3_graphtf":     dict(kind="bond", depth=3, d_h=32, graph="mols6", graph_transform=True),
+    "atom_d3_relu":        dict(kind="atom", depth=3, d_h=64, graph="mols6"),
+    "atom_d1":             dict(kind="atom", depth=1, d_h=48, graph="mols6"),
+    "atom_d3_bias_tanh":   dict(kind="atom", depth=3, d_h=64, bias=True, activation="tanh", graph="mols6"),
+    "atom_d3_shuffled":    dict(kind="atom", depth=3, d_h=64, graph="mols6_shuffled"),
+    "atom_d3_chain":       dict(kind="atom", depth=3, d_h=64, graph="chain5"),
+    "atom_d3_noedges":     dict(kind="atom", depth=3, d_h=32, graph="single_atoms4"),
+    "atom_d3_cgr":         dict(kind="atom", depth=3, d_h=64, d_v=106, d_e=28, graph="cgr3"),
+    "atom_d4_mixed":       dict(kind="atom", depth=4, d_h=64, graph="mixed"),
+}
+
+
+def make_batch(spec: str, d_v: int, d_e: int, seed: int):
+    from chemprop_b200.data.synthetic import make_chain_graph, make_molecule, make_molecules
+
+    rng = np.random.default_rng(seed)
+    if spec == "mols6":
+        return make_molecules(6, seed=seed, mean_atoms=12, std_atoms=5, d_v=d_v, d_e=d_e)
+    if spec == "mols6_shuffled":
+        return make_molecules(6, seed=seed, mean_atoms=12, std_atoms=5, d_v=d_v, d_e=d_e, shuffle_edges=True)
+    if spec == "chain5":
+        return [make_chain_graph(5, d_v, d_e)]
+    if spec == "single_atoms4":
+        return [make_molecule(rng, 1, d_v, d_e) for _ in range(4)]
+    if spec == "mixed":
+        sizes = [1, 7, 1, 2, 15, 1, 1, 30, 3]
+        return [make_molecule(rng, n, d_v, d_e) for n in sizes]
+    if spec == "bigmol":  # one molecule with > 128 directed edges (oversized tile) between small ones
+        return [make_molecule(rng, 5, d_v, d_e), make_molecule(rng, 90, d_v, d_e), make_molecule(rng, 8, d_v, d_e)]
+    if spec == "cgr3":
+        return make_molecules(3, seed=seed, mean_atoms=40, std_atoms=8, min_atoms=20, max_atoms=70, d_v=d_v, d_e=d_e,
+                              ring_frac=0.03)
+    raise KeyError(spec)
+
+
+def load_checkpoint_state(path: str) -> dict:
+    """Tensors of a reference checkpoint (needs the imported reference for unpickling hparams)."""
+    import pickle
+    import types
+
+    class _Anything(dict):  # stands in for classes of packages that are not installed (lightning.fabric ...)
+        def __init__(self, *a, **k):
+            pass
+
+        def __setstate__(self, state):
+            pass
+
+        def __call__(self, *a, **k):
+            return self
+
+    class _Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            try:
+                return super().find_class(module, name)
+            except Exception:
+                return type(name, (_Anything,), {})
+
+    pm = types.ModuleType("permissive_pickle")
+    pm.__dict__.update(pickle.__dict__)
+    pm.Unpickler = _Unpickler
+    d = torch.load(path, map_location="cpu", weights_only=False, pickle_module=pm)
+    return {k[len("message_passing."):]: v for k, v in d["state_dict"].items() if k.startswith("message_passing.")}
+
+
+def run_case(name: str, cfg: dict, seed: int) -> dict:
+    import_reference()
+    from chemprop.data import BatchMolGraph
+    from chemprop.data.molgraph import MolGraph
+    from chemprop.nn import (AtomMessagePassing, BondMessagePassing, MeanAggregation, NormAggregation,
+                             SumAggregation)
+    from chemprop.nn.transforms import GraphTransform, ScaleTransform
+
+    d_v, d_e, d_h = cfg.get("d_v", 72), cfg.get("d_e", 14), cfg["d_h"]
+    mgs = make_batch(cfg["graph"], d_v, d_e, seed)
+    ref_mgs = [MolGraph(m.V, m.E, m.edge_index, m.rev_edge_index) for m in mgs]
+    bmg = BatchMolGraph(ref_mgs)
+    torch.manual_seed(seed)
+    gt = None
+    rng = np.random.default_rng(seed + 1)
+    if cfg.get("graph_transform"):
+        gt = GraphTransform(ScaleTransform(rng.normal(0, 0.2, d_v), rng.uniform(0.5, 2.0, d_v)),
+                            ScaleTransform(rng.normal(0, 0.2, d_e), rng.uniform(0.5, 2.0, d_e)))
+    cls = BondMessagePassing if cfg["kind"] == "bond" else AtomMessagePassing
+    mp = cls(d_v=d_v, d_e=d_e, d_h=d_h, bias=cfg.get("bias", False), depth=cfg["depth"],
+             activation=cfg.get("activation", "relu"), undirected=cfg.get("undirected", False),
+             d_vd=cfg.get("d_vd"), graph_transform=gt)
+    if cfg.get("checkpoint"):
+        sd = load_checkpoint_state(os.path.join(REFERENCE_ROOT, "tests", "data", cfg["checkpoint"]))
+        mp.load_state_dict(sd)
+    if gt is not None:
+        mp.eval()  # transforms act in eval mode only (transforms.py:66-67)
+    V_d = None
+    if cfg.get("d_vd"):
+        V_d = torch.from_numpy(rng.normal(size=(bmg.V.shape[0], cfg["d_vd"])).astype(np.float32))
+    before = [t.clone() for t in (bmg.V, bmg.E, bmg.edge_index, bmg.rev_edge_index, bmg.batch)]
+    H_v = mp(bmg, V_d)
+    for a, b in zip(before, (bmg.V, bmg.E, bmg.edge_index, bmg.rev_edge_index, bmg.batch)):
+        assert torch.equal(a, b), "reference mutated its input"
+    aggs = {}
+    for nm, agg in (("mean", MeanAggregation()), ("sum", SumAggregation()), ("norm", NormAggregation())):
+        aggs[nm] = agg(H_v, bmg.batch)
+    G = torch.from_numpy(rng.normal(size=tuple(aggs["mean"].shape)).astype(np.float32))
+    loss = (aggs["mean"] * G).sum()
+    loss.backward()
+    out = dict(
+        V=bmg.V.numpy(), E=bmg.E.numpy(), edge_index=bmg.edge_index.numpy(),
+        rev_edge_index=bmg.rev_edge_index.numpy(), batch=bmg.batch.numpy(), n_mols=np.int64(len(bmg)),
+        H_v=H_v.detach().numpy(), agg_mean=aggs["mean"].detach().numpy(), agg_sum=aggs["sum"].detach().numpy(),
+        agg_norm=aggs["norm"].detach().numpy(), G=G.numpy(), loss=np.float64(loss.item()),
+        config=np.array(json.dumps(cfg)),
+    )
+    if V_d is not None:
+        out["V_d"] = V_d.numpy()
+    if gt is not None:
+        out["gt_V_mean"], out["gt_V_scale"] = gt.V_transform.mean.numpy(), gt.V_transform.scale.numpy()
+        out["gt_E_mean"], out["gt_E_scale"] = gt.E_transform.mean.numpy(), gt.E_transform.scale.numpy()
+    for k, v in mp.state_dict().items():
+        if k.startswith(("W_i", "W_h", "W_o", "W_d")):
+            out["param." + k] = v.detach().numpy()
+    for k, p in mp.named_parameters():
+        if p.grad is not None:
+            out["grad." + k] = p.grad.numpy()
+    return out
+
+
+def collate_case() -> dict:
+    """The reference's collate fixture (tests/unit/data/test_dataloader.py:10-84) through the real collate."""
+    import_reference()
+    from chemprop.data import BatchMolGraph
+    from chemprop.data.molgraph import MolGraph
+
+    mg1 = MolGraph(V=np.array([[1.0], [2.0], [3.0]]), E=np.array([[0.5], [1.5], [0.5], [1.5]]),
+                   edge_index=np.array([[0, 1, 0, 2], [1, 0, 2, 0]]), rev_edge_index=np.array([1, 0, 3, 2]))
+    mg2 = MolGraph(V=np.array([[4.0], [5.0]]), E=np.array([[2.5], [2.5]]), edge_index=np.array([[0, 1], [1, 0]]),
+                   rev_edge_index=np.array([1, 0]))
+    bmg = BatchMolGraph([mg1, mg2])
+    out = dict(V=bmg.V.numpy(), E=bmg.E.numpy(), edge_index=bmg.edge_index.numpy(),
+               rev_edge_index=bmg.rev_edge_index.numpy(), batch=bmg.batch.numpy(), n_mols=np.int64(2))
+    for i, mg in enumerate((mg1, mg2)):
+        out[f"mg{i}.V"], out[f"mg{i}.E"] = mg.V, mg.E
+        out[f"mg{i}.edge_index"], out[f"mg{i}.rev_edge_index"] = mg.edge_index, mg.rev_edge_index
+    return out
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(1)  # deterministic summation order
+    for i, (name, cfg) in enumerate(CASES.items()):
+        out = run_case(name, cfg, seed=100 + i)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"{name}.npz"), **out)
+        print(f"{name:24s} V={out['V'].shape[0]:4d} E={out['E'].shape[0]:4d} B={int(out['n_mols'])} "
+              f"|H_v|={np.abs(out['H_v']).mean():.4f} loss={float(out['loss']):+.5f}")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "collate_fixture.npz"), **collate_case())
+    print("collate_fixture")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,138 @@
+"""TEST INFRASTRUCTURE ONLY -- the oracle.  A CPU restatement, in plain torch ops, of the reference
+algorithm for the D-MPNN hot path (chemprop v2.3.1).  It exists because `/root/reference` does not
+travel to the GPU box; it is the checker the CUDA path is compared with, never the thing measured or
+shipped, and nothing under ``chemprop_b200/`` imports it.
+
+PARITY PINNING: this restatement is pinned against the *real* reference in two ways:
+  (1) tests/golden/*.npz were produced by running the unmodified reference modules
+      (oracle/make_golden.py, via oracle/ref_shim.py) -- tests/test_oracle.py checks the restatement
+      against every golden case (forward outputs, aggregation outputs, weight gradients);
+  (2) when /root/reference is reachable the same test also runs the reference live on fresh seeds.
+The reference has no numeric known-answer test for BondMessagePassing.forward itself
+(SURVEY.md section 8c); its structural fixtures (chain graph, E=0 batch, collate values) are among
+the golden cases.
+
+Every function cites the reference lines it follows (paths relative to the chemprop repo root).
+Works in float32 or float64 (pass tensors of that dtype); autograd gives the reference gradients.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch import Tensor
+from torch.nn import functional as F
+
+
+# --- activations: chemprop/nn/utils.py:43-55 ------------------------------------------------
+def activation(name: str):
+    name = name.lower()
+    if name == "relu":
+        return torch.relu
+    if name == "leakyrelu":
+        return lambda x: F.leaky_relu(x, 0.1)
+    if name == "tanh":
+        return torch.tanh
+    if name == "elu":
+        return F.elu
+    raise KeyError(name)
+
+
+# --- collate: chemprop/data/collate.py:37-62 ------------------------------------------------
+def collate(mgs):
+    """Returns (V f32, E f32, edge_index i64 2xE, rev_edge_index i64, batch i64) as numpy arrays."""
+    Vs, Es, eis, revs, batch = [], [], [], [], []
+    num_nodes = 0
+    num_edges = 0
+    for i, mg in enumerate(mgs):
+        Vs.append(mg.V)
+        Es.append(mg.E)
+        eis.append(mg.edge_index + num_nodes)            # collate.py:51
+        revs.append(mg.rev_edge_index + num_edges)       # collate.py:52
+        batch.append(np.full(len(mg.V), i, dtype=np.int64))  # collate.py:53
+        num_nodes += mg.V.shape[0]
+        num_edges += mg.edge_index.shape[1]
+    return (np.concatenate(Vs).astype(np.float32), np.concatenate(Es).astype(np.float32),
+            np.hstack(eis).astype(np.int64), np.concatenate(revs).astype(np.int64),
+            np.concatenate(batch).astype(np.int64))
+
+
+# --- scatter-sum idiom: mixins.py:12-15, base.py:208-211 -----------------------------------
+def _scatter_sum_rows(H: Tensor, index: Tensor, n_rows: int) -> Tensor:
+    index_torch = index.unsqueeze(1).repeat(1, H.shape[1])
+    return torch.zeros(n_rows, H.shape[1], dtype=H.dtype, device=H.device).scatter_reduce_(
+        0, index_torch, H, reduce="sum", include_self=False)
+
+
+# --- bond message passing -------------------------------------------------------------------
+def bond_initialize(V, E, edge_index, W_i, b_i=None):
+    """mixins.py:8-9"""
+    return F.linear(torch.cat([V[edge_index[0]], E], dim=1), W_i, b_i)
+
+
+def bond_message(H, edge_index, rev_edge_index, n_atoms):
+    """mixins.py:11-18"""
+    M_all = _scatter_sum_rows(H, edge_index[1], n_atoms)[edge_index[0]]
+    M_rev = H[rev_edge_index]
+    return M_all - M_rev
+
+
+def atom_initialize(V, edge_index, W_i, b_i=None):
+    """mixins.py:22-23"""
+    return F.linear(V[edge_index[0]], W_i, b_i)
+
+
+def atom_message(H, E, edge_index, n_atoms):
+    """mixins.py:25-30  (concat order is (H, E))"""
+    HE = torch.cat((H, E), dim=1)
+    return _scatter_sum_rows(HE, edge_index[1], n_atoms)[edge_index[0]]
+
+
+def update(M_t, H_0, W_h, b_h, tau):
+    """base.py:135-141 (dropout p = 0)"""
+    return tau(H_0 + F.linear(M_t, W_h, b_h))
+
+
+def finalize(M, V, W_o, b_o, tau, V_d=None, W_d=None, b_d=None):
+    """base.py:143-194 (dropout p = 0; note: no activation after W_d)"""
+    H = tau(F.linear(torch.cat((V, M), dim=1), W_o, b_o))
+    if V_d is not None:
+        H = F.linear(torch.cat((H, V_d), dim=1), W_d, b_d)
+    return H
+
+
+def message_passing_forward(kind, V, E, edge_index, rev_edge_index, W_i, b_i, W_h, b_h, W_o, b_o, depth, act="relu",
+                            undirected=False, V_d=None, W_d=None, b_d=None, return_intermediates=False):
+    """_MessagePassingBase.forward, base.py:196-212.  kind in {"bond", "atom"}."""
+    tau = activation(act)
+    n_atoms = V.shape[0]
+    H_0 = bond_initialize(V, E, edge_index, W_i, b_i) if kind == "bond" else atom_initialize(V, edge_index, W_i, b_i)
+    H = tau(H_0)                                                   # base.py:200
+    inter = {"H_0": H_0, "H": [H], "M": []}
+    for _ in range(1, depth):                                      # base.py:201
+        if undirected:
+            H = (H + H[rev_edge_index]) / 2                        # base.py:202-203
+        if kind == "bond":
+            M = bond_message(H, edge_index, rev_edge_index, n_atoms)
+        else:
+            M = atom_message(H, E, edge_index, n_atoms)
+        H = update(M, H_0, W_h, b_h, tau)                          # base.py:206
+        inter["M"].append(M)
+        inter["H"].append(H)
+    M_v = _scatter_sum_rows(H, edge_index[1], n_atoms)             # base.py:208-211
+    out = finalize(M_v, V, W_o, b_o, tau, V_d, W_d, b_d)
+    if return_intermediates:
+        inter["M_v"] = M_v
+        return out, inter
+    return out
+
+
+# --- aggregation: chemprop/nn/agg.py:65-113 --------------------------------------------------
+def aggregate(H, batch, mode="mean", norm=100.0, n_mols=None):
+    index_torch = batch.unsqueeze(1).repeat(1, H.shape[1])
+    dim_size = int(batch.max()) + 1 if n_mols is None else n_mols    # agg.py:75
+    red = "mean" if mode == "mean" else "sum"
+    out = torch.zeros(dim_size, H.shape[1], dtype=H.dtype, device=H.device).scatter_reduce_(
+        0, index_torch, H, reduce=red, include_self=False)           # agg.py:76-78 / 93-95
+    if mode == "norm":
+        out = out / norm                                             # agg.py:112-113
+    return out

@@ -1,0 +1,74 @@
+"""CPU tier: the C-ABI library loads and exports every symbol include/dmpnn.h declares
+(no compute is launched without a GPU), and the host-side entry point works."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from chemprop_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dmpnn.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dmpnn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/dmpnn.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+
+
+def test_version_and_error_string():
+    lib = _lib.load()
+    assert lib.dmpnn_version() == 100
+    assert isinstance(lib.dmpnn_last_error(), bytes)
+    assert lib.dmpnn_device_ok() in (0, 1)
+
+
+def test_bad_arguments_fail_loudly():
+    lib = _lib.load()
+    n = ctypes.c_size_t(0)
+    assert lib.dmpnn_layout_workspace_bytes(-1, 0, 0, ctypes.byref(n)) != 0
+    assert b"bad args" in lib.dmpnn_last_error()
+    with pytest.raises(_lib.DmpnnError):
+        _lib.check(lib.dmpnn_linear_wgrad_workspace_bytes(1, 0, 1, ctypes.byref(n)), "wgrad_workspace_bytes")
+
+
+def test_collate_host_matches_oracle_and_reference_fixture():
+    from chemprop_b200.data import BatchMolGraph, MolGraph, make_molecules
+    from oracle import restatement as R
+    from tests.util import load_golden
+
+    g = load_golden("collate_fixture")
+    mgs = [MolGraph(g[f"mg{i}.V"], g[f"mg{i}.E"], g[f"mg{i}.edge_index"], g[f"mg{i}.rev_edge_index"]) for i in range(2)]
+    bmg = BatchMolGraph(mgs)
+    for k in ("V", "E", "edge_index", "rev_edge_index", "batch"):
+        got = getattr(bmg, k)
+        assert got.numpy().dtype == g[k].dtype and np.array_equal(got.numpy(), g[k]), k
+    assert len(bmg) == 2
+    # ragged / shuffled / single-atom molecules
+    mgs = make_molecules(300, seed=3, shuffle_edges=True, min_atoms=1)
+    bmg = BatchMolGraph(mgs)
+    V, E, ei, rev, batch = R.collate(mgs)
+    assert np.array_equal(bmg.V.numpy(), V) and np.array_equal(bmg.E.numpy(), E)
+    assert np.array_equal(bmg.edge_index.numpy(), ei) and np.array_equal(bmg.rev_edge_index.numpy(), rev)
+    assert np.array_equal(bmg.batch.numpy(), batch)
+    assert bmg.V.dtype == torch.float32 and bmg.edge_index.dtype == torch.int64
+
+
+def test_collate_empty_edges():
+    from chemprop_b200.data import BatchMolGraph, make_molecule
+
+    rng = np.random.default_rng(0)
+    bmg = BatchMolGraph([make_molecule(rng, 1) for _ in range(4)])
+    assert bmg.E.shape == (0, 14) and bmg.edge_index.shape == (2, 0) and bmg.batch.tolist() == [0, 1, 2, 3]

