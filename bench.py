@@ -122,7 +122,7 @@ def cpu_step_fn(n_mols: int, seed: int):
         H = R.message_passing_forward("bond", V, E, ei, rev, Wi, None, Wh, None, Wo, bo, WORKLOAD["depth"])
         loss = R.aggregate(H, batch, "mean").square().mean()
         loss.backward()
-        return float(loss)
+        return loss.item()
 
     return step
 

@@ -196,7 +196,8 @@ __global__ void k_mol_ptr(const int64_t* __restrict__ batch, int64_t V, int64_t 
 // Greedy molecule-aligned packing into tiles of <= kTileRows rows and <= kTileAtoms atoms.
 // Sequential by nature; one thread walks the molecule offsets staged through shared memory.
 __global__ void k_tiles(const int32_t* __restrict__ mol_atom_ptr, const int32_t* __restrict__ mol_row_ptr,
-                        int64_t B, int32_t* tile_mol_ptr, int32_t* meta, const int32_t* viol) {
+                        int64_t B, int32_t* tile_mol_ptr, int32_t* tile_row_ptr, int32_t* tile_atom_ptr,
+                        int32_t* meta, const int32_t* viol) {
   constexpr int CH = 4096;
   __shared__ int32_t s_at[CH + 1];
   __shared__ int32_t s_rw[CH + 1];
@@ -216,6 +217,8 @@ __global__ void k_tiles(const int32_t* __restrict__ mol_atom_ptr, const int32_t*
         int32_t end_row = s_rw[i + 1], end_atom = s_at[i + 1];
         if (m > t_mol && (end_row - t_row > kTileRows || end_atom - t_atom > kTileAtoms)) {
           // close the open tile [t_mol, m)
+          tile_row_ptr[n_tiles] = t_row;
+          tile_atom_ptr[n_tiles] = t_atom;
           tile_mol_ptr[n_tiles++] = t_mol;
           int32_t rows = s_rw[i] - t_row, atoms = s_at[i] - t_atom;
           max_rows = rows > max_rows ? rows : max_rows;
@@ -225,15 +228,19 @@ __global__ void k_tiles(const int32_t* __restrict__ mol_atom_ptr, const int32_t*
       }
       if (base + n == B) {
         int32_t rows = s_rw[n] - t_row, atoms = s_at[n] - t_atom;
+        tile_row_ptr[n_tiles] = t_row;
+        tile_atom_ptr[n_tiles] = t_atom;
         tile_mol_ptr[n_tiles++] = t_mol;
         max_rows = rows > max_rows ? rows : max_rows;
         max_atoms = atoms > max_atoms ? atoms : max_atoms;
         tile_mol_ptr[n_tiles] = (int32_t)B;
+        tile_row_ptr[n_tiles] = s_rw[n];
+        tile_atom_ptr[n_tiles] = s_at[n];
       }
     }
   }
   if (threadIdx.x == 0) {
-    if (B == 0) { tile_mol_ptr[0] = 0; n_tiles = 0; }
+    if (B == 0) { tile_mol_ptr[0] = 0; tile_row_ptr[0] = 0; tile_atom_ptr[0] = 0; n_tiles = 0; }
     int32_t vb = viol[0];
     int32_t flags = 0;
     if (!(vb & V_RANGE)) flags |= DMPNN_FLAG_INDEX_IN_RANGE;
@@ -262,12 +269,13 @@ extern "C" int dmpnn_layout_build(const int64_t* edge_index, const int64_t* rev_
                                   const int64_t* batch, int64_t V, int64_t E, int64_t B,
                                   int32_t* perm, int32_t* inv_perm, int32_t* rowptr, int32_t* src_row,
                                   int32_t* dst_row, int32_t* rev_row, int32_t* mol_atom_ptr,
-                                  int32_t* mol_row_ptr, int32_t* tile_mol_ptr, int32_t* meta,
-                                  void* workspace, void* stream_) {
+                                  int32_t* mol_row_ptr, int32_t* tile_mol_ptr, int32_t* tile_row_ptr,
+                                  int32_t* tile_atom_ptr, int32_t* meta, void* workspace, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   DMPNN_CHECK_ARG(V >= 0 && E >= 0 && B >= 0, "layout_build: negative size");
   DMPNN_CHECK_ARG(V < (1LL << 31) - 4096 && E < (1LL << 31) - 4096, "layout_build: V/E exceed int32");
-  DMPNN_CHECK_ARG(workspace && rowptr && mol_atom_ptr && mol_row_ptr && tile_mol_ptr && meta,
+  DMPNN_CHECK_ARG(workspace && rowptr && mol_atom_ptr && mol_row_ptr && tile_mol_ptr && tile_row_ptr &&
+                      tile_atom_ptr && meta,
                   "layout_build: null pointer");
   LayoutWs ws;
   size_t total = carve(&ws, workspace, V, E);
@@ -289,7 +297,7 @@ extern "C" int dmpnn_layout_build(const int64_t* edge_index, const int64_t* rev_
                                                     src_row, dst_row, ws.viol);
   if (E > 0) k_rev_rows<<<ceil_div_i64(E, T), T, 0, st>>>(rev_edge_index, E, perm, inv_perm, rev_row);
   k_mol_ptr<<<ceil_div_i64(V + 1, T), T, 0, st>>>(batch, V, B, rowptr, mol_atom_ptr, mol_row_ptr);
-  k_tiles<<<1, 1024, 0, st>>>(mol_atom_ptr, mol_row_ptr, B, tile_mol_ptr, meta, ws.viol);
+  k_tiles<<<1, 1024, 0, st>>>(mol_atom_ptr, mol_row_ptr, B, tile_mol_ptr, tile_row_ptr, tile_atom_ptr, meta, ws.viol);
   DMPNN_CHECK_LAUNCH("layout_build", 10);
   return 0;
 }

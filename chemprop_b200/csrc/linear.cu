@@ -274,10 +274,10 @@ extern "C" int dmpnn_linear_fwd(const void* X1, int x1_dtype, int64_t ld1, const
   cudaStream_t st = (cudaStream_t)stream_;
   DMPNN_CHECK_ARG(R >= 0 && N > 0 && K1 > 0 && K2 >= 0, "linear_fwd: bad sizes R=%lld N=%lld K1=%lld K2=%lld",
                   (long long)R, (long long)N, (long long)K1, (long long)K2);
+  if (R == 0) return 0;
   DMPNN_CHECK_ARG(X1 && W && C, "linear_fwd: null pointer");
   DMPNN_CHECK_ARG(K2 == 0 || X2, "linear_fwd: X2 null with K2>0");
   DMPNN_CHECK_ARG(ldc >= N && ldc_pad <= ldc, "linear_fwd: ldc/ldc_pad too small");
-  if (R == 0) return 0;
   if (K2 == 0) { x2_dtype = x1_dtype; }
   if (!Rres) r_dtype = c_dtype;
   ASrc a{X1, X2, idx1, idx2, ld1, ld2, (int)K1, (int)K2};
@@ -308,8 +308,9 @@ extern "C" int dmpnn_linear_wgrad(const void* dY, int dy_dtype, int64_t lddy, co
                                   void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   DMPNN_CHECK_ARG(R >= 0 && N > 0 && K1 > 0 && K2 >= 0, "linear_wgrad: bad sizes");
-  DMPNN_CHECK_ARG(dY && X1 && dW && workspace, "linear_wgrad: null pointer");
-  DMPNN_CHECK_ARG(K2 == 0 || X2, "linear_wgrad: X2 null with K2>0");
+  DMPNN_CHECK_ARG(dW && workspace, "linear_wgrad: null pointer");
+  DMPNN_CHECK_ARG(R == 0 || (dY && X1), "linear_wgrad: null operand");
+  DMPNN_CHECK_ARG(R == 0 || K2 == 0 || X2, "linear_wgrad: X2 null with K2>0");
   const int64_t K = K1 + K2;
   if (K2 == 0) x2_dtype = x1_dtype;
   const int S = wgrad_splits(R);

@@ -1,10 +1,704 @@
-// placeholder: fused tcgen05 depth step (implemented next)
+// Fused Blackwell depth step of BondMessagePassing (bf16 hidden states), one launch per step:
+//
+//   H_next[rev(e')] = tau( H_0[rev(e')] + b + W_h . ( sum_{e'' in in(v)} g(H[e'']) - g(H[e']) ) ),  e' in in(v)
+//
+// = message (chemprop/nn/message_passing/mixins.py:11-18) + update (base.py:135-141).  g = tau when
+// first_step (H^0 = tau(H_0), base.py:200, recomputed on load) else identity.
+//
+// Persistent, warp-specialised, one CTA per SM, molecule-aligned tiles of <=128 dst-sorted edge rows:
+//   warp 0      TMA producer: H tile (5 boxes of 128 rows x 64 cols, SWIZZLE_128B) -> A buffer (x2)
+//   warp 1      TMA producer: W_h stages (pre-packed smem images, cp.async.bulk) -> 3-stage ring
+//   warp 2      tcgen05.mma issuer (one thread): D[128 x hp] (TMEM, fp32) = A . W_h^T
+//   warp 3      TMEM allocator
+//   warps 4-7   epilogue: tcgen05.ld -> + H_0[rev] + bias -> tau -> bf16 -> st.global to row rev(e')
+//   warps 8-15  message: per destination atom, in place in the swizzled A buffer:
+//               rows <- (sum of the atom's in-edge rows) - row      (the gather never leaves smem)
+// The row permutation by rev() is applied for free when the epilogue thread of TMEM lane e' writes
+// its result to global row rev(e').
+//
+// Algorithmic HBM bytes per step: read H_prev + H_0, write H_next = 3*E*h*2 (2*E*h*2 when first_step,
+// H_prev == H_0 comes from L2 the second time); W_h (<=190 KB) is L2-resident.
+#include <cuda.h>
+
 #include "common.cuh"
-extern "C" int dmpnn_pack_weight_bf16_bytes(int64_t N, int64_t K, size_t* bytes) { dmpnn::set_error("not built"); return -3; }
-extern "C" int dmpnn_pack_weight_bf16(const float* W, int64_t ldw, int64_t N, int64_t K, void* Wpk, void* stream) { dmpnn::set_error("not built"); return -3; }
+
+namespace dmpnn {
+namespace fused {
+
+constexpr int kTileM = 128;
+constexpr int kSlabBytes = kTileM * 128;        // one 64-column K slab of a 128-row tile: 16 KB
+constexpr int kMaxSlabs = 5;                    // hp <= 320
+constexpr int kABufBytes = kMaxSlabs * kSlabBytes;
+constexpr int kChunkN = 80;                     // W stage / accumulator chunk = 80 output features (5 x 16)
+constexpr int kMaxChunks = 4;
+constexpr int kWStageBytes = kChunkN * 128;     // 10 KB
+constexpr int kWStages = 3;
+constexpr int kHStages = 2;                     // H_0 / output staging slabs (16 KB each)
+constexpr int kThreads = 512;
+constexpr int kSWarps = 8;
+constexpr int kTmemCols = 512;
+constexpr int kMaxHp = 304;
+
+struct Params {
+  const __nv_bfloat16* H0;
+  __nv_bfloat16* Hn;
+  int64_t ld;
+  const uint8_t* Wpk;
+  const float* bias;
+  const int32_t* rowptr;
+  const int32_t* rev_row;
+  const int32_t* tile_row_ptr;
+  const int32_t* tile_atom_ptr;
+  int n_tiles, h, hp, nslab, ksteps_last, nchunks;
+  float act_param;
+};
+
+// shared memory carve-up (after 1024 B alignment)
+constexpr int kOffA = 0;
+constexpr int kOffW = 2 * kABufBytes;                        // 163840
+constexpr int kOffH = kOffW + kWStages * kWStageBytes;       // 194560 (1024-aligned)
+constexpr int kOffBar = kOffH + kHStages * kSlabBytes;       // 227328
+constexpr int kNumBars = 24;
+constexpr int kOffTmem = kOffBar + kNumBars * 8;
+constexpr int kOffRowptr = kOffTmem + 16;                    // int32 [2][132]
+constexpr int kOffBias = kOffRowptr + 2 * 132 * 4;           // float [304]
+constexpr int kSmemBytes = kOffBias + kMaxHp * 4;
+constexpr int kSmemAlloc = kSmemBytes + 1024;
+static_assert(kOffH % 1024 == 0, "staging slabs must be 1024-byte aligned for SWIZZLE_128B");
+static_assert(kSmemAlloc <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+
+enum {
+  B_AFULL = 0, B_AREADY = 2, B_AFREE = 4, B_WFULL = 6, B_WFREE = 9, B_ACCFULL = 12, B_ACCFREE = 16,
+  B_HFULL = 20, B_HFREE = 22
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  // suspend-time hint (ns): the thread sleeps in hardware until the phase completes (or the hint
+  // expires) instead of burning issue slots in a spin loop
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(200000u)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must fail loudly (trap) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("dmpnn fused step: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, SWIZZLE_128B operand descriptor (rows of 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;             // leading byte offset (unused for swizzled K-major) = 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+  // c=F32 (1<<4), a=BF16 (1<<7), b=BF16 (1<<10), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// byte offset of 16-byte chunk `c` (0..7) of row `r` inside a 128-row, 128-byte-row SWIZZLE_128B slab
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float p, float z) {
+  if constexpr (ACT == DMPNN_ACT_RELU) return fmaxf(z, 0.f);
+  else if constexpr (ACT == DMPNN_ACT_LEAKYRELU) return z > 0.f ? z : p * z;
+  else if constexpr (ACT == DMPNN_ACT_TANH) return tanhf(z);
+  else if constexpr (ACT == DMPNN_ACT_ELU) return z > 0.f ? z : p * expm1f(z);
+  else return z;
+}
+
+
+// ---- packed bf16x2 helpers for the in-place message computation -------------------------------
+using bf2 = __nv_bfloat162;
+__device__ __forceinline__ bf2 u2b(uint32_t w) { return *reinterpret_cast<bf2*>(&w); }
+__device__ __forceinline__ uint32_t b2u(bf2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+__device__ __forceinline__ uint4 add4(uint4 a, uint4 b) {
+  return make_uint4(b2u(__hadd2(u2b(a.x), u2b(b.x))), b2u(__hadd2(u2b(a.y), u2b(b.y))),
+                    b2u(__hadd2(u2b(a.z), u2b(b.z))), b2u(__hadd2(u2b(a.w), u2b(b.w))));
+}
+template <int ACT>
+__device__ __forceinline__ uint32_t act_word(uint32_t w, float ap) {
+  if constexpr (ACT == DMPNN_ACT_NONE) return w;
+  else if constexpr (ACT == DMPNN_ACT_RELU) return b2u(__hmax2(u2b(w), __float2bfloat162_rn(0.f)));
+  else return pack_bf2(act_t<ACT>(ap, bf_lo(w)), act_t<ACT>(ap, bf_hi(w)));
+}
+template <int ACT, bool FIRST>
+__device__ __forceinline__ uint4 s_load(uint32_t addr, float ap) {
+  uint4 u = lds128(addr);
+  if constexpr (FIRST) {
+    u.x = act_word<ACT>(u.x, ap); u.y = act_word<ACT>(u.y, ap);
+    u.z = act_word<ACT>(u.z, ap); u.w = act_word<ACT>(u.w, ap);
+  }
+  return u;
+}
+
+// One (atom, 16-byte column chunk): rows r0 .. r0+d-1 of the slab-swizzled A buffer are replaced by
+// the sum of the OTHER rows of the atom (= sum of all in-edge states minus the row's own, i.e. the
+// message M[rev(row)] of mixins.py:11-18).  d <= 4 (every organic atom) is done as explicit sums of
+// the others in packed bf16x2 -- at most two roundings per output; larger d falls back to an f32
+// sum-minus-self.
+template <int ACT, bool FIRST>
+__device__ __forceinline__ void message_atom_chunk(uint32_t abuf, int r0, int d, int c, float ap) {
+  const uint32_t cbase = abuf + (uint32_t)(c >> 3) * kSlabBytes;
+  const int cc = c & 7;
+  const uint32_t a0 = cbase + sw128_off(r0, cc);
+  if (d == 1) {
+    sts128(a0, make_uint4(0u, 0u, 0u, 0u));
+  } else if (d == 2) {
+    const uint32_t a1 = cbase + sw128_off(r0 + 1, cc);
+    const uint4 x0 = s_load<ACT, FIRST>(a0, ap), x1 = s_load<ACT, FIRST>(a1, ap);
+    sts128(a0, x1);
+    sts128(a1, x0);
+  } else if (d == 3) {
+    const uint32_t a1 = cbase + sw128_off(r0 + 1, cc), a2 = cbase + sw128_off(r0 + 2, cc);
+    const uint4 x0 = s_load<ACT, FIRST>(a0, ap), x1 = s_load<ACT, FIRST>(a1, ap), x2 = s_load<ACT, FIRST>(a2, ap);
+    sts128(a0, add4(x1, x2));
+    sts128(a1, add4(x0, x2));
+    sts128(a2, add4(x0, x1));
+  } else if (d == 4) {
+    const uint32_t a1 = cbase + sw128_off(r0 + 1, cc), a2 = cbase + sw128_off(r0 + 2, cc),
+                   a3 = cbase + sw128_off(r0 + 3, cc);
+    const uint4 x0 = s_load<ACT, FIRST>(a0, ap), x1 = s_load<ACT, FIRST>(a1, ap), x2 = s_load<ACT, FIRST>(a2, ap),
+                x3 = s_load<ACT, FIRST>(a3, ap);
+    const uint4 p = add4(x0, x1), q = add4(x2, x3);
+    sts128(a0, add4(x1, q));
+    sts128(a1, add4(x0, q));
+    sts128(a2, add4(p, x3));
+    sts128(a3, add4(p, x2));
+  } else {
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int r = r0; r < r0 + d; ++r) {
+      const uint4 u = s_load<ACT, FIRST>(cbase + sw128_off(r, cc), ap);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { acc[2 * q] += bf_lo(w[q]); acc[2 * q + 1] += bf_hi(w[q]); }
+    }
+    for (int r = r0; r < r0 + d; ++r) {
+      const uint32_t addr = cbase + sw128_off(r, cc);
+      const uint4 u = s_load<ACT, FIRST>(addr, ap);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = pack_bf2(acc[2 * q] - bf_lo(w[q]), acc[2 * q + 1] - bf_hi(w[q]));
+      sts128(addr, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int ACT, bool FIRST, bool HAS_BIAS>
+__global__ void __launch_bounds__(kThreads, 1)
+k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ CUtensorMap tmapH0, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t sA = sbase + kOffA, sW = sbase + kOffW, sH = sbase + kOffH, sBar = sbase + kOffBar;
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
+  int32_t* s_rowptr = reinterpret_cast<int32_t*>(smem + kOffRowptr);
+  float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(B_AFULL + i), 1);
+      mbar_init(bar(B_AREADY + i), kSWarps);
+      mbar_init(bar(B_AFREE + i), 1);
+      mbar_init(bar(B_HFULL + i), 1);
+      mbar_init(bar(B_HFREE + i), 128);
+    }
+    for (int i = 0; i < kWStages; ++i) {
+      mbar_init(bar(B_WFULL + i), 1);
+      mbar_init(bar(B_WFREE + i), 1);
+    }
+    for (int i = 0; i < kMaxChunks; ++i) {
+      mbar_init(bar(B_ACCFULL + i), 1);
+      mbar_init(bar(B_ACCFREE + i), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(s_tmem)), kTmemCols);
+  for (int i = threadIdx.x; i < kMaxHp; i += kThreads) s_bias[i] = (p.bias && i < p.h) ? p.bias[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===================== TMA producer: H_prev tiles -> A buffers =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+        const int b = it & 1, use = it >> 1;
+        mbar_wait(bar(B_AFREE + b), (use & 1) ^ 1);
+        const int row0 = __ldg(p.tile_row_ptr + t);
+        mbar_expect_tx(bar(B_AFULL + b), (uint32_t)p.nslab * kSlabBytes);
+        for (int s = 0; s < p.nslab; ++s)
+          tma_load_2d(sA + b * kABufBytes + s * kSlabBytes, &tmapH, bar(B_AFULL + b), s * 64, row0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== TMA producer: W_h stages (pre-packed smem images) =====================
+    if (lane == 0) {
+      uint32_t ws = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        for (int c = 0; c < p.nchunks; ++c) {
+          const int nc = min(kChunkN, p.hp - c * kChunkN);
+          const uint8_t* src0 = p.Wpk + (size_t)c * kChunkN * p.nslab * 128;
+          for (int s = 0; s < p.nslab; ++s, ++ws) {
+            const uint32_t st = ws % kWStages, use = ws / kWStages;
+            mbar_wait(bar(B_WFREE + st), (use & 1) ^ 1);
+            mbar_expect_tx(bar(B_WFULL + st), (uint32_t)nc * 128);
+            bulk_load(sW + st * kWStageBytes, src0 + (size_t)s * nc * 128, (uint32_t)nc * 128, bar(B_WFULL + st));
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      uint32_t ws = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+        const int b = it & 1, use = it >> 1;
+        mbar_wait(bar(B_AREADY + b), use & 1);
+        for (int c = 0; c < p.nchunks; ++c) {
+          const int nc = min(kChunkN, p.hp - c * kChunkN);
+          const uint32_t idesc = umma_idesc_bf16(kTileM, nc);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(c * kChunkN);
+          mbar_wait(bar(B_ACCFREE + c), (it & 1) ^ 1);  // epilogue of the previous tile drained these columns
+          tc_fence_after();
+          for (int s = 0; s < p.nslab; ++s, ++ws) {
+            const uint32_t st = ws % kWStages, usew = ws / kWStages;
+            mbar_wait(bar(B_WFULL + st), usew & 1);
+            tc_fence_after();
+            const int ks = (s == p.nslab - 1) ? p.ksteps_last : 4;
+            const uint32_t a0 = sA + b * kABufBytes + s * kSlabBytes;
+            const uint32_t b0 = sW + st * kWStageBytes;
+            for (int kk = 0; kk < ks; ++kk)
+              umma_bf16(d_tmem, umma_desc_sw128(a0 + kk * 32), umma_desc_sw128(b0 + kk * 32), idesc,
+                        (s > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(bar(B_WFREE + st));
+          }
+          umma_commit(bar(B_ACCFULL + c));
+        }
+        umma_commit(bar(B_AFREE + b));
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== TMA producer: H_0 slabs -> staging ring =====================
+    if (lane == 0) {
+      uint32_t hs = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const int row0 = __ldg(p.tile_row_ptr + t);
+        for (int s = 0; s < p.nslab; ++s, ++hs) {
+          const uint32_t q = hs % kHStages, use = hs / kHStages;
+          mbar_wait(bar(B_HFREE + q), (use & 1) ^ 1);
+          mbar_expect_tx(bar(B_HFULL + q), kSlabBytes);
+          tma_load_2d(sH + q * kSlabBytes, &tmapH0, bar(B_HFULL + q), s * 64, row0);
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== epilogue (warps 4-7, thread == TMEM lane == A row e') =====================
+    // Row e' of the accumulator is the update of edge rev(e'): it reads H_0 row rev(e') and writes
+    // H_next row rev(e'), both of which live inside this tile -> staged through shared memory slabs,
+    // loaded by TMA and written back with coalesced 16-byte stores.
+    const int et = threadIdx.x - 128;       // 0..127
+    const int r = et;                       // TMEM lane (warp & 3 == warp - 4)
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t hs = 0;
+    int it = 0;
+    int t = blockIdx.x;
+    int row0 = 0, nrows = 0, lr = 0;
+    if (t < p.n_tiles) {
+      row0 = __ldg(p.tile_row_ptr + t);
+      nrows = __ldg(p.tile_row_ptr + t + 1) - row0;
+      lr = (r < nrows) ? (__ldg(p.rev_row + row0 + r) - row0) : r;
+    }
+    for (; t < p.n_tiles; t += gridDim.x, ++it) {
+      // prefetch the next tile's metadata (hides the dependent global loads behind this tile's work)
+      const int tn = t + gridDim.x;
+      int row0n = 0, nrowsn = 0, lrn = 0;
+      if (tn < p.n_tiles) {
+        row0n = __ldg(p.tile_row_ptr + tn);
+        nrowsn = __ldg(p.tile_row_ptr + tn + 1) - row0n;
+        lrn = (r < nrowsn) ? __ldg(p.rev_row + row0n + r) : (row0n + r);
+      }
+      const int nj = p.hp >> 4;
+      int jc = 0, cidx = 0;          // position inside / index of the 80-column accumulator chunk
+      uint32_t hbuf = 0, q = 0;
+      for (int j = 0; j < nj; ++j) {
+        const int jj = j & 3;        // 16-column chunk inside the 64-column slab j >> 2
+        if (jj == 0) {
+          q = hs % kHStages;
+          hbuf = sH + q * kSlabBytes;
+          mbar_wait(bar(B_HFULL + q), (hs / kHStages) & 1);
+        }
+        if (jc == 0) {
+          mbar_wait(bar(B_ACCFULL + cidx), it & 1);
+          tc_fence_after();
+        }
+        uint32_t v[16];
+        tmem_ld16(taddr + j * 16, v);
+        const uint32_t a_lo = hbuf + sw128_off(lr, 2 * jj), a_hi = hbuf + sw128_off(lr, 2 * jj + 1);
+        const uint4 h0 = lds128(a_lo), h1 = lds128(a_hi);
+        tmem_wait_ld();
+        const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        uint32_t o[8];
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) {
+          float z0 = __uint_as_float(v[2 * qq]) + bf_lo(hw[qq]);
+          float z1 = __uint_as_float(v[2 * qq + 1]) + bf_hi(hw[qq]);
+          if constexpr (HAS_BIAS) {
+            z0 += s_bias[j * 16 + 2 * qq];
+            z1 += s_bias[j * 16 + 2 * qq + 1];
+          }
+          if constexpr (ACT == DMPNN_ACT_RELU) o[qq] = act_word<ACT>(pack_bf2(z0, z1), 0.f);  // max after rounding == rounding after max
+          else o[qq] = pack_bf2(act_t<ACT>(p.act_param, z0), act_t<ACT>(p.act_param, z1));
+        }
+        sts128(a_lo, make_uint4(o[0], o[1], o[2], o[3]));
+        sts128(a_hi, make_uint4(o[4], o[5], o[6], o[7]));
+        if (++jc == 5 || j == nj - 1) {   // accumulator chunk fully read: hand its TMEM columns back
+          tc_fence_before();
+          mbar_arrive(bar(B_ACCFREE + cidx));
+          jc = 0;
+          ++cidx;
+        }
+        if (jj == 3 || j == nj - 1) {
+          // all 128 rows of this slab are final -> coalesced copy-out of the valid rows
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          const int ncc = 2 * (jj + 1);  // valid 16-byte chunks per row in this slab
+          const int s = j >> 2;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int pidx = et + 128 * k;
+            const int rr = pidx >> 3, cc = pidx & 7;
+            if (rr < nrows && cc < ncc) {
+              const uint4 val = lds128(hbuf + sw128_off(rr, cc));
+              *reinterpret_cast<uint4*>(p.Hn + (int64_t)(row0 + rr) * p.ld + s * 64 + cc * 8) = val;
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(bar(B_HFREE + q));
+          ++hs;
+        }
+      }
+      row0 = row0n;
+      nrows = nrowsn;
+      lr = lrn - row0n;
+    }
+  } else {
+    // ===================== message: per-atom sum-minus-self, in place in the A buffer ==========
+    const int sw = warp - 8;
+    const int tS = threadIdx.x - 256;
+    const int nchunk16 = p.hp >> 3;  // 16-byte chunks per row
+    int it = 0;
+    int t = blockIdx.x;
+    // rowptr slice of the first tile
+    int row0 = 0, atom0 = 0, natoms = 0;
+    if (t < p.n_tiles) {
+      row0 = __ldg(p.tile_row_ptr + t);
+      atom0 = __ldg(p.tile_atom_ptr + t);
+      natoms = __ldg(p.tile_atom_ptr + t + 1) - atom0;
+      if (tS <= natoms) s_rowptr[tS] = __ldg(p.rowptr + atom0 + tS) - row0;
+    }
+    for (; t < p.n_tiles; t += gridDim.x, ++it) {
+      const int b = it & 1, use = it >> 1;
+      int32_t* rp = s_rowptr + b * 132;
+      // prefetch next tile's rowptr slice into a register
+      const int tn = t + gridDim.x;
+      int row0n = 0, atom0n = 0, natomsn = 0, rpn = 0;
+      if (tn < p.n_tiles) {
+        row0n = __ldg(p.tile_row_ptr + tn);
+        atom0n = __ldg(p.tile_atom_ptr + tn);
+        natomsn = __ldg(p.tile_atom_ptr + tn + 1) - atom0n;
+        if (tS <= natomsn) rpn = __ldg(p.rowptr + atom0n + tS) - row0n;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // rp[] of this tile is complete
+      mbar_wait(bar(B_AFULL + b), use & 1);
+      const uint32_t abuf = sA + b * kABufBytes;
+      // phase A: one warp per atom, lanes over the first 32 16-byte chunks of the row
+      const int nA = nchunk16 < 32 ? nchunk16 : 32;
+      for (int a = sw; a < natoms; a += kSWarps) {
+        const int r0 = rp[a], d = rp[a + 1] - r0;
+        if (d > 0 && lane < nA) message_atom_chunk<ACT, FIRST>(abuf, r0, d, lane, p.act_param);
+      }
+      // phase B: the remaining (<= 6) chunks, several atoms per warp so the lanes stay busy
+      const int extra = nchunk16 - 32;
+      if (extra > 0) {
+        const int G = 32 / extra;                 // atoms per warp pass
+        const int ai = lane / extra, c = 32 + lane % extra;
+        for (int base = sw * G; base < natoms; base += kSWarps * G) {
+          const int a = base + ai;
+          if (ai < G && a < natoms) {
+            const int r0 = rp[a], d = rp[a + 1] - r0;
+            if (d > 0) message_atom_chunk<ACT, FIRST>(abuf, r0, d, c, p.act_param);
+          }
+        }
+      }
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_AREADY + b));
+      // publish the next tile's rowptr slice (other buffer; readers of it finished a tile ago)
+      if (tn < p.n_tiles && tS <= natomsn) s_rowptr[(b ^ 1) * 132 + tS] = rpn;
+      row0 = row0n; atom0 = atom0n; natoms = natomsn;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- weight packing: W (f32, N x K) -> bf16 stage images in consumption order ----------------
+// image = for each 80-row output chunk c, for each 64-wide k slab s: a (rows_c x 128 B) block in the
+// K-major SWIZZLE_128B layout the tensor core reads; one cp.async.bulk per block lands it in smem.
+struct PackGeom {
+  int N, K, hpN, hpK, nslab, nchunks;
+};
+__host__ __device__ inline PackGeom pack_geom(int64_t N, int64_t K) {
+  PackGeom g;
+  g.N = (int)N; g.K = (int)K;
+  g.hpN = (int)((N + 15) / 16 * 16);
+  g.hpK = (int)((K + 15) / 16 * 16);
+  g.nslab = (g.hpK + 63) / 64;
+  g.nchunks = (g.hpN + kChunkN - 1) / kChunkN;
+  return g;
+}
+
+__global__ void k_pack_weight(const float* __restrict__ W, int64_t ldw, PackGeom g, __nv_bfloat16* __restrict__ out) {
+  const int n = blockIdx.x;                        // 0 .. hpN-1
+  const int c = n / kChunkN;
+  const int nl = n - c * kChunkN;
+  const int rows = min(kChunkN, g.hpN - c * kChunkN);
+  for (int k = threadIdx.x; k < g.nslab * 64; k += blockDim.x) {
+    const int s = k >> 6, kl = k & 63;
+    const size_t blk = (size_t)c * kChunkN * g.nslab * 128 + (size_t)s * rows * 128;
+    const size_t off = blk + (size_t)(nl >> 3) * 1024 + (nl & 7) * 128 + (((kl >> 3) ^ (nl & 7)) << 4) + (kl & 7) * 2;
+    const float v = (n < g.N && k < g.K) ? W[(int64_t)n * ldw + k] : 0.f;
+    out[off >> 1] = __float2bfloat16_rn(v);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static bool encode_rows_map(EncodeTiledFn enc, CUtensorMap* tmap, const void* base, int hp, int64_t rows, int64_t ld) {
+  cuuint64_t gdim[2] = {(cuuint64_t)hp, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)kTileM};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int ACT, bool FIRST, bool HAS_BIAS>
+static cudaError_t launch_variant(int grid, cudaStream_t st, const CUtensorMap& mH, const CUtensorMap& mH0, const Params& p) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_bond_step_fused<ACT, FIRST, HAS_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_bond_step_fused<ACT, FIRST, HAS_BIAS><<<grid, kThreads, kSmemAlloc, st>>>(mH, mH0, p);
+  return cudaSuccess;
+}
+
+}  // namespace fused
+}  // namespace dmpnn
+
+using namespace dmpnn;
+using namespace dmpnn::fused;
+
+extern "C" int dmpnn_pack_weight_bf16_bytes(int64_t N, int64_t K, size_t* bytes) {
+  DMPNN_CHECK_ARG(bytes && N > 0 && K > 0 && N <= kMaxHp && K <= kMaxHp, "pack_weight_bf16: need 0 < N,K <= %d", kMaxHp);
+  PackGeom g = pack_geom(N, K);
+  *bytes = (size_t)g.nslab * g.hpN * 128;
+  return 0;
+}
+
+extern "C" int dmpnn_pack_weight_bf16(const float* W, int64_t ldw, int64_t N, int64_t K, void* Wpk, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DMPNN_CHECK_ARG(W && Wpk && N > 0 && K > 0 && N <= kMaxHp && K <= kMaxHp, "pack_weight_bf16: bad args");
+  PackGeom g = pack_geom(N, K);
+  k_pack_weight<<<g.hpN, 128, 0, st>>>(W, ldw, g, (__nv_bfloat16*)Wpk);
+  DMPNN_CHECK_LAUNCH("pack_weight_bf16", 1);
+  return 0;
+}
+
 extern "C" int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, void* H_next, int64_t ld,
-                               int64_t n_rows_alloc, int64_t h, const void* Wpk, const float* bias,
-                               const int32_t* rowptr, const int32_t* rev_row,
-                               const int32_t* mol_atom_ptr, const int32_t* mol_row_ptr,
-                               const int32_t* tile_mol_ptr, int64_t n_tiles,
-                               int act, float act_param, int first_step, void* stream) { dmpnn::set_error("not built"); return -3; }
+                                          int64_t n_rows_alloc, int64_t h, const void* Wpk, const float* bias,
+                                          const int32_t* rowptr, const int32_t* rev_row, const int32_t* tile_row_ptr,
+                                          const int32_t* tile_atom_ptr, int64_t n_tiles, int act, float act_param,
+                                          int first_step, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DMPNN_CHECK_ARG(H_prev && H_0 && H_next && Wpk && rowptr && rev_row && tile_row_ptr && tile_atom_ptr,
+                  "bond_step_fused: null pointer");
+  DMPNN_CHECK_ARG(h > 0 && h <= kMaxHp, "bond_step_fused: h=%lld unsupported (max %d)", (long long)h, kMaxHp);
+  const int hp = (int)((h + 15) / 16 * 16);
+  DMPNN_CHECK_ARG(ld >= hp && ld % 8 == 0, "bond_step_fused: ld=%lld must be >= %d and a multiple of 8", (long long)ld, hp);
+  DMPNN_CHECK_ARG(n_rows_alloc > 0 && n_tiles >= 0, "bond_step_fused: bad sizes");
+  DMPNN_CHECK_ARG(act >= DMPNN_ACT_NONE && act <= DMPNN_ACT_ELU, "bond_step_fused: bad activation %d", act);
+  DMPNN_CHECK_ARG((reinterpret_cast<uintptr_t>(H_prev) & 15) == 0 && (reinterpret_cast<uintptr_t>(H_0) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(H_next) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wpk) & 15) == 0,
+                  "bond_step_fused: buffers must be 16-byte aligned");
+  DMPNN_CHECK_ARG(H_next != H_prev && H_next != H_0, "bond_step_fused: in-place update not supported");
+  if (n_tiles == 0) return 0;
+  EncodeTiledFn enc = get_encode_fn();
+  DMPNN_CHECK_ARG(enc != nullptr, "bond_step_fused: cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMap mH, mH0;
+  DMPNN_CHECK_ARG(encode_rows_map(enc, &mH, H_prev, hp, n_rows_alloc, ld) &&
+                      encode_rows_map(enc, &mH0, H_0, hp, n_rows_alloc, ld),
+                  "bond_step_fused: cuTensorMapEncodeTiled failed");
+
+  PackGeom g = pack_geom(h, h);
+  Params p;
+  p.H0 = (const __nv_bfloat16*)H_0;
+  p.Hn = (__nv_bfloat16*)H_next;
+  p.ld = ld;
+  p.Wpk = (const uint8_t*)Wpk;
+  p.bias = bias;
+  p.rowptr = rowptr;
+  p.rev_row = rev_row;
+  p.tile_row_ptr = tile_row_ptr;
+  p.tile_atom_ptr = tile_atom_ptr;
+  p.n_tiles = (int)n_tiles;
+  p.h = (int)h;
+  p.hp = hp;
+  p.nslab = g.nslab;
+  p.ksteps_last = (hp - 64 * (g.nslab - 1)) / 16;
+  p.nchunks = g.nchunks;
+  p.act_param = act_param;
+
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
+  cudaError_t e = cudaErrorInvalidValue;
+#define DMPNN_LAUNCH_ACT(A)                                                          \
+  case A:                                                                            \
+    e = first_step ? (bias ? launch_variant<A, true, true>(grid, st, mH, mH0, p) : launch_variant<A, true, false>(grid, st, mH, mH0, p))   \
+                   : (bias ? launch_variant<A, false, true>(grid, st, mH, mH0, p) : launch_variant<A, false, false>(grid, st, mH, mH0, p)); \
+    break;
+  switch (act) {
+    DMPNN_LAUNCH_ACT(DMPNN_ACT_NONE)
+    DMPNN_LAUNCH_ACT(DMPNN_ACT_RELU)
+    DMPNN_LAUNCH_ACT(DMPNN_ACT_LEAKYRELU)
+    DMPNN_LAUNCH_ACT(DMPNN_ACT_TANH)
+    DMPNN_LAUNCH_ACT(DMPNN_ACT_ELU)
+  }
+#undef DMPNN_LAUNCH_ACT
+  DMPNN_CHECK_ARG(e == cudaSuccess, "bond_step_fused: cannot configure %d B dynamic smem: %s", kSmemAlloc, cudaGetErrorString(e));
+  DMPNN_CHECK_LAUNCH("bond_step_fused", 1);
+  return 0;
+}

@@ -92,6 +92,8 @@ class Layout:
     mol_atom_ptr: Tensor
     mol_row_ptr: Tensor
     tile_mol_ptr: Tensor
+    tile_row_ptr: Tensor
+    tile_atom_ptr: Tensor
     meta: Tensor
     _meta_host: list | None = None
 
@@ -156,6 +158,8 @@ def build_layout(edge_index: Tensor, rev_edge_index: Tensor, batch: Tensor, n_mo
     mol_atom_ptr = torch.zeros(B + 1, **i32)
     mol_row_ptr = torch.zeros(B + 1, **i32)
     tile_mol_ptr = torch.zeros(B + 2, **i32)
+    tile_row_ptr = torch.zeros(B + 2, **i32)
+    tile_atom_ptr = torch.zeros(B + 2, **i32)
     meta = torch.zeros(_lib.META_WORDS, **i32)
     nbytes = C.c_size_t(0)
     _lib.check(lib.dmpnn_layout_workspace_bytes(V, E, B, C.byref(nbytes)), "dmpnn_layout_workspace_bytes")
@@ -164,11 +168,11 @@ def build_layout(edge_index: Tensor, rev_edge_index: Tensor, batch: Tensor, n_mo
         edge_index.data_ptr(), rev_edge_index.data_ptr(), batch.data_ptr(), V, E, B,
         perm.data_ptr(), inv_perm.data_ptr(), rowptr.data_ptr(), src_row.data_ptr(), dst_row.data_ptr(),
         rev_row.data_ptr(), mol_atom_ptr.data_ptr(), mol_row_ptr.data_ptr(), tile_mol_ptr.data_ptr(),
-        meta.data_ptr(), ws.data_ptr(), _stream(),
+        tile_row_ptr.data_ptr(), tile_atom_ptr.data_ptr(), meta.data_ptr(), ws.data_ptr(), _stream(),
     )
     _lib.check(rc, "dmpnn_layout_build")
     return Layout(V, E, B, perm[:E], inv_perm[:E], rowptr, src_row[:E], dst_row[:E], rev_row[:E], mol_atom_ptr,
-                  mol_row_ptr, tile_mol_ptr, meta)
+                  mol_row_ptr, tile_mol_ptr, tile_row_ptr, tile_atom_ptr, meta)
 
 
 def get_layout(bmg) -> Layout:
@@ -275,6 +279,8 @@ def segment_bcast(G: Tensor, seg_of_row: Tensor, ptr: Tensor | None, R: int, Cco
 def bond_message(X: Tensor, lay: Layout, Ccols: int, out: Tensor, *, act: int = ACT_NONE, act_param: float = 0.0,
                  permute_on_read: bool = False):
     lib = _lib.load()
+    if lay.E == 0:
+        return
     rc = lib.dmpnn_bond_message(X.data_ptr(), _dt(X), _ld(X), lay.rowptr.data_ptr(), lay.rev_row.data_ptr(),
                                 lay.V, Ccols, act, float(act_param), 1 if permute_on_read else 0,
                                 out.data_ptr(), _dt(out), _ld(out), _stream())
@@ -283,6 +289,8 @@ def bond_message(X: Tensor, lay: Layout, Ccols: int, out: Tensor, *, act: int = 
 
 def rev_average(X: Tensor, lay: Layout, Ccols: int, out: Tensor, *, act: int = ACT_NONE, act_param: float = 0.0):
     lib = _lib.load()
+    if lay.E == 0:
+        return
     rc = lib.dmpnn_rev_average(X.data_ptr(), _dt(X), _ld(X), lay.rev_row.data_ptr(), lay.E, Ccols, act,
                                float(act_param), out.data_ptr(), _dt(out), _ld(out), _stream())
     _lib.check(rc, "dmpnn_rev_average")
@@ -292,6 +300,8 @@ def act_bwd(G: Tensor, Yact: Tensor, R: int, Ccols: int, *, act: int, act_param:
             gidx: Tensor | None = None, from_preact: bool = False, dZ: Tensor | None = None,
             acc: Tensor | None = None):
     lib = _lib.load()
+    if R == 0:
+        return
     rc = lib.dmpnn_act_bwd(
         G.data_ptr(), _dt(G), _ld(G), _ptr(gidx), Yact.data_ptr(), _dt(Yact), _ld(Yact),
         1 if from_preact else 0, act, float(act_param),
@@ -352,8 +362,8 @@ def bond_step_fused(H_prev: Tensor, H0: Tensor, H_next: Tensor, h: int, Wpk: Ten
     lib = _lib.load()
     rc = lib.dmpnn_bond_step_fused_bf16(
         H_prev.data_ptr(), H0.data_ptr(), H_next.data_ptr(), _ld(H0), H0.shape[0], h, Wpk.data_ptr(), _ptr(bias),
-        lay.rowptr.data_ptr(), lay.rev_row.data_ptr(), lay.mol_atom_ptr.data_ptr(), lay.mol_row_ptr.data_ptr(),
-        lay.tile_mol_ptr.data_ptr(), lay.n_tiles, act, float(act_param), 1 if first_step else 0, _stream(),
+        lay.rowptr.data_ptr(), lay.rev_row.data_ptr(), lay.tile_row_ptr.data_ptr(), lay.tile_atom_ptr.data_ptr(),
+        lay.n_tiles, act, float(act_param), 1 if first_step else 0, _stream(),
     )
     _lib.check(rc, "dmpnn_bond_step_fused_bf16")
 

@@ -105,6 +105,8 @@ int dmpnn_layout_build(const int64_t* edge_index, const int64_t* rev_edge_index,
                        int32_t* src_row /*E*/, int32_t* dst_row /*E*/, int32_t* rev_row /*E*/,
                        int32_t* mol_atom_ptr /*B+1*/, int32_t* mol_row_ptr /*B+1*/,
                        int32_t* tile_mol_ptr /*B+1, first n_tiles+1 valid*/,
+                       int32_t* tile_row_ptr /*B+1: first internal row of each tile (+ sentinel)*/,
+                       int32_t* tile_atom_ptr /*B+1: first atom of each tile (+ sentinel)*/,
                        int32_t* meta /*DMPNN_META_WORDS*/,
                        void* workspace, void* stream);
 
@@ -209,8 +211,7 @@ int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, void* H_next
                                int64_t n_rows_alloc, int64_t h,
                                const void* Wpk, const float* bias,
                                const int32_t* rowptr, const int32_t* rev_row,
-                               const int32_t* mol_atom_ptr, const int32_t* mol_row_ptr,
-                               const int32_t* tile_mol_ptr, int64_t n_tiles,
+                               const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
                                int act, float act_param, int first_step, void* stream);
 
 #ifdef __cplusplus

@@ -38,6 +38,8 @@ def build_layout(edge_index: np.ndarray, rev: np.ndarray, batch: np.ndarray, n_m
         max_atoms = max(max_atoms, int(mol_atom_ptr[B] - mol_atom_ptr[t_mol]))
     n_tiles = len(tiles)
     tile_mol_ptr = np.array(tiles + [B], dtype=np.int32)
+    tile_row_ptr = mol_row_ptr[tile_mol_ptr].astype(np.int32)
+    tile_atom_ptr = mol_atom_ptr[tile_mol_ptr].astype(np.int32)
     # validity flags
     in_range = bool(E == 0 or (src.min() >= 0 and src.max() < V and dst.min() >= 0 and dst.max() < V
                                and rev.min() >= 0 and rev.max() < E))
@@ -48,5 +50,6 @@ def build_layout(edge_index: np.ndarray, rev: np.ndarray, batch: np.ndarray, n_m
     flags = (1 if invol else 0) | (2 if sorted_ else 0) | (4 if in_range else 0)
     max_indeg = int(np.diff(rowptr).max()) if V else 0
     return dict(perm=perm, inv_perm=inv_perm, rowptr=rowptr, src_row=src_row, dst_row=dst_row, rev_row=rev_row,
-                mol_atom_ptr=mol_atom_ptr, mol_row_ptr=mol_row_ptr, tile_mol_ptr=tile_mol_ptr, n_tiles=n_tiles,
+                mol_atom_ptr=mol_atom_ptr, mol_row_ptr=mol_row_ptr, tile_mol_ptr=tile_mol_ptr, tile_row_ptr=tile_row_ptr,
+                tile_atom_ptr=tile_atom_ptr, n_tiles=n_tiles,
                 flags=flags, max_indeg=max_indeg, max_tile_rows=max_rows, max_tile_atoms=max_atoms)

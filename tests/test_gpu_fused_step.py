@@ -1,0 +1,111 @@
+"""GPU tier: the fused tcgen05 depth-step kernel (dmpnn_bond_step_fused_bf16) against a plain
+PyTorch fp32 reference of the same op that emulates its roundings (bf16 message, bf16 W_h, fp32
+accumulate), and against the unfused fp32-accurate kernels."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(n_mols, h, seed, shuffle=True, min_atoms=2):
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.engine import get_layout, pad_hidden
+
+    mgs = make_molecules(n_mols, seed=seed, shuffle_edges=shuffle, min_atoms=min_atoms)
+    bmg = BatchMolGraph(mgs)
+    bmg.to("cuda")
+    lay = get_layout(bmg)
+    hp = pad_hidden(h)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    H0 = torch.zeros(lay.E, hp, dtype=torch.bfloat16, device="cuda")
+    H0[:, :h] = (torch.randn(lay.E, h, device="cuda", generator=g) * 0.7).bfloat16()
+    Hp = torch.zeros_like(H0)
+    Hp[:, :h] = torch.relu(torch.randn(lay.E, h, device="cuda", generator=g)).bfloat16()
+    W = torch.randn(h, h, device="cuda", generator=g) / h ** 0.5
+    b = torch.randn(h, device="cuda", generator=g) * 0.1
+    return lay, H0, Hp, W, b, hp
+
+
+def _torch_reference(lay, Hin, H0, W, b, h, act, first):
+    """fp32 torch restatement of the fused op with the kernel's rounding points."""
+    tau = {"relu": torch.relu, "tanh": torch.tanh}[act]
+    X = Hin[:, :h].float()
+    if first:
+        X = tau(X)
+    dst = lay.dst_row.long()
+    A = torch.zeros(lay.V, h, device=X.device).index_add_(0, dst, X)       # per-atom sums over in-edges
+    Mt = (A[dst] - X).bfloat16().float()                                    # row e' holds M[rev(e')] (bf16)
+    Z = Mt @ W.bfloat16().float().t()
+    rev = lay.rev_row.long()
+    out = torch.zeros_like(Hin)
+    z = Z + H0[rev, :h].float() + (b if b is not None else 0.0)
+    out[rev, :h] = tau(z).bfloat16()
+    return out
+
+
+@pytest.mark.parametrize("h,first,act,bias", [
+    (300, False, "relu", False), (300, True, "relu", False), (300, False, "tanh", True), (64, False, "relu", True),
+    (128, True, "tanh", False), (200, False, "relu", False), (160, False, "relu", True), (16, False, "relu", False),
+    (304, False, "relu", False),
+])
+def test_fused_step_vs_torch_reference(h, first, act, bias):
+    from chemprop_b200 import _lib
+    from chemprop_b200.engine import bond_step_fused, pack_weight_bf16
+
+    lay, H0, Hp, W, b, hp = _setup(700, h, seed=h + int(first))
+    assert lay.max_tile_rows <= 128
+    Hin = H0 if first else Hp
+    code = {"relu": _lib.ACT_RELU, "tanh": _lib.ACT_TANH}[act]
+    Wpk = pack_weight_bf16(W)
+    Hn = torch.full_like(H0, float("nan"))
+    bond_step_fused(Hin, H0, Hn, h, Wpk, b if bias else None, lay, code, 0.0, first)
+    torch.cuda.synchronize()
+    ref = _torch_reference(lay, Hin, H0, W, b if bias else None, h, act, first)
+    assert torch.isfinite(Hn.float()).all(), "rows/columns left unwritten"
+    assert float(Hn[:, h:].float().abs().max()) == 0.0 if hp > h else True, "row padding must stay zero"
+    torch.testing.assert_close(Hn.float(), ref.float(), rtol=2 ** -7, atol=4e-3)   # <= 1 bf16 ulp (+ tanh slack)
+    assert (Hn.float() - ref.float()).abs().mean().item() <= 1e-3
+
+
+def test_fused_step_matches_unfused_kernels():
+    from chemprop_b200 import _lib
+    from chemprop_b200.engine import bond_message, bond_step_fused, linear_fwd, pack_weight_bf16
+
+    h = 300
+    lay, H0, Hp, W, b, hp = _setup(2500, h, seed=3)
+    Hn = torch.zeros_like(H0)
+    bond_step_fused(Hp, H0, Hn, h, pack_weight_bf16(W), b, lay, _lib.ACT_RELU, 0.0, False)
+    M = torch.zeros_like(H0)
+    bond_message(Hp, lay, h, M)
+    Hu = torch.zeros_like(H0)
+    linear_fwd(M, h, W.contiguous(), Hu, h, bias=b, res=H0, act=_lib.ACT_RELU, R=lay.E, pad_to=hp)
+    torch.cuda.synchronize()
+    err = (Hn.float() - Hu.float()).abs().max().item()
+    assert err <= 5e-2, err      # bf16 W_h in the fused kernel vs f32 W_h in the SIMT kernel
+
+
+def test_fused_step_many_tiles_and_single_atoms():
+    """More tiles than SMs (persistent loop wraps) + 1-atom molecules (zero-row atoms inside tiles)."""
+    from chemprop_b200 import _lib
+    from chemprop_b200.engine import bond_step_fused, pack_weight_bf16
+
+    h = 96
+    lay, H0, Hp, W, b, hp = _setup(4000, h, seed=9, min_atoms=1)
+    assert lay.n_tiles > 148 * 2
+    Hn = torch.full_like(H0, float("nan"))
+    bond_step_fused(Hp, H0, Hn, h, pack_weight_bf16(W), None, lay, _lib.ACT_RELU, 0.0, False)
+    torch.cuda.synchronize()
+    ref = _torch_reference(lay, Hp, H0, W, None, h, "relu", False)
+    assert torch.isfinite(Hn.float()).all()
+    torch.testing.assert_close(Hn.float(), ref.float(), rtol=2 ** -7, atol=4e-3)
+
+
+def test_fused_rejects_unsupported():
+    from chemprop_b200 import DmpnnError, _lib
+    from chemprop_b200.engine import bond_step_fused
+
+    lay, H0, Hp, W, b, hp = _setup(10, 64, seed=1)
+    with pytest.raises(DmpnnError):
+        bond_step_fused(Hp, H0, torch.zeros_like(H0), 400, torch.zeros(16, dtype=torch.uint8, device="cuda"), None,
+                        lay, _lib.ACT_RELU, 0.0, False)
