@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import (ACT_ELU, ACT_LEAKYRELU, ACT_NONE, ACT_RELU, ACT_TANH, BF16, F32, SCALE_DIV_CONST,
                    SCALE_INV_COUNT, SCALE_NONE, DmpnnError)
 
-HIDDEN_ALIGN = 16  # hidden row stride is padded to a multiple of 16 elements (UMMA K granularity)
+HIDDEN_ALIGN = 64  # hidden row stride padded to 64 elements: bf16 rows start on 128-byte lines (one TMA request per box row)
 
 # Optional device-side timing of the depth step (bench.py's roofline): when a list, every depth step
 # appends (tag, start_event, end_event) recorded on the launching stream.

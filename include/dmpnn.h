@@ -205,6 +205,9 @@ int dmpnn_act_bwd(const void* G, int g_dtype, int64_t ldg, const int32_t* gidx,
  * Wpk is W_h packed by dmpnn_pack_weight_bf16.  Requires ld % 8 == 0, h <= 304, all tiles
  * <= 128 rows, DMPNN_FLAG_REV_INVOLUTION.  Returns <0 (and does nothing) otherwise.
  * ------------------------------------------------------------------------------------- */
+/* Debug aid: when set (device pointer to n_tiles x 12 uint64, zero-filled), block 0 of the fused
+ * kernel records %globaltimer stamps of its pipeline phases for its first n_tiles tiles. NULL = off. */
+int dmpnn_set_trace_buffer(void* dev_ptr, int64_t n_tiles);
 int dmpnn_pack_weight_bf16_bytes(int64_t N, int64_t K, size_t* bytes);
 int dmpnn_pack_weight_bf16(const float* W, int64_t ldw, int64_t N, int64_t K, void* Wpk, void* stream);
 int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, void* H_next, int64_t ld,
