@@ -16,11 +16,14 @@ struct LayoutWs {
   int32_t* tmp;     // E
   int32_t* bsum;    // nblk_scan + 1
   int32_t* viol;    // 4 words: [0]=violation bits, [1]=max indeg
+  int32_t* seg_tiles;  // n_chunks * kTileChunkWs
+  int32_t* seg_info;   // n_chunks * 4
 };
+constexpr int kTileChunkWs = 1024;
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static size_t carve(LayoutWs* ws, void* base, int64_t V, int64_t E) {
+static size_t carve(LayoutWs* ws, void* base, int64_t V, int64_t E, int64_t B) {
   size_t off = 0;
   char* b = (char*)base;
   auto take = [&](size_t bytes) { char* p = b ? b + off : nullptr; off += align_up(bytes, 256); return p; };
@@ -30,7 +33,12 @@ static size_t carve(LayoutWs* ws, void* base, int64_t V, int64_t E) {
   int64_t nblk = (V + 1 + 2047) / 2048;
   int32_t* bsum = (int32_t*)take(sizeof(int32_t) * (nblk + 1));
   int32_t* viol = (int32_t*)take(sizeof(int32_t) * 4);
-  if (ws) { ws->deg = deg; ws->cursor = cursor; ws->tmp = tmp; ws->bsum = bsum; ws->viol = viol; }
+  int64_t n_chunks = (B + kTileChunkWs - 1) / kTileChunkWs;
+  if (n_chunks < 1) n_chunks = 1;
+  int32_t* seg_tiles = (int32_t*)take(sizeof(int32_t) * n_chunks * kTileChunkWs);
+  int32_t* seg_info = (int32_t*)take(sizeof(int32_t) * n_chunks * 4);
+  if (ws) { ws->deg = deg; ws->cursor = cursor; ws->tmp = tmp; ws->bsum = bsum; ws->viol = viol;
+            ws->seg_tiles = seg_tiles; ws->seg_info = seg_info; }
   return off;
 }
 
@@ -193,54 +201,78 @@ __global__ void k_mol_ptr(const int64_t* __restrict__ batch, int64_t V, int64_t 
   }
 }
 
-// Greedy molecule-aligned packing into tiles of <= kTileRows rows and <= kTileAtoms atoms.
-// Sequential by nature; one thread walks the molecule offsets staged through shared memory.
-__global__ void k_tiles(const int32_t* __restrict__ mol_atom_ptr, const int32_t* __restrict__ mol_row_ptr,
-                        int64_t B, int32_t* tile_mol_ptr, int32_t* tile_row_ptr, int32_t* tile_atom_ptr,
-                        int32_t* meta, const int32_t* viol) {
-  constexpr int CH = 4096;
-  __shared__ int32_t s_at[CH + 1];
-  __shared__ int32_t s_rw[CH + 1];
-  int32_t n_tiles = 0, max_rows = 0, max_atoms = 0;
-  int32_t t_mol = 0, t_row = 0, t_atom = 0;  // start of the open tile
-  for (int64_t base = 0; base < B; base += CH) {
-    int64_t n = (B - base < CH) ? (B - base) : CH;
-    __syncthreads();
-    for (int64_t i = threadIdx.x; i <= n; i += blockDim.x) {
-      s_at[i] = mol_atom_ptr[base + i];
-      s_rw[i] = mol_row_ptr[base + i];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int64_t i = 0; i < n; ++i) {
-        int32_t m = (int32_t)(base + i);
-        int32_t end_row = s_rw[i + 1], end_atom = s_at[i + 1];
-        if (m > t_mol && (end_row - t_row > kTileRows || end_atom - t_atom > kTileAtoms)) {
-          // close the open tile [t_mol, m)
-          tile_row_ptr[n_tiles] = t_row;
-          tile_atom_ptr[n_tiles] = t_atom;
-          tile_mol_ptr[n_tiles++] = t_mol;
-          int32_t rows = s_rw[i] - t_row, atoms = s_at[i] - t_atom;
-          max_rows = rows > max_rows ? rows : max_rows;
-          max_atoms = atoms > max_atoms ? atoms : max_atoms;
-          t_mol = m; t_row = s_rw[i]; t_atom = s_at[i];
-        }
-      }
-      if (base + n == B) {
-        int32_t rows = s_rw[n] - t_row, atoms = s_at[n] - t_atom;
-        tile_row_ptr[n_tiles] = t_row;
-        tile_atom_ptr[n_tiles] = t_atom;
-        tile_mol_ptr[n_tiles++] = t_mol;
+// Greedy molecule-aligned packing into tiles of <= kTileRows rows and <= kTileAtoms atoms, restarted at
+// every kTileChunk-th molecule so that chunks are independent: one block per chunk walks its molecule
+// offsets (staged in shared memory) and writes its tile starts to a private segment; k_tiles_gather
+// then concatenates the segments in order.  (oracle/layout_np.py restates exactly this rule.)
+constexpr int kTileChunk = 1024;
+
+__global__ void k_tiles_chunk(const int32_t* __restrict__ mol_atom_ptr, const int32_t* __restrict__ mol_row_ptr,
+                              int64_t B, int32_t* __restrict__ seg_tiles /*[n_chunks][kTileChunk]*/,
+                              int32_t* __restrict__ seg_info /*[n_chunks][4]: count, max_rows, max_atoms*/) {
+  __shared__ int32_t s_at[kTileChunk + 1];
+  __shared__ int32_t s_rw[kTileChunk + 1];
+  const int64_t base = (int64_t)blockIdx.x * kTileChunk;
+  const int n = (int)((B - base < kTileChunk) ? (B - base) : kTileChunk);
+  for (int i = threadIdx.x; i <= n; i += blockDim.x) {
+    s_at[i] = mol_atom_ptr[base + i];
+    s_rw[i] = mol_row_ptr[base + i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t* out = seg_tiles + (int64_t)blockIdx.x * kTileChunk;
+    int cnt = 0, t0 = 0, max_rows = 0, max_atoms = 0;
+    for (int i = 1; i <= n; ++i) {
+      // close the open tile [t0, i) if molecule i does not fit any more (or the chunk ends)
+      if (i == n || s_rw[i + 1] - s_rw[t0] > kTileRows || s_at[i + 1] - s_at[t0] > kTileAtoms) {
+        out[cnt++] = (int32_t)(base + t0);
+        const int rows = s_rw[i] - s_rw[t0], atoms = s_at[i] - s_at[t0];
         max_rows = rows > max_rows ? rows : max_rows;
         max_atoms = atoms > max_atoms ? atoms : max_atoms;
-        tile_mol_ptr[n_tiles] = (int32_t)B;
-        tile_row_ptr[n_tiles] = s_rw[n];
-        tile_atom_ptr[n_tiles] = s_at[n];
+        t0 = i;
       }
+    }
+    seg_info[blockIdx.x * 4 + 0] = cnt;
+    seg_info[blockIdx.x * 4 + 1] = max_rows;
+    seg_info[blockIdx.x * 4 + 2] = max_atoms;
+  }
+}
+
+__global__ void k_tiles_gather(const int32_t* __restrict__ seg_tiles, const int32_t* __restrict__ seg_info, int n_chunks,
+                               const int32_t* __restrict__ mol_atom_ptr, const int32_t* __restrict__ mol_row_ptr, int64_t B,
+                               int32_t* tile_mol_ptr, int32_t* tile_row_ptr, int32_t* tile_atom_ptr, int32_t* meta,
+                               const int32_t* viol) {
+  __shared__ int32_t s_off[1024];
+  __shared__ int32_t s_tot, s_mr, s_ma;
+  // exclusive prefix of the per-chunk tile counts (n_chunks is small: B / 1024)
+  if (threadIdx.x == 0) {
+    int run = 0, mr = 0, ma = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+      if (c < 1024) s_off[c] = run;
+      run += seg_info[c * 4];
+      mr = max(mr, seg_info[c * 4 + 1]);
+      ma = max(ma, seg_info[c * 4 + 2]);
+    }
+    s_tot = run; s_mr = mr; s_ma = ma;
+  }
+  __syncthreads();
+  for (int c = 0; c < n_chunks; ++c) {
+    int off;
+    if (c < 1024) off = s_off[c];
+    else { off = 0; for (int q = 0; q < c; ++q) off += seg_info[q * 4]; }
+    const int cnt = seg_info[c * 4];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int32_t m = seg_tiles[(int64_t)c * kTileChunk + i];
+      tile_mol_ptr[off + i] = m;
+      tile_row_ptr[off + i] = mol_row_ptr[m];
+      tile_atom_ptr[off + i] = mol_atom_ptr[m];
     }
   }
   if (threadIdx.x == 0) {
-    if (B == 0) { tile_mol_ptr[0] = 0; tile_row_ptr[0] = 0; tile_atom_ptr[0] = 0; n_tiles = 0; }
+    const int n_tiles = s_tot;
+    tile_mol_ptr[n_tiles] = (int32_t)B;
+    tile_row_ptr[n_tiles] = mol_row_ptr[B];
+    tile_atom_ptr[n_tiles] = mol_atom_ptr[B];
     int32_t vb = viol[0];
     int32_t flags = 0;
     if (!(vb & V_RANGE)) flags |= DMPNN_FLAG_INDEX_IN_RANGE;
@@ -249,8 +281,8 @@ __global__ void k_tiles(const int32_t* __restrict__ mol_atom_ptr, const int32_t*
     meta[DMPNN_META_N_TILES] = n_tiles;
     meta[DMPNN_META_FLAGS] = flags;
     meta[DMPNN_META_MAX_INDEG] = viol[1];
-    meta[DMPNN_META_MAX_TILE_ROWS] = max_rows;
-    meta[DMPNN_META_MAX_TILE_ATOMS] = max_atoms;
+    meta[DMPNN_META_MAX_TILE_ROWS] = s_mr;
+    meta[DMPNN_META_MAX_TILE_ATOMS] = s_ma;
     meta[5] = 0; meta[6] = 0; meta[7] = 0;
   }
 }
@@ -261,7 +293,7 @@ using namespace dmpnn;
 
 extern "C" int dmpnn_layout_workspace_bytes(int64_t V, int64_t E, int64_t B, size_t* bytes) {
   DMPNN_CHECK_ARG(V >= 0 && E >= 0 && B >= 0 && bytes, "layout_workspace_bytes: bad args");
-  *bytes = carve(nullptr, nullptr, V, E);
+  *bytes = carve(nullptr, nullptr, V, E, B);
   return 0;
 }
 
@@ -278,7 +310,7 @@ extern "C" int dmpnn_layout_build(const int64_t* edge_index, const int64_t* rev_
                       tile_atom_ptr && meta,
                   "layout_build: null pointer");
   LayoutWs ws;
-  size_t total = carve(&ws, workspace, V, E);
+  size_t total = carve(&ws, workspace, V, E, B);
   cudaMemsetAsync(workspace, 0, total, st);
   const int T = 256;
   if (E > 0) {
@@ -297,8 +329,11 @@ extern "C" int dmpnn_layout_build(const int64_t* edge_index, const int64_t* rev_
                                                     src_row, dst_row, ws.viol);
   if (E > 0) k_rev_rows<<<ceil_div_i64(E, T), T, 0, st>>>(rev_edge_index, E, perm, inv_perm, rev_row);
   k_mol_ptr<<<ceil_div_i64(V + 1, T), T, 0, st>>>(batch, V, B, rowptr, mol_atom_ptr, mol_row_ptr);
-  k_tiles<<<1, 1024, 0, st>>>(mol_atom_ptr, mol_row_ptr, B, tile_mol_ptr, tile_row_ptr, tile_atom_ptr, meta, ws.viol);
-  DMPNN_CHECK_LAUNCH("layout_build", 10);
+  const int n_chunks = (int)((B + kTileChunk - 1) / kTileChunk);
+  if (n_chunks > 0) k_tiles_chunk<<<n_chunks, 256, 0, st>>>(mol_atom_ptr, mol_row_ptr, B, ws.seg_tiles, ws.seg_info);
+  k_tiles_gather<<<1, 1024, 0, st>>>(ws.seg_tiles, ws.seg_info, n_chunks, mol_atom_ptr, mol_row_ptr, B, tile_mol_ptr,
+                                     tile_row_ptr, tile_atom_ptr, meta, ws.viol);
+  DMPNN_CHECK_LAUNCH("layout_build", 11);
   return 0;
 }
 

@@ -244,6 +244,40 @@ __global__ void k_colsum_partial(const TY* __restrict__ dY, int64_t lddy, float*
   part[(int64_t)blockIdx.y * N + n] = s;
 }
 
+// column sums with 4-wide loads: block = 8 warps striding over the rows of its split, lanes over
+// column quads; per-block partial reduced through shared memory (fixed order: deterministic)
+template <typename TY>
+__global__ void __launch_bounds__(256)
+k_colsum_partial_v4(const TY* __restrict__ dY, int64_t lddy, float* __restrict__ part, int64_t R, int N,
+                    int64_t rows_per_split) {
+  extern __shared__ float s_part[];   // [8][Npad4]
+  const int Q = N / 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_split;
+  const int64_t r_end = min(R, r_begin + rows_per_split);
+  for (int q0 = 0; q0 < Q; q0 += 32) {
+    const int q = q0 + lane;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (q < Q)
+      for (int64_t r = r_begin + warp; r < r_end; r += 8) {
+        float v[4];
+        ld4(dY + r * lddy + 4 * q, v);
+        acc[0] += v[0]; acc[1] += v[1]; acc[2] += v[2]; acc[3] += v[3];
+      }
+    if (q < Q) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_part[warp * N + 4 * q + i] = acc[i];
+    }
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_part[w * N + n];
+    part[(int64_t)blockIdx.x * N + n] = s;
+  }
+}
+
 __global__ void k_reduce_splits(const float* __restrict__ part, int S, int64_t count, float* __restrict__ out,
                                 int64_t inner, int64_t ld_out, int accumulate) {
   // out[(i / inner) * ld_out + i % inner] (+)= sum_s part[s*count + i]
@@ -256,9 +290,9 @@ __global__ void k_reduce_splits(const float* __restrict__ part, int S, int64_t c
 }
 
 static int wgrad_splits(int64_t R) {
-  int64_t s = (R + 4095) / 4096;
+  int64_t s = (R + 1023) / 1024;
   if (s < 1) s = 1;
-  if (s > 48) s = 48;
+  if (s > 296) s = 296;
   return (int)s;
 }
 
@@ -333,5 +367,26 @@ extern "C" int dmpnn_linear_wgrad(const void* dY, int dy_dtype, int64_t lddy, co
     k_reduce_splits<<<ceil_div_i64(N, 256), 256, 0, st>>>(bpart, S, N, dbias, N, N, accumulate);
   }
   DMPNN_CHECK_LAUNCH("linear_wgrad", dbias ? 4 : 2);
+  return 0;
+}
+
+extern "C" int dmpnn_column_sum(const void* Y, int y_dtype, int64_t ldy, int64_t R, int64_t N, float* out, int accumulate,
+                                void* workspace, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DMPNN_CHECK_ARG(R >= 0 && N > 0 && out && workspace, "column_sum: bad args");
+  DMPNN_CHECK_ARG(R == 0 || Y, "column_sum: null operand");
+  const int S = wgrad_splits(R);
+  const int64_t rps = ((R + S - 1) / S + WR - 1) / WR * WR;
+  float* bpart = (float*)workspace;
+  DMPNN_DISPATCH_DTYPE(y_dtype, TY,
+    if (N % 4 == 0 && N <= 2048 && vec4_ok<TY>(Y, ldy)) {
+      k_colsum_partial_v4<TY><<<S, 256, 8 * N * sizeof(float), st>>>((const TY*)Y, ldy, bpart, R, (int)N, rps > 0 ? rps : WR);
+    } else {
+      dim3 g2(ceil_div_i64(N, 128), S);
+      k_colsum_partial<TY><<<g2, 128, 0, st>>>((const TY*)Y, ldy, bpart, R, (int)N, rps > 0 ? rps : WR);
+    }
+  )
+  k_reduce_splits<<<ceil_div_i64(N, 256), 256, 0, st>>>(bpart, S, N, out, N, N, accumulate);
+  DMPNN_CHECK_LAUNCH("column_sum", 2);
   return 0;
 }

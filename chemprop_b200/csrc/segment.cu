@@ -105,9 +105,181 @@ __global__ void k_act_bwd(const TG* __restrict__ G, int64_t ldg, const int32_t* 
   }
 }
 
+
+// ---- 4-wide variants (used when every pointer / row stride is 4-element aligned and C % 4 == 0) --------
+template <typename TX, typename TY>
+__global__ void k_segment_sum_v4(const TX* __restrict__ X, int64_t ldx, const int32_t* __restrict__ idx,
+                                 const int32_t* __restrict__ ptr, int64_t n_seg, int Q, int act, float ap,
+                                 int scale_mode, float scale, TY* __restrict__ Y, int64_t ldy, int Qpad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= n_seg) return;
+  const int32_t a = ptr[s], b = ptr[s + 1];
+  for (int q = lane; q < Qpad; q += 32) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (q < Q) {
+      for (int32_t r = a; r < b; ++r) {
+        const int64_t rr = idx ? (int64_t)idx[r] : (int64_t)r;
+        float v[4];
+        ld4(X + rr * ldx + 4 * q, v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += act_apply(act, ap, v[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (scale_mode == DMPNN_SCALE_INV_COUNT) acc[i] = (b > a) ? acc[i] / (float)(b - a) : 0.f;
+        else if (scale_mode == DMPNN_SCALE_DIV_CONST) acc[i] = acc[i] / scale;
+      }
+    }
+    st4(Y + s * ldy + 4 * q, acc);
+  }
+}
+
+template <typename TG, typename TY>
+__global__ void k_segment_bcast_v4(const TG* __restrict__ G, int64_t ldg, const int32_t* __restrict__ seg_of_row,
+                                   const int32_t* __restrict__ ptr, int64_t R, int Q, int scale_mode, float scale,
+                                   TY* __restrict__ Y, int64_t ldy) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * Q) return;
+  const int64_t r = i / Q;
+  const int q = (int)(i - r * Q);
+  const int32_t s = seg_of_row[r];
+  float v[4];
+  ld4(G + (int64_t)s * ldg + 4 * q, v);
+  const float div = (scale_mode == DMPNN_SCALE_INV_COUNT) ? (float)(ptr[s + 1] - ptr[s])
+                                                          : (scale_mode == DMPNN_SCALE_DIV_CONST ? scale : 1.f);
+  if (scale_mode != DMPNN_SCALE_NONE) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = v[k] / div;
+  }
+  st4(Y + r * ldy + 4 * q, v);
+}
+
+template <typename TX, typename TO>
+__global__ void k_bond_message_v4(const TX* __restrict__ X, int64_t ldx, const int32_t* __restrict__ rowptr,
+                                  const int32_t* __restrict__ rev_row, int64_t V, int Q, int act, float ap,
+                                  int permute_on_read, TO* __restrict__ OUT, int64_t ldo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (v >= V) return;
+  const int32_t a = rowptr[v], b = rowptr[v + 1];
+  if (b <= a) return;
+  for (int q = lane; q < Q; q += 32) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int32_t r = a; r < b; ++r) {
+      const int64_t rd = permute_on_read ? (int64_t)rev_row[r] : (int64_t)r;
+      float x[4];
+      ld4(X + rd * ldx + 4 * q, x);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[i] += act_apply(act, ap, x[i]);
+    }
+    for (int32_t r = a; r < b; ++r) {
+      const int64_t qq = (int64_t)rev_row[r];
+      const int64_t rd = permute_on_read ? qq : (int64_t)r;
+      const int64_t wr = permute_on_read ? (int64_t)r : qq;
+      float x[4], o[4];
+      ld4(X + rd * ldx + 4 * q, x);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = s[i] - act_apply(act, ap, x[i]);
+      st4(OUT + wr * ldo + 4 * q, o);
+    }
+  }
+}
+
+template <typename TG, typename TYA, typename TZ, typename TA>
+__global__ void k_act_bwd_v4(const TG* __restrict__ G, int64_t ldg, const int32_t* __restrict__ gidx,
+                             const TYA* __restrict__ Yact, int64_t ldy, int from_preact, int act, float ap,
+                             TZ* __restrict__ dZ, int64_t lddz, TA* __restrict__ ACC, int64_t ldacc, int64_t R, int Q) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * Q) return;
+  const int64_t r = i / Q;
+  const int q = (int)(i - r * Q);
+  const int64_t gr = gidx ? (int64_t)gidx[r] : r;
+  float g[4], y[4], dz[4];
+  ld4(G + gr * ldg + 4 * q, g);
+  ld4(Yact + r * ldy + 4 * q, y);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    dz[k] = g[k] * (from_preact ? act_grad_from_pre(act, ap, y[k]) : act_grad_from_out(act, ap, y[k]));
+  if (dZ) st4(dZ + r * lddz + 4 * q, dz);
+  if (ACC) {
+    float a[4];
+    ld4(ACC + r * ldacc + 4 * q, a);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] += dz[k];
+    st4(ACC + r * ldacc + 4 * q, a);
+  }
+}
+
+template <typename TX, typename TO>
+__global__ void k_rev_average_v4(const TX* __restrict__ X, int64_t ldx, const int32_t* __restrict__ rev_row, int64_t R,
+                                 int Q, int act, float ap, TO* __restrict__ OUT, int64_t ldo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * Q) return;
+  const int64_t r = i / Q;
+  const int q = (int)(i - r * Q);
+  float a[4], b[4], o[4];
+  ld4(X + r * ldx + 4 * q, a);
+  ld4(X + (int64_t)rev_row[r] * ldx + 4 * q, b);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k] = (act_apply(act, ap, a[k]) + act_apply(act, ap, b[k])) / 2.f;
+  st4(OUT + r * ldo + 4 * q, o);
+}
+
+// OUT[r, :] = bf16([X1[i1(r), 0:K1] || X2[i2(r), 0:K2] || 0 ...])  -- the A operand of the tensor-core
+// linear layers: torch.cat([V[src], E], 1) (mixins.py:9) and torch.cat((V, M), 1) (base.py:180)
+template <typename T1, typename T2>
+__global__ void k_concat_bf16(const T1* __restrict__ X1, int64_t ld1, const int32_t* __restrict__ idx1, int K1,
+                              const T2* __restrict__ X2, int64_t ld2, const int32_t* __restrict__ idx2, int K2,
+                              __nv_bfloat16* __restrict__ OUT, int64_t ldo, int width, int64_t R) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+  if (r >= R) return;
+  const int64_t r1 = idx1 ? (int64_t)idx1[r] : r;
+  const int64_t r2 = (K2 > 0 && idx2) ? (int64_t)idx2[r] : r;
+  const bool vec = (width % 4 == 0) && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(OUT) & 7) == 0);
+  if (vec) {
+    for (int c4 = threadIdx.x * 4; c4 < width; c4 += blockDim.x * 4) {
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c4 + i;
+        v[i] = 0.f;
+        if (c < K1) v[i] = ld_as_float(X1 + r1 * ld1 + c);
+        else if (c < K1 + K2) v[i] = ld_as_float(X2 + r2 * ld2 + (c - K1));
+      }
+      st4(OUT + r * ldo + c4, v);
+    }
+  } else {
+    for (int c = threadIdx.x; c < width; c += blockDim.x) {
+      float v = 0.f;
+      if (c < K1) v = ld_as_float(X1 + r1 * ld1 + c);
+      else if (c < K1 + K2) v = ld_as_float(X2 + r2 * ld2 + (c - K1));
+      OUT[r * ldo + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 }  // namespace dmpnn
 
 using namespace dmpnn;
+
+extern "C" int dmpnn_concat_bf16(const void* X1, int x1_dtype, int64_t ld1, const int32_t* idx1, int64_t K1,
+                                 const void* X2, int x2_dtype, int64_t ld2, const int32_t* idx2, int64_t K2,
+                                 void* OUT, int64_t ldo, int64_t width, int64_t R, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DMPNN_CHECK_ARG(R >= 0 && K1 > 0 && K2 >= 0 && width >= K1 + K2 && ldo >= width, "concat_bf16: bad sizes");
+  if (R == 0) return 0;
+  DMPNN_CHECK_ARG(X1 && OUT && (K2 == 0 || X2), "concat_bf16: null pointer");
+  if (K2 == 0) x2_dtype = x1_dtype;
+  dim3 block(32, 8), grid(ceil_div_i64(R, 8));
+  DMPNN_DISPATCH_DTYPE(x1_dtype, T1,
+    DMPNN_DISPATCH_DTYPE(x2_dtype, T2,
+      k_concat_bf16<T1, T2><<<grid, block, 0, st>>>((const T1*)X1, ld1, idx1, (int)K1, (const T2*)X2, ld2, idx2, (int)K2,
+                                                   (__nv_bfloat16*)OUT, ldo, (int)width, R);
+    ))
+  DMPNN_CHECK_LAUNCH("concat_bf16", 1);
+  return 0;
+}
 
 extern "C" int dmpnn_segment_sum(const void* X, int x_dtype, int64_t ldx, const int32_t* idx, const int32_t* ptr,
                                  int64_t n_seg, int64_t C, int act, float act_param, int scale_mode, float scale,
@@ -119,8 +291,13 @@ extern "C" int dmpnn_segment_sum(const void* X, int x_dtype, int64_t ldx, const 
   const int warps = 8;
   DMPNN_DISPATCH_DTYPE(x_dtype, TX,
     DMPNN_DISPATCH_DTYPE(y_dtype, TY,
-      k_segment_sum<TX, TY><<<ceil_div_i64(n_seg, warps), warps * 32, 0, st>>>(
-          (const TX*)X, ldx, idx, ptr, n_seg, (int)C, act, act_param, scale_mode, scale, (TY*)Y, ldy, (int)ldy_pad);
+      const int64_t padc = ldy_pad > C ? ldy_pad : C;
+      if (C % 4 == 0 && padc % 4 == 0 && vec4_ok<TX>(X, ldx) && vec4_ok<TY>(Y, ldy))
+        k_segment_sum_v4<TX, TY><<<ceil_div_i64(n_seg, warps), warps * 32, 0, st>>>(
+            (const TX*)X, ldx, idx, ptr, n_seg, (int)(C / 4), act, act_param, scale_mode, scale, (TY*)Y, ldy, (int)(padc / 4));
+      else
+        k_segment_sum<TX, TY><<<ceil_div_i64(n_seg, warps), warps * 32, 0, st>>>(
+            (const TX*)X, ldx, idx, ptr, n_seg, (int)C, act, act_param, scale_mode, scale, (TY*)Y, ldy, (int)ldy_pad);
     ))
   DMPNN_CHECK_LAUNCH("segment_sum", 1);
   return 0;
@@ -136,8 +313,12 @@ extern "C" int dmpnn_segment_bcast(const void* G, int g_dtype, int64_t ldg, cons
   dim3 block(64, 4), grid(ceil_div_i64(R, 4), ceil_div_i64(C, 64));
   DMPNN_DISPATCH_DTYPE(g_dtype, TG,
     DMPNN_DISPATCH_DTYPE(y_dtype, TY,
-      k_segment_bcast<TG, TY><<<grid, block, 0, st>>>((const TG*)G, ldg, seg_of_row, ptr, R, (int)C, scale_mode,
-                                                      scale, (TY*)Y, ldy);
+      if (C % 4 == 0 && vec4_ok<TG>(G, ldg) && vec4_ok<TY>(Y, ldy))
+        k_segment_bcast_v4<TG, TY><<<ceil_div_i64(R * (C / 4), 256), 256, 0, st>>>((const TG*)G, ldg, seg_of_row, ptr, R,
+                                                                                   (int)(C / 4), scale_mode, scale, (TY*)Y, ldy);
+      else
+        k_segment_bcast<TG, TY><<<grid, block, 0, st>>>((const TG*)G, ldg, seg_of_row, ptr, R, (int)C, scale_mode,
+                                                        scale, (TY*)Y, ldy);
     ))
   DMPNN_CHECK_LAUNCH("segment_bcast", 1);
   return 0;
@@ -153,8 +334,12 @@ extern "C" int dmpnn_bond_message(const void* X, int x_dtype, int64_t ldx, const
   const int warps = 8;
   DMPNN_DISPATCH_DTYPE(x_dtype, TX,
     DMPNN_DISPATCH_DTYPE(out_dtype, TO,
-      k_bond_message<TX, TO><<<ceil_div_i64(V, warps), warps * 32, 0, st>>>(
-          (const TX*)X, ldx, rowptr, rev_row, V, (int)C, act, act_param, permute_on_read, (TO*)OUT, ldo);
+      if (C % 4 == 0 && vec4_ok<TX>(X, ldx) && vec4_ok<TO>(OUT, ldo))
+        k_bond_message_v4<TX, TO><<<ceil_div_i64(V, warps), warps * 32, 0, st>>>(
+            (const TX*)X, ldx, rowptr, rev_row, V, (int)(C / 4), act, act_param, permute_on_read, (TO*)OUT, ldo);
+      else
+        k_bond_message<TX, TO><<<ceil_div_i64(V, warps), warps * 32, 0, st>>>(
+            (const TX*)X, ldx, rowptr, rev_row, V, (int)C, act, act_param, permute_on_read, (TO*)OUT, ldo);
     ))
   DMPNN_CHECK_LAUNCH("bond_message", 1);
   return 0;
@@ -170,7 +355,11 @@ extern "C" int dmpnn_rev_average(const void* X, int x_dtype, int64_t ldx, const 
   dim3 block(64, 4), grid(ceil_div_i64(R, 4), ceil_div_i64(C, 64));
   DMPNN_DISPATCH_DTYPE(x_dtype, TX,
     DMPNN_DISPATCH_DTYPE(out_dtype, TO,
-      k_rev_average<TX, TO><<<grid, block, 0, st>>>((const TX*)X, ldx, rev_row, R, (int)C, act, act_param, (TO*)OUT, ldo);
+      if (C % 4 == 0 && vec4_ok<TX>(X, ldx) && vec4_ok<TO>(OUT, ldo))
+        k_rev_average_v4<TX, TO><<<ceil_div_i64(R * (C / 4), 256), 256, 0, st>>>((const TX*)X, ldx, rev_row, R, (int)(C / 4),
+                                                                                 act, act_param, (TO*)OUT, ldo);
+      else
+        k_rev_average<TX, TO><<<grid, block, 0, st>>>((const TX*)X, ldx, rev_row, R, (int)C, act, act_param, (TO*)OUT, ldo);
     ))
   DMPNN_CHECK_LAUNCH("rev_average", 1);
   return 0;
@@ -191,9 +380,15 @@ extern "C" int dmpnn_act_bwd(const void* G, int g_dtype, int64_t ldg, const int3
     DMPNN_DISPATCH_DTYPE(y_dtype, TYA,
       DMPNN_DISPATCH_DTYPE(dz_dtype, TZ,
         DMPNN_DISPATCH_DTYPE(acc_dtype, TA,
-          k_act_bwd<TG, TYA, TZ, TA><<<grid, block, 0, st>>>((const TG*)G, ldg, gidx, (const TYA*)Yact, ldy,
-                                                            from_preact, act, act_param, (TZ*)dZ, lddz, (TA*)ACC,
-                                                            ldacc, R, (int)C);
+          if (C % 4 == 0 && vec4_ok<TG>(G, ldg) && vec4_ok<TYA>(Yact, ldy) && vec4_ok<TZ>(dZ, dZ ? lddz : 4) &&
+              vec4_ok<TA>(ACC, ACC ? ldacc : 4))
+            k_act_bwd_v4<TG, TYA, TZ, TA><<<ceil_div_i64(R * (C / 4), 256), 256, 0, st>>>(
+                (const TG*)G, ldg, gidx, (const TYA*)Yact, ldy, from_preact, act, act_param, (TZ*)dZ, lddz, (TA*)ACC, ldacc,
+                R, (int)(C / 4));
+          else
+            k_act_bwd<TG, TYA, TZ, TA><<<grid, block, 0, st>>>((const TG*)G, ldg, gidx, (const TYA*)Yact, ldy,
+                                                              from_preact, act, act_param, (TZ*)dZ, lddz, (TA*)ACC,
+                                                              ldacc, R, (int)C);
         ))))
   DMPNN_CHECK_LAUNCH("act_bwd", 1);
   return 0;

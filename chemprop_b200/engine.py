@@ -357,6 +357,64 @@ def pack_weight_bf16(W: Tensor) -> Tensor:
     return out
 
 
+def pack_weight_tc(W: Tensor, transpose: bool = False) -> Tensor:
+    """Pack an nn.Linear weight (N x K; or, with transpose, a K x N matrix used as B[n][k] = W[k][n]) for
+    dmpnn_linear_tc_bf16."""
+    lib = _lib.load()
+    Wc = W.detach().float()
+    if Wc.stride(1) != 1:
+        Wc = Wc.contiguous()
+    N, K = (Wc.shape[1], Wc.shape[0]) if transpose else (Wc.shape[0], Wc.shape[1])
+    n = C.c_size_t(0)
+    _lib.check(lib.dmpnn_pack_weight_tc_bytes(N, K, C.byref(n)), "dmpnn_pack_weight_tc_bytes")
+    out = torch.empty(n.value, dtype=torch.uint8, device=W.device)
+    _lib.check(lib.dmpnn_pack_weight_tc(Wc.data_ptr(), Wc.stride(0), N, K, 1 if transpose else 0, out.data_ptr(),
+                                        _stream()), "dmpnn_pack_weight_tc")
+    return out
+
+
+def linear_tc(A: Tensor, K: int, Wpk: Tensor, N: int, out: Tensor, *, bias: Tensor | None = None,
+              act: int = ACT_NONE, act_param: float = 0.0, R: int | None = None):
+    lib = _lib.load()
+    R = out.shape[0] if R is None else R
+    assert A.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+    rc = lib.dmpnn_linear_tc_bf16(A.data_ptr(), _ld(A), R, K, Wpk.data_ptr(), N, _ptr(bias), act, float(act_param),
+                                  out.data_ptr(), _ld(out), _stream())
+    _lib.check(rc, "dmpnn_linear_tc_bf16")
+
+
+def wgrad_tc(dY: Tensor, X: Tensor, R: int, N: int, K: int, dW: Tensor, *, accumulate: bool = False):
+    """dW[n, :K] (+)= sum_r dY[r, n] X[r, :K] on the tensor cores (bf16 operands)."""
+    lib = _lib.load()
+    assert dY.dtype == torch.bfloat16 and X.dtype == torch.bfloat16 and dW.dtype == torch.float32
+    n = C.c_size_t(0)
+    _lib.check(lib.dmpnn_wgrad_tc_workspace_bytes(N, K, C.byref(n)), "dmpnn_wgrad_tc_workspace_bytes")
+    ws = torch.empty(n.value, dtype=torch.uint8, device=dW.device)
+    rc = lib.dmpnn_wgrad_tc_bf16(dY.data_ptr(), _ld(dY), X.data_ptr(), _ld(X), R, N, K, dW.data_ptr(), dW.stride(0),
+                                 1 if accumulate else 0, ws.data_ptr(), _stream())
+    _lib.check(rc, "dmpnn_wgrad_tc_bf16")
+
+
+def column_sum(Y: Tensor, R: int, N: int, out: Tensor, *, accumulate: bool = False):
+    lib = _lib.load()
+    n = C.c_size_t(0)
+    _lib.check(lib.dmpnn_linear_wgrad_workspace_bytes(R, N, 1, C.byref(n)), "wgrad_workspace_bytes")
+    ws = torch.empty(n.value, dtype=torch.uint8, device=out.device)
+    rc = lib.dmpnn_column_sum(Y.data_ptr(), _dt(Y), _ld(Y), R, N, out.data_ptr(), 1 if accumulate else 0,
+                              ws.data_ptr(), _stream())
+    _lib.check(rc, "dmpnn_column_sum")
+
+
+def concat_bf16(X1: Tensor, K1: int, out: Tensor, R: int, *, idx1: Tensor | None = None, X2: Tensor | None = None,
+                K2: int = 0, idx2: Tensor | None = None, width: int | None = None):
+    lib = _lib.load()
+    width = out.shape[1] if width is None else width
+    rc = lib.dmpnn_concat_bf16(X1.data_ptr(), _dt(X1), _ld(X1), _ptr(idx1), K1,
+                               _ptr(X2), _dt(X2) if X2 is not None else F32, _ld(X2) if X2 is not None else 0,
+                               _ptr(idx2), K2, out.data_ptr(), _ld(out), width, R, _stream())
+    _lib.check(rc, "dmpnn_concat_bf16")
+
+
 def bond_step_fused(H_prev: Tensor, H0: Tensor, H_next: Tensor, h: int, Wpk: Tensor, bias: Tensor | None,
                     lay: Layout, act: int, act_param: float, first_step: bool):
     lib = _lib.load()
@@ -366,6 +424,17 @@ def bond_step_fused(H_prev: Tensor, H0: Tensor, H_next: Tensor, h: int, Wpk: Ten
         lay.n_tiles, act, float(act_param), 1 if first_step else 0, _stream(),
     )
     _lib.check(rc, "dmpnn_bond_step_fused_bf16")
+
+
+def _tc_ok(cfg: MPConfig, h: int, *Ks: int) -> bool:
+    """Tensor-core linear kernels apply: bf16 tier, fused kernels enabled, sizes inside the kernel limits."""
+    return (cfg.fused and cfg.hidden_dtype == torch.bfloat16 and h <= 304 and all(k <= 384 for k in Ks)
+            and _fused_available())
+
+
+def _empty_hidden(rows: int, hp: int, dtype, dev) -> Tensor:
+    """Uninitialised hidden buffer: only for producers that write every column below pad16(h)."""
+    return torch.empty((max(rows, 1), hp), dtype=dtype, device=dev)
 
 
 def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, bh, Wo: Tensor, bo,
@@ -379,16 +448,25 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
     T = cfg.hidden_dtype
     nE, nV = lay.E, lay.V
     a, ap = cfg.act, cfg.act_param
+    tc = _tc_ok(cfg, h, d_v + d_e, d_v + h)
     # H_0 = W_i([V[src] || E])   (mixins.py:8-9); rows in dst-sorted order
-    H0 = _hidden(nE, hp, T, dev)
-    linear_fwd(V, d_v, Wi, H0, h, idx1=lay.src_row, X2=E, K2=d_e, idx2=lay.perm, bias=bi, R=nE, pad_to=hp)
+    if tc and nE > 0:
+        kx = (d_v + d_e + 15) // 16 * 16
+        X0 = torch.empty((nE, kx), dtype=T, device=dev)
+        concat_bf16(V, d_v, X0, nE, idx1=lay.src_row, X2=E, K2=d_e, idx2=lay.perm)
+        H0 = _empty_hidden(nE, hp, T, dev)
+        linear_tc(X0, d_v + d_e, pack_weight_tc(Wi), h, H0, bias=bi, R=nE)
+    else:
+        X0 = None
+        H0 = _hidden(nE, hp, T, dev)
+        linear_fwd(V, d_v, Wi, H0, h, idx1=lay.src_row, X2=E, K2=d_e, idx2=lay.perm, bias=bi, R=nE, pad_to=hp)
     Hs, Ms, Hbars = [], [], []
     Hprev, first = H0, True  # H^0 = tau(H_0) is applied on load (base.py:200)
     use_fused = cfg.depth > 1 and _fused_step_ok(cfg, lay, h)
     Wpk = pack_weight_bf16(Wh) if use_fused else None
     for _ in range(1, cfg.depth):
         if use_fused:
-            Hn = _hidden(nE, hp, T, dev)
+            Hn = _empty_hidden(nE, hp, T, dev)
             with _StepTimer("fused_first" if first else "fused"):
                 bond_step_fused(Hprev, H0, Hn, h, Wpk, bh, lay, a, ap, first)
             Ms.append(None)
@@ -407,13 +485,25 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
             Ms.append(M)
         Hs.append(Hn)
         Hprev, first = Hn, False
-    # M_v = sum_{dst(e)=v} H[e]   (base.py:208-211)
-    Mv = _hidden(nV, hp, T, dev)
-    segment_sum(Hprev, lay.rowptr, nV, h, Mv, act=(a if first else ACT_NONE), act_param=ap, pad_to=hp)
-    # H_v = tau(W_o([V || M_v]))   (base.py:180-182)
-    Hv = torch.empty((nV, h), dtype=T, device=dev)
-    linear_fwd(V, d_v, Wo, Hv, h, X2=Mv, K2=h, bias=bo, act=a, act_param=ap, R=nV, pad_to=h)
-    saved = dict(H0=H0, Hs=Hs, Ms=Ms, Hbars=Hbars, Mv=Mv, Hv=Hv)
+    if tc:
+        # [V || M_v] assembled once in bf16 (torch.cat of base.py:180), M_v written in place by the segment sum
+        ko = (d_v + h + 15) // 16 * 16
+        XO = torch.zeros((max(nV, 1), ko), dtype=T, device=dev)
+        concat_bf16(V, d_v, XO, nV, width=d_v)
+        Mv = XO[:, d_v:d_v + h]
+        segment_sum(Hprev, lay.rowptr, nV, h, Mv, act=(a if first else ACT_NONE), act_param=ap, pad_to=h)
+        Hvp = torch.empty((max(nV, 1), pad_hidden(h)), dtype=T, device=dev)
+        linear_tc(XO, d_v + h, pack_weight_tc(Wo), h, Hvp, bias=bo, act=a, act_param=ap, R=nV)
+        Hv = Hvp[:nV, :h]
+    else:
+        XO = None
+        # M_v = sum_{dst(e)=v} H[e]   (base.py:208-211)
+        Mv = _hidden(nV, hp, T, dev)
+        segment_sum(Hprev, lay.rowptr, nV, h, Mv, act=(a if first else ACT_NONE), act_param=ap, pad_to=hp)
+        # H_v = tau(W_o([V || M_v]))   (base.py:180-182)
+        Hv = torch.empty((nV, h), dtype=T, device=dev)
+        linear_fwd(V, d_v, Wo, Hv, h, X2=Mv, K2=h, bias=bo, act=a, act_param=ap, R=nV, pad_to=h)
+    saved = dict(H0=H0, Hs=Hs, Ms=Ms, Hbars=Hbars, Mv=Mv, Hv=Hv, X0=X0, XO=XO, tc=tc)
     return Hv, saved
 
 
@@ -436,21 +526,33 @@ def bond_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo:
     dbi = torch.zeros(h, **f32) if need_bias[0] else None
     dbh = torch.zeros(h, **f32) if need_bias[1] else None
     dbo = torch.zeros(h, **f32) if need_bias[2] else None
-    gHv = gHv.contiguous()
+    tc = bool(saved.get("tc"))
+    if gHv.stride(1) != 1:
+        gHv = gHv.contiguous()
     # readout: dY = g * tau'(Y); dW_o = dY^T [V || M_v]; dM_v = dY . W_o[:, d_v:]
     dY = _hidden(nV, hp, T, dev)
     act_bwd(gHv, Hv, nV, h, act=a, act_param=ap, dZ=dY)
-    linear_wgrad(dY, V, d_v, dWo, h, X2=Mv, K2=h, dbias=dbo, R=nV)
-    WoT = Wo[:, d_v:].t().contiguous()
-    dMv = _hidden(nV, hp, T, dev)
-    linear_fwd(dY, h, WoT, dMv, h, R=nV, pad_to=hp)
+    if tc:
+        wgrad_tc(dY, saved["XO"], nV, h, d_v + h, dWo)
+        if dbo is not None:
+            column_sum(dY, nV, h, dbo)
+    else:
+        linear_wgrad(dY, V, d_v, dWo, h, X2=Mv, K2=h, dbias=dbo, R=nV)
+    if tc:
+        dMv = _empty_hidden(nV, hp, T, dev)
+        linear_tc(dY, h, pack_weight_tc(Wo[:, d_v:], transpose=True), h, dMv, R=nV)
+    else:
+        WoT = Wo[:, d_v:].t().contiguous()
+        dMv = _hidden(nV, hp, T, dev)
+        linear_fwd(dY, h, WoT, dMv, h, R=nV, pad_to=hp)
     dH0 = torch.zeros((max(nE, 1), hp), **f32)  # f32 accumulator of dH_0 over all depth steps
     if nE > 0:
         if cfg.depth == 1:
             # dH^0[e] = dM_v[dst(e)];  dH_0 = dH^0 * tau'(H_0)
             act_bwd(dMv, H0, nE, h, act=a, act_param=ap, gidx=lay.dst_row, from_preact=True, acc=dH0)
         else:
-            WhT = Wh.t().contiguous()
+            WhT = None if tc else Wh.t().contiguous()
+            WhT_pk = pack_weight_tc(Wh, transpose=True) if tc else None
             dZ = _hidden(nE, hp, T, dev)
             act_bwd(dMv, Hs[-1], nE, h, act=a, act_param=ap, gidx=lay.dst_row, dZ=dZ, acc=dH0)
             for t in range(cfg.depth - 1, 0, -1):
@@ -461,9 +563,18 @@ def bond_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo:
                 if M is None:  # fused forward did not materialise M^t: recompute it
                     M = _hidden(nE, hp, T, dev)
                     bond_message(Hin, lay, h, M, act=(a if first else ACT_NONE), act_param=ap)
-                linear_wgrad(dZ, M, h, dWh, h, dbias=dbh, accumulate=True, R=nE)
-                dM = _hidden(nE, hp, T, dev)
-                linear_fwd(dZ, h, WhT, dM, h, R=nE, pad_to=hp)
+                if tc:
+                    wgrad_tc(dZ, M, nE, h, h, dWh, accumulate=True)
+                    if dbh is not None:
+                        column_sum(dZ, nE, h, dbh, accumulate=True)
+                else:
+                    linear_wgrad(dZ, M, h, dWh, h, dbias=dbh, accumulate=True, R=nE)
+                if tc:
+                    dM = _empty_hidden(nE, hp, T, dev)
+                    linear_tc(dZ, h, WhT_pk, h, dM, R=nE)
+                else:
+                    dM = _hidden(nE, hp, T, dev)
+                    linear_fwd(dZ, h, WhT, dM, h, R=nE, pad_to=hp)
                 dHin = _hidden(nE, hp, T, dev)
                 bond_message(dM, lay, h, dHin, permute_on_read=True)
                 if cfg.undirected:
@@ -475,7 +586,14 @@ def bond_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo:
                 else:
                     dZ = _hidden(nE, hp, T, dev)
                     act_bwd(dHin, Hin, nE, h, act=a, act_param=ap, dZ=dZ, acc=dH0)
-        linear_wgrad(dH0, V, d_v, dWi, h, idx1=lay.src_row, X2=E, K2=d_e, idx2=lay.perm, dbias=dbi, R=nE)
+        if tc and saved.get("X0") is not None:
+            dH0b = torch.empty((nE, hp), dtype=T, device=dev)
+            concat_bf16(dH0, h, dH0b, nE)                      # f32 accumulator -> bf16 operand
+            wgrad_tc(dH0b, saved["X0"], nE, h, d_v + d_e, dWi)
+            if dbi is not None:
+                column_sum(dH0, nE, h, dbi)
+        else:
+            linear_wgrad(dH0, V, d_v, dWi, h, idx1=lay.src_row, X2=E, K2=d_e, idx2=lay.perm, dbias=dbi, R=nE)
     return dWi, dbi, dWh, dbh, dWo, dbo
 
 
@@ -630,7 +748,7 @@ class SegmentAggFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, H, mol_atom_ptr, atom_mol, n_mols, scale_mode, scale):
         _require_cuda(H)
-        Hc = H.contiguous()
+        Hc = H if H.stride(1) == 1 else H.contiguous()
         out = torch.empty((n_mols, H.shape[1]), dtype=H.dtype, device=H.device)
         segment_sum(Hc, mol_atom_ptr, n_mols, H.shape[1], out, scale_mode=scale_mode, scale=scale,
                     pad_to=H.shape[1])

@@ -205,6 +205,33 @@ int dmpnn_act_bwd(const void* G, int g_dtype, int64_t ldg, const int32_t* gidx,
  * Wpk is W_h packed by dmpnn_pack_weight_bf16.  Requires ld % 8 == 0, h <= 304, all tiles
  * <= 128 rows, DMPNN_FLAG_REV_INVOLUTION.  Returns <0 (and does nothing) otherwise.
  * ------------------------------------------------------------------------------------- */
+/* ---------------------------------------------------------------------------------------
+ * Tensor-core linear layers of the bf16 tier (tcgen05 / TMEM / TMA), for the GEMMs outside the fused
+ * depth step: W_i (mixins.py:8-9, 22-23), W_o (base.py:180-182) and dX = dY.W of their autograd mirror.
+ *   dmpnn_concat_bf16     A[r] = bf16([X1[i1(r)] || X2[i2(r)] || 0..])  (torch.cat of mixins.py:9 / base.py:180)
+ *   dmpnn_pack_weight_tc  nn.Linear weight (or its transpose: transpose != 0 packs B[n][k] = W[k][n]) ->
+ *                         per-k-slab shared-memory images
+ *   dmpnn_linear_tc_bf16  C[r, 0:N] = act(A[r, 0:K] . B^T + bias); A, C bf16 row-major, lda/ldc % 8 == 0,
+ *                         ldc >= pad16(N), K <= 384, N <= 304; C columns [N, pad16(N)) are written as zeros.
+ * ------------------------------------------------------------------------------------- */
+int dmpnn_concat_bf16(const void* X1, int x1_dtype, int64_t ld1, const int32_t* idx1, int64_t K1,
+                      const void* X2, int x2_dtype, int64_t ld2, const int32_t* idx2, int64_t K2,
+                      void* OUT, int64_t ldo, int64_t width, int64_t R, void* stream);
+int dmpnn_pack_weight_tc_bytes(int64_t N, int64_t K, size_t* bytes);
+int dmpnn_pack_weight_tc(const float* W, int64_t ldw, int64_t N, int64_t K, int transpose, void* Wpk, void* stream);
+int dmpnn_linear_tc_bf16(const void* A, int64_t lda, int64_t R, int64_t K, const void* Wpk, int64_t N,
+                         const float* bias, int act, float act_param, void* C, int64_t ldc, void* stream);
+
+/* Tensor-core weight gradient (bf16 operands, f32 accumulate, deterministic two-pass reduction):
+ *   dW[n, 0:K] (+)= sum_r dY[r, n] * X[r, 0:K]      dY: R x N (ld lddy), X: R x K (ld ldx), both bf16 row-major
+ * N, K <= 384; lddy, ldx multiples of 8.  Workspace from dmpnn_wgrad_tc_workspace_bytes. */
+int dmpnn_wgrad_tc_workspace_bytes(int64_t N, int64_t K, size_t* bytes);
+int dmpnn_wgrad_tc_bf16(const void* dY, int64_t lddy, const void* X, int64_t ldx, int64_t R, int64_t N, int64_t K,
+                        float* dW, int64_t lddw, int accumulate, void* workspace, void* stream);
+/* Column sums (bias gradient): out[n] (+)= sum_r Y[r, n].  Workspace: dmpnn_linear_wgrad_workspace_bytes(R, N, 1). */
+int dmpnn_column_sum(const void* Y, int y_dtype, int64_t ldy, int64_t R, int64_t N, float* out, int accumulate,
+                     void* workspace, void* stream);
+
 /* Debug aid: when set (device pointer to n_tiles x 12 uint64, zero-filled), block 0 of the fused
  * kernel records %globaltimer stamps of its pipeline phases for its first n_tiles tiles. NULL = off. */
 int dmpnn_set_trace_buffer(void* dev_ptr, int64_t n_tiles);

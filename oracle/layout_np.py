@@ -8,6 +8,7 @@ import numpy as np
 
 TILE_ROWS = 128
 TILE_ATOMS = 128
+TILE_CHUNK = 1024   # greedy packing restarts every TILE_CHUNK molecules (chunks are packed independently)
 
 
 def build_layout(edge_index: np.ndarray, rev: np.ndarray, batch: np.ndarray, n_mols: int) -> dict:
@@ -26,7 +27,7 @@ def build_layout(edge_index: np.ndarray, rev: np.ndarray, batch: np.ndarray, n_m
     tiles = []
     t_mol, max_rows, max_atoms = 0, 0, 0
     for m in range(B):
-        if m > t_mol and (mol_row_ptr[m + 1] - mol_row_ptr[t_mol] > TILE_ROWS
+        if m > t_mol and (m % TILE_CHUNK == 0 or mol_row_ptr[m + 1] - mol_row_ptr[t_mol] > TILE_ROWS
                           or mol_atom_ptr[m + 1] - mol_atom_ptr[t_mol] > TILE_ATOMS):
             tiles.append(t_mol)
             max_rows = max(max_rows, int(mol_row_ptr[m] - mol_row_ptr[t_mol]))

@@ -77,7 +77,31 @@ def test_bf16_tier_matches_reference_golden(name):
         if k.startswith("grad."):
             got = grads[k[len("grad."):]].float().cpu().numpy()
             scale = max(1e-3, float(np.abs(v).max()))
-            assert np.abs(got - v).max() <= (1.5e-2 if smooth else 0.2) * scale, (k, np.abs(got - v).max(), scale)
+            fro = float(np.linalg.norm(got - v) / max(1e-6, np.linalg.norm(v)))
+            if smooth:
+                assert np.abs(got - v).max() <= 2e-2 * scale and fro <= 2e-2, (k, np.abs(got - v).max(), scale, fro)
+            else:
+                assert np.abs(got - v).max() <= 0.5 * scale and fro <= 0.2, (k, np.abs(got - v).max(), scale, fro)
+
+
+@pytest.mark.parametrize("n_mols,min_atoms", [(3000, 1), (1024, 2), (1025, 2), (5000, 2)])
+def test_layout_bit_exact_many_molecules(n_mols, min_atoms):
+    """More molecules than one packing chunk (1024): chunk-boundary tile breaks, bit-exact vs numpy."""
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.engine import get_layout
+    from oracle import layout_np
+
+    bmg = BatchMolGraph(make_molecules(n_mols, seed=n_mols, shuffle_edges=True, min_atoms=min_atoms))
+    L = layout_np.build_layout(bmg.edge_index.numpy(), bmg.rev_edge_index.numpy(), bmg.batch.numpy(), n_mols)
+    bmg.to("cuda")
+    lay = get_layout(bmg)
+    for k in ("perm", "inv_perm", "rowptr", "src_row", "dst_row", "rev_row", "mol_atom_ptr", "mol_row_ptr"):
+        assert np.array_equal(getattr(lay, k).cpu().numpy(), L[k]), k
+    assert lay.n_tiles == L["n_tiles"]
+    for k in ("tile_mol_ptr", "tile_row_ptr", "tile_atom_ptr"):
+        assert np.array_equal(getattr(lay, k).cpu().numpy()[: L["n_tiles"] + 1], L[k]), k
+    assert (lay.flags, lay.max_indeg, lay.max_tile_rows, lay.max_tile_atoms) == (
+        L["flags"], L["max_indeg"], L["max_tile_rows"], L["max_tile_atoms"])
 
 
 def test_inputs_not_mutated():

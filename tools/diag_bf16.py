@@ -21,5 +21,5 @@ for fused in (True, False):
         for k, v in g.items():
             if k.startswith("grad."):
                 got = dict(mp.named_parameters())[k[5:]].grad.float().cpu().numpy()
-                gr.append(f"{k[5:]}:{np.abs(got - v).max() / max(1e-12, np.abs(v).max()):.3f}")
+                gr.append(f"{k[5:]}:{np.abs(got - v).max() / max(1e-12, np.abs(v).max()):.3f}/{np.linalg.norm(got - v) / max(1e-12, np.linalg.norm(v)):.3f}")
         print(f"  {name:22s} |H|max={np.abs(g['H_v']).max():.2f} errH={eh:.2e} errAgg={ea:.2e} gradrel " + " ".join(gr))
