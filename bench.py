@@ -75,7 +75,7 @@ class ClockSampler:
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
-                time.sleep(0.05)
+                time.sleep(0.005)
         except Exception as e:  # noqa: BLE001
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -128,8 +128,21 @@ def cpu_step_fn(n_mols: int, seed: int):
 
 
 def run_cpu(n_mols: int, steps: int, warmup: int):
-    torch.set_num_threads(os.cpu_count() or 1)
+    """Times the oracle port on the host.  torch's CPU scatter / index kernels stop scaling (and regress) well
+    before 128 threads, so the thread count is probed (8, 16, 32, all cores: one step each) and the fastest is
+    used for the timed steps -- the baseline gets the best configuration the host offers."""
+    ncpu = os.cpu_count() or 1
     step = cpu_step_fn(n_mols, seed=1)
+    best_t, best_dt = ncpu, float("inf")
+    for nt in sorted({min(8, ncpu), min(16, ncpu), min(32, ncpu), ncpu}):
+        torch.set_num_threads(nt)
+        step()                                   # warm-up at this thread count
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if dt < best_dt:
+            best_t, best_dt = nt, dt
+    torch.set_num_threads(best_t)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -153,7 +166,8 @@ def main_reference(args):
         "config": {"workload": "C2: BondMessagePassing h=300 depth=3 + MeanAggregation, ~25-atom synthetic mols",
                    "timed_sample": f"{sample} molecules per step (bounded sample of the 10k-molecule batch)"},
         "cpu_baseline": {"value": v, "unit": "molecules/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} molecules x {args.steps} steps, torch CPU, {cores} threads"},
+                         "sample": f"{sample} molecules x {args.steps} steps, torch CPU, {cores} threads "
+                                   f"(fastest of 8/16/32/{os.cpu_count()} threads)"},
         "e2e": {"value": v, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -286,7 +300,8 @@ def main_gpu(args):
         sample = 1000
         v, dt = run_cpu(sample, 3, 1)
         cpu = {"value": v, "unit": "molecules/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{sample} molecules x 3 steps (1 warm-up), oracle restatement on torch CPU"}
+               "sample": f"{sample} molecules x 3 steps (1 warm-up), oracle restatement on torch CPU, "
+                         f"{torch.get_num_threads()} threads (fastest of 8/16/32/{os.cpu_count()})"}
 
     line = {
         "metric": "molecules/sec fwd+bwd (h=300 d=3)", "value": value, "unit": "molecules/s", "n_gpus": world,

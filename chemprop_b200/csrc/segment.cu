@@ -158,7 +158,8 @@ __global__ void k_segment_bcast_v4(const TG* __restrict__ G, int64_t ldg, const 
 template <typename TX, typename TO>
 __global__ void k_bond_message_v4(const TX* __restrict__ X, int64_t ldx, const int32_t* __restrict__ rowptr,
                                   const int32_t* __restrict__ rev_row, int64_t V, int Q, int act, float ap,
-                                  int permute_on_read, TO* __restrict__ OUT, int64_t ldo) {
+                                  int permute_on_read, TO* __restrict__ OUT, int64_t ldo,
+                                  const TO* __restrict__ Ymask, int64_t ldm, int mask_act) {
   const int lane = threadIdx.x & 31;
   const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (v >= V) return;
@@ -181,6 +182,12 @@ __global__ void k_bond_message_v4(const TX* __restrict__ X, int64_t ldx, const i
       ld4(X + rd * ldx + 4 * q, x);
 #pragma unroll
       for (int i = 0; i < 4; ++i) o[i] = s[i] - act_apply(act, ap, x[i]);
+      if (Ymask) {   // fused tau'(.) of the autograd mirror: OUT = (sum - x) * tau'(Y[wr])
+        float y[4];
+        ld4(Ymask + wr * ldm + 4 * q, y);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] *= act_grad_from_out(mask_act, ap, y[i]);
+      }
       st4(OUT + wr * ldo + 4 * q, o);
     }
   }
@@ -224,6 +231,33 @@ __global__ void k_rev_average_v4(const TX* __restrict__ X, int64_t ldx, const in
 #pragma unroll
   for (int k = 0; k < 4; ++k) o[k] = (act_apply(act, ap, a[k]) + act_apply(act, ap, b[k])) / 2.f;
   st4(OUT + r * ldo + 4 * q, o);
+}
+
+// OUT[r] = sum_k Z_k[r] + G[r] * tau'(Ypre[r])  -- the dH_0 total of the autograd mirror in one pass
+struct SumSrcs { const void* z[8]; int n; };
+template <typename TZ, typename TO>
+__global__ void k_sum_act_bwd_v4(SumSrcs srcs, int64_t ldz, const TZ* __restrict__ G, int64_t ldg,
+                                 const TZ* __restrict__ Ypre, int64_t ldy, int act, float ap, TO* __restrict__ OUT,
+                                 int64_t ldo, int64_t R, int Q) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * Q) return;
+  const int64_t r = i / Q;
+  const int q = (int)(i - r * Q);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (G) {
+    float g[4], y[4];
+    ld4(G + r * ldg + 4 * q, g);
+    ld4(Ypre + r * ldy + 4 * q, y);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = g[k] * act_grad_from_pre(act, ap, y[k]);
+  }
+  for (int s = 0; s < srcs.n; ++s) {
+    float z[4];
+    ld4(reinterpret_cast<const TZ*>(srcs.z[s]) + r * ldz + 4 * q, z);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] += z[k];
+  }
+  st4(OUT + r * ldo + 4 * q, acc);
 }
 
 // OUT[r, :] = bf16([X1[i1(r), 0:K1] || X2[i2(r), 0:K2] || 0 ...])  -- the A operand of the tensor-core
@@ -336,7 +370,8 @@ extern "C" int dmpnn_bond_message(const void* X, int x_dtype, int64_t ldx, const
     DMPNN_DISPATCH_DTYPE(out_dtype, TO,
       if (C % 4 == 0 && vec4_ok<TX>(X, ldx) && vec4_ok<TO>(OUT, ldo))
         k_bond_message_v4<TX, TO><<<ceil_div_i64(V, warps), warps * 32, 0, st>>>(
-            (const TX*)X, ldx, rowptr, rev_row, V, (int)(C / 4), act, act_param, permute_on_read, (TO*)OUT, ldo);
+            (const TX*)X, ldx, rowptr, rev_row, V, (int)(C / 4), act, act_param, permute_on_read, (TO*)OUT, ldo,
+            (const TO*)nullptr, 0, 0);
       else
         k_bond_message<TX, TO><<<ceil_div_i64(V, warps), warps * 32, 0, st>>>(
             (const TX*)X, ldx, rowptr, rev_row, V, (int)C, act, act_param, permute_on_read, (TO*)OUT, ldo);
@@ -391,5 +426,45 @@ extern "C" int dmpnn_act_bwd(const void* G, int g_dtype, int64_t ldg, const int3
                                                               ldacc, R, (int)C);
         ))))
   DMPNN_CHECK_LAUNCH("act_bwd", 1);
+  return 0;
+}
+
+// Masked backward message: OUT[r] = (sum_{r' in seg(dst r)} X[rev r'] - X[rev r]) * tau'(Y[r])   (4-wide path only)
+extern "C" int dmpnn_bond_message_bwd_masked(const void* X, int dtype, int64_t ldx, const int32_t* rowptr,
+                                             const int32_t* rev_row, int64_t V, int64_t C, const void* Yact, int64_t ldy,
+                                             int act, float act_param, void* OUT, int64_t ldo, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DMPNN_CHECK_ARG(V >= 0 && C > 0 && C % 4 == 0 && X && rowptr && rev_row && Yact && OUT && X != OUT,
+                  "bond_message_bwd_masked: bad args (C must be a multiple of 4)");
+  if (V == 0) return 0;
+  const int warps = 8;
+  DMPNN_DISPATCH_DTYPE(dtype, T,
+    DMPNN_CHECK_ARG(vec4_ok<T>(X, ldx) && vec4_ok<T>(OUT, ldo) && vec4_ok<T>(Yact, ldy), "bond_message_bwd_masked: unaligned");
+    k_bond_message_v4<T, T><<<ceil_div_i64(V, warps), warps * 32, 0, st>>>(
+        (const T*)X, ldx, rowptr, rev_row, V, (int)(C / 4), DMPNN_ACT_NONE, act_param, 1, (T*)OUT, ldo, (const T*)Yact, ldy, act);
+  )
+  DMPNN_CHECK_LAUNCH("bond_message_bwd_masked", 1);
+  return 0;
+}
+
+extern "C" int dmpnn_sum_act_bwd(const void* const* Z, int n_z, int64_t ldz, const void* G, int64_t ldg, const void* Ypre,
+                                 int64_t ldy, int dtype, int act, float act_param, void* OUT, int out_dtype, int64_t ldo,
+                                 int64_t R, int64_t C, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DMPNN_CHECK_ARG(R >= 0 && C > 0 && C % 4 == 0 && n_z >= 0 && n_z <= 8 && OUT && (n_z == 0 || Z) && (!G || Ypre),
+                  "sum_act_bwd: bad args (C %% 4 == 0, at most 8 addends)");
+  if (R == 0) return 0;
+  SumSrcs srcs;
+  srcs.n = n_z;
+  for (int i = 0; i < 8; ++i) srcs.z[i] = i < n_z ? Z[i] : nullptr;
+  DMPNN_DISPATCH_DTYPE(dtype, TZ,
+    DMPNN_DISPATCH_DTYPE(out_dtype, TO,
+      bool ok = vec4_ok<TZ>(G, ldg) && vec4_ok<TZ>(Ypre, ldy) && vec4_ok<TO>(OUT, ldo) && ldz % 4 == 0;
+      for (int i = 0; i < n_z; ++i) ok = ok && vec4_ok<TZ>(Z[i], ldz);
+      DMPNN_CHECK_ARG(ok, "sum_act_bwd: unaligned operands");
+      k_sum_act_bwd_v4<TZ, TO><<<ceil_div_i64(R * (C / 4), 256), 256, 0, st>>>(srcs, ldz, (const TZ*)G, ldg, (const TZ*)Ypre, ldy,
+                                                                              act, act_param, (TO*)OUT, ldo, R, (int)(C / 4));
+    ))
+  DMPNN_CHECK_LAUNCH("sum_act_bwd", 1);
   return 0;
 }

@@ -405,6 +405,36 @@ def column_sum(Y: Tensor, R: int, N: int, out: Tensor, *, accumulate: bool = Fal
     _lib.check(rc, "dmpnn_column_sum")
 
 
+def bond_message_bwd_masked(dM: Tensor, Yact: Tensor, lay: Layout, Ccols: int, out: Tensor, *, act: int,
+                            act_param: float = 0.0):
+    lib = _lib.load()
+    if lay.E == 0:
+        return
+    rc = lib.dmpnn_bond_message_bwd_masked(dM.data_ptr(), _dt(dM), _ld(dM), lay.rowptr.data_ptr(),
+                                           lay.rev_row.data_ptr(), lay.V, Ccols, Yact.data_ptr(), _ld(Yact), act,
+                                           float(act_param), out.data_ptr(), _ld(out), _stream())
+    _lib.check(rc, "dmpnn_bond_message_bwd_masked")
+
+
+def sum_act_bwd(Zs: list, G: Tensor | None, Ypre: Tensor | None, out: Tensor, R: int, Ccols: int, *, act: int,
+                act_param: float = 0.0):
+    """out = sum(Zs) + G * tau'(Ypre) in one pass (<= 8 addends per call; longer lists are folded)."""
+    lib = _lib.load()
+    if R == 0:
+        return
+    Zs = list(Zs)
+    while len(Zs) > 8:   # fold the first eight into one buffer
+        tmp = torch.empty_like(Zs[0])
+        sum_act_bwd(Zs[:8], None, None, tmp, R, Ccols, act=act, act_param=act_param)
+        Zs = [tmp] + Zs[8:]
+    ref = Zs[0] if Zs else G
+    arr = (C.c_void_p * 8)(*[z.data_ptr() for z in Zs] + [None] * (8 - len(Zs)))
+    rc = lib.dmpnn_sum_act_bwd(C.cast(arr, C.c_void_p), len(Zs), _ld(ref), _ptr(G), _ld(G) if G is not None else 0,
+                               _ptr(Ypre), _ld(Ypre) if Ypre is not None else 0, _dt(ref), act, float(act_param),
+                               out.data_ptr(), _dt(out), _ld(out), R, Ccols, _stream())
+    _lib.check(rc, "dmpnn_sum_act_bwd")
+
+
 def concat_bf16(X1: Tensor, K1: int, out: Tensor, R: int, *, idx1: Tensor | None = None, X2: Tensor | None = None,
                 K2: int = 0, idx2: Tensor | None = None, width: int | None = None):
     lib = _lib.load()
@@ -424,6 +454,10 @@ def bond_step_fused(H_prev: Tensor, H0: Tensor, H_next: Tensor, h: int, Wpk: Ten
         lay.n_tiles, act, float(act_param), 1 if first_step else 0, _stream(),
     )
     _lib.check(rc, "dmpnn_bond_step_fused_bf16")
+
+
+def h_is_mult4(Wh: Tensor) -> bool:
+    return Wh.shape[0] % 4 == 0
 
 
 def _tc_ok(cfg: MPConfig, h: int, *Ks: int) -> bool:
@@ -488,7 +522,7 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
     if tc:
         # [V || M_v] assembled once in bf16 (torch.cat of base.py:180), M_v written in place by the segment sum
         ko = (d_v + h + 15) // 16 * 16
-        XO = torch.zeros((max(nV, 1), ko), dtype=T, device=dev)
+        XO = torch.empty((max(nV, 1), ko), dtype=T, device=dev)   # columns >= d_v+h are clipped by the TMA descriptor
         concat_bf16(V, d_v, XO, nV, width=d_v)
         Mv = XO[:, d_v:d_v + h]
         segment_sum(Hprev, lay.rowptr, nV, h, Mv, act=(a if first else ACT_NONE), act_param=ap, pad_to=h)
@@ -597,6 +631,69 @@ def bond_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo:
     return dWi, dbi, dWh, dbh, dWo, dbo
 
 
+def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo: Tensor, cfg: MPConfig,
+                     saved: dict, gHv: Tensor, need_bias: tuple[bool, bool, bool]):
+    """bf16-tier autograd mirror on the tensor-core kernels (directed bonds).  Differences from the generic
+    mirror: every GEMM is tcgen05; tau' is fused into the backward message kernel; dH_0 is never kept as an f32
+    read-modify-write accumulator -- the per-step dZ^t stay in bf16 and are summed once, in f32, at the end."""
+    dev = V.device
+    h = Wh.shape[0]
+    hp = pad_hidden(h)
+    d_v, d_e = V.shape[1], E.shape[1]
+    T = cfg.hidden_dtype
+    nE, nV = lay.E, lay.V
+    a, ap = cfg.act, cfg.act_param
+    H0, Hs, Hv = saved["H0"], saved["Hs"], saved["Hv"]
+    f32 = dict(dtype=torch.float32, device=dev)
+    dWi = torch.zeros_like(Wi, dtype=torch.float32)
+    dWh = torch.zeros_like(Wh, dtype=torch.float32)
+    dWo = torch.zeros_like(Wo, dtype=torch.float32)
+    dbi = torch.zeros(h, **f32) if need_bias[0] else None
+    dbh = torch.zeros(h, **f32) if need_bias[1] else None
+    dbo = torch.zeros(h, **f32) if need_bias[2] else None
+    if gHv.stride(1) != 1:
+        gHv = gHv.contiguous()
+    dY = _empty_hidden(nV, hp, T, dev)
+    act_bwd(gHv, Hv, nV, h, act=a, act_param=ap, dZ=dY)
+    wgrad_tc(dY, saved["XO"], nV, h, d_v + h, dWo)
+    if dbo is not None:
+        column_sum(dY, nV, h, dbo)
+    if nE == 0:
+        return dWi, dbi, dWh, dbh, dWo, dbo
+    dMv = _empty_hidden(nV, hp, T, dev)
+    linear_tc(dY, h, pack_weight_tc(Wo[:, d_v:], transpose=True), h, dMv, R=nV)
+    dH0b = _empty_hidden(nE, hp, T, dev)
+    if cfg.depth == 1:
+        act_bwd(dMv, H0, nE, h, act=a, act_param=ap, gidx=lay.dst_row, from_preact=True, dZ=dH0b)
+    else:
+        WhT_pk = pack_weight_tc(Wh, transpose=True)
+        dZ = _empty_hidden(nE, hp, T, dev)
+        act_bwd(dMv, Hs[-1], nE, h, act=a, act_param=ap, gidx=lay.dst_row, dZ=dZ)     # dZ^{T-1}
+        dZs, dH_first = [dZ], None
+        for t in range(cfg.depth - 1, 0, -1):
+            first = t == 1
+            Hin = H0 if first else Hs[t - 2]
+            M = _empty_hidden(nE, hp, T, dev)                # M^t, recomputed (the fused forward never stores it)
+            bond_message(Hin, lay, h, M, act=(a if first else ACT_NONE), act_param=ap)
+            wgrad_tc(dZ, M, nE, h, h, dWh, accumulate=True)
+            if dbh is not None:
+                column_sum(dZ, nE, h, dbh, accumulate=True)
+            dM = _empty_hidden(nE, hp, T, dev)
+            linear_tc(dZ, h, WhT_pk, h, dM, R=nE)
+            if first:
+                dH_first = _empty_hidden(nE, hp, T, dev)     # dH^0 (tau' from the pre-activation H_0 is applied below)
+                bond_message(dM, lay, h, dH_first, permute_on_read=True)
+            else:
+                dZ = _empty_hidden(nE, hp, T, dev)           # dZ^{t-1} = S.P(dM) * tau'(H^{t-1})
+                bond_message_bwd_masked(dM, Hin, lay, h, dZ, act=a, act_param=ap)
+                dZs.append(dZ)
+        sum_act_bwd(dZs, dH_first, H0, dH0b, nE, h, act=a, act_param=ap)
+    wgrad_tc(dH0b, saved["X0"], nE, h, d_v + d_e, dWi)
+    if dbi is not None:
+        column_sum(dH0b, nE, h, dbi)
+    return dWi, dbi, dWh, dbh, dWo, dbo
+
+
 class BondMPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, V, E, Wi, bi, Wh, bh, Wo, bo, lay, cfg):
@@ -619,7 +716,9 @@ class BondMPFunction(torch.autograd.Function):
     def backward(ctx, gHv):
         V, E = ctx.VE
         Wi, Wh, Wo = ctx.W
-        dWi, dbi, dWh, dbh, dWo, dbo = bond_backward(ctx.lay, V, E, Wi, Wh, Wo, ctx.cfg, ctx.saved, gHv, ctx.has_bias)
+        bwd = bond_backward_tc if (ctx.saved.get("tc") and not ctx.cfg.undirected and ctx.saved.get("X0") is not None
+                                   and h_is_mult4(Wh)) else bond_backward
+        dWi, dbi, dWh, dbh, dWo, dbo = bwd(ctx.lay, V, E, Wi, Wh, Wo, ctx.cfg, ctx.saved, gHv, ctx.has_bias)
         ctx.saved = None
         d0, d1, d2 = ctx.wdtypes
         cast = lambda g, d: None if g is None else g.to(d)

@@ -176,6 +176,17 @@ int dmpnn_bond_message(const void* X, int x_dtype, int64_t ldx,
                        int act, float act_param, int permute_on_read,
                        void* OUT, int out_dtype, int64_t ldo, void* stream);
 
+/* Autograd mirror of the message with tau' fused: OUT[r] = (sum_{r' in seg(dst r)} X[rev r'] - X[rev r]) * tau'(Y[r])
+ * (= dZ^{t-1} from dM^t and the stored H^{t-1}); one dtype for X / Y / OUT; C % 4 == 0, 4-element aligned. */
+int dmpnn_bond_message_bwd_masked(const void* X, int dtype, int64_t ldx, const int32_t* rowptr, const int32_t* rev_row,
+                                  int64_t V, int64_t C, const void* Yact, int64_t ldy, int act, float act_param,
+                                  void* OUT, int64_t ldo, void* stream);
+/* OUT[r] = sum_{k<n_z} Z_k[r] + G[r] * tau'(Ypre[r])  (tau' from the PRE-activation; G may be NULL): the total dH_0 of
+ * base.py:135-141's autograd mirror in one pass.  Z: host array of <= 8 device pointers sharing ldz / dtype. */
+int dmpnn_sum_act_bwd(const void* const* Z, int n_z, int64_t ldz, const void* G, int64_t ldg, const void* Ypre, int64_t ldy,
+                      int dtype, int act, float act_param, void* OUT, int out_dtype, int64_t ldo, int64_t R, int64_t C,
+                      void* stream);
+
 /* Undirected averaging (base.py:202-203): OUT[r] = (f(X[r]) + f(X[rev(r)])) / 2, f = `act` on
  * load (identity for ACT_NONE).  Self-adjoint when rev is an involution, so with ACT_NONE the
  * same call is its own autograd mirror. */
