@@ -19,7 +19,7 @@ bond_step_fused(Hp, H0, Hn, h, Wpk, None, lay, _lib.ACT_RELU, 0.0, False)
 torch.cuda.synchronize(); lib.dmpnn_set_trace_buffer(None, 0)
 t = tr.cpu().view(NT, 16).numpy().astype("float64")
 t0 = t[t > 0].min()
-names = ["A_issue", "S_start", "S_done", "MMA_ready", "MMA_c0go", "MMA_issued", "E0_start", "E1_start", "E0_end", "E1_end", "H0_issue", "S_meta", "S_afull", "S_loop", "S_stwait", "-"]
-print("tile " + " ".join(f"{n:>10s}" for n in names[:15]))
+names = ["A_issue", "S_start", "S_done", "MMA_ready", "MMA_c0go", "MMA_issued", "E0_start", "E1_start", "E0_end", "E1_end", "H0_issue", "s2_wait", "s2_full", "s2_done", "s2_bar", "s2_out"]
+print("tile " + " ".join(f"{n:>10s}" for n in names[:16]))
 for i in range(NT):
-    print(f"{i:4d} " + " ".join(f"{(t[i, k] - t0) / 1000 if t[i, k] > 0 else float('nan'):10.2f}" for k in range(15)))
+    print(f"{i:4d} " + " ".join(f"{(t[i, k] - t0) / 1000 if t[i, k] > 0 else float('nan'):10.2f}" for k in range(16)))
