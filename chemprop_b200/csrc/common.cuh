@@ -72,6 +72,41 @@ template <typename T>
 static inline bool vec4_ok(const void* p, int64_t ld) {
   return p == nullptr || ((reinterpret_cast<uintptr_t>(p) % (4 * sizeof(T))) == 0 && ld % 4 == 0);
 }
+// VW-element vector access: VW = 4 or 8 (8 bf16 = one 16-byte access; 8 f32 = two)
+template <int VW, typename T>
+__device__ __forceinline__ void ldv(const T* p, float (&v)[VW]) {
+  if constexpr (VW == 4) {
+    ld4(p, v);
+  } else if constexpr (sizeof(T) == 2) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  } else {
+    float a[4], b[4];
+    ld4(p, a); ld4(p + 4, b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] = a[i]; v[4 + i] = b[i]; }
+  }
+}
+template <int VW, typename T>
+__device__ __forceinline__ void stv(T* p, const float (&v)[VW]) {
+  if constexpr (VW == 4) {
+    st4(p, v);
+  } else if constexpr (sizeof(T) == 2) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&t); }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    const float a[4] = {v[0], v[1], v[2], v[3]}, b[4] = {v[4], v[5], v[6], v[7]};
+    st4(p, a); st4(p + 4, b);
+  }
+}
+template <typename T>
+static inline bool vec8_ok(const void* p, int64_t ld) {
+  return p == nullptr || ((reinterpret_cast<uintptr_t>(p) % (8 * sizeof(T) > 16 ? 16 : 8 * sizeof(T))) == 0 && ld % 8 == 0);
+}
 
 // ---- activations (chemprop/nn/utils.py:43-55) ------------------------------------------
 __device__ __forceinline__ float act_apply(int act, float p, float z) {

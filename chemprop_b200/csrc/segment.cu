@@ -155,7 +155,7 @@ __global__ void k_segment_bcast_v4(const TG* __restrict__ G, int64_t ldg, const 
   st4(Y + r * ldy + 4 * q, v);
 }
 
-template <typename TX, typename TO>
+template <int VW, typename TX, typename TO>
 __global__ void k_bond_message_v4(const TX* __restrict__ X, int64_t ldx, const int32_t* __restrict__ rowptr,
                                   const int32_t* __restrict__ rev_row, int64_t V, int Q, int act, float ap,
                                   int permute_on_read, TO* __restrict__ OUT, int64_t ldo,
@@ -166,34 +166,36 @@ __global__ void k_bond_message_v4(const TX* __restrict__ X, int64_t ldx, const i
   const int32_t a = rowptr[v], b = rowptr[v + 1];
   if (b <= a) return;
   for (int q = lane; q < Q; q += 32) {
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    float s[VW];
+#pragma unroll
+    for (int i = 0; i < VW; ++i) s[i] = 0.f;
     for (int32_t r = a; r < b; ++r) {
       const int64_t rd = permute_on_read ? (int64_t)rev_row[r] : (int64_t)r;
-      float x[4];
-      ld4(X + rd * ldx + 4 * q, x);
+      float x[VW];
+      ldv<VW>(X + rd * ldx + VW * q, x);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) s[i] += act_apply(act, ap, x[i]);
+      for (int i = 0; i < VW; ++i) s[i] += act_apply(act, ap, x[i]);
     }
     for (int32_t r = a; r < b; ++r) {
       const int64_t qq = (int64_t)rev_row[r];
       const int64_t rd = permute_on_read ? qq : (int64_t)r;
       const int64_t wr = permute_on_read ? (int64_t)r : qq;
-      float x[4], o[4];
-      ld4(X + rd * ldx + 4 * q, x);
+      float x[VW], o[VW];
+      ldv<VW>(X + rd * ldx + VW * q, x);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = s[i] - act_apply(act, ap, x[i]);
+      for (int i = 0; i < VW; ++i) o[i] = s[i] - act_apply(act, ap, x[i]);
       if (Ymask) {   // fused tau'(.) of the autograd mirror: OUT = (sum - x) * tau'(Y[wr])
-        float y[4];
-        ld4(Ymask + wr * ldm + 4 * q, y);
+        float y[VW];
+        ldv<VW>(Ymask + wr * ldm + VW * q, y);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] *= act_grad_from_out(mask_act, ap, y[i]);
+        for (int i = 0; i < VW; ++i) o[i] *= act_grad_from_out(mask_act, ap, y[i]);
       }
-      st4(OUT + wr * ldo + 4 * q, o);
+      stv<VW>(OUT + wr * ldo + VW * q, o);
     }
   }
 }
 
-template <typename TG, typename TYA, typename TZ, typename TA>
+template <int VW, typename TG, typename TYA, typename TZ, typename TA>
 __global__ void k_act_bwd_v4(const TG* __restrict__ G, int64_t ldg, const int32_t* __restrict__ gidx,
                              const TYA* __restrict__ Yact, int64_t ldy, int from_preact, int act, float ap,
                              TZ* __restrict__ dZ, int64_t lddz, TA* __restrict__ ACC, int64_t ldacc, int64_t R, int Q) {
@@ -202,19 +204,19 @@ __global__ void k_act_bwd_v4(const TG* __restrict__ G, int64_t ldg, const int32_
   const int64_t r = i / Q;
   const int q = (int)(i - r * Q);
   const int64_t gr = gidx ? (int64_t)gidx[r] : r;
-  float g[4], y[4], dz[4];
-  ld4(G + gr * ldg + 4 * q, g);
-  ld4(Yact + r * ldy + 4 * q, y);
+  float g[VW], y[VW], dz[VW];
+  ldv<VW>(G + gr * ldg + VW * q, g);
+  ldv<VW>(Yact + r * ldy + VW * q, y);
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < VW; ++k)
     dz[k] = g[k] * (from_preact ? act_grad_from_pre(act, ap, y[k]) : act_grad_from_out(act, ap, y[k]));
-  if (dZ) st4(dZ + r * lddz + 4 * q, dz);
+  if (dZ) stv<VW>(dZ + r * lddz + VW * q, dz);
   if (ACC) {
-    float a[4];
-    ld4(ACC + r * ldacc + 4 * q, a);
+    float a[VW];
+    ldv<VW>(ACC + r * ldacc + VW * q, a);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) a[k] += dz[k];
-    st4(ACC + r * ldacc + 4 * q, a);
+    for (int k = 0; k < VW; ++k) a[k] += dz[k];
+    stv<VW>(ACC + r * ldacc + VW * q, a);
   }
 }
 
@@ -235,7 +237,7 @@ __global__ void k_rev_average_v4(const TX* __restrict__ X, int64_t ldx, const in
 
 // OUT[r] = sum_k Z_k[r] + G[r] * tau'(Ypre[r])  -- the dH_0 total of the autograd mirror in one pass
 struct SumSrcs { const void* z[8]; int n; };
-template <typename TZ, typename TO>
+template <int VW, typename TZ, typename TO>
 __global__ void k_sum_act_bwd_v4(SumSrcs srcs, int64_t ldz, const TZ* __restrict__ G, int64_t ldg,
                                  const TZ* __restrict__ Ypre, int64_t ldy, int act, float ap, TO* __restrict__ OUT,
                                  int64_t ldo, int64_t R, int Q) {
@@ -243,21 +245,23 @@ __global__ void k_sum_act_bwd_v4(SumSrcs srcs, int64_t ldz, const TZ* __restrict
   if (i >= R * Q) return;
   const int64_t r = i / Q;
   const int q = (int)(i - r * Q);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (G) {
-    float g[4], y[4];
-    ld4(G + r * ldg + 4 * q, g);
-    ld4(Ypre + r * ldy + 4 * q, y);
+  float acc[VW];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] = g[k] * act_grad_from_pre(act, ap, y[k]);
+  for (int k = 0; k < VW; ++k) acc[k] = 0.f;
+  if (G) {
+    float g[VW], y[VW];
+    ldv<VW>(G + r * ldg + VW * q, g);
+    ldv<VW>(Ypre + r * ldy + VW * q, y);
+#pragma unroll
+    for (int k = 0; k < VW; ++k) acc[k] = g[k] * act_grad_from_pre(act, ap, y[k]);
   }
   for (int s = 0; s < srcs.n; ++s) {
-    float z[4];
-    ld4(reinterpret_cast<const TZ*>(srcs.z[s]) + r * ldz + 4 * q, z);
+    float z[VW];
+    ldv<VW>(reinterpret_cast<const TZ*>(srcs.z[s]) + r * ldz + VW * q, z);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] += z[k];
+    for (int k = 0; k < VW; ++k) acc[k] += z[k];
   }
-  st4(OUT + r * ldo + 4 * q, acc);
+  stv<VW>(OUT + r * ldo + VW * q, acc);
 }
 
 // OUT[r, :] = bf16([X1[i1(r), 0:K1] || X2[i2(r), 0:K2] || 0 ...])  -- the A operand of the tensor-core
@@ -368,8 +372,12 @@ extern "C" int dmpnn_bond_message(const void* X, int x_dtype, int64_t ldx, const
   const int warps = 8;
   DMPNN_DISPATCH_DTYPE(x_dtype, TX,
     DMPNN_DISPATCH_DTYPE(out_dtype, TO,
-      if (C % 4 == 0 && vec4_ok<TX>(X, ldx) && vec4_ok<TO>(OUT, ldo))
-        k_bond_message_v4<TX, TO><<<ceil_div_i64(V, warps), warps * 32, 0, st>>>(
+      if (C % 8 == 0 && vec8_ok<TX>(X, ldx) && vec8_ok<TO>(OUT, ldo))
+        k_bond_message_v4<8, TX, TO><<<ceil_div_i64(V, warps), warps * 32, 0, st>>>(
+            (const TX*)X, ldx, rowptr, rev_row, V, (int)(C / 8), act, act_param, permute_on_read, (TO*)OUT, ldo,
+            (const TO*)nullptr, 0, 0);
+      else if (C % 4 == 0 && vec4_ok<TX>(X, ldx) && vec4_ok<TO>(OUT, ldo))
+        k_bond_message_v4<4, TX, TO><<<ceil_div_i64(V, warps), warps * 32, 0, st>>>(
             (const TX*)X, ldx, rowptr, rev_row, V, (int)(C / 4), act, act_param, permute_on_read, (TO*)OUT, ldo,
             (const TO*)nullptr, 0, 0);
       else
@@ -416,11 +424,17 @@ extern "C" int dmpnn_act_bwd(const void* G, int g_dtype, int64_t ldg, const int3
       DMPNN_DISPATCH_DTYPE(dz_dtype, TZ,
         DMPNN_DISPATCH_DTYPE(acc_dtype, TA,
           if (C % 4 == 0 && vec4_ok<TG>(G, ldg) && vec4_ok<TYA>(Yact, ldy) && vec4_ok<TZ>(dZ, dZ ? lddz : 4) &&
-              vec4_ok<TA>(ACC, ACC ? ldacc : 4))
-            k_act_bwd_v4<TG, TYA, TZ, TA><<<ceil_div_i64(R * (C / 4), 256), 256, 0, st>>>(
-                (const TG*)G, ldg, gidx, (const TYA*)Yact, ldy, from_preact, act, act_param, (TZ*)dZ, lddz, (TA*)ACC, ldacc,
-                R, (int)(C / 4));
-          else
+              vec4_ok<TA>(ACC, ACC ? ldacc : 4)) {
+            if (C % 8 == 0 && vec8_ok<TG>(G, ldg) && vec8_ok<TYA>(Yact, ldy) && vec8_ok<TZ>(dZ, dZ ? lddz : 8) &&
+                vec8_ok<TA>(ACC, ACC ? ldacc : 8))
+              k_act_bwd_v4<8, TG, TYA, TZ, TA><<<ceil_div_i64(R * (C / 8), 256), 256, 0, st>>>(
+                  (const TG*)G, ldg, gidx, (const TYA*)Yact, ldy, from_preact, act, act_param, (TZ*)dZ, lddz, (TA*)ACC, ldacc,
+                  R, (int)(C / 8));
+            else
+              k_act_bwd_v4<4, TG, TYA, TZ, TA><<<ceil_div_i64(R * (C / 4), 256), 256, 0, st>>>(
+                  (const TG*)G, ldg, gidx, (const TYA*)Yact, ldy, from_preact, act, act_param, (TZ*)dZ, lddz, (TA*)ACC, ldacc,
+                  R, (int)(C / 4));
+          } else
             k_act_bwd<TG, TYA, TZ, TA><<<grid, block, 0, st>>>((const TG*)G, ldg, gidx, (const TYA*)Yact, ldy,
                                                               from_preact, act, act_param, (TZ*)dZ, lddz, (TA*)ACC,
                                                               ldacc, R, (int)C);
@@ -440,8 +454,12 @@ extern "C" int dmpnn_bond_message_bwd_masked(const void* X, int dtype, int64_t l
   const int warps = 8;
   DMPNN_DISPATCH_DTYPE(dtype, T,
     DMPNN_CHECK_ARG(vec4_ok<T>(X, ldx) && vec4_ok<T>(OUT, ldo) && vec4_ok<T>(Yact, ldy), "bond_message_bwd_masked: unaligned");
-    k_bond_message_v4<T, T><<<ceil_div_i64(V, warps), warps * 32, 0, st>>>(
-        (const T*)X, ldx, rowptr, rev_row, V, (int)(C / 4), DMPNN_ACT_NONE, act_param, 1, (T*)OUT, ldo, (const T*)Yact, ldy, act);
+    if (C % 8 == 0 && vec8_ok<T>(X, ldx) && vec8_ok<T>(OUT, ldo) && vec8_ok<T>(Yact, ldy))
+      k_bond_message_v4<8, T, T><<<ceil_div_i64(V, warps), warps * 32, 0, st>>>(
+          (const T*)X, ldx, rowptr, rev_row, V, (int)(C / 8), DMPNN_ACT_NONE, act_param, 1, (T*)OUT, ldo, (const T*)Yact, ldy, act);
+    else
+      k_bond_message_v4<4, T, T><<<ceil_div_i64(V, warps), warps * 32, 0, st>>>(
+          (const T*)X, ldx, rowptr, rev_row, V, (int)(C / 4), DMPNN_ACT_NONE, act_param, 1, (T*)OUT, ldo, (const T*)Yact, ldy, act);
   )
   DMPNN_CHECK_LAUNCH("bond_message_bwd_masked", 1);
   return 0;
@@ -462,8 +480,14 @@ extern "C" int dmpnn_sum_act_bwd(const void* const* Z, int n_z, int64_t ldz, con
       bool ok = vec4_ok<TZ>(G, ldg) && vec4_ok<TZ>(Ypre, ldy) && vec4_ok<TO>(OUT, ldo) && ldz % 4 == 0;
       for (int i = 0; i < n_z; ++i) ok = ok && vec4_ok<TZ>(Z[i], ldz);
       DMPNN_CHECK_ARG(ok, "sum_act_bwd: unaligned operands");
-      k_sum_act_bwd_v4<TZ, TO><<<ceil_div_i64(R * (C / 4), 256), 256, 0, st>>>(srcs, ldz, (const TZ*)G, ldg, (const TZ*)Ypre, ldy,
-                                                                              act, act_param, (TO*)OUT, ldo, R, (int)(C / 4));
+      bool ok8 = C % 8 == 0 && vec8_ok<TZ>(G, ldg) && vec8_ok<TZ>(Ypre, ldy) && vec8_ok<TO>(OUT, ldo) && ldz % 8 == 0;
+      for (int i = 0; i < n_z; ++i) ok8 = ok8 && vec8_ok<TZ>(Z[i], ldz);
+      if (ok8)
+        k_sum_act_bwd_v4<8, TZ, TO><<<ceil_div_i64(R * (C / 8), 256), 256, 0, st>>>(srcs, ldz, (const TZ*)G, ldg, (const TZ*)Ypre, ldy,
+                                                                                   act, act_param, (TO*)OUT, ldo, R, (int)(C / 8));
+      else
+        k_sum_act_bwd_v4<4, TZ, TO><<<ceil_div_i64(R * (C / 4), 256), 256, 0, st>>>(srcs, ldz, (const TZ*)G, ldg, (const TZ*)Ypre, ldy,
+                                                                                   act, act_param, (TO*)OUT, ldo, R, (int)(C / 4));
     ))
   DMPNN_CHECK_LAUNCH("sum_act_bwd", 1);
   return 0;

@@ -643,6 +643,9 @@ def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
     T = cfg.hidden_dtype
     nE, nV = lay.E, lay.V
     a, ap = cfg.act, cfg.act_param
+    # pure streaming passes run over the 16-padded width (16-byte vectors; padding columns only ever feed
+    # consumers that clip at h); the gather kernels keep 8-byte lanes (75 of 96 lanes busy beats 38 of 64)
+    hc = (h + 15) // 16 * 16
     H0, Hs, Hv = saved["H0"], saved["Hs"], saved["Hv"]
     f32 = dict(dtype=torch.float32, device=dev)
     dWi = torch.zeros_like(Wi, dtype=torch.float32)
@@ -664,11 +667,11 @@ def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
     linear_tc(dY, h, pack_weight_tc(Wo[:, d_v:], transpose=True), h, dMv, R=nV)
     dH0b = _empty_hidden(nE, hp, T, dev)
     if cfg.depth == 1:
-        act_bwd(dMv, H0, nE, h, act=a, act_param=ap, gidx=lay.dst_row, from_preact=True, dZ=dH0b)
+        act_bwd(dMv, H0, nE, hc, act=a, act_param=ap, gidx=lay.dst_row, from_preact=True, dZ=dH0b)
     else:
         WhT_pk = pack_weight_tc(Wh, transpose=True)
         dZ = _empty_hidden(nE, hp, T, dev)
-        act_bwd(dMv, Hs[-1], nE, h, act=a, act_param=ap, gidx=lay.dst_row, dZ=dZ)     # dZ^{T-1}
+        act_bwd(dMv, Hs[-1], nE, hc, act=a, act_param=ap, gidx=lay.dst_row, dZ=dZ)    # dZ^{T-1}
         dZs, dH_first = [dZ], None
         for t in range(cfg.depth - 1, 0, -1):
             first = t == 1
@@ -687,7 +690,7 @@ def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
                 dZ = _empty_hidden(nE, hp, T, dev)           # dZ^{t-1} = S.P(dM) * tau'(H^{t-1})
                 bond_message_bwd_masked(dM, Hin, lay, h, dZ, act=a, act_param=ap)
                 dZs.append(dZ)
-        sum_act_bwd(dZs, dH_first, H0, dH0b, nE, h, act=a, act_param=ap)
+        sum_act_bwd(dZs, dH_first, H0, dH0b, nE, hc, act=a, act_param=ap)
     wgrad_tc(dH0b, saved["X0"], nE, h, d_v + d_e, dWi)
     if dbi is not None:
         column_sum(dH0b, nE, h, dbi)
