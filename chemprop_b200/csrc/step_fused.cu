@@ -70,7 +70,8 @@ constexpr int kOffBar = kOffH + kHStages * kSlabBytes;       // 217088
 constexpr int kNumBars = 40;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kOffRowptr = kOffTmem + 16;                    // int32 [2][132]
-constexpr int kOffBias = kOffRowptr + 2 * 132 * 4;           // float [304]
+constexpr int kOffRevl = kOffRowptr + 2 * 132 * 4;           // int16 [2][128]: tile-local rev() (backward mode)
+constexpr int kOffBias = kOffRevl + 2 * 128 * 2;             // float [304]
 constexpr int kSmemBytes = kOffBias + kMaxHp * 4;
 constexpr int kSmemAlloc = kSmemBytes + 1024;
 static_assert(kOffH % 1024 == 0, "staging slabs must be 1024-byte aligned for SWIZZLE_128B");
@@ -148,7 +149,12 @@ __device__ __forceinline__ void message_atom_chunk(uint32_t abuf, int r0, int d,
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int ACT, bool FIRST, bool HAS_BIAS>
+// MODE 0: forward step (message of H, epilogue tau(H_0[rev] + bias + acc) written to row rev(e'))
+// MODE 1: autograd mirror, masked:  A row e' = sum of dZ[rev(x)] over the siblings x of e';  out[e'] = acc * tau'(Y[e'])
+// MODE 2: autograd mirror, plain:   same gather;  out[e'] = acc
+enum { MODE_FWD = 0, MODE_BWD_MASK = 1, MODE_BWD_COPY = 2 };
+
+template <int ACT, bool FIRST, bool HAS_BIAS, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ CUtensorMap tmapH0, Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -157,6 +163,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
   const uint32_t sA = sbase + kOffA, sW = sbase + kOffW, sH = sbase + kOffH, sBar = sbase + kOffBar;
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
   int32_t* s_rowptr = reinterpret_cast<int32_t*>(smem + kOffRowptr);
+  int16_t* s_revl = reinterpret_cast<int16_t*>(smem + kOffRevl);
   float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
@@ -278,7 +285,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
   } else if (warp == 3) {
     // ===================== TMA producer: H_0 slabs -> staging buffers (two per epilogue group) ==========
     uint32_t cnt[2] = {0u, 0u};   // slabs handed to each group so far
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; MODE != MODE_BWD_COPY && t < p.n_tiles; t += gridDim.x) {
       const int row0 = __ldg(p.tile_row_ptr + t);
       const int tn = t + gridDim.x;
       const int rown = (tn < p.n_tiles && !(p.exp_flags & 2048)) ? __ldg(p.tile_row_ptr + tn) : -1;
@@ -315,7 +322,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
     if (t < p.n_tiles) {
       row0 = __ldg(p.tile_row_ptr + t);
       nrows = __ldg(p.tile_row_ptr + t + 1) - row0;
-      lr = (r < nrows) ? (__ldg(p.rev_row + row0 + r) - row0) : r;
+      lr = (MODE == MODE_FWD && r < nrows) ? (__ldg(p.rev_row + row0 + r) - row0) : r;
     }
     for (; t < p.n_tiles; t += gridDim.x, ++it) {
       // prefetch the next tile's metadata (hides the dependent global loads behind this tile's work)
@@ -324,13 +331,13 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       if (tn < p.n_tiles) {
         row0n = __ldg(p.tile_row_ptr + tn);
         nrowsn = __ldg(p.tile_row_ptr + tn + 1) - row0n;
-        lrn = (r < nrowsn) ? __ldg(p.rev_row + row0n + r) : (row0n + r);
+        lrn = (MODE == MODE_FWD && r < nrowsn) ? __ldg(p.rev_row + row0n + r) : (row0n + r);
       }
       int cready = -1;                             // highest accumulator chunk already waited for
       for (int s = eg; s < p.nslab; s += kEpiGroups, ++hcnt) {
         const uint32_t q = (uint32_t)eg * 2 + (hcnt & 1);
         const uint32_t hbuf = sH + q * kSlabBytes;
-        mbar_wait(bar(B_HFULL + q), (hcnt >> 1) & 1);
+        if (MODE != MODE_BWD_COPY) mbar_wait(bar(B_HFULL + q), (hcnt >> 1) & 1);
         const int njj = (s == p.nslab - 1) ? p.ksteps_last : 4;
         for (int jj = 0; jj < njj; ++jj) {
           const int j = 4 * s + jj;
@@ -345,12 +352,21 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
           if (!(p.exp_flags & 512)) tmem_ld16(taddr + j * 16, v);
           const uint32_t a_lo = hbuf + sw128_off(lr, 2 * jj), a_hi = hbuf + sw128_off(lr, 2 * jj + 1);
           uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
-          if (!(p.exp_flags & 1024)) { h0 = lds128(a_lo); h1 = lds128(a_hi); }
+          if (MODE != MODE_BWD_COPY && !(p.exp_flags & 1024)) { h0 = lds128(a_lo); h1 = lds128(a_hi); }
           if (!(p.exp_flags & 512)) tmem_wait_ld();
           const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
           uint32_t o[8];
 #pragma unroll
           for (int qq = 0; qq < 8; ++qq) {
+            if constexpr (MODE == MODE_BWD_COPY) {          // dOut = (S.P)(dZ) . W_h
+              o[qq] = pack_bf2(__uint_as_float(v[2 * qq]), __uint_as_float(v[2 * qq + 1]));
+              continue;
+            } else if constexpr (MODE == MODE_BWD_MASK) {   // ... * tau'(Y), Y = the activation the row came from
+              const float g0 = act_grad_from_out(ACT, p.act_param, bf_lo(hw[qq]));
+              const float g1 = act_grad_from_out(ACT, p.act_param, bf_hi(hw[qq]));
+              o[qq] = pack_bf2(__uint_as_float(v[2 * qq]) * g0, __uint_as_float(v[2 * qq + 1]) * g1);
+              continue;
+            }
             float z0 = __uint_as_float(v[2 * qq]) + bf_lo(hw[qq]);
             float z1 = __uint_as_float(v[2 * qq + 1]) + bf_hi(hw[qq]);
             if constexpr (HAS_BIAS) {
@@ -387,7 +403,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
           }
         }
         fence_proxy_async();
-        mbar_arrive(bar(B_HFREE + q));
+        if (MODE != MODE_BWD_COPY) mbar_arrive(bar(B_HFREE + q));
       }
       if (et == 0) trace_ev(p, it, 8 + eg);
       row0 = row0n;
@@ -415,10 +431,15 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       atom0 = __ldg(p.tile_atom_ptr + t);
       natoms = __ldg(p.tile_atom_ptr + t + 1) - atom0;
       if (tS <= natoms) s_rowptr[tS] = __ldg(p.rowptr + atom0 + tS) - row0;
+      if (MODE != MODE_FWD && tS < 128) {
+        const int nr = __ldg(p.tile_row_ptr + t + 1) - row0;
+        s_revl[tS] = (int16_t)(tS < nr ? __ldg(p.rev_row + row0 + tS) - row0 : tS);
+      }
     }
     for (; t < p.n_tiles; t += gridDim.x, ++it) {
       const int b = it & 1;
       const int32_t* rp = s_rowptr + b * 132;
+      const int16_t* rvl = s_revl + b * 128;
       // prefetch next tile's rowptr slice into a register
       const int tn = t + gridDim.x;
       int row0n = 0, atom0n = 0, natomsn = 0, rpn = 0;
@@ -428,7 +449,12 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         natomsn = __ldg(p.tile_atom_ptr + tn + 1) - atom0n;
         if (tS <= natomsn) rpn = __ldg(p.rowptr + atom0n + tS) - row0n;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // rp[] of this tile is complete
+      int rvn = tS;
+      if (MODE != MODE_FWD && tn < p.n_tiles && tS < 128) {
+        const int nrn = __ldg(p.tile_row_ptr + tn + 1) - row0n;
+        if (tS < nrn) rvn = __ldg(p.rev_row + row0n + tS) - row0n;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // rp[] (and rvl[]) of this tile are complete
       // segment (atom) of row r: largest a with rp[a] <= r
       int g0 = 0, d = 0;
       if (r < rp[natoms]) {
@@ -450,6 +476,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         if (x >= r) ++x;
         sval[k] = (k < d - 1) && d <= 4;
         if (!sval[k]) x = r;               // harmless in-bounds address for the predicated-off slot
+        if (MODE != MODE_FWD) x = rvl[x];  // autograd mirror: the sibling contributes the row of its reverse edge
         soff[k] = (uint32_t)((x >> 3) * 1024 + (x & 7) * 128);
         sxr[k] = x & 7;
       }
@@ -496,8 +523,9 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
           float acc[16];
 #pragma unroll
           for (int q = 0; q < 16; ++q) acc[q] = 0.f;
-          for (int x = g0; x < g0 + d; ++x) {
-            if (x == r) continue;
+          for (int xx = g0; xx < g0 + d; ++xx) {
+            if (xx == r) continue;
+            const int x = (MODE != MODE_FWD) ? (int)rvl[xx] : xx;
             const uint4 u0 = s_load<ACT, FIRST>(sbase + sw128_off(x, c0), p.act_param);
             const uint4 u1 = s_load<ACT, FIRST>(sbase + sw128_off(x, c0 + 1), p.act_param);
             const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
@@ -521,6 +549,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       if (tS == 0) trace_ev(p, it, 2);
       // publish the next tile's rowptr slice (other buffer; readers of it finished a tile ago)
       if (tn < p.n_tiles && tS <= natomsn) s_rowptr[(b ^ 1) * 132 + tS] = rpn;
+      if (MODE != MODE_FWD && tn < p.n_tiles && tS < 128) s_revl[(b ^ 1) * 128 + tS] = (int16_t)rvn;
       row0 = row0n; atom0 = atom0n; natoms = natomsn;
     }
   }
@@ -589,15 +618,15 @@ static bool encode_rows_map(EncodeTiledFn enc, CUtensorMap* tmap, const void* ba
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int ACT, bool FIRST, bool HAS_BIAS>
+template <int ACT, bool FIRST, bool HAS_BIAS, int MODE = MODE_FWD>
 static cudaError_t launch_variant(int grid, cudaStream_t st, const CUtensorMap& mH, const CUtensorMap& mH0, const Params& p) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_bond_step_fused<ACT, FIRST, HAS_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc);
+    cudaError_t e = cudaFuncSetAttribute(k_bond_step_fused<ACT, FIRST, HAS_BIAS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_bond_step_fused<ACT, FIRST, HAS_BIAS><<<grid, kThreads, kSmemAlloc, st>>>(mH, mH0, p);
+  k_bond_step_fused<ACT, FIRST, HAS_BIAS, MODE><<<grid, kThreads, kSmemAlloc, st>>>(mH, mH0, p);
   return cudaSuccess;
 }
 
@@ -631,30 +660,28 @@ extern "C" int dmpnn_pack_weight_bf16(const float* W, int64_t ldw, int64_t N, in
   return 0;
 }
 
-extern "C" int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, void* H_next, int64_t ld,
-                                          int64_t n_rows_alloc, int64_t h, const void* Wpk, const float* bias,
-                                          const int32_t* rowptr, const int32_t* rev_row, const int32_t* tile_row_ptr,
-                                          const int32_t* tile_atom_ptr, int64_t n_tiles, int act, float act_param,
-                                          int first_step, void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
-  DMPNN_CHECK_ARG(H_prev && H_0 && H_next && Wpk && rowptr && rev_row && tile_row_ptr && tile_atom_ptr,
-                  "bond_step_fused: null pointer");
-  DMPNN_CHECK_ARG(h > 0 && h <= kMaxHp, "bond_step_fused: h=%lld unsupported (max %d)", (long long)h, kMaxHp);
+static int launch_step(const char* what, const void* H_prev, const void* H_0, void* H_next, int64_t ld, int64_t n_rows_alloc,
+                       int64_t h, const void* Wpk, const float* bias, const int32_t* rowptr, const int32_t* rev_row,
+                       const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles, int act, float act_param,
+                       int first_step, int mode, cudaStream_t st) {
+  DMPNN_CHECK_ARG(H_prev && H_next && Wpk && rowptr && rev_row && tile_row_ptr && tile_atom_ptr && (H_0 || mode == MODE_BWD_COPY),
+                  "%s: null pointer", what);
+  DMPNN_CHECK_ARG(h > 0 && h <= kMaxHp, "%s: h=%lld unsupported (max %d)", what, (long long)h, kMaxHp);
   const int hp = (int)((h + 15) / 16 * 16);
-  DMPNN_CHECK_ARG(ld >= hp && ld % 8 == 0, "bond_step_fused: ld=%lld must be >= %d and a multiple of 8", (long long)ld, hp);
-  DMPNN_CHECK_ARG(n_rows_alloc > 0 && n_tiles >= 0, "bond_step_fused: bad sizes");
-  DMPNN_CHECK_ARG(act >= DMPNN_ACT_NONE && act <= DMPNN_ACT_ELU, "bond_step_fused: bad activation %d", act);
+  DMPNN_CHECK_ARG(ld >= hp && ld % 8 == 0, "%s: ld=%lld must be >= %d and a multiple of 8", what, (long long)ld, hp);
+  DMPNN_CHECK_ARG(n_rows_alloc > 0 && n_tiles >= 0, "%s: bad sizes", what);
+  DMPNN_CHECK_ARG(act >= DMPNN_ACT_NONE && act <= DMPNN_ACT_ELU, "%s: bad activation %d", what, act);
   DMPNN_CHECK_ARG((reinterpret_cast<uintptr_t>(H_prev) & 15) == 0 && (reinterpret_cast<uintptr_t>(H_0) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(H_next) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wpk) & 15) == 0,
-                  "bond_step_fused: buffers must be 16-byte aligned");
-  DMPNN_CHECK_ARG(H_next != H_prev && H_next != H_0, "bond_step_fused: in-place update not supported");
+                  "%s: buffers must be 16-byte aligned", what);
+  DMPNN_CHECK_ARG(H_next != H_prev && H_next != H_0, "%s: in-place update not supported", what);
   if (n_tiles == 0) return 0;
   EncodeTiledFn enc = get_encode_fn();
-  DMPNN_CHECK_ARG(enc != nullptr, "bond_step_fused: cuTensorMapEncodeTiled not available from the driver");
+  DMPNN_CHECK_ARG(enc != nullptr, "%s: cuTensorMapEncodeTiled not available from the driver", what);
   CUtensorMap mH, mH0;
   DMPNN_CHECK_ARG(encode_rows_map(enc, &mH, H_prev, hp, n_rows_alloc, ld) &&
-                      encode_rows_map(enc, &mH0, H_0, hp, n_rows_alloc, ld),
-                  "bond_step_fused: cuTensorMapEncodeTiled failed");
+                      encode_rows_map(enc, &mH0, H_0 ? H_0 : H_prev, hp, n_rows_alloc, ld),
+                  "%s: cuTensorMapEncodeTiled failed", what);
 
   PackGeom g = pack_geom(h, h);
   Params p;
@@ -690,20 +717,49 @@ extern "C" int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, v
   }
   const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
   cudaError_t e = cudaErrorInvalidValue;
+  if (mode == MODE_FWD) {
 #define DMPNN_LAUNCH_ACT(A)                                                          \
   case A:                                                                            \
     e = first_step ? (bias ? launch_variant<A, true, true>(grid, st, mH, mH0, p) : launch_variant<A, true, false>(grid, st, mH, mH0, p))   \
                    : (bias ? launch_variant<A, false, true>(grid, st, mH, mH0, p) : launch_variant<A, false, false>(grid, st, mH, mH0, p)); \
     break;
-  switch (act) {
-    DMPNN_LAUNCH_ACT(DMPNN_ACT_NONE)
-    DMPNN_LAUNCH_ACT(DMPNN_ACT_RELU)
-    DMPNN_LAUNCH_ACT(DMPNN_ACT_LEAKYRELU)
-    DMPNN_LAUNCH_ACT(DMPNN_ACT_TANH)
-    DMPNN_LAUNCH_ACT(DMPNN_ACT_ELU)
-  }
+    switch (act) {
+      DMPNN_LAUNCH_ACT(DMPNN_ACT_NONE)
+      DMPNN_LAUNCH_ACT(DMPNN_ACT_RELU)
+      DMPNN_LAUNCH_ACT(DMPNN_ACT_LEAKYRELU)
+      DMPNN_LAUNCH_ACT(DMPNN_ACT_TANH)
+      DMPNN_LAUNCH_ACT(DMPNN_ACT_ELU)
+    }
 #undef DMPNN_LAUNCH_ACT
-  DMPNN_CHECK_ARG(e == cudaSuccess, "bond_step_fused: cannot configure %d B dynamic smem: %s", kSmemAlloc, cudaGetErrorString(e));
-  DMPNN_CHECK_LAUNCH("bond_step_fused", 1);
+  } else if (mode == MODE_BWD_COPY) {
+    e = launch_variant<DMPNN_ACT_NONE, false, false, MODE_BWD_COPY>(grid, st, mH, mH0, p);
+  } else {
+    switch (act) {
+      case DMPNN_ACT_NONE: e = launch_variant<DMPNN_ACT_NONE, false, false, MODE_BWD_MASK>(grid, st, mH, mH0, p); break;
+      case DMPNN_ACT_RELU: e = launch_variant<DMPNN_ACT_RELU, false, false, MODE_BWD_MASK>(grid, st, mH, mH0, p); break;
+      case DMPNN_ACT_LEAKYRELU: e = launch_variant<DMPNN_ACT_LEAKYRELU, false, false, MODE_BWD_MASK>(grid, st, mH, mH0, p); break;
+      case DMPNN_ACT_TANH: e = launch_variant<DMPNN_ACT_TANH, false, false, MODE_BWD_MASK>(grid, st, mH, mH0, p); break;
+      case DMPNN_ACT_ELU: e = launch_variant<DMPNN_ACT_ELU, false, false, MODE_BWD_MASK>(grid, st, mH, mH0, p); break;
+    }
+  }
+  DMPNN_CHECK_ARG(e == cudaSuccess, "%s: cannot configure %d B dynamic smem: %s", what, kSmemAlloc, cudaGetErrorString(e));
+  DMPNN_CHECK_LAUNCH(what, 1);
   return 0;
+}
+
+extern "C" int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, void* H_next, int64_t ld,
+                                          int64_t n_rows_alloc, int64_t h, const void* Wpk, const float* bias,
+                                          const int32_t* rowptr, const int32_t* rev_row, const int32_t* tile_row_ptr,
+                                          const int32_t* tile_atom_ptr, int64_t n_tiles, int act, float act_param,
+                                          int first_step, void* stream_) {
+  return launch_step("bond_step_fused", H_prev, H_0, H_next, ld, n_rows_alloc, h, Wpk, bias, rowptr, rev_row, tile_row_ptr,
+                     tile_atom_ptr, n_tiles, act, act_param, first_step, MODE_FWD, (cudaStream_t)stream_);
+}
+
+extern "C" int dmpnn_bond_step_bwd_fused_bf16(const void* dZ, const void* Yact, void* dOut, int64_t ld, int64_t n_rows_alloc,
+                                              int64_t h, const void* WpkT, const int32_t* rowptr, const int32_t* rev_row,
+                                              const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
+                                              int act, float act_param, void* stream_) {
+  return launch_step("bond_step_bwd_fused", dZ, Yact, dOut, ld, n_rows_alloc, h, WpkT, nullptr, rowptr, rev_row, tile_row_ptr,
+                     tile_atom_ptr, n_tiles, act, act_param, 0, Yact ? MODE_BWD_MASK : MODE_BWD_COPY, (cudaStream_t)stream_);
 }

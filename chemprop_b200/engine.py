@@ -471,6 +471,17 @@ def _empty_hidden(rows: int, hp: int, dtype, dev) -> Tensor:
     return torch.empty((max(rows, 1), hp), dtype=dtype, device=dev)
 
 
+def bond_step_bwd_fused(dZ: Tensor, Yact: Tensor | None, dOut: Tensor, h: int, WpkT: Tensor, lay: Layout, act: int,
+                        act_param: float):
+    """dOut = (S.P)(dZ . W_h) [* tau'(Yact)] in one fused launch (WpkT = pack_weight_bf16(W_h.t()))."""
+    lib = _lib.load()
+    rc = lib.dmpnn_bond_step_bwd_fused_bf16(
+        dZ.data_ptr(), _ptr(Yact), dOut.data_ptr(), _ld(dZ), dZ.shape[0], h, WpkT.data_ptr(),
+        lay.rowptr.data_ptr(), lay.rev_row.data_ptr(), lay.tile_row_ptr.data_ptr(), lay.tile_atom_ptr.data_ptr(),
+        lay.n_tiles, act, float(act_param), _stream())
+    _lib.check(rc, "dmpnn_bond_step_bwd_fused_bf16")
+
+
 def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, bh, Wo: Tensor, bo,
                  cfg: MPConfig):
     """BondMessagePassing.forward up to W_o (chemprop/nn/message_passing/base.py:196-212 with
@@ -669,7 +680,9 @@ def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
     if cfg.depth == 1:
         act_bwd(dMv, H0, nE, hc, act=a, act_param=ap, gidx=lay.dst_row, from_preact=True, dZ=dH0b)
     else:
-        WhT_pk = pack_weight_tc(Wh, transpose=True)
+        fused_bwd = _fused_step_ok(cfg, lay, h)      # the depth step's mirror on the same fused tcgen05 kernel
+        WhT_pk = None if fused_bwd else pack_weight_tc(Wh, transpose=True)
+        WhT_pkf = pack_weight_bf16(Wh.t().contiguous()) if fused_bwd else None
         dZ = _empty_hidden(nE, hp, T, dev)
         act_bwd(dMv, Hs[-1], nE, hc, act=a, act_param=ap, gidx=lay.dst_row, dZ=dZ)    # dZ^{T-1}
         dZs, dH_first = [dZ], None
@@ -681,6 +694,17 @@ def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
             wgrad_tc(dZ, M, nE, h, h, dWh, accumulate=True)
             if dbh is not None:
                 column_sum(dZ, nE, h, dbh, accumulate=True)
+            if fused_bwd:
+                # dH^{t-1} = (S.P)(dZ . W_h) = ((S.P) dZ) . W_h: gather on the A operand, tau' in the epilogue
+                if first:
+                    dH_first = _empty_hidden(nE, hp, T, dev)
+                    bond_step_bwd_fused(dZ, None, dH_first, h, WhT_pkf, lay, a, ap)
+                else:
+                    dZn = _empty_hidden(nE, hp, T, dev)
+                    bond_step_bwd_fused(dZ, Hin, dZn, h, WhT_pkf, lay, a, ap)
+                    dZ = dZn
+                    dZs.append(dZ)
+                continue
             dM = _empty_hidden(nE, hp, T, dev)
             linear_tc(dZ, h, WhT_pk, h, dM, R=nE)
             if first:

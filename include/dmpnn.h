@@ -233,6 +233,16 @@ int dmpnn_pack_weight_tc(const float* W, int64_t ldw, int64_t N, int64_t K, int 
 int dmpnn_linear_tc_bf16(const void* A, int64_t lda, int64_t R, int64_t K, const void* Wpk, int64_t N,
                          const float* bias, int act, float act_param, void* C, int64_t ldc, void* stream);
 
+/* Autograd mirror of one depth step on the same fused kernel (gather-by-rev mode):
+ *   dOut[e] = ( sum_{e'' : src(e'') = dst(e)} dM[e''] - dM[rev(e)] ) * tau'(Yact[e]),   dM = dZ . W_h
+ * computed as ((S.P) dZ) . W_h with the row mixing done on the A operand; WpkT = dmpnn_pack_weight_bf16 of W_h^T.
+ * Yact = the stored activation output H^{t-1} (tau' is evaluated from it); Yact == NULL -> no mask (dH^0).
+ * Same size / layout requirements as dmpnn_bond_step_fused_bf16. */
+int dmpnn_bond_step_bwd_fused_bf16(const void* dZ, const void* Yact, void* dOut, int64_t ld, int64_t n_rows_alloc,
+                                   int64_t h, const void* WpkT, const int32_t* rowptr, const int32_t* rev_row,
+                                   const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
+                                   int act, float act_param, void* stream);
+
 /* Tensor-core weight gradient (bf16 operands, f32 accumulate, deterministic two-pass reduction):
  *   dW[n, 0:K] (+)= sum_r dY[r, n] * X[r, 0:K]      dY: R x N (ld lddy), X: R x K (ld ldx), both bf16 row-major
  * N, K <= 384; lddy, ldx multiples of 8.  Workspace from dmpnn_wgrad_tc_workspace_bytes. */

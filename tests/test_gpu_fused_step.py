@@ -111,3 +111,32 @@ def test_fused_rejects_unsupported():
     with pytest.raises(DmpnnError):
         bond_step_fused(Hp, H0, torch.zeros_like(H0), 400, torch.zeros(16, dtype=torch.uint8, device="cuda"), None,
                         lay, _lib.ACT_RELU, 0.0, False)
+
+
+@pytest.mark.parametrize("h,act,masked", [(300, "relu", True), (300, "relu", False), (64, "tanh", True), (200, "relu", True)])
+def test_fused_backward_step_vs_torch_reference(h, act, masked):
+    """Autograd mirror of the depth step on the fused kernel: dOut = (S.P)(dZ . W_h) * tau'(Y)."""
+    from chemprop_b200 import _lib
+    from chemprop_b200.engine import bond_step_bwd_fused, pack_weight_bf16
+
+    lay, H0, Hp, W, b, hp = _setup(900, h, seed=17 + h)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dZ = torch.zeros_like(H0)
+    dZ[:, :h] = torch.randn(lay.E, h, device="cuda", generator=g).bfloat16()
+    Y = Hp if act == "relu" else torch.tanh(H0.float()).bfloat16()
+    out = torch.zeros_like(H0)
+    out[:, :h] = float("nan")
+    code = {"relu": _lib.ACT_RELU, "tanh": _lib.ACT_TANH}[act]
+    bond_step_bwd_fused(dZ, Y if masked else None, out, h, pack_weight_bf16(W.t().contiguous()), lay, code, 0.0)
+    torch.cuda.synchronize()
+    # reference: dM = dZ . W_h ; dH[e] = sum_{x in seg(e)} dM[rev x] - dM[rev e] ; times tau'(Y)
+    rev, dst = lay.rev_row.long(), lay.dst_row.long()
+    X = dZ[:, :h].float()[rev]                                            # (P dZ)
+    A = torch.zeros(lay.V, h, device="cuda").index_add_(0, dst, X)
+    G = (A[dst] - X).bfloat16().float() @ W.bfloat16().float()            # ((S.P) dZ) . W_h   (W_h: out x in)
+    if masked:
+        y = Y[:, :h].float()
+        G = G * ((y > 0).float() if act == "relu" else (1 - y * y))
+    assert torch.isfinite(out.float()).all()
+    torch.testing.assert_close(out[:, :h].float(), G.bfloat16().float(), rtol=2 ** -6, atol=2e-2)
+    assert hp == h or float(out[:, h:].float().abs().max()) == 0.0
