@@ -258,12 +258,21 @@ k_colsum_partial_v4(const TY* __restrict__ dY, int64_t lddy, float* __restrict__
   for (int q0 = 0; q0 < Q; q0 += 32) {
     const int q = q0 + lane;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (q < Q)
-      for (int64_t r = r_begin + warp; r < r_end; r += 8) {
+    if (q < Q) {
+      int64_t r = r_begin + warp;
+      for (; r + 56 < r_end; r += 64) {      // 8 independent row loads in flight per lane
+        float v[8][4];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) ld4(dY + (r + 8 * u) * lddy + 4 * q, v[u]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { acc[0] += v[u][0]; acc[1] += v[u][1]; acc[2] += v[u][2]; acc[3] += v[u][3]; }
+      }
+      for (; r < r_end; r += 8) {
         float v[4];
         ld4(dY + r * lddy + 4 * q, v);
         acc[0] += v[0]; acc[1] += v[1]; acc[2] += v[2]; acc[3] += v[3];
       }
+    }
     if (q < Q) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) s_part[warp * N + 4 * q + i] = acc[i];

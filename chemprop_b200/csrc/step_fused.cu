@@ -48,6 +48,7 @@ constexpr int kMaxHp = 304;
 struct Params {
   const __nv_bfloat16* H0;
   __nv_bfloat16* Hn;
+  __nv_bfloat16* G;   // optional: the gathered A operand rows (M^1 forward / (S.P)dZ backward) for the W_h gradient
   int64_t ld;
   const uint8_t* Wpk;
   const float* bias;
@@ -423,6 +424,8 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
     const int tS = threadIdx.x - 384;        // 0..255
     const uint32_t at_base = tmem_base + kTmemAOff + ((uint32_t)(sq * 32) << 16);
     const int nj = p.hp >> 4;
+    constexpr bool kCanEmit = FIRST || MODE != MODE_FWD;   // variants that may also write the gathered operand out
+    constexpr bool kNeedRev = MODE != MODE_FWD || FIRST;    // ... and those that need the tile-local rev() table
     int it = 0;
     int t = blockIdx.x;
     int row0 = 0, atom0 = 0, natoms = 0;
@@ -431,7 +434,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       atom0 = __ldg(p.tile_atom_ptr + t);
       natoms = __ldg(p.tile_atom_ptr + t + 1) - atom0;
       if (tS <= natoms) s_rowptr[tS] = __ldg(p.rowptr + atom0 + tS) - row0;
-      if (MODE != MODE_FWD && tS < 128) {
+      if (kNeedRev && tS < 128) {
         const int nr = __ldg(p.tile_row_ptr + t + 1) - row0;
         s_revl[tS] = (int16_t)(tS < nr ? __ldg(p.rev_row + row0 + tS) - row0 : tS);
       }
@@ -450,7 +453,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         if (tS <= natomsn) rpn = __ldg(p.rowptr + atom0n + tS) - row0n;
       }
       int rvn = tS;
-      if (MODE != MODE_FWD && tn < p.n_tiles && tS < 128) {
+      if (kNeedRev && tn < p.n_tiles && tS < 128) {
         const int nrn = __ldg(p.tile_row_ptr + tn + 1) - row0n;
         if (tS < nrn) rvn = __ldg(p.rev_row + row0n + tS) - row0n;
       }
@@ -479,6 +482,11 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         if (MODE != MODE_FWD) x = rvl[x];  // autograd mirror: the sibling contributes the row of its reverse edge
         soff[k] = (uint32_t)((x >> 3) * 1024 + (x & 7) * 128);
         sxr[k] = x & 7;
+      }
+      __nv_bfloat16* gout = nullptr;
+      if constexpr (kCanEmit) {
+        if (p.G != nullptr && r < rp[natoms])
+          gout = p.G + (int64_t)(row0 + (MODE == MODE_FWD ? (int)rvl[r] : r)) * p.ld;
       }
       mbar_wait(bar(B_AFULL), it & 1);               // H tile landed in shared memory
       if (tS == 0) trace_ev(p, it, 1);
@@ -536,6 +544,11 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
           for (int q = 0; q < 8; ++q) o[q] = pack_bf2(acc[2 * q], acc[2 * q + 1]);
         }
         tmem_st8(at_base + (uint32_t)(j * 8), o);
+        if constexpr (kCanEmit) {
+          // forward: A row r is M[rev(r)] (mixins.py:11-18); backward: A row r is ((S.P) dZ)[r].  One 32-byte
+          // sector per thread and block (STG.256), consumed by the W_h weight-gradient GEMM.
+          if (gout != nullptr) st_global_256(gout + j * 16, o);
+        }
       }
       mbar_arrive(bar(B_AFREE));         // shared-memory tile no longer needed: TMA may refill it
       tmem_wait_st();
@@ -549,7 +562,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       if (tS == 0) trace_ev(p, it, 2);
       // publish the next tile's rowptr slice (other buffer; readers of it finished a tile ago)
       if (tn < p.n_tiles && tS <= natomsn) s_rowptr[(b ^ 1) * 132 + tS] = rpn;
-      if (MODE != MODE_FWD && tn < p.n_tiles && tS < 128) s_revl[(b ^ 1) * 128 + tS] = (int16_t)rvn;
+      if (kNeedRev && tn < p.n_tiles && tS < 128) s_revl[(b ^ 1) * 128 + tS] = (int16_t)rvn;
       row0 = row0n; atom0 = atom0n; natoms = natomsn;
     }
   }
@@ -663,7 +676,11 @@ extern "C" int dmpnn_pack_weight_bf16(const float* W, int64_t ldw, int64_t N, in
 static int launch_step(const char* what, const void* H_prev, const void* H_0, void* H_next, int64_t ld, int64_t n_rows_alloc,
                        int64_t h, const void* Wpk, const float* bias, const int32_t* rowptr, const int32_t* rev_row,
                        const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles, int act, float act_param,
-                       int first_step, int mode, cudaStream_t st) {
+                       int first_step, int mode, void* gather_out, cudaStream_t st) {
+  DMPNN_CHECK_ARG(gather_out == nullptr || mode != MODE_FWD || first_step,
+                  "%s: the gathered operand can only be written by the first forward step", what);
+  DMPNN_CHECK_ARG(gather_out == nullptr || ((reinterpret_cast<uintptr_t>(gather_out) & 31) == 0 && ld % 16 == 0),
+                  "%s: gather output needs a 32-byte aligned base and ld %% 16 == 0", what);
   DMPNN_CHECK_ARG(H_prev && H_next && Wpk && rowptr && rev_row && tile_row_ptr && tile_atom_ptr && (H_0 || mode == MODE_BWD_COPY),
                   "%s: null pointer", what);
   DMPNN_CHECK_ARG(h > 0 && h <= kMaxHp, "%s: h=%lld unsupported (max %d)", what, (long long)h, kMaxHp);
@@ -687,6 +704,7 @@ static int launch_step(const char* what, const void* H_prev, const void* H_0, vo
   Params p;
   p.H0 = (const __nv_bfloat16*)H_0;
   p.Hn = (__nv_bfloat16*)H_next;
+  p.G = (__nv_bfloat16*)gather_out;
   p.ld = ld;
   p.Wpk = (const uint8_t*)Wpk;
   p.bias = bias;
@@ -751,15 +769,16 @@ extern "C" int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, v
                                           int64_t n_rows_alloc, int64_t h, const void* Wpk, const float* bias,
                                           const int32_t* rowptr, const int32_t* rev_row, const int32_t* tile_row_ptr,
                                           const int32_t* tile_atom_ptr, int64_t n_tiles, int act, float act_param,
-                                          int first_step, void* stream_) {
+                                          int first_step, void* M_out, void* stream_) {
   return launch_step("bond_step_fused", H_prev, H_0, H_next, ld, n_rows_alloc, h, Wpk, bias, rowptr, rev_row, tile_row_ptr,
-                     tile_atom_ptr, n_tiles, act, act_param, first_step, MODE_FWD, (cudaStream_t)stream_);
+                     tile_atom_ptr, n_tiles, act, act_param, first_step, MODE_FWD, M_out, (cudaStream_t)stream_);
 }
 
 extern "C" int dmpnn_bond_step_bwd_fused_bf16(const void* dZ, const void* Yact, void* dOut, int64_t ld, int64_t n_rows_alloc,
                                               int64_t h, const void* WpkT, const int32_t* rowptr, const int32_t* rev_row,
                                               const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
-                                              int act, float act_param, void* stream_) {
+                                              int act, float act_param, void* G_out, void* stream_) {
   return launch_step("bond_step_bwd_fused", dZ, Yact, dOut, ld, n_rows_alloc, h, WpkT, nullptr, rowptr, rev_row, tile_row_ptr,
-                     tile_atom_ptr, n_tiles, act, act_param, 0, Yact ? MODE_BWD_MASK : MODE_BWD_COPY, (cudaStream_t)stream_);
+                     tile_atom_ptr, n_tiles, act, act_param, 0, Yact ? MODE_BWD_MASK : MODE_BWD_COPY, G_out,
+                     (cudaStream_t)stream_);
 }

@@ -446,12 +446,13 @@ def concat_bf16(X1: Tensor, K1: int, out: Tensor, R: int, *, idx1: Tensor | None
 
 
 def bond_step_fused(H_prev: Tensor, H0: Tensor, H_next: Tensor, h: int, Wpk: Tensor, bias: Tensor | None,
-                    lay: Layout, act: int, act_param: float, first_step: bool):
+                    lay: Layout, act: int, act_param: float, first_step: bool, M_out: Tensor | None = None):
+    """One fused depth step; M_out (first step only) also receives the message M^1 the step consumed."""
     lib = _lib.load()
     rc = lib.dmpnn_bond_step_fused_bf16(
         H_prev.data_ptr(), H0.data_ptr(), H_next.data_ptr(), _ld(H0), H0.shape[0], h, Wpk.data_ptr(), _ptr(bias),
         lay.rowptr.data_ptr(), lay.rev_row.data_ptr(), lay.tile_row_ptr.data_ptr(), lay.tile_atom_ptr.data_ptr(),
-        lay.n_tiles, act, float(act_param), 1 if first_step else 0, _stream(),
+        lay.n_tiles, act, float(act_param), 1 if first_step else 0, _ptr(M_out), _stream(),
     )
     _lib.check(rc, "dmpnn_bond_step_fused_bf16")
 
@@ -472,18 +473,19 @@ def _empty_hidden(rows: int, hp: int, dtype, dev) -> Tensor:
 
 
 def bond_step_bwd_fused(dZ: Tensor, Yact: Tensor | None, dOut: Tensor, h: int, WpkT: Tensor, lay: Layout, act: int,
-                        act_param: float):
-    """dOut = (S.P)(dZ . W_h) [* tau'(Yact)] in one fused launch (WpkT = pack_weight_bf16(W_h.t()))."""
+                        act_param: float, G_out: Tensor | None = None):
+    """dOut = (S.P)(dZ . W_h) [* tau'(Yact)] in one fused launch (WpkT = pack_weight_bf16(W_h.t()));
+    G_out also receives (S.P) dZ, the left operand of this step's W_h gradient."""
     lib = _lib.load()
     rc = lib.dmpnn_bond_step_bwd_fused_bf16(
         dZ.data_ptr(), _ptr(Yact), dOut.data_ptr(), _ld(dZ), dZ.shape[0], h, WpkT.data_ptr(),
         lay.rowptr.data_ptr(), lay.rev_row.data_ptr(), lay.tile_row_ptr.data_ptr(), lay.tile_atom_ptr.data_ptr(),
-        lay.n_tiles, act, float(act_param), _stream())
+        lay.n_tiles, act, float(act_param), _ptr(G_out), _stream())
     _lib.check(rc, "dmpnn_bond_step_bwd_fused_bf16")
 
 
 def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, bh, Wo: Tensor, bo,
-                 cfg: MPConfig):
+                 cfg: MPConfig, for_backward: bool = False):
     """BondMessagePassing.forward up to W_o (chemprop/nn/message_passing/base.py:196-212 with
     mixins.py:8-18 and base.py:135-141, 180-182).  Returns (H_v, saved-for-backward)."""
     dev = V.device
@@ -512,9 +514,12 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
     for _ in range(1, cfg.depth):
         if use_fused:
             Hn = _empty_hidden(nE, hp, T, dev)
+            # training: the first step also stores M^1 (it is tau(H_0)-gathered, which no later kernel can rebuild
+            # from a stored activation); the later steps' W_h gradients use (S.P) dZ from the backward kernel instead
+            M1 = _empty_hidden(nE, hp, T, dev) if (first and for_backward) else None
             with _StepTimer("fused_first" if first else "fused"):
-                bond_step_fused(Hprev, H0, Hn, h, Wpk, bh, lay, a, ap, first)
-            Ms.append(None)
+                bond_step_fused(Hprev, H0, Hn, h, Wpk, bh, lay, a, ap, first, M_out=M1)
+            Ms.append(M1)
         else:
             src_in, fa = Hprev, (a if first else ACT_NONE)
             if cfg.undirected:  # H = (H + H[rev]) / 2   (base.py:202-203)
@@ -689,22 +694,32 @@ def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
         for t in range(cfg.depth - 1, 0, -1):
             first = t == 1
             Hin = H0 if first else Hs[t - 2]
-            M = _empty_hidden(nE, hp, T, dev)                # M^t, recomputed (the fused forward never stores it)
-            bond_message(Hin, lay, h, M, act=(a if first else ACT_NONE), act_param=ap)
-            wgrad_tc(dZ, M, nE, h, h, dWh, accumulate=True)
             if dbh is not None:
                 column_sum(dZ, nE, h, dbh, accumulate=True)
             if fused_bwd:
-                # dH^{t-1} = (S.P)(dZ . W_h) = ((S.P) dZ) . W_h: gather on the A operand, tau' in the epilogue
+                # dH^{t-1} = (S.P)(dZ . W_h) = ((S.P) dZ) . W_h: gather on the A operand, tau' in the epilogue.
+                # W_h gradient without recomputing M^t:  dZ^T . M^t = dZ^T . (P.S) H^{t-1} = ((S.P) dZ)^T . H^{t-1};
+                # the kernel writes its gathered operand G = (S.P) dZ out.  t = 1 has no stored tau(H_0): it uses
+                # the M^1 the forward kernel saved.
+                M1 = saved["Ms"][0] if first else None
+                if first and M1 is None:
+                    M1 = _empty_hidden(nE, hp, T, dev)
+                    bond_message(H0, lay, h, M1, act=a, act_param=ap)
                 if first:
+                    wgrad_tc(dZ, M1, nE, h, h, dWh, accumulate=True)
                     dH_first = _empty_hidden(nE, hp, T, dev)
                     bond_step_bwd_fused(dZ, None, dH_first, h, WhT_pkf, lay, a, ap)
                 else:
                     dZn = _empty_hidden(nE, hp, T, dev)
-                    bond_step_bwd_fused(dZ, Hin, dZn, h, WhT_pkf, lay, a, ap)
+                    G = _empty_hidden(nE, hp, T, dev)
+                    bond_step_bwd_fused(dZ, Hin, dZn, h, WhT_pkf, lay, a, ap, G_out=G)
+                    wgrad_tc(G, Hin, nE, h, h, dWh, accumulate=True)
                     dZ = dZn
                     dZs.append(dZ)
                 continue
+            M = _empty_hidden(nE, hp, T, dev)                # M^t, recomputed
+            bond_message(Hin, lay, h, M, act=(a if first else ACT_NONE), act_param=ap)
+            wgrad_tc(dZ, M, nE, h, h, dWh, accumulate=True)
             dM = _empty_hidden(nE, hp, T, dev)
             linear_tc(dZ, h, WhT_pk, h, dM, R=nE)
             if first:
@@ -731,7 +746,7 @@ class BondMPFunction(torch.autograd.Function):
         bi_ = None if bi is None else bi.detach().contiguous().float()
         bh_ = None if bh is None else bh.detach().contiguous().float()
         bo_ = None if bo is None else bo.detach().contiguous().float()
-        Hv, saved = bond_forward(lay, V, E, Wi_, bi_, Wh_, bh_, Wo_, bo_, cfg)
+        Hv, saved = bond_forward(lay, V, E, Wi_, bi_, Wh_, bh_, Wo_, bo_, cfg, for_backward=any(ctx.needs_input_grad))
         ctx.lay, ctx.cfg, ctx.saved = lay, cfg, saved
         ctx.VE = (V, E)
         ctx.W = (Wi_, Wh_, Wo_)

@@ -215,6 +215,8 @@ int dmpnn_act_bwd(const void* G, int g_dtype, int64_t ldg, const int32_t* gidx,
  * (H_prev = H_0 and H^0 = tau(H_0) is recomputed on load), identity otherwise.
  * Wpk is W_h packed by dmpnn_pack_weight_bf16.  Requires ld % 8 == 0, h <= 304, all tiles
  * <= 128 rows, DMPNN_FLAG_REV_INVOLUTION.  Returns <0 (and does nothing) otherwise.
+ * M_out (nullable; first_step only; bf16, same ld, 32-byte aligned, ld % 16 == 0): also stores the message
+ * M^1[e] (mixins.py:11-18) that the step consumed, saved for the W_h gradient instead of being recomputed.
  * ------------------------------------------------------------------------------------- */
 /* ---------------------------------------------------------------------------------------
  * Tensor-core linear layers of the bf16 tier (tcgen05 / TMEM / TMA), for the GEMMs outside the fused
@@ -237,11 +239,13 @@ int dmpnn_linear_tc_bf16(const void* A, int64_t lda, int64_t R, int64_t K, const
  *   dOut[e] = ( sum_{e'' : src(e'') = dst(e)} dM[e''] - dM[rev(e)] ) * tau'(Yact[e]),   dM = dZ . W_h
  * computed as ((S.P) dZ) . W_h with the row mixing done on the A operand; WpkT = dmpnn_pack_weight_bf16 of W_h^T.
  * Yact = the stored activation output H^{t-1} (tau' is evaluated from it); Yact == NULL -> no mask (dH^0).
+ * G_out (nullable, bf16, same ld, 32-byte aligned, ld % 16 == 0): also writes the gathered operand G = (S.P) dZ, so
+ * that the W_h gradient of this step is the plain GEMM dW_h += G^T . H^{t-1} (dZ^T . M^t == ((S.P) dZ)^T . H^{t-1}).
  * Same size / layout requirements as dmpnn_bond_step_fused_bf16. */
 int dmpnn_bond_step_bwd_fused_bf16(const void* dZ, const void* Yact, void* dOut, int64_t ld, int64_t n_rows_alloc,
                                    int64_t h, const void* WpkT, const int32_t* rowptr, const int32_t* rev_row,
                                    const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
-                                   int act, float act_param, void* stream);
+                                   int act, float act_param, void* G_out, void* stream);
 
 /* Tensor-core weight gradient (bf16 operands, f32 accumulate, deterministic two-pass reduction):
  *   dW[n, 0:K] (+)= sum_r dY[r, n] * X[r, 0:K]      dY: R x N (ld lddy), X: R x K (ld ldx), both bf16 row-major
@@ -263,7 +267,7 @@ int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, void* H_next
                                const void* Wpk, const float* bias,
                                const int32_t* rowptr, const int32_t* rev_row,
                                const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
-                               int act, float act_param, int first_step, void* stream);
+                               int act, float act_param, int first_step, void* M_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -60,9 +60,15 @@ def test_fused_step_vs_torch_reference(h, first, act, bias):
     Wpk = pack_weight_bf16(W)
     Hn = torch.zeros_like(H0)
     Hn[:, :h] = float("nan")                   # every data column must be written; the row padding stays zero
-    bond_step_fused(Hin, H0, Hn, h, Wpk, b if bias else None, lay, code, 0.0, first)
+    M1 = torch.full_like(H0, float("nan")) if first else None   # first step: the consumed message is also stored
+    bond_step_fused(Hin, H0, Hn, h, Wpk, b if bias else None, lay, code, 0.0, first, M_out=M1)
     torch.cuda.synchronize()
     ref = _torch_reference(lay, Hin, H0, W, b if bias else None, h, act, first)
+    if first:
+        tau = {"relu": torch.relu, "tanh": torch.tanh}[act]
+        X, dst, rev = tau(H0[:, :h].float()), lay.dst_row.long(), lay.rev_row.long()
+        Mref = torch.zeros(lay.V, h, device="cuda").index_add_(0, dst, X)[dst[rev]] - X[rev]   # M[e] (mixins.py:11-18)
+        torch.testing.assert_close(M1[:, :h].float(), Mref.bfloat16().float(), rtol=2 ** -6, atol=2e-2)
     assert torch.isfinite(Hn.float()).all(), "rows/columns left unwritten"
     assert hp == h or float(Hn[:, h:].float().abs().max()) == 0.0, "row padding must stay zero"
     torch.testing.assert_close(Hn.float(), ref.float(), rtol=2 ** -6, atol=2e-2)   # a couple of bf16 ulps (message summed in packed bf16)
@@ -127,12 +133,14 @@ def test_fused_backward_step_vs_torch_reference(h, act, masked):
     out = torch.zeros_like(H0)
     out[:, :h] = float("nan")
     code = {"relu": _lib.ACT_RELU, "tanh": _lib.ACT_TANH}[act]
-    bond_step_bwd_fused(dZ, Y if masked else None, out, h, pack_weight_bf16(W.t().contiguous()), lay, code, 0.0)
+    Gk = torch.full_like(H0, float("nan"))
+    bond_step_bwd_fused(dZ, Y if masked else None, out, h, pack_weight_bf16(W.t().contiguous()), lay, code, 0.0, G_out=Gk)
     torch.cuda.synchronize()
     # reference: dM = dZ . W_h ; dH[e] = sum_{x in seg(e)} dM[rev x] - dM[rev e] ; times tau'(Y)
     rev, dst = lay.rev_row.long(), lay.dst_row.long()
     X = dZ[:, :h].float()[rev]                                            # (P dZ)
     A = torch.zeros(lay.V, h, device="cuda").index_add_(0, dst, X)
+    torch.testing.assert_close(Gk[:, :h].float(), (A[dst] - X).bfloat16().float(), rtol=2 ** -6, atol=2e-2)   # (S.P) dZ
     G = (A[dst] - X).bfloat16().float() @ W.bfloat16().float()            # ((S.P) dZ) . W_h   (W_h: out x in)
     if masked:
         y = Y[:, :h].float()
