@@ -54,28 +54,38 @@ class ClockSampler:
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         self._stop = threading.Event()
         self._t = None
-
-    def _run(self):
-        try:
+        self._nv = self._h = None
+        try:                                    # NVML is initialised here, outside the timed region
             import pynvml as nv
 
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
-                "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
-                "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
-            }
+            self._nv, self._h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def _sample(self):
+        nv, h = self._nv, self._h
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for k, bit in names.items():
+            if r & bit:
+                self.reasons.add(k)
+
+    def _run(self):
+        if self._nv is None:
+            return
+        try:
             while not self._stop.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-                time.sleep(0.005)
+                self._sample()
+                time.sleep(0.002)
         except Exception as e:  # noqa: BLE001
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -85,6 +95,12 @@ class ClockSampler:
         return self
 
     def __exit__(self, *a):
+        # called right after the closing synchronize: one more sample while the clocks are still at their load value
+        try:
+            if self._nv is not None:
+                self._sample()
+        except Exception:  # noqa: BLE001
+            pass
         self._stop.set()
         self._t.join(timeout=2)
 
@@ -93,11 +109,11 @@ class ClockSampler:
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def make_host_batch(n_mols: int, seed: int, pin: bool):
+def make_host_batch(n_mols: int, seed: int, pin: bool, transfer_dtype=None):
     from chemprop_b200.data import BatchMolGraph, make_molecules
 
     mgs = make_molecules(n_mols, seed=seed, mean_atoms=WORKLOAD["mean_atoms"])
-    return BatchMolGraph(mgs, pin_memory=pin), mgs
+    return BatchMolGraph(mgs, pin_memory=pin, transfer_dtype=transfer_dtype), mgs
 
 
 # ------------------------------------------------------------------------------------------------
@@ -204,18 +220,22 @@ def main_gpu(args):
     params = list(mp.parameters())
     reducer = FlatGradAllReducer(params)
 
-    host_bmg, _ = make_host_batch(n_mols, seed=1 + rank, pin=True)  # weak scaling: every rank its own batch
+    # weak scaling: every rank its own batch.  The pinned host batch is what a loader hands over: for the bf16 tier
+    # it carries the compact transfer copy (bf16 features, int32 indices -- result-identical, see BatchMolGraph);
+    # `host_f32` is the same batch in the reference's f32 / int64 host format, timed as a second e2e figure.
+    host_bmg, mgs = make_host_batch(n_mols, seed=1 + rank, pin=True,
+                                    transfer_dtype=torch.bfloat16 if precision == "bf16" else None)
     V_atoms, E_rows = host_bmg.V.shape[0], host_bmg.E.shape[0]
-    h2d_bytes = sum(t.numel() * t.element_size() for t in
-                    (host_bmg.V, host_bmg.E, host_bmg.edge_index, host_bmg.rev_edge_index, host_bmg.batch))
+    h2d_bytes = host_bmg.transfer_nbytes()
 
     from chemprop_b200.data import BatchMolGraph
 
+    host_f32 = BatchMolGraph(mgs, pin_memory=True) if precision == "bf16" else host_bmg
+    del mgs
+    src = {"bmg": host_bmg}
+
     def to_device():
-        return BatchMolGraph.from_tensors(
-            host_bmg.V.to(dev, non_blocking=True), host_bmg.E.to(dev, non_blocking=True),
-            host_bmg.edge_index.to(dev, non_blocking=True), host_bmg.rev_edge_index.to(dev, non_blocking=True),
-            host_bmg.batch.to(dev, non_blocking=True), len(host_bmg))
+        return src["bmg"].cuda_copy(dev, non_blocking=True)
 
     resident = to_device()
 
@@ -274,8 +294,15 @@ def main_gpu(args):
             ev.record(copy_stream)
         return b, ev
 
+    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+
     def e2e_loop(k):
+        # The loss of step i is copied to pinned host memory right after its backward is queued and READ by the host
+        # one step later (after step i+1 is queued), as a logging training loop does: the GPU queue never drains on
+        # the host's read.  All k H2D batches and all k D2H loss reads are inside the timed region.
         nxt = issue_copy()
+        pending = None
+        losses = []
         for i in range(k):
             bmg, ev = nxt
             torch.cuda.current_stream().wait_event(ev)
@@ -284,11 +311,30 @@ def main_gpu(args):
             if i + 1 < k:
                 nxt = issue_copy()
             loss = step(bmg)
-            float(loss.item())                   # D2H read of the step's result
+            slot = loss_host[i & 1:(i & 1) + 1]
+            slot.copy_(loss.detach().float().reshape(1), non_blocking=True)   # D2H of the step's result
+            done = torch.cuda.Event()
+            done.record()
+            if pending is not None:
+                pending[0].synchronize()
+                losses.append(float(pending[1][0]))
+            pending = (done, slot)
+        pending[0].synchronize()
+        losses.append(float(pending[1][0]))
+        assert len(losses) == k and all(np.isfinite(losses))
 
     e2e_loop(2)
     ms_e2e = timed(lambda: e2e_loop(args.steps), 1) / args.steps
     e2e_value = world * n_mols / (ms_e2e * 1e-3)
+    e2e_f32 = None
+    if host_f32 is not host_bmg:
+        src["bmg"] = host_f32
+        e2e_loop(2)
+        ms_f32 = timed(lambda: e2e_loop(args.steps), 1) / args.steps
+        e2e_f32 = {"value": world * n_mols / (ms_f32 * 1e-3), "unit": "molecules/s", "ms_per_step": ms_f32,
+                   "h2d_bytes_per_step": host_f32.transfer_nbytes(), "d2h_bytes_per_step": 4,
+                   "host_format": "f32 features + int64 indices (the reference's BatchMolGraph dtypes)"}
+        src["bmg"] = host_bmg
 
     # ---- roofline of the depth step ----------------------------------------------------------
     s = 2 if precision == "bf16" else 4
@@ -343,7 +389,11 @@ def main_gpu(args):
                    "l2": "working set (>=0.3 GB hidden buffers per step) exceeds the 126 MB L2; no explicit flush"},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "molecules/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "host_format": ("bf16 features + int32 indices staged by BatchMolGraph(transfer_dtype=bfloat16); the bf16 "
+                                "tier rounds V/E to bf16 on the GPU anyway, results are bit-identical"
+                                if precision == "bf16" else "f32 features + int64 indices")},
+        "e2e_f32_host": e2e_f32,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

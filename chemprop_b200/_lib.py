@@ -37,7 +37,7 @@ SIGNATURES = {
                                      _vp, _i64, _vp, _i32, _i64, _i64, _vp, _vp]),
     "dmpnn_segment_sum": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _i64, _i64, _i32, _f32, _i32, _f32,
                                     _vp, _i32, _i64, _i64, _vp]),
-    "dmpnn_segment_bcast": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _i64, _i64, _i32, _f32, _vp, _i32, _i64, _vp]),
+    "dmpnn_segment_bcast": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _vp, _i32, _i64, _vp]),
     "dmpnn_bond_message": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _i64, _i64, _i32, _f32, _i32, _vp, _i32, _i64, _vp]),
     "dmpnn_bond_message_bwd_masked": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _f32, _vp, _i64, _vp]),
     "dmpnn_sum_act_bwd": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp, _i32, _i64, _i64, _i64, _vp]),
@@ -45,7 +45,7 @@ SIGNATURES = {
     "dmpnn_act_bwd": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _i32, _i64, _i32, _i32, _f32, _vp, _i32, _i64,
                                 _vp, _i32, _i64, _i64, _i64, _vp]),
     "dmpnn_bond_step_bwd_fused_bf16": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32,
-                                                 _vp, _vp]),
+                                                 _i32, _vp, _vp, _vp, _vp]),
     "dmpnn_concat_bf16": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _i32, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "dmpnn_pack_weight_tc_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
     "dmpnn_pack_weight_tc": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp]),

@@ -118,7 +118,20 @@ __global__ void k_segment_sum_v4(const TX* __restrict__ X, int64_t ldx, const in
   for (int q = lane; q < Qpad; q += 32) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (q < Q) {
-      for (int32_t r = a; r < b; ++r) {
+      int32_t r = a;
+      for (; r + 4 <= b; r += 4) {     // four independent row loads in flight (long segments: molecules)
+        float v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t rr = idx ? (int64_t)idx[r + u] : (int64_t)(r + u);
+          ld4(X + rr * ldx + 4 * q, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] += act_apply(act, ap, v[u][i]);
+      }
+      for (; r < b; ++r) {
         const int64_t rr = idx ? (int64_t)idx[r] : (int64_t)r;
         float v[4];
         ld4(X + rr * ldx + 4 * q, v);
@@ -135,24 +148,108 @@ __global__ void k_segment_sum_v4(const TX* __restrict__ X, int64_t ldx, const in
   }
 }
 
+// flat segmented sum for SHORT segments (atoms: 2-4 in-edge rows): thread = one 8-column chunk of `par` interleaved
+// segments, so the warps stay full (a warp-per-segment mapping has 3 passes of 32/32/11 lanes at h = 300) and every
+// row of a segment is an independent 16-byte load.  Columns in [C, QW*8) are written as zeros.
+template <bool HAS_ACT, typename TX, typename TY>
+__global__ void __launch_bounds__(256)
+k_segment_sum_flat8(const TX* __restrict__ X, int64_t ldx, const int32_t* __restrict__ idx,
+                    const int32_t* __restrict__ ptr, int64_t n_seg, int C, int QW, int act, float ap, int scale_mode,
+                    float scale, TY* __restrict__ Y, int64_t ldy, int segs_per_block) {
+  const int par = blockDim.x / QW;
+  const int sub = threadIdx.x / QW;
+  const int c0 = 8 * (threadIdx.x - sub * QW);
+  if (sub >= par) return;
+  const int64_t s_end = min(n_seg, ((int64_t)blockIdx.x + 1) * segs_per_block);
+  for (int64_t s = (int64_t)blockIdx.x * segs_per_block + sub; s < s_end; s += par) {
+    const int32_t a = ptr[s], b = ptr[s + 1];
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (c0 < C) {
+      int32_t r = a;
+      for (; r + 4 <= b; r += 4) {
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t rr = idx ? (int64_t)idx[r + u] : (int64_t)(r + u);
+          ldv<8>(X + rr * ldx + c0, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += HAS_ACT ? act_apply(act, ap, v[u][i]) : v[u][i];
+      }
+      if (r < b) {                        // 1..3 remaining rows, loaded together
+        float v[3][8];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int32_t ru = min(r + u, b - 1);
+          const int64_t rr = idx ? (int64_t)idx[ru] : (int64_t)ru;
+          ldv<8>(X + rr * ldx + c0, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          if (r + u < b) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += HAS_ACT ? act_apply(act, ap, v[u][i]) : v[u][i];
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (scale_mode == DMPNN_SCALE_INV_COUNT) acc[i] = (b > a) ? acc[i] / (float)(b - a) : 0.f;
+        else if (scale_mode == DMPNN_SCALE_DIV_CONST) acc[i] = acc[i] / scale;
+        if (c0 + i >= C) acc[i] = 0.f;    // the chunk straddling C: whatever the source padding held is dropped
+      }
+    }
+    stv<8>(Y + s * ldy + c0, acc);
+  }
+}
+
+// thread = one column quad of `rows_par` interleaved rows (one integer division per thread, not per element)
 template <typename TG, typename TY>
-__global__ void k_segment_bcast_v4(const TG* __restrict__ G, int64_t ldg, const int32_t* __restrict__ seg_of_row,
-                                   const int32_t* __restrict__ ptr, int64_t R, int Q, int scale_mode, float scale,
-                                   TY* __restrict__ Y, int64_t ldy) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R * Q) return;
-  const int64_t r = i / Q;
-  const int q = (int)(i - r * Q);
-  const int32_t s = seg_of_row[r];
+__global__ void __launch_bounds__(256)
+k_segment_bcast_v4(const TG* __restrict__ G, int64_t ldg, const int32_t* __restrict__ seg_of_row,
+                   const int32_t* __restrict__ ptr, int64_t R, int Q, int scale_mode, float scale,
+                   TY* __restrict__ Y, int64_t ldy, int rows_per_block) {
+  const int rows_par = blockDim.x / Q;
+  const int rsub = threadIdx.x / Q;
+  const int q = threadIdx.x - rsub * Q;
+  if (rsub >= rows_par) return;
+  const int64_t r_end = min(R, ((int64_t)blockIdx.x + 1) * rows_per_block);
+  for (int64_t r = (int64_t)blockIdx.x * rows_per_block + rsub; r < r_end; r += rows_par) {
+    const int32_t s = seg_of_row[r];
+    float v[4];
+    ld4(G + (int64_t)s * ldg + 4 * q, v);
+    if (scale_mode != DMPNN_SCALE_NONE) {
+      const float div = (scale_mode == DMPNN_SCALE_INV_COUNT) ? (float)(ptr[s + 1] - ptr[s]) : scale;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = v[k] / div;
+    }
+    st4(Y + r * ldy + 4 * q, v);
+  }
+}
+
+// segment walk: one block per segment, thread = (row lane, column quad); the scaled row of G stays in registers
+template <typename TG, typename TY>
+__global__ void __launch_bounds__(256)
+k_segment_bcast_seg_v4(const TG* __restrict__ G, int64_t ldg, const int32_t* __restrict__ ptr, int Q, int scale_mode,
+                       float scale, TY* __restrict__ Y, int64_t ldy) {
+  const int rows_par = blockDim.x / Q;
+  const int rsub = threadIdx.x / Q;
+  const int q = threadIdx.x - rsub * Q;
+  if (rsub >= rows_par) return;
+  const int64_t s = blockIdx.x;
+  const int32_t a = ptr[s], b = ptr[s + 1];
+  if (b <= a) return;
   float v[4];
-  ld4(G + (int64_t)s * ldg + 4 * q, v);
-  const float div = (scale_mode == DMPNN_SCALE_INV_COUNT) ? (float)(ptr[s + 1] - ptr[s])
-                                                          : (scale_mode == DMPNN_SCALE_DIV_CONST ? scale : 1.f);
+  ld4(G + s * ldg + 4 * q, v);
   if (scale_mode != DMPNN_SCALE_NONE) {
+    const float div = (scale_mode == DMPNN_SCALE_INV_COUNT) ? (float)(b - a) : scale;
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] = v[k] / div;
   }
-  st4(Y + r * ldy + 4 * q, v);
+  for (int32_t r = a + rsub; r < b; r += rows_par) st4(Y + (int64_t)r * ldy + 4 * q, v);
 }
 
 template <int VW, typename TX, typename TO>
@@ -274,26 +371,42 @@ __global__ void k_concat_bf16(const T1* __restrict__ X1, int64_t ld1, const int3
   if (r >= R) return;
   const int64_t r1 = idx1 ? (int64_t)idx1[r] : r;
   const int64_t r2 = (K2 > 0 && idx2) ? (int64_t)idx2[r] : r;
-  const bool vec = (width % 4 == 0) && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(OUT) & 7) == 0);
-  if (vec) {
-    for (int c4 = threadIdx.x * 4; c4 < width; c4 += blockDim.x * 4) {
-      float v[4];
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    float v = 0.f;
+    if (c < K1) v = ld_as_float(X1 + r1 * ld1 + c);
+    else if (c < K1 + K2) v = ld_as_float(X2 + r2 * ld2 + (c - K1));
+    OUT[r * ldo + c] = __float2bfloat16_rn(v);
+  }
+}
+
+// 4-wide variant: thread = one column quad of `rows_par` interleaved rows, so every lane of a warp stores
+// (rows are 18..24 quads wide: a lane-per-quad-of-one-row mapping would idle a quarter of the warp)
+template <typename T1, typename T2>
+__global__ void __launch_bounds__(256)
+k_concat_bf16_v4(const T1* __restrict__ X1, int64_t ld1, const int32_t* __restrict__ idx1, int K1,
+                 const T2* __restrict__ X2, int64_t ld2, const int32_t* __restrict__ idx2, int K2,
+                 __nv_bfloat16* __restrict__ OUT, int64_t ldo, int QW, int64_t R, int rows_per_block, int x1_vec) {
+  const int rows_par = blockDim.x / QW;
+  const int rsub = threadIdx.x / QW;
+  const int c4 = 4 * (threadIdx.x - rsub * QW);
+  if (rsub >= rows_par) return;
+  const int64_t r_end = min(R, ((int64_t)blockIdx.x + 1) * rows_per_block);
+  for (int64_t r = (int64_t)blockIdx.x * rows_per_block + rsub; r < r_end; r += rows_par) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c4 + 4 <= K1 && x1_vec) {
+      const int64_t r1 = idx1 ? (int64_t)idx1[r] : r;
+      ld4(X1 + r1 * ld1 + c4, v);
+    } else if (c4 < K1 + K2) {
+      const int64_t r1 = idx1 ? (int64_t)idx1[r] : r;
+      const int64_t r2 = (K2 > 0 && idx2) ? (int64_t)idx2[r] : r;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = c4 + i;
-        v[i] = 0.f;
         if (c < K1) v[i] = ld_as_float(X1 + r1 * ld1 + c);
         else if (c < K1 + K2) v[i] = ld_as_float(X2 + r2 * ld2 + (c - K1));
       }
-      st4(OUT + r * ldo + c4, v);
     }
-  } else {
-    for (int c = threadIdx.x; c < width; c += blockDim.x) {
-      float v = 0.f;
-      if (c < K1) v = ld_as_float(X1 + r1 * ld1 + c);
-      else if (c < K1 + K2) v = ld_as_float(X2 + r2 * ld2 + (c - K1));
-      OUT[r * ldo + c] = __float2bfloat16_rn(v);
-    }
+    st4(OUT + r * ldo + c4, v);
   }
 }
 
@@ -310,10 +423,16 @@ extern "C" int dmpnn_concat_bf16(const void* X1, int x1_dtype, int64_t ld1, cons
   DMPNN_CHECK_ARG(X1 && OUT && (K2 == 0 || X2), "concat_bf16: null pointer");
   if (K2 == 0) x2_dtype = x1_dtype;
   dim3 block(32, 8), grid(ceil_div_i64(R, 8));
+  const bool vec = width % 4 == 0 && width / 4 <= 256 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(OUT) & 7) == 0;
   DMPNN_DISPATCH_DTYPE(x1_dtype, T1,
     DMPNN_DISPATCH_DTYPE(x2_dtype, T2,
-      k_concat_bf16<T1, T2><<<grid, block, 0, st>>>((const T1*)X1, ld1, idx1, (int)K1, (const T2*)X2, ld2, idx2, (int)K2,
-                                                   (__nv_bfloat16*)OUT, ldo, (int)width, R);
+      if (vec)
+        k_concat_bf16_v4<T1, T2><<<ceil_div_i64(R, 64), 256, 0, st>>>(
+            (const T1*)X1, ld1, idx1, (int)K1, (const T2*)X2, ld2, idx2, (int)K2, (__nv_bfloat16*)OUT, ldo, (int)(width / 4), R,
+            64, vec4_ok<T1>(X1, ld1) ? 1 : 0);
+      else
+        k_concat_bf16<T1, T2><<<grid, block, 0, st>>>((const T1*)X1, ld1, idx1, (int)K1, (const T2*)X2, ld2, idx2, (int)K2,
+                                                     (__nv_bfloat16*)OUT, ldo, (int)width, R);
     ))
   DMPNN_CHECK_LAUNCH("concat_bf16", 1);
   return 0;
@@ -330,7 +449,16 @@ extern "C" int dmpnn_segment_sum(const void* X, int x_dtype, int64_t ldx, const 
   DMPNN_DISPATCH_DTYPE(x_dtype, TX,
     DMPNN_DISPATCH_DTYPE(y_dtype, TY,
       const int64_t padc = ldy_pad > C ? ldy_pad : C;
-      if (C % 4 == 0 && padc % 4 == 0 && vec4_ok<TX>(X, ldx) && vec4_ok<TY>(Y, ldy))
+      const int64_t c8 = (C + 7) / 8 * 8;
+      if (padc % 8 == 0 && padc >= c8 && c8 <= ldx && padc / 8 <= 256 && vec8_ok<TX>(X, ldx) && vec8_ok<TY>(Y, ldy)) {
+        const int spb = 64;
+        if (act == DMPNN_ACT_NONE)
+          k_segment_sum_flat8<false, TX, TY><<<ceil_div_i64(n_seg, spb), 256, 0, st>>>(
+              (const TX*)X, ldx, idx, ptr, n_seg, (int)C, (int)(padc / 8), act, act_param, scale_mode, scale, (TY*)Y, ldy, spb);
+        else
+          k_segment_sum_flat8<true, TX, TY><<<ceil_div_i64(n_seg, spb), 256, 0, st>>>(
+              (const TX*)X, ldx, idx, ptr, n_seg, (int)C, (int)(padc / 8), act, act_param, scale_mode, scale, (TY*)Y, ldy, spb);
+      } else if (C % 4 == 0 && padc % 4 == 0 && vec4_ok<TX>(X, ldx) && vec4_ok<TY>(Y, ldy))
         k_segment_sum_v4<TX, TY><<<ceil_div_i64(n_seg, warps), warps * 32, 0, st>>>(
             (const TX*)X, ldx, idx, ptr, n_seg, (int)(C / 4), act, act_param, scale_mode, scale, (TY*)Y, ldy, (int)(padc / 4));
       else
@@ -342,8 +470,8 @@ extern "C" int dmpnn_segment_sum(const void* X, int x_dtype, int64_t ldx, const 
 }
 
 extern "C" int dmpnn_segment_bcast(const void* G, int g_dtype, int64_t ldg, const int32_t* seg_of_row,
-                                   const int32_t* ptr, int64_t R, int64_t C, int scale_mode, float scale, void* Y,
-                                   int y_dtype, int64_t ldy, void* stream_) {
+                                   const int32_t* ptr, int64_t n_seg, int64_t R, int64_t C, int scale_mode, float scale,
+                                   void* Y, int y_dtype, int64_t ldy, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   DMPNN_CHECK_ARG(R >= 0 && C > 0 && G && seg_of_row && Y, "segment_bcast: bad args");
   DMPNN_CHECK_ARG(scale_mode != DMPNN_SCALE_INV_COUNT || ptr, "segment_bcast: ptr needed for mean");
@@ -351,9 +479,12 @@ extern "C" int dmpnn_segment_bcast(const void* G, int g_dtype, int64_t ldg, cons
   dim3 block(64, 4), grid(ceil_div_i64(R, 4), ceil_div_i64(C, 64));
   DMPNN_DISPATCH_DTYPE(g_dtype, TG,
     DMPNN_DISPATCH_DTYPE(y_dtype, TY,
-      if (C % 4 == 0 && vec4_ok<TG>(G, ldg) && vec4_ok<TY>(Y, ldy))
-        k_segment_bcast_v4<TG, TY><<<ceil_div_i64(R * (C / 4), 256), 256, 0, st>>>((const TG*)G, ldg, seg_of_row, ptr, R,
-                                                                                   (int)(C / 4), scale_mode, scale, (TY*)Y, ldy);
+      if (n_seg > 0 && ptr && C % 4 == 0 && C / 4 <= 256 && vec4_ok<TG>(G, ldg) && vec4_ok<TY>(Y, ldy))
+        k_segment_bcast_seg_v4<TG, TY><<<n_seg, 256, 0, st>>>((const TG*)G, ldg, ptr, (int)(C / 4), scale_mode, scale,
+                                                            (TY*)Y, ldy);
+      else if (C % 4 == 0 && C / 4 <= 256 && vec4_ok<TG>(G, ldg) && vec4_ok<TY>(Y, ldy))
+        k_segment_bcast_v4<TG, TY><<<ceil_div_i64(R, 64), 256, 0, st>>>((const TG*)G, ldg, seg_of_row, ptr, R,
+                                                                       (int)(C / 4), scale_mode, scale, (TY*)Y, ldy, 64);
       else
         k_segment_bcast<TG, TY><<<grid, block, 0, st>>>((const TG*)G, ldg, seg_of_row, ptr, R, (int)C, scale_mode,
                                                         scale, (TY*)Y, ldy);

@@ -48,6 +48,8 @@ constexpr int kMaxHp = 304;
 struct Params {
   const __nv_bfloat16* H0;
   __nv_bfloat16* Hn;
+  const __nv_bfloat16* add0;   // MODE_BWD_LAST: optional addends (same ld), summed in the copy-out
+  const __nv_bfloat16* add1;
   __nv_bfloat16* G;   // optional: the gathered A operand rows (M^1 forward / (S.P)dZ backward) for the W_h gradient
   int64_t ld;
   const uint8_t* Wpk;
@@ -153,7 +155,10 @@ __device__ __forceinline__ void message_atom_chunk(uint32_t abuf, int r0, int d,
 // MODE 0: forward step (message of H, epilogue tau(H_0[rev] + bias + acc) written to row rev(e'))
 // MODE 1: autograd mirror, masked:  A row e' = sum of dZ[rev(x)] over the siblings x of e';  out[e'] = acc * tau'(Y[e'])
 // MODE 2: autograd mirror, plain:   same gather;  out[e'] = acc
-enum { MODE_FWD = 0, MODE_BWD_MASK = 1, MODE_BWD_COPY = 2 };
+// MODE_BWD_LAST: mask from the PRE-activation (Y = H_0) and up to two row-aligned addends summed into the output:
+// the t = 1 step then produces dH_0 = dZ^{T-1} + ... + dZ^1 + dH^0 * tau'(H_0) directly.
+enum { MODE_FWD = 0, MODE_BWD_MASK = 1, MODE_BWD_COPY = 2, MODE_BWD_LAST = 3 };
+constexpr int kAddBatch = 4;   // 16-byte chunks per thread whose addend loads are in flight together
 
 template <int ACT, bool FIRST, bool HAS_BIAS, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -293,6 +298,18 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       if (rown >= 0 && elect_one())
         for (int s = 0; s < p.nslab; ++s) tma_prefetch_2d(&tmapH0, s * 64, rown);
       __syncwarp();
+      if (MODE == MODE_BWD_LAST && p.add0 != nullptr) {
+        // the copy-out of this tile reads the addend rows with plain loads: pull them into L2 now (the rows of a
+        // tile are one contiguous byte range; this warp runs most of a tile ahead of the epilogue)
+        const int nr = __ldg(p.tile_row_ptr + t + 1) - row0;
+        const int64_t lines = ((int64_t)nr * p.ld * 2 + 127) >> 7;
+        const char* b0 = reinterpret_cast<const char*>(p.add0 + (int64_t)row0 * p.ld);
+        const char* b1 = p.add1 ? reinterpret_cast<const char*>(p.add1 + (int64_t)row0 * p.ld) : nullptr;
+        for (int64_t i = lane; i < lines; i += 32) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + (i << 7)));
+          if (b1) asm volatile("prefetch.global.L2 [%0];" ::"l"(b1 + (i << 7)));
+        }
+      }
       for (int s = 0; s < p.nslab; ++s) {
         const uint32_t g = s & 1, k = cnt[g]++;
         const uint32_t q = g * 2 + (k & 1), use = k >> 1;
@@ -362,9 +379,12 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
             if constexpr (MODE == MODE_BWD_COPY) {          // dOut = (S.P)(dZ) . W_h
               o[qq] = pack_bf2(__uint_as_float(v[2 * qq]), __uint_as_float(v[2 * qq + 1]));
               continue;
-            } else if constexpr (MODE == MODE_BWD_MASK) {   // ... * tau'(Y), Y = the activation the row came from
-              const float g0 = act_grad_from_out(ACT, p.act_param, bf_lo(hw[qq]));
-              const float g1 = act_grad_from_out(ACT, p.act_param, bf_hi(hw[qq]));
+            } else if constexpr (MODE == MODE_BWD_MASK || MODE == MODE_BWD_LAST) {
+              // ... * tau'(.): from the activation output the row came from, or (LAST) from the pre-activation H_0
+              const float g0 = MODE == MODE_BWD_LAST ? act_grad_from_pre(ACT, p.act_param, bf_lo(hw[qq]))
+                                                     : act_grad_from_out(ACT, p.act_param, bf_lo(hw[qq]));
+              const float g1 = MODE == MODE_BWD_LAST ? act_grad_from_pre(ACT, p.act_param, bf_hi(hw[qq]))
+                                                     : act_grad_from_out(ACT, p.act_param, bf_hi(hw[qq]));
               o[qq] = pack_bf2(__uint_as_float(v[2 * qq]) * g0, __uint_as_float(v[2 * qq + 1]) * g1);
               continue;
             }
@@ -392,7 +412,41 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         if (eg == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
         else asm volatile("bar.sync 3, 128;" ::: "memory");
         const int ncc = 2 * njj;  // valid 16-byte chunks per row in this slab
-        if (!(p.exp_flags & 256)) {
+        if (MODE == MODE_BWD_LAST && p.add0 != nullptr) {
+          // dH_0 = (this step's masked gradient) + the earlier steps' dZ: coalesced 16-byte loads of the addends
+          // at the output position (L2 hits: prefetched by the staging warp), f32 sum, one rounding.
+#pragma unroll
+          for (int kb = 0; kb < 8; kb += kAddBatch) {
+            uint4 a0[kAddBatch], a1[kAddBatch];
+#pragma unroll
+            for (int k = 0; k < kAddBatch; ++k) {
+              const int pidx = et + 128 * (kb + k);
+              const int rr = pidx >> 3, cc = pidx & 7;
+              a0[k] = make_uint4(0, 0, 0, 0); a1[k] = make_uint4(0, 0, 0, 0);
+              if (rr < nrows && cc < ncc) {
+                const int64_t off = (int64_t)(row0 + rr) * p.ld + s * 64 + cc * 8;
+                a0[k] = __ldg(reinterpret_cast<const uint4*>(p.add0 + off));
+                if (p.add1 != nullptr) a1[k] = __ldg(reinterpret_cast<const uint4*>(p.add1 + off));
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < kAddBatch; ++k) {
+              const int pidx = et + 128 * (kb + k);
+              const int rr = pidx >> 3, cc = pidx & 7;
+              if (rr < nrows && cc < ncc) {
+                const uint4 val = lds128(hbuf + sw128_off(rr, cc));
+                const uint32_t vw[4] = {val.x, val.y, val.z, val.w};
+                const uint32_t w0[4] = {a0[k].x, a0[k].y, a0[k].z, a0[k].w};
+                const uint32_t w1[4] = {a1[k].x, a1[k].y, a1[k].z, a1[k].w};
+                uint32_t ow[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  ow[q] = pack_bf2(bf_lo(vw[q]) + bf_lo(w0[q]) + bf_lo(w1[q]), bf_hi(vw[q]) + bf_hi(w0[q]) + bf_hi(w1[q]));
+                *reinterpret_cast<uint4*>(p.Hn + (int64_t)(row0 + rr) * p.ld + s * 64 + cc * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+              }
+            }
+          }
+        } else if (!(p.exp_flags & 256)) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const int pidx = et + 128 * k;
@@ -676,7 +730,12 @@ extern "C" int dmpnn_pack_weight_bf16(const float* W, int64_t ldw, int64_t N, in
 static int launch_step(const char* what, const void* H_prev, const void* H_0, void* H_next, int64_t ld, int64_t n_rows_alloc,
                        int64_t h, const void* Wpk, const float* bias, const int32_t* rowptr, const int32_t* rev_row,
                        const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles, int act, float act_param,
-                       int first_step, int mode, void* gather_out, cudaStream_t st) {
+                       int first_step, int mode, void* gather_out, const void* add0, const void* add1, cudaStream_t st) {
+  DMPNN_CHECK_ARG((add0 == nullptr && add1 == nullptr) || (mode == MODE_BWD_LAST && add0 != nullptr),
+                  "%s: addends need y_is_preact (and add0 before add1)", what);
+  DMPNN_CHECK_ARG(((reinterpret_cast<uintptr_t>(add0) | reinterpret_cast<uintptr_t>(add1)) & 15) == 0,
+                  "%s: addends must be 16-byte aligned", what);
+  DMPNN_CHECK_ARG(add0 != H_next && add1 != H_next, "%s: an addend may not alias the output", what);
   DMPNN_CHECK_ARG(gather_out == nullptr || mode != MODE_FWD || first_step,
                   "%s: the gathered operand can only be written by the first forward step", what);
   DMPNN_CHECK_ARG(gather_out == nullptr || ((reinterpret_cast<uintptr_t>(gather_out) & 31) == 0 && ld % 16 == 0),
@@ -705,6 +764,8 @@ static int launch_step(const char* what, const void* H_prev, const void* H_0, vo
   p.H0 = (const __nv_bfloat16*)H_0;
   p.Hn = (__nv_bfloat16*)H_next;
   p.G = (__nv_bfloat16*)gather_out;
+  p.add0 = (const __nv_bfloat16*)add0;
+  p.add1 = (const __nv_bfloat16*)add1;
   p.ld = ld;
   p.Wpk = (const uint8_t*)Wpk;
   p.bias = bias;
@@ -751,6 +812,14 @@ static int launch_step(const char* what, const void* H_prev, const void* H_0, vo
 #undef DMPNN_LAUNCH_ACT
   } else if (mode == MODE_BWD_COPY) {
     e = launch_variant<DMPNN_ACT_NONE, false, false, MODE_BWD_COPY>(grid, st, mH, mH0, p);
+  } else if (mode == MODE_BWD_LAST) {
+    switch (act) {
+      case DMPNN_ACT_NONE: e = launch_variant<DMPNN_ACT_NONE, false, false, MODE_BWD_LAST>(grid, st, mH, mH0, p); break;
+      case DMPNN_ACT_RELU: e = launch_variant<DMPNN_ACT_RELU, false, false, MODE_BWD_LAST>(grid, st, mH, mH0, p); break;
+      case DMPNN_ACT_LEAKYRELU: e = launch_variant<DMPNN_ACT_LEAKYRELU, false, false, MODE_BWD_LAST>(grid, st, mH, mH0, p); break;
+      case DMPNN_ACT_TANH: e = launch_variant<DMPNN_ACT_TANH, false, false, MODE_BWD_LAST>(grid, st, mH, mH0, p); break;
+      case DMPNN_ACT_ELU: e = launch_variant<DMPNN_ACT_ELU, false, false, MODE_BWD_LAST>(grid, st, mH, mH0, p); break;
+    }
   } else {
     switch (act) {
       case DMPNN_ACT_NONE: e = launch_variant<DMPNN_ACT_NONE, false, false, MODE_BWD_MASK>(grid, st, mH, mH0, p); break;
@@ -771,14 +840,17 @@ extern "C" int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, v
                                           const int32_t* tile_atom_ptr, int64_t n_tiles, int act, float act_param,
                                           int first_step, void* M_out, void* stream_) {
   return launch_step("bond_step_fused", H_prev, H_0, H_next, ld, n_rows_alloc, h, Wpk, bias, rowptr, rev_row, tile_row_ptr,
-                     tile_atom_ptr, n_tiles, act, act_param, first_step, MODE_FWD, M_out, (cudaStream_t)stream_);
+                     tile_atom_ptr, n_tiles, act, act_param, first_step, MODE_FWD, M_out, nullptr, nullptr, (cudaStream_t)stream_);
 }
 
 extern "C" int dmpnn_bond_step_bwd_fused_bf16(const void* dZ, const void* Yact, void* dOut, int64_t ld, int64_t n_rows_alloc,
                                               int64_t h, const void* WpkT, const int32_t* rowptr, const int32_t* rev_row,
                                               const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
-                                              int act, float act_param, void* G_out, void* stream_) {
+                                              int act, float act_param, int y_is_preact, const void* add0,
+                                              const void* add1, void* G_out, void* stream_) {
+  DMPNN_CHECK_ARG(!y_is_preact || Yact, "bond_step_bwd_fused: y_is_preact needs Yact");
   return launch_step("bond_step_bwd_fused", dZ, Yact, dOut, ld, n_rows_alloc, h, WpkT, nullptr, rowptr, rev_row, tile_row_ptr,
-                     tile_atom_ptr, n_tiles, act, act_param, 0, Yact ? MODE_BWD_MASK : MODE_BWD_COPY, G_out,
+                     tile_atom_ptr, n_tiles, act, act_param, 0,
+                     Yact ? (y_is_preact ? MODE_BWD_LAST : MODE_BWD_MASK) : MODE_BWD_COPY, G_out, add0, add1,
                      (cudaStream_t)stream_);
 }

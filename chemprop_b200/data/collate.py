@@ -24,11 +24,17 @@ from .molgraph import MolGraph
 
 
 class BatchMolGraph:
-    __slots__ = ("V", "E", "edge_index", "rev_edge_index", "batch", "_size", "_layout")
+    __slots__ = ("V", "E", "edge_index", "rev_edge_index", "batch", "_size", "_layout", "_xfer")
 
-    def __init__(self, mgs: Sequence[MolGraph], pin_memory: bool = False):
+    def __init__(self, mgs: Sequence[MolGraph], pin_memory: bool = False, transfer_dtype: torch.dtype | None = None):
+        """``transfer_dtype=torch.bfloat16`` (opt-in, for the bf16 tier) additionally keeps a compact host staging
+        copy -- features in bf16, indices in int32 -- that `.to(cuda)` / `.cuda_copy()` ship over PCIe instead of
+        the f32 / int64 tensors (half the bytes); the public device tensors are widened back to f32 / int64 on
+        the GPU.  The bf16 tier rounds V and E to bf16 when it assembles its GEMM operands anyway, so its results
+        are bit-identical; the fp32 tier would see bf16-rounded features, hence opt-in."""
         self._size = len(mgs)
         self._layout = None
+        self._xfer = None
         n = len(mgs)
         n_atoms = np.fromiter((mg.V.shape[0] for mg in mgs), dtype=np.int64, count=n)
         n_edges = np.fromiter((mg.edge_index.shape[1] for mg in mgs), dtype=np.int64, count=n)
@@ -61,6 +67,19 @@ class BatchMolGraph:
             self.rev_edge_index.data_ptr(), self.batch.data_ptr(),
         )
         _lib.check(rc, "dmpnn_collate_host")
+        if transfer_dtype is not None:
+            if transfer_dtype != torch.bfloat16:
+                raise ValueError("transfer_dtype must be torch.bfloat16 or None")
+            if max(Vt, Et) >= 2 ** 31:
+                raise ValueError("batch too large for int32 transfer indices")
+
+            def stage(t, dt):
+                out = torch.empty(t.shape, dtype=dt, **kw)
+                out.copy_(t)
+                return out
+
+            self._xfer = (stage(self.V, torch.bfloat16), stage(self.E, torch.bfloat16), stage(self.edge_index, torch.int32),
+                          stage(self.rev_edge_index, torch.int32), stage(self.batch, torch.int32))
 
     @classmethod
     def from_tensors(cls, V: Tensor, E: Tensor, edge_index: Tensor, rev_edge_index: Tensor, batch: Tensor,
@@ -70,21 +89,37 @@ class BatchMolGraph:
         bmg.V, bmg.E, bmg.edge_index, bmg.rev_edge_index, bmg.batch = V, E, edge_index, rev_edge_index, batch
         bmg._size = int(size)
         bmg._layout = None
+        bmg._xfer = None
         return bmg
 
     def __len__(self) -> int:
         return self._size
+
+    def _moved(self, dev: torch.device, non_blocking: bool):
+        """The five public tensors on `dev` (through the compact staging copy when there is one)."""
+        if self._xfer is not None and dev.type == "cuda" and not self.V.is_cuda:
+            Vb, Eb, ei, rv, bt = (t.to(dev, non_blocking=non_blocking) for t in self._xfer)
+            return Vb.float(), Eb.float(), ei.long(), rv.long(), bt.long()
+        return tuple(t.to(dev, non_blocking=non_blocking)
+                     for t in (self.V, self.E, self.edge_index, self.rev_edge_index, self.batch))
+
+    def transfer_nbytes(self) -> int:
+        """Bytes a host -> device move of this batch copies."""
+        ts = self._xfer if self._xfer is not None else (self.V, self.E, self.edge_index, self.rev_edge_index, self.batch)
+        return sum(t.numel() * t.element_size() for t in ts)
 
     def to(self, device, non_blocking: bool = False):
         """In place, returns None (chemprop/data/collate.py:68-73)."""
         dev = torch.device(device)
         if self.V.device != dev:
             self._layout = None
-        self.V = self.V.to(dev, non_blocking=non_blocking)
-        self.E = self.E.to(dev, non_blocking=non_blocking)
-        self.edge_index = self.edge_index.to(dev, non_blocking=non_blocking)
-        self.rev_edge_index = self.rev_edge_index.to(dev, non_blocking=non_blocking)
-        self.batch = self.batch.to(dev, non_blocking=non_blocking)
+        self.V, self.E, self.edge_index, self.rev_edge_index, self.batch = self._moved(dev, non_blocking)
+        if dev.type == "cuda":
+            self._xfer = None
+
+    def cuda_copy(self, device="cuda", non_blocking: bool = True) -> "BatchMolGraph":
+        """A device-resident copy; this (pinned) host batch stays intact, e.g. for reuse by a loader."""
+        return BatchMolGraph.from_tensors(*self._moved(torch.device(device), non_blocking), self._size)
 
     def __copy__(self):
         # GraphTransform makes a shallow copy and replaces V / E (chemprop/nn/transforms.py:69-72);

@@ -16,6 +16,10 @@ from . import _lib
 from ._lib import (ACT_ELU, ACT_LEAKYRELU, ACT_NONE, ACT_RELU, ACT_TANH, BF16, F32, SCALE_DIV_CONST,
                    SCALE_INV_COUNT, SCALE_NONE, DmpnnError)
 
+# backward of the bf16 tier: True = the last mirror step sums the dZ^t into dH_0 in its epilogue (one W_i GEMM);
+# False = the terms stay apart and the W_i gradient accumulates one GEMM per term (measured faster at depth 3)
+SUM_IN_EPILOGUE = False
+
 HIDDEN_ALIGN = 64  # hidden row stride padded to 64 elements: bf16 rows start on 128-byte lines (one TMA request per box row)
 
 # Optional device-side timing of the depth step (bench.py's roofline): when a list, every depth step
@@ -269,9 +273,11 @@ def segment_sum(X: Tensor, ptr: Tensor, n_seg: int, Ccols: int, out: Tensor, *, 
 
 
 def segment_bcast(G: Tensor, seg_of_row: Tensor, ptr: Tensor | None, R: int, Ccols: int, out: Tensor, *,
-                  scale_mode: int = SCALE_NONE, scale: float = 1.0):
+                  scale_mode: int = SCALE_NONE, scale: float = 1.0, n_seg: int = 0):
+    """n_seg > 0: rows of segment s are [ptr[s], ptr[s+1]) -- walk segments instead of looking every row up."""
     lib = _lib.load()
-    rc = lib.dmpnn_segment_bcast(G.data_ptr(), _dt(G), _ld(G), seg_of_row.data_ptr(), _ptr(ptr), R, Ccols,
+    rc = lib.dmpnn_segment_bcast(G.data_ptr(), _dt(G), _ld(G), seg_of_row.data_ptr(), _ptr(ptr),
+                                 n_seg if ptr is not None else 0, R, Ccols,
                                  scale_mode, float(scale), out.data_ptr(), _dt(out), _ld(out), _stream())
     _lib.check(rc, "dmpnn_segment_bcast")
 
@@ -473,14 +479,17 @@ def _empty_hidden(rows: int, hp: int, dtype, dev) -> Tensor:
 
 
 def bond_step_bwd_fused(dZ: Tensor, Yact: Tensor | None, dOut: Tensor, h: int, WpkT: Tensor, lay: Layout, act: int,
-                        act_param: float, G_out: Tensor | None = None):
+                        act_param: float, G_out: Tensor | None = None, y_is_preact: bool = False,
+                        addends: tuple = ()):
     """dOut = (S.P)(dZ . W_h) [* tau'(Yact)] in one fused launch (WpkT = pack_weight_bf16(W_h.t()));
     G_out also receives (S.P) dZ, the left operand of this step's W_h gradient."""
     lib = _lib.load()
     rc = lib.dmpnn_bond_step_bwd_fused_bf16(
         dZ.data_ptr(), _ptr(Yact), dOut.data_ptr(), _ld(dZ), dZ.shape[0], h, WpkT.data_ptr(),
         lay.rowptr.data_ptr(), lay.rev_row.data_ptr(), lay.tile_row_ptr.data_ptr(), lay.tile_atom_ptr.data_ptr(),
-        lay.n_tiles, act, float(act_param), _ptr(G_out), _stream())
+        lay.n_tiles, act, float(act_param), 1 if y_is_preact else 0,
+        addends[0].data_ptr() if len(addends) > 0 else None, addends[1].data_ptr() if len(addends) > 1 else None,
+        _ptr(G_out), _stream())
     _lib.check(rc, "dmpnn_bond_step_bwd_fused_bf16")
 
 
@@ -541,7 +550,9 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
         XO = torch.empty((max(nV, 1), ko), dtype=T, device=dev)   # columns >= d_v+h are clipped by the TMA descriptor
         concat_bf16(V, d_v, XO, nV, width=d_v)
         Mv = XO[:, d_v:d_v + h]
-        segment_sum(Hprev, lay.rowptr, nV, h, Mv, act=(a if first else ACT_NONE), act_param=ap, pad_to=h)
+        hc = (h + 15) // 16 * 16       # zero columns up to pad16(h) when the row has room: 16-byte stores in the sum
+        segment_sum(Hprev, lay.rowptr, nV, h, Mv, act=(a if first else ACT_NONE), act_param=ap,
+                    pad_to=(hc if d_v + hc <= ko else h))
         Hvp = torch.empty((max(nV, 1), pad_hidden(h)), dtype=T, device=dev)
         linear_tc(XO, d_v + h, pack_weight_tc(Wo), h, Hvp, bias=bo, act=a, act_param=ap, R=nV)
         Hv = Hvp[:nV, :h]
@@ -690,7 +701,7 @@ def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
         WhT_pkf = pack_weight_bf16(Wh.t().contiguous()) if fused_bwd else None
         dZ = _empty_hidden(nE, hp, T, dev)
         act_bwd(dMv, Hs[-1], nE, hc, act=a, act_param=ap, gidx=lay.dst_row, dZ=dZ)    # dZ^{T-1}
-        dZs, dH_first = [dZ], None
+        dZs, dH_first, fused_sum, dH0_terms = [dZ], None, False, None
         for t in range(cfg.depth - 1, 0, -1):
             first = t == 1
             Hin = H0 if first else Hs[t - 2]
@@ -707,8 +718,19 @@ def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
                     bond_message(H0, lay, h, M1, act=a, act_param=ap)
                 if first:
                     wgrad_tc(dZ, M1, nE, h, h, dWh, accumulate=True)
-                    dH_first = _empty_hidden(nE, hp, T, dev)
-                    bond_step_bwd_fused(dZ, None, dH_first, h, WhT_pkf, lay, a, ap)
+                    if SUM_IN_EPILOGUE and len(dZs) <= 2:
+                        # last mirror step writes dH_0 itself: tau'(H_0) mask and the sum over the dZ^t in its epilogue
+                        bond_step_bwd_fused(dZ, H0, dH0b, h, WhT_pkf, lay, a, ap, y_is_preact=True, addends=tuple(dZs))
+                        fused_sum = True
+                    elif not SUM_IN_EPILOGUE:
+                        # dH_0 = sum_t dZ^t + dH^0 * tau'(H_0) is only ever contracted with X_0 (and summed for the
+                        # bias): keep the terms apart -- the last mirror step applies tau'(H_0) in its epilogue and
+                        # the W_i gradient accumulates one GEMM per term instead of a 5-stream summing pass
+                        bond_step_bwd_fused(dZ, H0, dH0b, h, WhT_pkf, lay, a, ap, y_is_preact=True)
+                        dH0_terms = dZs + [dH0b]
+                    else:
+                        dH_first = _empty_hidden(nE, hp, T, dev)
+                        bond_step_bwd_fused(dZ, None, dH_first, h, WhT_pkf, lay, a, ap)
                 else:
                     dZn = _empty_hidden(nE, hp, T, dev)
                     G = _empty_hidden(nE, hp, T, dev)
@@ -729,7 +751,14 @@ def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
                 dZ = _empty_hidden(nE, hp, T, dev)           # dZ^{t-1} = S.P(dM) * tau'(H^{t-1})
                 bond_message_bwd_masked(dM, Hin, lay, h, dZ, act=a, act_param=ap)
                 dZs.append(dZ)
-        sum_act_bwd(dZs, dH_first, H0, dH0b, nE, hc, act=a, act_param=ap)
+        if dH0_terms is not None:
+            for i, P in enumerate(dH0_terms):
+                wgrad_tc(P, saved["X0"], nE, h, d_v + d_e, dWi, accumulate=i > 0)
+                if dbi is not None:
+                    column_sum(P, nE, h, dbi, accumulate=i > 0)
+            return dWi, dbi, dWh, dbh, dWo, dbo
+        if not fused_sum:
+            sum_act_bwd(dZs, dH_first, H0, dH0b, nE, hc, act=a, act_param=ap)
     wgrad_tc(dH0b, saved["X0"], nE, h, d_v + d_e, dWi)
     if dbi is not None:
         column_sum(dH0b, nE, h, dbi)
@@ -901,5 +930,6 @@ class SegmentAggFunction(torch.autograd.Function):
     def backward(ctx, g):
         g = g.contiguous()
         dH = torch.empty((ctx.nV, g.shape[1]), dtype=g.dtype, device=g.device)
-        segment_bcast(g, ctx.atom_mol, ctx.ptr, ctx.nV, g.shape[1], dH, scale_mode=ctx.mode, scale=ctx.scale)
+        segment_bcast(g, ctx.atom_mol, ctx.ptr, ctx.nV, g.shape[1], dH, scale_mode=ctx.mode, scale=ctx.scale,
+                      n_seg=g.shape[0])
         return dH, None, None, None, None, None

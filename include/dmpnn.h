@@ -158,9 +158,12 @@ int dmpnn_segment_sum(const void* X, int x_dtype, int64_t ldx, const int32_t* id
                       void* Y, int y_dtype, int64_t ldy, int64_t ldy_pad, void* stream);
 
 /* Row broadcast (autograd mirror of segment_sum with identity f):
- * Y[r, 0:C] = scale(seg(r)) * G[seg_of_row[r], 0:C]; for SCALE_INV_COUNT, `ptr` gives counts. */
+ * Y[r, 0:C] = scale(seg(r)) * G[seg_of_row[r], 0:C]; for SCALE_INV_COUNT, `ptr` gives counts.
+ * n_seg > 0 (with ptr): the rows of segment s are exactly [ptr[s], ptr[s+1]) (the segment_sum convention,
+ * ptr[n_seg] == R); the kernel then walks segments -- one scaled row of G held in registers, streamed to its
+ * rows -- and never reads seg_of_row.  n_seg == 0: per-row lookup through seg_of_row. */
 int dmpnn_segment_bcast(const void* G, int g_dtype, int64_t ldg, const int32_t* seg_of_row,
-                        const int32_t* ptr, int64_t R, int64_t C, int scale_mode, float scale,
+                        const int32_t* ptr, int64_t n_seg, int64_t R, int64_t C, int scale_mode, float scale,
                         void* Y, int y_dtype, int64_t ldy, void* stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -239,13 +242,17 @@ int dmpnn_linear_tc_bf16(const void* A, int64_t lda, int64_t R, int64_t K, const
  *   dOut[e] = ( sum_{e'' : src(e'') = dst(e)} dM[e''] - dM[rev(e)] ) * tau'(Yact[e]),   dM = dZ . W_h
  * computed as ((S.P) dZ) . W_h with the row mixing done on the A operand; WpkT = dmpnn_pack_weight_bf16 of W_h^T.
  * Yact = the stored activation output H^{t-1} (tau' is evaluated from it); Yact == NULL -> no mask (dH^0).
+ * y_is_preact != 0: Yact holds the PRE-activation (H_0) and tau' is evaluated from it -- the t = 1 step; then
+ * add0 / add1 (nullable, bf16, same ld, 16-byte aligned, must not alias dOut) are summed into the output in f32
+ * before the single rounding, so that step writes dH_0 = dZ^{T-1} + .. + dZ^1 + dH^0 * tau'(H_0) directly.
  * G_out (nullable, bf16, same ld, 32-byte aligned, ld % 16 == 0): also writes the gathered operand G = (S.P) dZ, so
  * that the W_h gradient of this step is the plain GEMM dW_h += G^T . H^{t-1} (dZ^T . M^t == ((S.P) dZ)^T . H^{t-1}).
  * Same size / layout requirements as dmpnn_bond_step_fused_bf16. */
 int dmpnn_bond_step_bwd_fused_bf16(const void* dZ, const void* Yact, void* dOut, int64_t ld, int64_t n_rows_alloc,
                                    int64_t h, const void* WpkT, const int32_t* rowptr, const int32_t* rev_row,
                                    const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
-                                   int act, float act_param, void* G_out, void* stream);
+                                   int act, float act_param, int y_is_preact, const void* add0, const void* add1,
+                                   void* G_out, void* stream);
 
 /* Tensor-core weight gradient (bf16 operands, f32 accumulate, deterministic two-pass reduction):
  *   dW[n, 0:K] (+)= sum_r dY[r, n] * X[r, 0:K]      dY: R x N (ld lddy), X: R x K (ld ldx), both bf16 row-major

@@ -148,3 +148,39 @@ def test_fused_backward_step_vs_torch_reference(h, act, masked):
     assert torch.isfinite(out.float()).all()
     torch.testing.assert_close(out[:, :h].float(), G.bfloat16().float(), rtol=2 ** -6, atol=2e-2)
     assert hp == h or float(out[:, h:].float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("h,act,n_add", [(300, "relu", 2), (300, "relu", 1), (64, "tanh", 2), (200, "relu", 0)])
+def test_fused_backward_last_step_masks_from_preactivation_and_sums(h, act, n_add):
+    """t = 1 mirror step: dH_0 = ((S.P) dZ . W_h) * tau'(H_0) + addends, one rounding after the f32 sum."""
+    from chemprop_b200 import _lib
+    from chemprop_b200.engine import bond_step_bwd_fused, pack_weight_bf16
+
+    lay, H0, Hp, W, b, hp = _setup(900, h, seed=29 + h)
+    g = torch.Generator(device="cuda").manual_seed(7)
+
+    def rnd():
+        t = torch.zeros_like(H0)
+        t[:, :h] = torch.randn(lay.E, h, device="cuda", generator=g).bfloat16()
+        return t
+
+    dZ = rnd()
+    adds = [dZ, rnd()][:n_add]                      # the step's own input is one of the addends in the engine
+    out = torch.full_like(H0, float("nan"))
+    code = {"relu": _lib.ACT_RELU, "tanh": _lib.ACT_TANH}[act]
+    bond_step_bwd_fused(dZ, H0, out, h, pack_weight_bf16(W.t().contiguous()), lay, code, 0.0, y_is_preact=True,
+                        addends=tuple(adds))
+    torch.cuda.synchronize()
+    rev, dst = lay.rev_row.long(), lay.dst_row.long()
+    X = dZ[:, :h].float()[rev]
+    A = torch.zeros(lay.V, h, device="cuda").index_add_(0, dst, X)
+    G = (A[dst] - X).bfloat16().float() @ W.bfloat16().float()
+    z = H0[:, :h].float()
+    G = (G * ((z > 0).float() if act == "relu" else (1 - torch.tanh(z) ** 2))).bfloat16().float()   # staged in bf16
+    for a in adds:
+        G = G + a[:, :h].float()
+    torch.testing.assert_close(out[:, :h].float(), G.bfloat16().float(), rtol=2 ** -6, atol=6.5e-2)   # 2 ulp at |x| in [4, 8): cancelling terms
+    pad16 = (h + 15) // 16 * 16
+    assert pad16 == h or float(out[:, h:pad16].float().abs().max()) == 0.0
+    with pytest.raises(Exception):                  # addends are a property of the pre-activation (last) mode
+        bond_step_bwd_fused(dZ, Hp, out, h, pack_weight_bf16(W.t().contiguous()), lay, code, 0.0, addends=(dZ,))

@@ -55,3 +55,28 @@ def test_predictions_stay_same_across_calls_and_layout_cache():
         a = MeanAggregation()(mp(bmg), bmg.batch)
         b = MeanAggregation()(mp(bmg), bmg.batch)
     assert torch.equal(a, b)            # deterministic kernels: bitwise reproducible
+
+
+def test_compact_transfer_is_bit_identical_for_the_bf16_tier():
+    """Shipping bf16 features / int32 indices over PCIe (BatchMolGraph(transfer_dtype=bfloat16)) changes nothing
+    for the bf16 tier: it rounds V and E to bf16 when it assembles the GEMM operands anyway."""
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.nn import BondMessagePassing, MeanAggregation
+
+    mgs = make_molecules(300, seed=11)
+    torch.manual_seed(0)
+    mp = BondMessagePassing(d_h=300, depth=3, precision="bf16").cuda()
+    agg = MeanAggregation()
+    outs = []
+    for kw in ({}, {"transfer_dtype": torch.bfloat16}):
+        host = BatchMolGraph(mgs, pin_memory=True, **kw)
+        bmg = host.cuda_copy("cuda")
+        assert bmg.V.dtype == torch.float32 and bmg.edge_index.dtype == torch.int64 and host.V.device.type == "cpu"
+        for p in mp.parameters():
+            p.grad = None
+        out = agg(mp(bmg), bmg.batch)
+        out.float().square().mean().backward()
+        outs.append((out.detach().float().clone(), [p.grad.clone() for p in mp.parameters()]))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for g0, g1 in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(g0, g1)

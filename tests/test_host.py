@@ -75,3 +75,19 @@ def test_collate_batch_contract():
     assert isinstance(tb.bmg, BatchMolGraph) and tb.V_d.shape == (tb.bmg.V.shape[0], 2)
     assert tb.X_d.shape == (2, 2) and tb.Y.shape == (2, 1) and tb.w.tolist() == [[2.0], [2.0]]
     assert tb.lt_mask.dtype == torch.bool
+
+
+def test_compact_transfer_staging_is_the_rounded_batch():
+    """transfer_dtype=bfloat16 stages bf16 features / int32 indices next to the public f32 / int64 view."""
+    mgs = make_molecules(40, seed=3)
+    plain, compact = BatchMolGraph(mgs), BatchMolGraph(mgs, transfer_dtype=torch.bfloat16)
+    assert compact.V.dtype == torch.float32 and compact.edge_index.dtype == torch.int64      # public view unchanged
+    assert torch.equal(compact.V, plain.V) and torch.equal(compact.edge_index, plain.edge_index)
+    Vb, Eb, ei, rv, bt = compact._xfer
+    assert (Vb.dtype, Eb.dtype, ei.dtype, rv.dtype, bt.dtype) == (torch.bfloat16, torch.bfloat16, torch.int32, torch.int32, torch.int32)
+    assert torch.equal(Vb, plain.V.bfloat16()) and torch.equal(Eb, plain.E.bfloat16())
+    assert torch.equal(ei.long(), plain.edge_index) and torch.equal(rv.long(), plain.rev_edge_index)
+    assert torch.equal(bt.long(), plain.batch)
+    assert compact.transfer_nbytes() * 2 == plain.transfer_nbytes()
+    with pytest.raises(ValueError):
+        BatchMolGraph(mgs, transfer_dtype=torch.float16)

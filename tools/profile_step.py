@@ -7,6 +7,9 @@ from chemprop_b200.data import BatchMolGraph, make_molecules
 from chemprop_b200.nn import BondMessagePassing, MeanAggregation
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+if len(sys.argv) > 2:
+    import chemprop_b200.engine as _eng
+    _eng.SUM_IN_EPILOGUE = bool(int(sys.argv[2]))
 steps = 5
 dev = torch.device("cuda")
 torch.manual_seed(0)
@@ -31,10 +34,13 @@ span0, span1 = None, None
 for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:
         k = ev.name.split("(")[0].replace("void ", "")[:80]
-        a = agg_t.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+        a = agg_t.setdefault(k, [0, 0.0, []]); a[0] += 1; a[1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+        a[2].append(ev.device_time if hasattr(ev, "device_time") else ev.cuda_time)
         t0 = ev.time_range.start; t1 = ev.time_range.end
         span0 = t0 if span0 is None else min(span0, t0); span1 = t1 if span1 is None else max(span1, t1)
 tot = sum(v[1] for v in agg_t.values())
 print(f"{steps} steps: kernel-time sum {tot/steps:.0f} us/step; device span {(span1-span0)/steps:.0f} us/step")
-for k, (c, v) in sorted(agg_t.items(), key=lambda kv: -kv[1][1]):
-    print(f"{100*v/tot:5.1f}%  {v/steps:8.1f} us/step  {c/steps:5.1f}/step  {k}")
+for k, (c, v, ds) in sorted(agg_t.items(), key=lambda kv: -kv[1][1]):
+    per = c // steps
+    each = " [" + " ".join(f"{d:.0f}" for d in ds[-per:]) + "]" if 1 < per <= 6 else ""
+    print(f"{100*v/tot:5.1f}%  {v/steps:8.1f} us/step  {c/steps:5.1f}/step  {k}{each}")
