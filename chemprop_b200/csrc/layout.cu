@@ -219,18 +219,29 @@ __global__ void k_tiles_chunk(const int32_t* __restrict__ mol_atom_ptr, const in
     s_rw[i] = mol_row_ptr[base + i];
   }
   __syncthreads();
+  // nxt[t0] = first molecule that no longer fits a tile opened at t0 (the greedy rule's closing index): both limits
+  // are monotone in the closing index, so each thread finds it by bisection; thread 0 then only follows the chain.
+  __shared__ int32_t s_nxt[kTileChunk];
+  for (int t0 = threadIdx.x; t0 < n; t0 += blockDim.x) {
+    const int32_t rlim = s_rw[t0] + kTileRows, alim = s_at[t0] + kTileAtoms;
+    int lo = t0 + 1, hi = n;               // smallest i in [t0+1, n) with s_rw[i+1] > rlim or s_at[i+1] > alim, else n
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_rw[mid + 1] > rlim || s_at[mid + 1] > alim) hi = mid; else lo = mid + 1;
+    }
+    s_nxt[t0] = lo;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     int32_t* out = seg_tiles + (int64_t)blockIdx.x * kTileChunk;
-    int cnt = 0, t0 = 0, max_rows = 0, max_atoms = 0;
-    for (int i = 1; i <= n; ++i) {
-      // close the open tile [t0, i) if molecule i does not fit any more (or the chunk ends)
-      if (i == n || s_rw[i + 1] - s_rw[t0] > kTileRows || s_at[i + 1] - s_at[t0] > kTileAtoms) {
-        out[cnt++] = (int32_t)(base + t0);
-        const int rows = s_rw[i] - s_rw[t0], atoms = s_at[i] - s_at[t0];
-        max_rows = rows > max_rows ? rows : max_rows;
-        max_atoms = atoms > max_atoms ? atoms : max_atoms;
-        t0 = i;
-      }
+    int cnt = 0, max_rows = 0, max_atoms = 0;
+    for (int t0 = 0; t0 < n;) {
+      const int i = s_nxt[t0];
+      out[cnt++] = (int32_t)(base + t0);
+      const int rows = s_rw[i] - s_rw[t0], atoms = s_at[i] - s_at[t0];
+      max_rows = rows > max_rows ? rows : max_rows;
+      max_atoms = atoms > max_atoms ? atoms : max_atoms;
+      t0 = i;
     }
     seg_info[blockIdx.x * 4 + 0] = cnt;
     seg_info[blockIdx.x * 4 + 1] = max_rows;
