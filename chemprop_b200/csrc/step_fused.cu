@@ -34,9 +34,14 @@ constexpr int kMaxSlabs = 5;                    // hp <= 320
 constexpr int kABufBytes = kMaxSlabs * kSlabBytes;
 constexpr int kChunkN = 80;                     // W stage / accumulator chunk = 80 output features (5 x 16)
 constexpr int kMaxChunks = 4;
-constexpr int kWHalfSlabs = 3;                 // a W stage = an 80-column chunk x up to 3 k slabs (k halves {0,1,2} | {3,4})
+// A W stage = an 80-column chunk x up to kWHalfSlabs k slabs; the A tile is handed over in k passes of that many slabs.
+// 3 slabs (passes {0,1,2} | {3,4}, 12 + 7 MMAs per stage, 2 stages of 30 KB) measured 211 us per step at the bench
+// size; 2 slabs (three passes, 3 stages of 20 KB, 8 MMAs per stage) 256 us: the per-stage barrier round trip is not
+// amortised by 8 MMAs.
+constexpr int kWHalfSlabs = 3;
+constexpr int kMaxPasses = (kMaxSlabs + kWHalfSlabs - 1) / kWHalfSlabs;   // 2
 constexpr int kWStageBytes = kWHalfSlabs * kChunkN * 128;   // 30 KB
-constexpr int kWStages = 2;                    // 100 KB in flight; 19 MMAs per stage amortise the per-stage barrier round trip
+constexpr int kWStages = 2;
 constexpr int kHStages = 4;                     // H_0 / output staging slabs (16 KB each): two per epilogue group
 constexpr int kThreads = 640;
 constexpr int kSWarps = 8;          // message warps (12..19)
@@ -83,7 +88,8 @@ static_assert(kSmemAlloc <= 232448, "exceeds the 227 KB per-CTA shared memory li
 
 enum {
   B_AFULL = 0, B_AFREE = B_AFULL + kMaxSlabs,        // the H tile is handed over slab by slab (64 columns)
-  B_AREADY = B_AFREE + kMaxSlabs, B_ATFREE = B_AREADY + 2, B_ACCFULL = B_ATFREE + 2, B_ACCFREE = B_ACCFULL + 4,
+  B_AREADY = B_AFREE + kMaxSlabs, B_ATFREE = B_AREADY + kMaxPasses, B_ACCFULL = B_ATFREE + kMaxPasses,
+  B_ACCFREE = B_ACCFULL + 4,
   B_HFULL = B_ACCFREE + 4, B_HFREE = B_HFULL + 4, B_WFULL = B_HFREE + 4, B_WFREE = B_WFULL + kWStages
 };
 static_assert(B_WFREE + kWStages <= kNumBars, "barrier table too small");
@@ -183,7 +189,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       mbar_init(bar(B_AFULL + i), 1);
       mbar_init(bar(B_AFREE + i), kSWarps * 32);  // every message thread is done reading this slab of the tile
     }
-    for (int i = 0; i < 2; ++i) {               // the TMEM A tile is handed over in two k halves (slabs {0,1,2} | {3,4})
+    for (int i = 0; i < kMaxPasses; ++i) {      // the TMEM A tile is handed over k pass by k pass (slabs {0,1} | {2,3} | {4})
       mbar_init(bar(B_AREADY + i), kSWarps * 32);   // message threads have written this k half of their row
       mbar_init(bar(B_ATFREE + i), 1);              // tensor core finished reading this k half
     }
@@ -560,17 +566,18 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       }
       int cur_slab = -1;                              // slab whose AFULL this thread has waited for
       uint32_t left = (1u << p.nslab) - 1u;           // slabs this thread still has to release
-      const int jsplit = min(nj, kWHalfSlabs * 4);   // 16-column blocks of the first k half (slabs 0..2)
-      mbar_wait(bar(B_ATFREE + 0), (it & 1) ^ 1);    // tensor core is done with the first k half of the previous tile
+      const int npass = (p.nslab + kWHalfSlabs - 1) / kWHalfSlabs;
+      int cur_pass = 0;                               // k pass being written; earlier ones are published by this thread
+      mbar_wait(bar(B_ATFREE + 0), (it & 1) ^ 1);    // tensor core is done with the first k pass of the previous tile
       tc_fence_after();
-      bool crossed = false;
       for (int j = shalf; j < nj; j += 2) {
-        if (j >= jsplit && j - 2 < jsplit) {         // crossing into the second k half: publish the first, wait for the second
-          crossed = true;
+        const int pj = (j >> 2) / kWHalfSlabs;
+        if (pj != cur_pass) {                        // crossing into a later k pass: publish the finished ones, wait for the next
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(bar(B_AREADY + 0));
-          mbar_wait(bar(B_ATFREE + 1), (it & 1) ^ 1);
+          for (int q = cur_pass; q < pj; ++q) mbar_arrive(bar(B_AREADY + q));
+          cur_pass = pj;
+          mbar_wait(bar(B_ATFREE + pj), (it & 1) ^ 1);
           tc_fence_after();
         }
         if ((j >> 2) != cur_slab) {                   // entering a new 64-column slab of the H tile
@@ -633,12 +640,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         if (left & (1u << sl)) mbar_arrive(bar(B_AFREE + sl));
       tmem_wait_st();
       tc_fence_before();
-      if (nj <= jsplit) {                // single k half (small h): nothing was published inside the loop
-        mbar_arrive(bar(B_AREADY + 0));
-      } else {
-        if (!crossed) mbar_arrive(bar(B_AREADY + 0));   // this thread owned no block of the second half
-        mbar_arrive(bar(B_AREADY + 1));  // second k half complete (all 256 message threads arrive)
-      }
+      for (int q = cur_pass; q < npass; ++q) mbar_arrive(bar(B_AREADY + q));   // every thread arrives once per pass
       if (tS == 0) trace_ev(p, it, 2);
       // publish the next tile's rowptr slice (other buffer; readers of it finished a tile ago)
       if (tn < p.n_tiles && tS <= natomsn) s_rowptr[(b ^ 1) * 132 + tS] = rpn;

@@ -1,5 +1,5 @@
 """Turn the ncu artefacts in gpurun_out/ into the committed summaries under profiles/."""
-import collections, csv, io, os, subprocess, sys
+import collections, csv, io, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles"); os.makedirs(OUT, exist_ok=True)
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
@@ -59,9 +59,33 @@ def full(rep, md_path, title, extra=""):
 
 g = os.path.join(ROOT, "gpurun_out")
 launches(os.path.join(g, f"launches_{tag}b.csv"), os.path.join(OUT, f"{tag}_launches.md"),
-         "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 140 -c 140 --csv python bench.py --steps 2 --warmup 3 --no-cpu` "
-         "(bf16 tier, 10 k molecules; the window covers about one and a half fwd+bwd steps).")
+         "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 170 -c 140 --csv python bench.py --steps 2 --warmup 3 --no-cpu` "
+         "(bf16 tier, 10 k molecules; the window covers about two fwd+bwd steps).")
 full(os.path.join(g, f"prof_fused_{tag}.ncu-rep"), os.path.join(OUT, f"{tag}_fused_step_ncu.md"), f"Fused depth-step kernel ({tag})",
-     " First launch = first depth step (`FIRST`, reads H_0 only), second = a t>=2 step. Algorithmic bytes of the t>=2 step at this size: 910.6 MB.")
+     " Template arguments <ACT, FIRST, HAS_BIAS, MODE>: launches in order = forward first step (`FIRST`, reads H_0 only, also stores M^1), "
+     "forward t>=2 step (the roofline kernel; algorithmic bytes at this size: 910.6 MB), backward mirror step with tau' mask + G output "
+     "(MODE 1), last backward mirror step with the tau'(H_0) mask (MODE 3).")
 full(os.path.join(g, f"prof_gemm_{tag}.ncu-rep"), os.path.join(OUT, f"{tag}_gemm_ncu.md"), f"tcgen05 linear / weight-gradient kernels ({tag})")
+
+# DRAM traffic of the forward t>=2 launch -> profiles/fused_step_traffic.json (bench.py reports it as roofline.traffic)
+import json
+raw = subprocess.run(["ncu", "-i", os.path.join(g, f"prof_fused_{tag}.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw))); hdr = rows[0]
+def num(r, name):
+    i = hdr.index(name); v = float(r[i].replace(",", "")); u = rows[1][i]
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+for r in rows[2:]:
+    name = r[hdr.index("Kernel Name")]
+    m = re.search(r"k_bond_step_fused<([^>]*)>", name)
+    targs = [int(re.sub(r"[^0-9]", "", a.replace("true", "1").replace("false", "0")) or 0) for a in m.group(1).split(",")] if m else []
+    if len(targs) == 4 and targs[1] == 0 and targs[3] == 0:      # <ACT, FIRST=0, HAS_BIAS, MODE=0>: forward, t >= 2
+        rd, wr = num(r, "dram__bytes_read.sum"), num(r, "dram__bytes_write.sum")
+        json.dump({"kernel": "k_bond_step_fused<RELU, t>=2, forward>", "directed_edges": 502000, "atoms": 249437, "precision": "bf16",
+                   "dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "dram_bytes_per_launch": int(rd + wr),
+                   "algorithmic_bytes": 910621748, "source": f"profiles/{tag}_fused_step_ncu.md (ncu --set full, one launch)"},
+                  open(os.path.join(OUT, "fused_step_traffic.json"), "w"), indent=1)
+        print("traffic:", rd + wr)
+        break
+else:
+    print("WARNING: forward t>=2 launch not found in the fused report; kernels:", [r[hdr.index("Kernel Name")][:80] for r in rows[2:]])
 print(open(os.path.join(OUT, f"{tag}_launches.md")).read()[:2500])
