@@ -49,7 +49,7 @@ SIGNATURES = {
     "dmpnn_concat_bf16": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _i32, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "dmpnn_pack_weight_tc_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
     "dmpnn_pack_weight_tc": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp]),
-    "dmpnn_linear_tc_bf16": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i32, _f32, _vp, _i64, _vp]),
+    "dmpnn_linear_tc_bf16": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _f32, _vp, _i64, _vp]),
     "dmpnn_wgrad_tc_workspace_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
     "dmpnn_wgrad_tc_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _vp, _vp]),
     "dmpnn_column_sum": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _vp, _i32, _vp, _vp]),

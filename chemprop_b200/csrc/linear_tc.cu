@@ -50,6 +50,8 @@ enum { B_FULL = 0, B_EMPTY = 4, B_ACCFULL = 8, B_ACCFREE = 9 };
 struct Params {
   const uint8_t* Wpk;
   const float* bias;
+  const __nv_bfloat16* res;   // optional residual rows (bf16, row stride ldres), added before the activation
+  int64_t ldres;
   int64_t R;
   int K, N, Npad, nslab, ksteps_last, n_tiles;
   float act_param;
@@ -162,11 +164,22 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ C
           const int j = 4 * s + jj;
           uint32_t v[16];
           tmem_ld16(taddr + j * 16, v);
+          // residual (base.py:138, H_0 + W_h M): the thread's own output row, one 32-byte sector per 16 columns
+          uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+          if (p.res != nullptr) {
+            const int64_t grow = (int64_t)t * kTileM + et;
+            if (grow < p.R) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.res + grow * p.ldres + j * 16);
+              r0 = __ldg(rp);
+              r1 = __ldg(rp + 1);
+            }
+          }
           tmem_wait_ld();
+          const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
           uint32_t o[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            float z0 = __uint_as_float(v[2 * q]), z1 = __uint_as_float(v[2 * q + 1]);
+            float z0 = __uint_as_float(v[2 * q]) + bf_lo(rw[q]), z1 = __uint_as_float(v[2 * q + 1]) + bf_hi(rw[q]);
             if constexpr (HAS_BIAS) { z0 += s_bias[j * 16 + 2 * q]; z1 += s_bias[j * 16 + 2 * q + 1]; }
             if constexpr (ACT == DMPNN_ACT_RELU) o[q] = act_word<ACT>(pack_bf2(z0, z1), 0.f);
             else o[q] = pack_bf2(act_t<ACT>(p.act_param, z0), act_t<ACT>(p.act_param, z1));
@@ -287,8 +300,8 @@ extern "C" int dmpnn_pack_weight_tc(const float* W, int64_t ldw, int64_t N, int6
 }
 
 extern "C" int dmpnn_linear_tc_bf16(const void* A, int64_t lda, int64_t R, int64_t K, const void* Wpk, int64_t N,
-                                    const float* bias, int act, float act_param, void* Cout, int64_t ldc,
-                                    void* stream_) {
+                                    const float* bias, const void* res, int64_t ldres, int act, float act_param,
+                                    void* Cout, int64_t ldc, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   DMPNN_CHECK_ARG(R >= 0 && K > 0 && K <= kMaxK && N > 0 && N <= kMaxN, "linear_tc: unsupported sizes K=%lld N=%lld",
                   (long long)K, (long long)N);
@@ -299,6 +312,8 @@ extern "C" int dmpnn_linear_tc_bf16(const void* A, int64_t lda, int64_t R, int64
   DMPNN_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(Cout) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(Wpk) & 15) == 0, "linear_tc: buffers must be 16-byte aligned");
   DMPNN_CHECK_ARG(act >= DMPNN_ACT_NONE && act <= DMPNN_ACT_ELU, "linear_tc: bad activation %d", act);
+  DMPNN_CHECK_ARG(res == nullptr || (ldres >= g.Npad && ldres % 8 == 0 && (reinterpret_cast<uintptr_t>(res) & 15) == 0 && res != Cout),
+                  "linear_tc: residual needs ldres >= %d, a multiple of 8, 16-byte alignment, and may not alias C", g.Npad);
   EncodeTiledFn enc = get_encode_fn();
   DMPNN_CHECK_ARG(enc != nullptr, "linear_tc: cuTensorMapEncodeTiled not available from the driver");
   CUtensorMap mA, mC;
@@ -308,6 +323,8 @@ extern "C" int dmpnn_linear_tc_bf16(const void* A, int64_t lda, int64_t R, int64
   Params p;
   p.Wpk = (const uint8_t*)Wpk;
   p.bias = bias;
+  p.res = (const __nv_bfloat16*)res;
+  p.ldres = ldres;
   p.R = R;
   p.K = (int)K;
   p.N = (int)N;

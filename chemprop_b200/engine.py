@@ -380,11 +380,13 @@ def pack_weight_tc(W: Tensor, transpose: bool = False) -> Tensor:
 
 
 def linear_tc(A: Tensor, K: int, Wpk: Tensor, N: int, out: Tensor, *, bias: Tensor | None = None,
-              act: int = ACT_NONE, act_param: float = 0.0, R: int | None = None):
+              res: Tensor | None = None, act: int = ACT_NONE, act_param: float = 0.0, R: int | None = None):
+    """out = act(A[:, :K] . W^T + bias + res) on the tensor cores (bf16 operands, f32 accumulate)."""
     lib = _lib.load()
     R = out.shape[0] if R is None else R
-    assert A.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
-    rc = lib.dmpnn_linear_tc_bf16(A.data_ptr(), _ld(A), R, K, Wpk.data_ptr(), N, _ptr(bias), act, float(act_param),
+    assert A.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and (res is None or res.dtype == torch.bfloat16)
+    rc = lib.dmpnn_linear_tc_bf16(A.data_ptr(), _ld(A), R, K, Wpk.data_ptr(), N, _ptr(bias), _ptr(res),
+                                  _ld(res) if res is not None else 0, act, float(act_param),
                                   out.data_ptr(), _ld(out), _stream())
     _lib.check(rc, "dmpnn_linear_tc_bf16")
 
@@ -879,6 +881,113 @@ def atom_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo:
     return dWi, dbi, dWh, dbh, dWo, dbo
 
 
+def _atom_tc_ok(cfg: MPConfig, h: int, d_v: int, d_e: int) -> bool:
+    return _tc_ok(cfg, h, d_v, h + d_e, d_v + h) and h % 4 == 0
+
+
+def atom_forward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, bh, Wo: Tensor, bo, cfg: MPConfig):
+    """bf16 tier of atom_forward on the tensor cores: every GEMM is dmpnn_linear_tc_bf16 (the H_0 residual of
+    base.py:138 is added in its epilogue), the neighbour sums write straight into the GEMM's A operand."""
+    dev = V.device
+    h = Wi.shape[0]
+    hp = pad_hidden(h)
+    hc = (h + 15) // 16 * 16
+    d_v, d_e = V.shape[1], E.shape[1]
+    T = cfg.hidden_dtype
+    nV = lay.V
+    a, ap = cfg.act, cfg.act_param
+    rows = max(nV, 1)
+    kv = (d_v + 15) // 16 * 16
+    Xv = torch.empty((rows, kv), dtype=T, device=dev)
+    concat_bf16(V, d_v, Xv, nV, width=kv)
+    H0 = _empty_hidden(nV, hp, T, dev)
+    linear_tc(Xv, d_v, pack_weight_tc(Wi), h, H0, bias=bi, R=nV)                              # mixins.py:22-23
+    SE = None
+    if d_e > 0:                                                                               # loop-invariant bond term
+        SE = torch.zeros((rows, d_e), dtype=torch.float32, device=dev)
+        segment_sum(E, lay.rowptr, nV, d_e, SE, idx=lay.perm)
+    ka = (h + d_e + 15) // 16 * 16
+    Whpk = pack_weight_tc(Wh) if cfg.depth > 1 else None
+    Hs, XAs = [], []
+    Hprev, first = H0, True
+    for _ in range(1, cfg.depth):
+        XA = torch.empty((rows, ka), dtype=T, device=dev)   # [sum_{u in N(v)} Ha[u] || sum_in E]   (mixins.py:25-30)
+        segment_sum(Hprev, lay.rowptr, nV, h, XA[:, :h], idx=lay.src_row, act=(a if first else ACT_NONE), act_param=ap,
+                    pad_to=h)
+        if d_e > 0:
+            concat_bf16(SE, d_e, XA[:, h:], nV, width=d_e)
+        Hn = _empty_hidden(nV, hp, T, dev)
+        linear_tc(XA, h + d_e, Whpk, h, Hn, bias=bh, res=H0, act=a, act_param=ap, R=nV)       # base.py:135-141
+        Hs.append(Hn)
+        XAs.append(XA)
+        Hprev, first = Hn, False
+    ko = (d_v + h + 15) // 16 * 16
+    XO = torch.empty((rows, ko), dtype=T, device=dev)
+    concat_bf16(V, d_v, XO, nV, width=d_v)
+    segment_sum(Hprev, lay.rowptr, nV, h, XO[:, d_v:d_v + h], idx=lay.src_row, act=(a if first else ACT_NONE),
+                act_param=ap, pad_to=(hc if d_v + hc <= ko else h))                           # base.py:208-211
+    Hvp = torch.empty((rows, hp), dtype=T, device=dev)
+    linear_tc(XO, d_v + h, pack_weight_tc(Wo), h, Hvp, bias=bo, act=a, act_param=ap, R=nV)    # base.py:180-182
+    Hv = Hvp[:nV, :h]
+    return Hv, dict(H0=H0, Hs=Hs, XAs=XAs, XO=XO, Xv=Xv, Hv=Hv, tc=True)
+
+
+def atom_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo: Tensor, cfg: MPConfig,
+                     saved: dict, gHv: Tensor, need_bias):
+    """Autograd mirror of atom_forward_tc (tcgen05 GEMMs; dH_0 is kept as separate terms, one W_i GEMM each)."""
+    dev = V.device
+    h = Wi.shape[0]
+    hp = pad_hidden(h)
+    hc = (h + 15) // 16 * 16
+    d_v, d_e = V.shape[1], E.shape[1]
+    T = cfg.hidden_dtype
+    nV = lay.V
+    a, ap = cfg.act, cfg.act_param
+    H0, Hs, XAs, XO, Xv, Hv = saved["H0"], saved["Hs"], saved["XAs"], saved["XO"], saved["Xv"], saved["Hv"]
+    f32 = dict(dtype=torch.float32, device=dev)
+    dWi = torch.zeros_like(Wi, dtype=torch.float32)
+    dWh = torch.zeros_like(Wh, dtype=torch.float32)
+    dWo = torch.zeros_like(Wo, dtype=torch.float32)
+    dbi = torch.zeros(h, **f32) if need_bias[0] else None
+    dbh = torch.zeros(h, **f32) if need_bias[1] else None
+    dbo = torch.zeros(h, **f32) if need_bias[2] else None
+    if nV == 0:
+        return dWi, dbi, dWh, dbh, dWo, dbo
+    if gHv.stride(1) != 1:
+        gHv = gHv.contiguous()
+    dY = _empty_hidden(nV, hp, T, dev)
+    act_bwd(gHv, Hv, nV, h, act=a, act_param=ap, dZ=dY)
+    wgrad_tc(dY, XO, nV, h, d_v + h, dWo)
+    if dbo is not None:
+        column_sum(dY, nV, h, dbo)
+    dMv = _empty_hidden(nV, hp, T, dev)
+    linear_tc(dY, h, pack_weight_tc(Wo[:, d_v:], transpose=True), h, dMv, R=nV)
+    # d(Ha^{T-1})[u] = sum_{e' in in(u)} dM_v[src(e')]   (rev is an involution)
+    dHa = _empty_hidden(nV, hp, T, dev)
+    segment_sum(dMv, lay.rowptr, nV, h, dHa, idx=lay.src_row, pad_to=hc)
+    WhT_pk = pack_weight_tc(Wh[:, :h], transpose=True) if cfg.depth > 1 else None
+    terms = []
+    for t in range(cfg.depth - 1, 0, -1):
+        dZ = _empty_hidden(nV, hp, T, dev)
+        act_bwd(dHa, Hs[t - 1], nV, hc, act=a, act_param=ap, dZ=dZ)
+        terms.append(dZ)
+        wgrad_tc(dZ, XAs[t - 1], nV, h, h + d_e, dWh, accumulate=True)
+        if dbh is not None:
+            column_sum(dZ, nV, h, dbh, accumulate=True)
+        dN = _empty_hidden(nV, hp, T, dev)
+        linear_tc(dZ, h, WhT_pk, h, dN, R=nV)
+        dHa = _empty_hidden(nV, hp, T, dev)
+        segment_sum(dN, lay.rowptr, nV, h, dHa, idx=lay.src_row, pad_to=hc)
+    dH0l = _empty_hidden(nV, hp, T, dev)
+    act_bwd(dHa, H0, nV, hc, act=a, act_param=ap, from_preact=True, dZ=dH0l)
+    terms.append(dH0l)
+    for i, P in enumerate(terms):           # dH_0 = sum_t dZ^t + dHa^0 * tau'(H_0), contracted term by term
+        wgrad_tc(P, Xv, nV, h, d_v, dWi, accumulate=i > 0)
+        if dbi is not None:
+            column_sum(P, nV, h, dbi, accumulate=i > 0)
+    return dWi, dbi, dWh, dbh, dWo, dbo
+
+
 class AtomMPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, V, E, Wi, bi, Wh, bh, Wo, bo, lay, cfg):
@@ -889,7 +998,8 @@ class AtomMPFunction(torch.autograd.Function):
         bi_ = None if bi is None else bi.detach().contiguous().float()
         bh_ = None if bh is None else bh.detach().contiguous().float()
         bo_ = None if bo is None else bo.detach().contiguous().float()
-        Hv, saved = atom_forward(lay, V, E, Wi_, bi_, Wh_, bh_, Wo_, bo_, cfg)
+        fwd = atom_forward_tc if (_atom_tc_ok(cfg, Wi_.shape[0], V.shape[1], E.shape[1]) and lay.V > 0) else atom_forward
+        Hv, saved = fwd(lay, V, E, Wi_, bi_, Wh_, bh_, Wo_, bo_, cfg)
         ctx.lay, ctx.cfg, ctx.saved = lay, cfg, saved
         ctx.VE = (V, E)
         ctx.W = (Wi_, Wh_, Wo_)
@@ -901,7 +1011,8 @@ class AtomMPFunction(torch.autograd.Function):
     def backward(ctx, gHv):
         V, E = ctx.VE
         Wi, Wh, Wo = ctx.W
-        dWi, dbi, dWh, dbh, dWo, dbo = atom_backward(ctx.lay, V, E, Wi, Wh, Wo, ctx.cfg, ctx.saved, gHv, ctx.has_bias)
+        bwd = atom_backward_tc if ctx.saved.get("tc") else atom_backward
+        dWi, dbi, dWh, dbh, dWo, dbo = bwd(ctx.lay, V, E, Wi, Wh, Wo, ctx.cfg, ctx.saved, gHv, ctx.has_bias)
         ctx.saved = None
         d0, d1, d2 = ctx.wdtypes
         cast = lambda g, d: None if g is None else g.to(d)

@@ -227,7 +227,8 @@ int dmpnn_act_bwd(const void* G, int g_dtype, int64_t ldg, const int32_t* gidx,
  *   dmpnn_concat_bf16     A[r] = bf16([X1[i1(r)] || X2[i2(r)] || 0..])  (torch.cat of mixins.py:9 / base.py:180)
  *   dmpnn_pack_weight_tc  nn.Linear weight (or its transpose: transpose != 0 packs B[n][k] = W[k][n]) ->
  *                         per-k-slab shared-memory images
- *   dmpnn_linear_tc_bf16  C[r, 0:N] = act(A[r, 0:K] . B^T + bias); A, C bf16 row-major, lda/ldc % 8 == 0,
+ *   dmpnn_linear_tc_bf16  C[r, 0:N] = act(A[r, 0:K] . B^T + bias + res[r, 0:N]); A, C, res (nullable; the H_0
+ *                         residual of base.py:138, ldres % 8 == 0) bf16 row-major, lda/ldc % 8 == 0,
  *                         ldc >= pad16(N), K <= 384, N <= 304; C columns [N, pad16(N)) are written as zeros.
  * ------------------------------------------------------------------------------------- */
 int dmpnn_concat_bf16(const void* X1, int x1_dtype, int64_t ld1, const int32_t* idx1, int64_t K1,
@@ -236,7 +237,8 @@ int dmpnn_concat_bf16(const void* X1, int x1_dtype, int64_t ld1, const int32_t* 
 int dmpnn_pack_weight_tc_bytes(int64_t N, int64_t K, size_t* bytes);
 int dmpnn_pack_weight_tc(const float* W, int64_t ldw, int64_t N, int64_t K, int transpose, void* Wpk, void* stream);
 int dmpnn_linear_tc_bf16(const void* A, int64_t lda, int64_t R, int64_t K, const void* Wpk, int64_t N,
-                         const float* bias, int act, float act_param, void* C, int64_t ldc, void* stream);
+                         const float* bias, const void* res, int64_t ldres, int act, float act_param,
+                         void* C, int64_t ldc, void* stream);
 
 /* Autograd mirror of one depth step on the same fused kernel (gather-by-rev mode):
  *   dOut[e] = ( sum_{e'' : src(e'') = dst(e)} dM[e''] - dM[rev(e)] ) * tau'(Yact[e]),   dM = dZ . W_h

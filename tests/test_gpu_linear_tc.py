@@ -102,3 +102,30 @@ def test_column_sum():
     out = torch.zeros(300, device="cuda")
     column_sum(Y, 70001, 300, out)
     torch.testing.assert_close(out, Y[:, :300].float().sum(0), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("R,K,N,act", [(3000, 314, 300, "relu"), (130, 142, 128, "tanh"), (5000, 64, 64, "none")])
+def test_linear_tc_residual(R, K, N, act):
+    """C = act(A . W^T + b + res): the H_0 residual of the update (base.py:138) added in the GEMM epilogue
+    (AtomMessagePassing's depth step on the tensor cores)."""
+    from chemprop_b200 import _lib
+    from chemprop_b200.engine import linear_tc, pack_weight_tc
+
+    g = torch.Generator(device="cuda").manual_seed(R + K)
+    lda = (K + 15) // 16 * 16
+    A = torch.zeros(R, lda, dtype=torch.bfloat16, device="cuda")
+    A[:, :K] = torch.randn(R, K, device="cuda", generator=g).bfloat16()
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    ldc = (N + 63) // 64 * 64
+    res = torch.zeros(R, ldc, dtype=torch.bfloat16, device="cuda")
+    res[:, :N] = torch.randn(R, N, device="cuda", generator=g).bfloat16()
+    out = torch.full((R, ldc), float("nan"), dtype=torch.bfloat16, device="cuda")
+    code = {"none": _lib.ACT_NONE, "relu": _lib.ACT_RELU, "tanh": _lib.ACT_TANH}[act]
+    linear_tc(A, K, pack_weight_tc(W), N, out, bias=b, res=res, act=code)
+    torch.cuda.synchronize()
+    z = A[:, :K].float() @ W.bfloat16().float().t() + b + res[:, :N].float()
+    ref = {"none": lambda x: x, "relu": torch.relu, "tanh": torch.tanh}[act](z)
+    torch.testing.assert_close(out[:, :N].float(), ref.bfloat16().float(), rtol=2 ** -7, atol=4e-3)
+    with pytest.raises(Exception):
+        linear_tc(A, K, pack_weight_tc(W), N, out, res=out)          # the residual may not alias the output

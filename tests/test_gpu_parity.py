@@ -155,6 +155,10 @@ def test_medium_batch_vs_oracle(kind, precision, n_mols, d_h, depth):
     tol = FP32_ATOL if precision == "fp32" else BF16_ATOL
     if precision == "fp32" and depth >= 6:
         tol = 5e-5  # fp32 round-off grows with depth x width (reference itself is only fp32-accurate here)
+    if precision == "bf16":
+        # 1e-2 is relative to the hidden-state scale: with |H| up to 2.5 (atom, depth 4) one bf16 ulp of the stored
+        # output alone is 1.6e-2, so the bound scales with max|H| once that exceeds 1
+        tol = tol * max(1.0, H_ref.detach().abs().max().item())
     assert (H.detach().double().cpu() - H_ref.detach()).abs().max().item() <= tol
     assert (a.detach().double().cpu() - a_ref.detach()).abs().max().item() <= tol
     for k, p in mp.named_parameters():
