@@ -28,7 +28,7 @@ using namespace dmpnn::tc;
 constexpr int kTileM = 128;
 constexpr int kSlabBytes = kTileM * 128;          // A stage: 128 rows x 64 bf16
 constexpr int kMaxN = 304;
-constexpr int kMaxK = 384;
+constexpr int kMaxK = 448;                       // 7 k slabs (CGR dims: d_v + h = 406)
 constexpr int kWSlabBytes = kMaxN * 128;          // W stage: up to 304 rows x 64 bf16 = 38912
 constexpr int kStageBytes = kSlabBytes + kWSlabBytes;   // 55296 (multiple of 1024)
 constexpr int kStages = 3;

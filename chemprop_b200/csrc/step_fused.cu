@@ -6,16 +6,23 @@
 // first_step (H^0 = tau(H_0), base.py:200, recomputed on load) else identity.
 //
 // Persistent, warp-specialised, one CTA per SM, molecule-aligned tiles of <=128 dst-sorted edge rows:
-//   warp 0      TMA producer: H tile (5 boxes of 128 rows x 64 cols, SWIZZLE_128B) -> shared memory; L2 prefetch
-//   warp 1      TMA producer: W_h stages (pre-packed smem images, cp.async.bulk) -> 10-stage ring (100 KB)
+//   warp 0      TMA producer: H tile (5 boxes of 128 rows x 64 cols, SWIZZLE_128B) -> one shared-memory tile, handed
+//               over slab by slab (box s of the next tile is loaded when the message warps have left slab s); L2 prefetch
+//   warp 1      TMA producer: W_h stages (pre-packed smem images, cp.async.bulk): an 80-column output chunk x one
+//               k pass (slabs {0,1,2} | {3,4}), 2-stage ring of 30 KB
 //   warp 2      tcgen05.mma issuer (converged warp, elected lane) + TMEM allocator:
 //               D[128 x hp] (TMEM, fp32) = A (TMEM, bf16) . W_h^T (smem)
-//   warp 3      TMA producer: H_0 slabs -> two staging buffers
-//   warps 4-11  epilogue (2 groups): tcgen05.ld -> + H_0[rev] + bias -> tau -> bf16 in the staging slab at row
-//               rev(e') -> coalesced copy-out
+//   warp 3      TMA producer: H_0 slabs -> four staging buffers (two per epilogue group)
+//   warps 4-11  epilogue (2 groups, alternating slab parity per tile): tcgen05.ld -> + H_0[rev] + bias -> tau -> bf16
+//               in the staging slab at row rev(e') -> coalesced copy-out
 //   warps 12-19 message: thread = row e': sums the sibling rows of e' (same destination atom) out of the
-//               shared-memory tile and writes the bf16 result row into tensor memory (tcgen05.st) = A operand
+//               shared-memory tile and writes the bf16 result row into tensor memory (tcgen05.st) = A operand;
+//               optionally also to HBM (M_out / G_out, one 32-byte sector per thread) for the W_h gradient
 // The row permutation by rev() is applied for free where the epilogue writes row rev(e').
+//
+// The same kernel runs the autograd mirror of the step (MODE_BWD_*, dmpnn_bond_step_bwd_fused_bf16):
+//   dOut = ((S.P) dZ) . W_h [* tau'(Y)]  -- the message warps read the sibling rows through a tile-local rev() table,
+//   W is the packed W_h^T, the epilogue writes row e' itself and multiplies by tau' of the staged Y.
 //
 // Algorithmic HBM bytes per step: read H_prev + H_0, write H_next = 3*E*h*2 (2*E*h*2 when first_step,
 // H_prev == H_0 comes from L2 the second time); W_h (<=190 KB) is L2-resident.

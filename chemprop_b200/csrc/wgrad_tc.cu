@@ -24,8 +24,8 @@ using namespace dmpnn::tc;
 
 constexpr int kRowsPerStage = 64;
 constexpr int kBoxBytes = kRowsPerStage * 128;    // 64 rows x 64 bf16 = 8 KB
-constexpr int kMaxXBoxes = 6;                     // K <= 384
-constexpr int kStageBytes = (2 + kMaxXBoxes) * kBoxBytes;   // 64 KB
+constexpr int kMaxXBoxes = 7;                     // K <= 448 (TMEM: 448 of 512 accumulator columns)
+constexpr int kStageBytes = (2 + kMaxXBoxes) * kBoxBytes;   // 72 KB
 constexpr int kStages = 3;
 constexpr int kThreads = 256;
 constexpr int kTmemCols = 512;
@@ -221,7 +221,7 @@ using namespace dmpnn;
 using namespace dmpnn::wgtc;
 
 extern "C" int dmpnn_wgrad_tc_workspace_bytes(int64_t N, int64_t Kx, size_t* bytes) {
-  DMPNN_CHECK_ARG(bytes && N > 0 && N <= 384 && Kx > 0 && Kx <= 384, "wgrad_tc: need 0 < N, K <= 384");
+  DMPNN_CHECK_ARG(bytes && N > 0 && N <= 384 && Kx > 0 && Kx <= 64 * kMaxXBoxes, "wgrad_tc: need 0 < N <= 384, 0 < K <= 448");
   Geom g = geom(N, Kx);
   *bytes = (size_t)g.grid * 128 * g.Kpad * sizeof(float);
   return 0;
@@ -231,7 +231,7 @@ extern "C" int dmpnn_wgrad_tc_bf16(const void* dY, int64_t lddy, const void* X, 
                                    int64_t Kx, float* dW, int64_t lddw, int accumulate, void* workspace,
                                    void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  DMPNN_CHECK_ARG(R >= 0 && N > 0 && N <= 384 && Kx > 0 && Kx <= 384, "wgrad_tc: unsupported sizes N=%lld K=%lld",
+  DMPNN_CHECK_ARG(R >= 0 && N > 0 && N <= 384 && Kx > 0 && Kx <= 64 * kMaxXBoxes, "wgrad_tc: unsupported sizes N=%lld K=%lld",
                   (long long)N, (long long)Kx);
   DMPNN_CHECK_ARG(dW && workspace, "wgrad_tc: null pointer");
   DMPNN_CHECK_ARG(R == 0 || (dY && X), "wgrad_tc: null operand");

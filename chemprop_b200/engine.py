@@ -471,7 +471,7 @@ def h_is_mult4(Wh: Tensor) -> bool:
 
 def _tc_ok(cfg: MPConfig, h: int, *Ks: int) -> bool:
     """Tensor-core linear kernels apply: bf16 tier, fused kernels enabled, sizes inside the kernel limits."""
-    return (cfg.fused and cfg.hidden_dtype == torch.bfloat16 and h <= 304 and all(k <= 384 for k in Ks)
+    return (cfg.fused and cfg.hidden_dtype == torch.bfloat16 and h <= 304 and all(k <= 448 for k in Ks)
             and _fused_available())
 
 

@@ -229,7 +229,7 @@ int dmpnn_act_bwd(const void* G, int g_dtype, int64_t ldg, const int32_t* gidx,
  *                         per-k-slab shared-memory images
  *   dmpnn_linear_tc_bf16  C[r, 0:N] = act(A[r, 0:K] . B^T + bias + res[r, 0:N]); A, C, res (nullable; the H_0
  *                         residual of base.py:138, ldres % 8 == 0) bf16 row-major, lda/ldc % 8 == 0,
- *                         ldc >= pad16(N), K <= 384, N <= 304; C columns [N, pad16(N)) are written as zeros.
+ *                         ldc >= pad16(N), K <= 448, N <= 304; C columns [N, pad16(N)) are written as zeros.
  * ------------------------------------------------------------------------------------- */
 int dmpnn_concat_bf16(const void* X1, int x1_dtype, int64_t ld1, const int32_t* idx1, int64_t K1,
                       const void* X2, int x2_dtype, int64_t ld2, const int32_t* idx2, int64_t K2,
@@ -258,7 +258,7 @@ int dmpnn_bond_step_bwd_fused_bf16(const void* dZ, const void* Yact, void* dOut,
 
 /* Tensor-core weight gradient (bf16 operands, f32 accumulate, deterministic two-pass reduction):
  *   dW[n, 0:K] (+)= sum_r dY[r, n] * X[r, 0:K]      dY: R x N (ld lddy), X: R x K (ld ldx), both bf16 row-major
- * N, K <= 384; lddy, ldx multiples of 8.  Workspace from dmpnn_wgrad_tc_workspace_bytes. */
+ * N <= 384, K <= 448; lddy, ldx multiples of 8.  Workspace from dmpnn_wgrad_tc_workspace_bytes. */
 int dmpnn_wgrad_tc_workspace_bytes(int64_t N, int64_t K, size_t* bytes);
 int dmpnn_wgrad_tc_bf16(const void* dY, int64_t lddy, const void* X, int64_t ldx, int64_t R, int64_t N, int64_t K,
                         float* dW, int64_t lddw, int accumulate, void* workspace, void* stream);
