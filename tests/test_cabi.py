@@ -28,6 +28,39 @@ def test_header_symbols_exported_and_bound():
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
 
 
+def test_binding_matches_header_prototypes():
+    """Every ctypes signature has the parameter count and the scalar kinds (pointer / 64-bit / 32-bit / float) of the
+    prototype in include/dmpnn.h -- an ABI drift between header and binding would corrupt the call silently."""
+    text = open(os.path.join(ROOT, "include", "dmpnn.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict(re.findall(r"\b(dmpnn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert set(protos) == set(_lib.SIGNATURES)
+
+    def kind_of_c(param: str) -> str:
+        param = param.strip()
+        if "*" in param:
+            return "ptr"
+        if re.search(r"\b(int64_t|size_t)\b", param):
+            return "i64"
+        if re.search(r"\bfloat\b", param):
+            return "f32"
+        if re.search(r"\bint\b", param):
+            return "i32"
+        raise AssertionError(f"unrecognised parameter {param!r}")
+
+    def kind_of_ctypes(t) -> str:
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or hasattr(t, "_type_") and isinstance(t._type_, type):
+            return "ptr"
+        return {ctypes.c_int64: "i64", ctypes.c_size_t: "i64", ctypes.c_int: "i32", ctypes.c_float: "f32"}[t]
+
+    for name, params in protos.items():
+        plist = [] if params.strip() in ("", "void") else [x for x in params.split(",")]
+        _, argtypes = _lib.SIGNATURES[name]
+        assert len(plist) == len(argtypes), (name, len(plist), len(argtypes))
+        for i, (cp, at) in enumerate(zip(plist, argtypes)):
+            assert kind_of_c(cp) == kind_of_ctypes(at), (name, i, cp.strip(), at)
+
+
 def test_version_and_error_string():
     lib = _lib.load()
     assert lib.dmpnn_version() == 100
