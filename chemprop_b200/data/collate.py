@@ -51,7 +51,7 @@ class BatchMolGraph:
                 raise ValueError(f"MolGraph.E has {e.shape[0]} rows but edge_index has {ne} edges")
 
         def ptrs(arrs):
-            return np.fromiter((a.ctypes.data for a in arrs), dtype=np.uint64, count=n)
+            return np.fromiter((a.__array_interface__["data"][0] for a in arrs), dtype=np.uint64, count=n)
 
         pV, pE, pEI, pRV = ptrs(Vs), ptrs(Es), ptrs(EIs), ptrs(RVs)
         kw = dict(pin_memory=True) if pin_memory else {}
@@ -72,14 +72,14 @@ class BatchMolGraph:
                 raise ValueError("transfer_dtype must be torch.bfloat16 or None")
             if max(Vt, Et) >= 2 ** 31:
                 raise ValueError("batch too large for int32 transfer indices")
-
-            def stage(t, dt):
-                out = torch.empty(t.shape, dtype=dt, **kw)
-                out.copy_(t)
-                return out
-
-            self._xfer = (stage(self.V, torch.bfloat16), stage(self.E, torch.bfloat16), stage(self.edge_index, torch.int32),
-                          stage(self.rev_edge_index, torch.int32), stage(self.batch, torch.int32))
+            xf = (torch.empty((Vt, d_v), dtype=torch.bfloat16, **kw), torch.empty((Et, d_e), dtype=torch.bfloat16, **kw),
+                  torch.empty((2, Et), dtype=torch.int32, **kw), torch.empty((Et,), dtype=torch.int32, **kw),
+                  torch.empty((Vt,), dtype=torch.int32, **kw))
+            rc = lib.dmpnn_collate_host_compact(
+                n, n_atoms.ctypes.data, n_edges.ctypes.data, pV.ctypes.data, pE.ctypes.data, pEI.ctypes.data,
+                pRV.ctypes.data, d_v, d_e, *(t.data_ptr() for t in xf))
+            _lib.check(rc, "dmpnn_collate_host_compact")
+            self._xfer = xf
 
     @classmethod
     def from_tensors(cls, V: Tensor, E: Tensor, edge_index: Tensor, rev_edge_index: Tensor, batch: Tensor,

@@ -87,6 +87,17 @@ int dmpnn_collate_host(int64_t n_mols, const int64_t* n_atoms, const int64_t* n_
                        float* V_out, float* E_out, int64_t* edge_index_out /*2 x E_tot*/,
                        int64_t* rev_out, int64_t* batch_out);
 
+/* The same batch in the compact transfer format (bf16 features, round-to-nearest-even; int32 indices): what
+ * BatchMolGraph(transfer_dtype=bfloat16) copies host -> device instead of the f32 / int64 tensors.  The bf16 tier
+ * rounds V / E to bf16 when it assembles its GEMM operands, so its results do not change.  Fails (< 0) when the
+ * batch does not fit int32 indices. */
+int dmpnn_collate_host_compact(int64_t n_mols, const int64_t* n_atoms, const int64_t* n_edges,
+                               const float* const* V_ptrs, const float* const* E_ptrs,
+                               const int64_t* const* edge_index_ptrs, const int64_t* const* rev_ptrs,
+                               int64_t d_v, int64_t d_e,
+                               uint16_t* V_out, uint16_t* E_out, int32_t* edge_index_out /*2 x E_tot*/,
+                               int32_t* rev_out, int32_t* batch_out);
+
 /* ---------------------------------------------------------------------------------------
  * Device layout build.  Consumes the reference's BatchMolGraph index tensors
  * (chemprop/data/collate.py:24-33: edge_index int64 2xE, rev_edge_index int64 E, batch int64 V)
