@@ -24,6 +24,38 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def collate_ext_path() -> Path:
+    import sysconfig
+
+    return PKG / "lib" / ("_collate_ext" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_collate_ext(force: bool = False) -> Path | None:
+    """The host-side collate as a CPython extension (gcc; no CUDA).  Optional: BatchMolGraph falls back to the ctypes
+    path without it, so a missing compiler / header only costs collate speed."""
+    import sysconfig
+
+    src, out = CSRC / "collate_ext.c", collate_ext_path()
+    if not src.exists():
+        return None
+    if not force and out.exists() and out.stat().st_mtime > src.stat().st_mtime:
+        return out
+    try:
+        import numpy as np
+
+        cc = os.environ.get("CC") or shutil.which("gcc") or shutil.which("cc")
+        inc = sysconfig.get_paths()["include"]
+        if not cc or not os.path.exists(os.path.join(inc, "Python.h")):
+            return None
+        out.parent.mkdir(parents=True, exist_ok=True)
+        cmd = [cc, "-O2", "-fPIC", "-shared", "-I", inc, "-I", np.get_include(), str(src), "-o", str(out)]
+        subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return out
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write(f"[collate_ext] not built: {e}\n")
+        return None
+
+
 def needs_build() -> bool:
     if not LIB.exists():
         return True
@@ -33,6 +65,7 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = True) -> Path:
+    build_collate_ext(force)
     if not force and not needs_build():
         return LIB
     LIB.parent.mkdir(parents=True, exist_ok=True)

@@ -23,10 +23,35 @@ from .. import _lib
 from .molgraph import MolGraph
 
 
+_EXT = None          # the CPython collate extension (chemprop_b200/csrc/collate_ext.c); False = unavailable
+
+
+def _collate_ext():
+    """Loads lib/_collate_ext*.so once.  Host-side convenience only: without it the ctypes path below is used."""
+    global _EXT
+    if _EXT is None:
+        _EXT = False
+        try:
+            import importlib.util
+
+            from ..build import collate_ext_path
+
+            path = collate_ext_path()
+            if path.exists():
+                spec = importlib.util.spec_from_file_location("chemprop_b200._collate_ext", path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                _EXT = mod
+        except Exception:  # noqa: BLE001
+            _EXT = False
+    return _EXT or None
+
+
 class BatchMolGraph:
     __slots__ = ("V", "E", "edge_index", "rev_edge_index", "batch", "_size", "_layout", "_xfer")
 
-    def __init__(self, mgs: Sequence[MolGraph], pin_memory: bool = False, transfer_dtype: torch.dtype | None = None):
+    def __init__(self, mgs: Sequence[MolGraph], pin_memory: bool = False, transfer_dtype: torch.dtype | None = None,
+                 use_extension: bool = True):
         """``transfer_dtype=torch.bfloat16`` (opt-in, for the bf16 tier) additionally keeps a compact host staging
         copy -- features in bf16, indices in int32 -- that `.to(cuda)` / `.cuda_copy()` ship over PCIe instead of
         the f32 / int64 tensors (half the bytes); the public device tensors are widened back to f32 / int64 on
@@ -35,6 +60,40 @@ class BatchMolGraph:
         self._size = len(mgs)
         self._layout = None
         self._xfer = None
+        if transfer_dtype is not None and transfer_dtype != torch.bfloat16:
+            raise ValueError("transfer_dtype must be torch.bfloat16 or None")
+        kw = dict(pin_memory=True) if pin_memory else {}
+        ext = _collate_ext() if use_extension else None
+        if ext is not None:
+            self._init_ext(ext, mgs, kw, transfer_dtype is not None)
+        else:
+            self._init_ctypes(mgs, kw, transfer_dtype is not None)
+
+    def _alloc(self, Vt: int, Et: int, d_v: int, d_e: int, kw: dict, compact: bool):
+        self.V = torch.empty((Vt, d_v), dtype=torch.float32, **kw)
+        self.E = torch.empty((Et, d_e), dtype=torch.float32, **kw)
+        self.edge_index = torch.empty((2, Et), dtype=torch.int64, **kw)
+        self.rev_edge_index = torch.empty((Et,), dtype=torch.int64, **kw)
+        self.batch = torch.empty((Vt,), dtype=torch.int64, **kw)
+        if not compact:
+            return None
+        if max(Vt, Et) >= 2 ** 31:
+            raise ValueError("batch too large for int32 transfer indices")
+        return (torch.empty((Vt, d_v), dtype=torch.bfloat16, **kw), torch.empty((Et, d_e), dtype=torch.bfloat16, **kw),
+                torch.empty((2, Et), dtype=torch.int32, **kw), torch.empty((Et,), dtype=torch.int32, **kw),
+                torch.empty((Vt,), dtype=torch.int32, **kw))
+
+    def _init_ext(self, ext, mgs, kw: dict, compact: bool):
+        """One C call per phase: the extension walks the MolGraph list through the CPython / NumPy C API."""
+        mgs = mgs if isinstance(mgs, (list, tuple)) else list(mgs)
+        n_atoms, n_edges, d_v, d_e = ext.sizes(mgs)
+        Vt, Et = int(n_atoms.sum()), int(n_edges.sum())
+        xf = self._alloc(Vt, Et, d_v, d_e, kw, compact)
+        out = (self.V, self.E, self.edge_index, self.rev_edge_index, self.batch) + (xf or ())
+        ext.fill(mgs, d_v, d_e, Et, *(t.data_ptr() for t in out))
+        self._xfer = xf
+
+    def _init_ctypes(self, mgs, kw: dict, compact: bool):
         n = len(mgs)
         n_atoms = np.fromiter((mg.V.shape[0] for mg in mgs), dtype=np.int64, count=n)
         n_edges = np.fromiter((mg.edge_index.shape[1] for mg in mgs), dtype=np.int64, count=n)
@@ -54,12 +113,7 @@ class BatchMolGraph:
             return np.fromiter((a.__array_interface__["data"][0] for a in arrs), dtype=np.uint64, count=n)
 
         pV, pE, pEI, pRV = ptrs(Vs), ptrs(Es), ptrs(EIs), ptrs(RVs)
-        kw = dict(pin_memory=True) if pin_memory else {}
-        self.V = torch.empty((Vt, d_v), dtype=torch.float32, **kw)
-        self.E = torch.empty((Et, d_e), dtype=torch.float32, **kw)
-        self.edge_index = torch.empty((2, Et), dtype=torch.int64, **kw)
-        self.rev_edge_index = torch.empty((Et,), dtype=torch.int64, **kw)
-        self.batch = torch.empty((Vt,), dtype=torch.int64, **kw)
+        xf = self._alloc(Vt, Et, d_v, d_e, kw, compact)
         lib = _lib.load()
         rc = lib.dmpnn_collate_host(
             n, n_atoms.ctypes.data, n_edges.ctypes.data, pV.ctypes.data, pE.ctypes.data, pEI.ctypes.data,
@@ -67,19 +121,12 @@ class BatchMolGraph:
             self.rev_edge_index.data_ptr(), self.batch.data_ptr(),
         )
         _lib.check(rc, "dmpnn_collate_host")
-        if transfer_dtype is not None:
-            if transfer_dtype != torch.bfloat16:
-                raise ValueError("transfer_dtype must be torch.bfloat16 or None")
-            if max(Vt, Et) >= 2 ** 31:
-                raise ValueError("batch too large for int32 transfer indices")
-            xf = (torch.empty((Vt, d_v), dtype=torch.bfloat16, **kw), torch.empty((Et, d_e), dtype=torch.bfloat16, **kw),
-                  torch.empty((2, Et), dtype=torch.int32, **kw), torch.empty((Et,), dtype=torch.int32, **kw),
-                  torch.empty((Vt,), dtype=torch.int32, **kw))
+        if xf is not None:
             rc = lib.dmpnn_collate_host_compact(
                 n, n_atoms.ctypes.data, n_edges.ctypes.data, pV.ctypes.data, pE.ctypes.data, pEI.ctypes.data,
                 pRV.ctypes.data, d_v, d_e, *(t.data_ptr() for t in xf))
             _lib.check(rc, "dmpnn_collate_host_compact")
-            self._xfer = xf
+        self._xfer = xf
 
     @classmethod
     def from_tensors(cls, V: Tensor, E: Tensor, edge_index: Tensor, rev_edge_index: Tensor, batch: Tensor,

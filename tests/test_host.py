@@ -91,3 +91,31 @@ def test_compact_transfer_staging_is_the_rounded_batch():
     assert compact.transfer_nbytes() * 2 == plain.transfer_nbytes()
     with pytest.raises(ValueError):
         BatchMolGraph(mgs, transfer_dtype=torch.float16)
+
+
+def test_collate_extension_and_ctypes_paths_agree():
+    """BatchMolGraph built through the CPython collate extension == through the ctypes C-ABI path, including dtype /
+    layout coercion of the inputs (float64, Fortran-ordered, int32 indices) and the compact transfer copy."""
+    from chemprop_b200.data import MolGraph
+    from chemprop_b200.data.collate import _collate_ext
+
+    mgs = make_molecules(60, seed=12, shuffle_edges=True, min_atoms=1)
+    odd = [MolGraph(np.asfortranarray(mg.V.astype(np.float64)), mg.E[:, ::1].astype(np.float64), mg.edge_index.astype(np.int32),
+                    mg.rev_edge_index.astype(np.int32)) for mg in mgs[:10]] + list(mgs[10:])
+    ref = BatchMolGraph(mgs, transfer_dtype=torch.bfloat16, use_extension=False)
+    for src in (mgs, odd, tuple(mgs)):
+        for ext in (True, False):
+            got = BatchMolGraph(src, transfer_dtype=torch.bfloat16, use_extension=ext)
+            for k in ("V", "E", "edge_index", "rev_edge_index", "batch"):
+                assert torch.equal(getattr(got, k), getattr(ref, k)), (k, ext)
+            for a, b in zip(got._xfer, ref._xfer):
+                assert a.dtype == b.dtype and torch.equal(a.float() if a.is_floating_point() else a,
+                                                          b.float() if b.is_floating_point() else b)
+    assert len(BatchMolGraph([])) == 0 and BatchMolGraph([]).V.shape[0] == 0
+    if _collate_ext() is None:
+        pytest.skip("collate extension not built here (ctypes path covered)")
+    m0 = next(mg for mg in mgs if mg.E.shape[0] > 0)
+    bad = [MolGraph(m0.V, m0.E[:-1], m0.edge_index, m0.rev_edge_index)]
+    for ext in (True, False):
+        with pytest.raises(ValueError, match="MolGraph.E has"):
+            BatchMolGraph(bad, use_extension=ext)
