@@ -1,0 +1,225 @@
+"""Composed tier: the reference's own op sequence (chemprop/nn/message_passing/base.py:196-212) with every
+tensor op on the path executed by a kernel of libdmpnn_sm100.so, glued together by torch autograd.
+
+It serves the configurations the monolithic tiers (engine.BondMPFunction / AtomMPFunction, which fuse tau into
+their kernels) do not cover:
+
+  * activation modules the kernels have no code for -- PReLU (learnable slope: chemprop/nn/utils.py:48), SELU
+    (utils.py:35-41), or any user `nn.Module` (utils.py:37-42 returns it as is);
+  * dropout > 0 in training mode (base.py:139, :182, :188);
+  * AtomMessagePassing(undirected=True) (base.py:202-203 on mixins.py:25-30, which is no longer atom-granular).
+
+`tau` and `dropout` are the caller's own torch modules applied between our kernels -- exactly where the reference
+applies them -- so the gradient of a learnable activation and the dropout RNG stream are torch's.  Everything else
+(gathers, the three linear layers and their weight gradients, message, reverse averaging, atom scatter-sum) is a
+libdmpnn kernel with a hand-written autograd mirror.  Hidden states are f32 `[rows, h]` (unpadded) in the
+engine's internal edge order (stable sort by destination atom), so this tier satisfies the tolerance of both
+precision settings.  There is no CPU path here either: the wrappers in engine.py refuse CPU tensors.
+"""
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+from . import engine as K
+
+
+def _buf(rows: int, cols: int, like: Tensor) -> Tensor:
+    """Uninitialised f32 [rows, cols]; an empty one still has a non-null data pointer (it is a slice of one row)."""
+    if rows > 0 and cols > 0:
+        return torch.empty((rows, cols), dtype=torch.float32, device=like.device)
+    return torch.empty((max(rows, 1), max(cols, 1)), dtype=torch.float32, device=like.device)[:rows, :cols]
+
+
+def _c(t: Tensor | None) -> Tensor | None:
+    if t is None:
+        return None
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class GatherLinear(torch.autograd.Function):
+    """Y[r] = [X1[i1(r)] || X2[i2(r)]] . W^T + b + res[r]   (r < R)  -- dmpnn_linear_fwd.
+    Covers W_i (mixins.py:8-9, :22-23), W_h with the H_0 residual (base.py:136-138) and W_o (base.py:180).
+    Gradients: W, b (dmpnn_linear_wgrad), res (identity), and X1 / X2 when they are not gathered."""
+
+    @staticmethod
+    def forward(ctx, X1, idx1, X2, idx2, W, b, res, R):
+        X1c, X2c, Wc, bc, resc = _c(X1), _c(X2), _c(W), _c(b), _c(res)
+        K1 = X1c.shape[1]
+        K2 = 0 if X2c is None else X2c.shape[1]
+        N = Wc.shape[0]
+        out = _buf(R, N, Wc)
+        if R > 0:
+            K.linear_fwd(X1c, K1, Wc, out, N, idx1=idx1, X2=X2c, K2=K2, idx2=idx2, bias=bc, res=resc, R=R, pad_to=N)
+        ctx.args = (X1c, idx1, X2c, idx2, Wc, K1, K2, N, R)
+        ctx.wdtype = W.dtype
+        ctx.bdtype = None if b is None else b.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dY):
+        X1c, idx1, X2c, idx2, Wc, K1, K2, N, R = ctx.args
+        need_x1, _, need_x2, _, need_w, need_b, need_res, _ = ctx.needs_input_grad
+        dY = _c(dY)
+        dX1 = dX2 = dW = db = None
+        if need_w or need_b:
+            dW = torch.zeros_like(Wc)
+            db = torch.zeros(N, dtype=torch.float32, device=Wc.device) if need_b else None
+            if R > 0:
+                K.linear_wgrad(dY, X1c, K1, dW, N, idx1=idx1, X2=X2c, K2=K2, idx2=idx2, dbias=db, R=R)
+            dW = dW.to(ctx.wdtype)
+            db = None if db is None else db.to(ctx.bdtype)
+        if need_x1:
+            if idx1 is not None:
+                raise K.DmpnnError("GatherLinear: no gradient through a gathered operand")
+            dX1 = _buf(R, K1, Wc)
+            if R > 0:
+                K.linear_fwd(dY, N, Wc[:, :K1].t().contiguous(), dX1, K1, R=R, pad_to=K1)
+        if need_x2:
+            if idx2 is not None:
+                raise K.DmpnnError("GatherLinear: no gradient through a gathered operand")
+            dX2 = _buf(R, K2, Wc)
+            if R > 0:
+                K.linear_fwd(dY, N, Wc[:, K1:].t().contiguous(), dX2, K2, R=R, pad_to=K2)
+        return dX1, None, dX2, None, dW, db, (dY if need_res else None), None
+
+
+class BondMessage(torch.autograd.Function):
+    """M[e] = sum_{dst(e') = src(e)} H[e'] - H[rev(e)]   (mixins.py:11-18) -- dmpnn_bond_message; the mirror is the
+    same kernel reading through `rev` instead of writing through it."""
+
+    @staticmethod
+    def forward(ctx, H, lay):
+        Hc = _c(H)
+        M = _buf(lay.E, Hc.shape[1], Hc)
+        K.bond_message(Hc, lay, Hc.shape[1], M)
+        ctx.lay = lay
+        return M
+
+    @staticmethod
+    def backward(ctx, dM):
+        dM = _c(dM)
+        dH = _buf(ctx.lay.E, dM.shape[1], dM)
+        K.bond_message(dM, ctx.lay, dM.shape[1], dH, permute_on_read=True)
+        return dH, None
+
+
+class RevAverage(torch.autograd.Function):
+    """H[e] <- (H[e] + H[rev(e)]) / 2   (base.py:202-203) -- dmpnn_rev_average; self-adjoint (rev is an involution)."""
+
+    @staticmethod
+    def forward(ctx, H, lay):
+        Hc = _c(H)
+        out = _buf(lay.E, Hc.shape[1], Hc)
+        K.rev_average(Hc, lay, Hc.shape[1], out)
+        ctx.lay = lay
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _c(g)
+        out = _buf(ctx.lay.E, g.shape[1], g)
+        K.rev_average(g, ctx.lay, g.shape[1], out)
+        return out, None
+
+
+class SumByDst(torch.autograd.Function):
+    """A[v] = sum_{dst(e) = v} H[e]   (base.py:208-211, first half of mixins.py:26-29) -- dmpnn_segment_sum over the
+    dst-sorted rows; mirror: dH[e] = dA[dst(e)] (dmpnn_segment_bcast)."""
+
+    @staticmethod
+    def forward(ctx, H, lay):
+        Hc = _c(H)
+        if lay.E == 0:     # no edges: every atom's sum is empty (the kernel is not launched on a 0-row operand)
+            A = torch.zeros((lay.V, Hc.shape[1]), dtype=torch.float32, device=Hc.device)
+        else:
+            A = _buf(lay.V, Hc.shape[1], Hc)
+            K.segment_sum(Hc, lay.rowptr, lay.V, Hc.shape[1], A, pad_to=Hc.shape[1])
+        ctx.lay = lay
+        return A
+
+    @staticmethod
+    def backward(ctx, dA):
+        lay = ctx.lay
+        dA = _c(dA)
+        dH = _buf(lay.E, dA.shape[1], dA)
+        if lay.E > 0:
+            K.segment_bcast(dA, lay.dst_row, None, lay.E, dA.shape[1], dH)
+        return dH, None
+
+
+class GatherBySrc(torch.autograd.Function):
+    """M[e] = A[src(e)]   (the `[bmg.edge_index[0]]` of mixins.py:29) -- dmpnn_segment_bcast; mirror:
+    dA[v] = sum_{src(e) = v} dM[e] = sum_{e' in in(v)} dM[rev(e')] (dmpnn_segment_sum gathering through rev)."""
+
+    @staticmethod
+    def forward(ctx, A, lay):
+        Ac = _c(A)
+        M = _buf(lay.E, Ac.shape[1], Ac)
+        if lay.E > 0:
+            K.segment_bcast(Ac, lay.src_row, None, lay.E, Ac.shape[1], M)
+        ctx.lay = lay
+        return M
+
+    @staticmethod
+    def backward(ctx, dM):
+        lay = ctx.lay
+        dM = _c(dM)
+        if lay.E == 0:
+            return torch.zeros((lay.V, dM.shape[1]), dtype=torch.float32, device=dM.device), None
+        dA = _buf(lay.V, dM.shape[1], dM)
+        K.segment_sum(dM, lay.rowptr, lay.V, dM.shape[1], dA, idx=lay.rev_row, pad_to=dM.shape[1])
+        return dA, None
+
+
+def _inputs(bmg):
+    K._require_cuda(bmg.V, bmg.E)
+    return bmg.V.contiguous().float(), bmg.E.contiguous().float()
+
+
+def bond_forward(mp, bmg, lay) -> Tensor:
+    """BondMessagePassing.forward up to and including dropout(tau(W_o(.))) (base.py:196-212, :180-182)."""
+    V, E = _inputs(bmg)
+    tau, drop = mp.tau, mp.dropout
+    # a batch without edges (tests/integration/test_export.py:15-46) flows through as 0-row tensors, as in the reference
+    H0 = GatherLinear.apply(V, lay.src_row, E, lay.perm, mp.W_i.weight, mp.W_i.bias, None, lay.E)      # mixins.py:8-9
+    H = tau(H0)                                                                                       # base.py:200
+    for _ in range(1, int(mp.depth)):
+        if mp.undirected:
+            H = RevAverage.apply(H, lay)                                                              # base.py:202-203
+        M = BondMessage.apply(H, lay)                                                                 # mixins.py:11-18
+        Z = GatherLinear.apply(M, None, None, None, mp.W_h.weight, mp.W_h.bias, H0, lay.E)            # base.py:137-138
+        H = drop(tau(Z))                                                                              # base.py:138-139
+    Mv = SumByDst.apply(H, lay)                                                                       # base.py:208-211
+    Y = GatherLinear.apply(V, None, Mv, None, mp.W_o.weight, mp.W_o.bias, None, lay.V)                # base.py:180
+    return drop(tau(Y))                                                                               # base.py:181-182
+
+
+def atom_forward(mp, bmg, lay) -> Tensor:
+    """AtomMessagePassing.forward, edge-granular as in the reference (mixins.py:22-30) so that `undirected`
+    (base.py:202-203) keeps its meaning."""
+    V, E = _inputs(bmg)
+    tau, drop = mp.tau, mp.dropout
+    d_e = E.shape[1]
+    H0 = GatherLinear.apply(V, lay.src_row, None, None, mp.W_i.weight, mp.W_i.bias, None, lay.E)       # mixins.py:22-23
+    AE = None
+    if d_e > 0:   # sum of the in-edge bond features of every atom: the loop-invariant half of mixins.py:26-29
+        if lay.E > 0:
+            AE = _buf(lay.V, d_e, V)
+            K.segment_sum(E, lay.rowptr, lay.V, d_e, AE, idx=lay.perm, pad_to=d_e)
+        else:
+            AE = torch.zeros((lay.V, d_e), dtype=torch.float32, device=V.device)
+    H = tau(H0)
+    for _ in range(1, int(mp.depth)):
+        if mp.undirected:
+            H = RevAverage.apply(H, lay)
+        M = GatherBySrc.apply(SumByDst.apply(H, lay), lay)                                            # mixins.py:26-29
+        Z = GatherLinear.apply(M, None, AE, lay.src_row if AE is not None else None, mp.W_h.weight, mp.W_h.bias,
+                               H0, lay.E)                                                             # W_h([M_H || M_E]) + H_0
+        H = drop(tau(Z))
+    Mv = SumByDst.apply(H, lay)
+    Y = GatherLinear.apply(V, None, Mv, None, mp.W_o.weight, mp.W_o.bias, None, lay.V)
+    return drop(tau(Y))

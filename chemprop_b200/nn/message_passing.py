@@ -5,13 +5,18 @@ W_i / W_h / W_o / W_d, `output_dim`, `forward(bmg, V_d=None)`), executed by the 
 Differences a user can see: the module must live on a CUDA device (there is no CPU fallback), and a
 `precision` keyword selects the hidden-state storage type: "fp32" (default; matches the reference
 within 1e-5) or "bf16" (bf16 hidden states + tensor-core depth step; within 1e-2).
+
+Two execution tiers sit behind `forward`: the monolithic autograd functions of engine.py (tau fused into the
+kernels: ReLU / LeakyReLU / Tanh / ELU, dropout inactive) and the composed tier of composed.py (the reference's op
+sequence, one libdmpnn kernel per op, `self.tau` / `self.dropout` applied by torch in between) for everything else:
+PReLU, SELU or user activation modules, dropout > 0 in training, AtomMessagePassing(undirected=True).
 """
 from __future__ import annotations
 
 import torch
 from torch import Tensor, nn
 
-from .. import _lib
+from .. import _lib, composed
 from ..engine import AtomMPFunction, BondMPFunction, MPConfig, get_layout
 from ..exceptions import InvalidShapeError
 
@@ -19,6 +24,7 @@ DEFAULT_ATOM_FDIM, DEFAULT_BOND_FDIM, DEFAULT_HIDDEN_DIM = 72, 14, 300  # chempr
 
 _ACT_NAMES = {"relu": nn.ReLU, "leakyrelu": lambda: nn.LeakyReLU(0.1), "prelu": nn.PReLU, "tanh": nn.Tanh,
               "elu": nn.ELU}
+_FUSED_ACTS = (nn.ReLU, nn.LeakyReLU, nn.Tanh, nn.ELU, nn.Identity)
 
 
 def get_activation_function(activation) -> nn.Module:
@@ -36,24 +42,30 @@ def get_activation_function(activation) -> nn.Module:
 
 def engine_activation(tau: nn.Module) -> tuple[int, float]:
     """Map a torch activation module to the engine's fused activation code."""
-    if isinstance(tau, nn.ReLU):
+    if type(tau) is nn.ReLU:
         return _lib.ACT_RELU, 0.0
-    if isinstance(tau, nn.LeakyReLU):
+    if type(tau) is nn.LeakyReLU:
         return _lib.ACT_LEAKYRELU, float(tau.negative_slope)
-    if isinstance(tau, nn.Tanh):
+    if type(tau) is nn.Tanh:
         return _lib.ACT_TANH, 0.0
-    if isinstance(tau, nn.ELU):
+    if type(tau) is nn.ELU:
         return _lib.ACT_ELU, float(tau.alpha)
-    if isinstance(tau, nn.Identity):
+    if type(tau) is nn.Identity:
         return _lib.ACT_NONE, 0.0
     raise NotImplementedError(
-        f"activation {type(tau).__name__} is not fused by the sm_100a engine "
-        "(supported: ReLU, LeakyReLU, Tanh, ELU)"
+        f"activation {type(tau).__name__} is not fused into the sm_100a kernels "
+        "(fused: ReLU, LeakyReLU, Tanh, ELU; anything else runs on the composed tier)"
     )
+
+
+def is_fused_activation(tau: nn.Module) -> bool:
+    """Exact stock classes only: a user subclass may override forward, so it goes to the composed tier."""
+    return type(tau) in _FUSED_ACTS
 
 
 class _MessagePassingBase(nn.Module):
     _function = None
+    _composed_forward = None
 
     def __init__(self, d_v: int = DEFAULT_ATOM_FDIM, d_e: int = DEFAULT_BOND_FDIM, d_h: int = DEFAULT_HIDDEN_DIM,
                  bias: bool = False, depth: int = 3, dropout: float = 0.0, activation="relu",
@@ -90,15 +102,22 @@ class _MessagePassingBase(nn.Module):
                         hidden_dtype=torch.bfloat16 if self.precision == "bf16" else torch.float32,
                         fused=bool(self.fused))
 
+    def uses_composed_tier(self) -> bool:
+        """True when this call cannot run on the monolithic functions (see the module docstring)."""
+        return not is_fused_activation(self.tau) or (self.training and self.dropout.p > 0)
+
     def forward(self, bmg, V_d: Tensor | None = None) -> Tensor:
-        if self.training and self.dropout.p > 0:
-            raise NotImplementedError("dropout > 0 inside the fused depth loop is not implemented yet")
         bmg = self.graph_transform(bmg)
         lay = get_layout(bmg)
-        H = type(self)._function.apply(
-            bmg.V, bmg.E, self.W_i.weight, self.W_i.bias, self.W_h.weight, self.W_h.bias,
-            self.W_o.weight, self.W_o.bias, lay, self._config(),
-        )
+        if self.uses_composed_tier():
+            H = type(self)._composed_forward(self, bmg, lay)
+            if self.precision == "bf16":
+                H = H.to(torch.bfloat16)     # same output dtype as the fused bf16 tier (computed in f32)
+        else:
+            H = type(self)._function.apply(
+                bmg.V, bmg.E, self.W_i.weight, self.W_i.bias, self.W_h.weight, self.W_h.bias,
+                self.W_o.weight, self.W_o.bias, lay, self._config(),
+            )
         return self.finalize_descriptors(H, V_d)
 
     def finalize_descriptors(self, H: Tensor, V_d: Tensor | None) -> Tensor:
@@ -117,6 +136,7 @@ class _MessagePassingBase(nn.Module):
 class BondMessagePassing(_MessagePassingBase):
     """Directed-bond message passing (chemprop/nn/message_passing/base.py:215-251)."""
     _function = BondMPFunction
+    _composed_forward = staticmethod(composed.bond_forward)
 
     def setup(self, d_v=DEFAULT_ATOM_FDIM, d_e=DEFAULT_BOND_FDIM, d_h=DEFAULT_HIDDEN_DIM, d_vd=None, bias=False):
         W_i = nn.Linear(d_v + d_e, d_h, bias)
@@ -129,6 +149,7 @@ class BondMessagePassing(_MessagePassingBase):
 class AtomMessagePassing(_MessagePassingBase):
     """Atom message passing (chemprop/nn/message_passing/base.py:254-289)."""
     _function = AtomMPFunction
+    _composed_forward = staticmethod(composed.atom_forward)
 
     def setup(self, d_v=DEFAULT_ATOM_FDIM, d_e=DEFAULT_BOND_FDIM, d_h=DEFAULT_HIDDEN_DIM, d_vd=None, bias=False):
         W_i = nn.Linear(d_v, d_h, bias)
@@ -137,7 +158,6 @@ class AtomMessagePassing(_MessagePassingBase):
         W_d = nn.Linear(d_h + d_vd, d_h + d_vd) if d_vd else None
         return W_i, W_h, W_o, W_d
 
-    def forward(self, bmg, V_d: Tensor | None = None) -> Tensor:
-        if self.undirected:
-            raise NotImplementedError("AtomMessagePassing(undirected=True) is not supported by the engine yet")
-        return super().forward(bmg, V_d)
+    def uses_composed_tier(self) -> bool:
+        # undirected averaging (base.py:202-203) breaks the atom-granular restatement the monolithic tier relies on
+        return bool(self.undirected) or super().uses_composed_tier()

@@ -50,6 +50,16 @@ CASES = {
     "atom_d3_noedges":     dict(kind="atom", depth=3, d_h=32, graph="single_atoms4"),
     "atom_d3_cgr":         dict(kind="atom", depth=3, d_h=64, d_v=106, d_e=28, graph="cgr3"),
     "atom_d4_mixed":       dict(kind="atom", depth=4, d_h=64, graph="mixed"),
+    # composed-tier configurations (chemprop_b200/composed.py): activations the kernels do not fuse, AtomMP undirected
+    "bond_d3_prelu":       dict(kind="bond", depth=3, d_h=64, activation="prelu", graph="mols6"),
+    "atom_d3_prelu_bias":  dict(kind="atom", depth=3, d_h=64, activation="prelu", bias=True, graph="mols6"),
+    "bond_d3_selu":        dict(kind="bond", depth=3, d_h=64, activation="selu", graph="mols6"),
+    "bond_d3_softplus":    dict(kind="bond", depth=3, d_h=48, activation_module="Softplus", bias=True, graph="mols6_shuffled"),
+    "atom_d3_undirected":  dict(kind="atom", depth=3, d_h=64, undirected=True, graph="mols6"),
+    "atom_d4_undir_elu":   dict(kind="atom", depth=4, d_h=40, undirected=True, activation="elu", bias=True, graph="mixed"),
+    "bond_d3_undir_prelu": dict(kind="bond", depth=3, d_h=64, undirected=True, activation="prelu", graph="mols6_shuffled"),
+    "atom_d3_noedges_prelu": dict(kind="atom", depth=3, d_h=32, activation="prelu", graph="single_atoms4"),
+    "bond_d3_dropout_eval": dict(kind="bond", depth=3, d_h=64, dropout=0.3, eval=True, graph="mols6"),
 }
 
 
@@ -124,14 +134,15 @@ def run_case(name: str, cfg: dict, seed: int) -> dict:
         gt = GraphTransform(ScaleTransform(rng.normal(0, 0.2, d_v), rng.uniform(0.5, 2.0, d_v)),
                             ScaleTransform(rng.normal(0, 0.2, d_e), rng.uniform(0.5, 2.0, d_e)))
     cls = BondMessagePassing if cfg["kind"] == "bond" else AtomMessagePassing
+    activation = getattr(torch.nn, cfg["activation_module"])() if cfg.get("activation_module") else cfg.get("activation", "relu")
     mp = cls(d_v=d_v, d_e=d_e, d_h=d_h, bias=cfg.get("bias", False), depth=cfg["depth"],
-             activation=cfg.get("activation", "relu"), undirected=cfg.get("undirected", False),
+             activation=activation, undirected=cfg.get("undirected", False), dropout=cfg.get("dropout", 0.0),
              d_vd=cfg.get("d_vd"), graph_transform=gt)
     if cfg.get("checkpoint"):
         sd = load_checkpoint_state(os.path.join(REFERENCE_ROOT, "tests", "data", cfg["checkpoint"]))
         mp.load_state_dict(sd)
-    if gt is not None:
-        mp.eval()  # transforms act in eval mode only (transforms.py:66-67)
+    if gt is not None or cfg.get("eval"):
+        mp.eval()  # transforms act in eval mode only (transforms.py:66-67); dropout is the identity
     V_d = None
     if cfg.get("d_vd"):
         V_d = torch.from_numpy(rng.normal(size=(bmg.V.shape[0], cfg["d_vd"])).astype(np.float32))
@@ -158,7 +169,7 @@ def run_case(name: str, cfg: dict, seed: int) -> dict:
         out["gt_V_mean"], out["gt_V_scale"] = gt.V_transform.mean.numpy(), gt.V_transform.scale.numpy()
         out["gt_E_mean"], out["gt_E_scale"] = gt.E_transform.mean.numpy(), gt.E_transform.scale.numpy()
     for k, v in mp.state_dict().items():
-        if k.startswith(("W_i", "W_h", "W_o", "W_d")):
+        if k.startswith(("W_i", "W_h", "W_o", "W_d", "tau.")):
             out["param." + k] = v.detach().numpy()
     for k, p in mp.named_parameters():
         if p.grad is not None:
@@ -186,15 +197,22 @@ def collate_case() -> dict:
 
 
 def main():
+    """`python -m oracle.make_golden [name ...]`: all cases, or only the named ones (a case's seed is its position in
+    CASES, so adding cases at the end never changes the committed ones)."""
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)  # deterministic summation order
+    only = set(sys.argv[1:])
+    assert only <= set(CASES), only - set(CASES)
     for i, (name, cfg) in enumerate(CASES.items()):
+        if only and name not in only:
+            continue
         out = run_case(name, cfg, seed=100 + i)
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"{name}.npz"), **out)
         print(f"{name:24s} V={out['V'].shape[0]:4d} E={out['E'].shape[0]:4d} B={int(out['n_mols'])} "
               f"|H_v|={np.abs(out['H_v']).mean():.4f} loss={float(out['loss']):+.5f}")
-    np.savez_compressed(os.path.join(GOLDEN_DIR, "collate_fixture.npz"), **collate_case())
-    print("collate_fixture")
+    if not only:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "collate_fixture.npz"), **collate_case())
+        print("collate_fixture")
 
 
 if __name__ == "__main__":

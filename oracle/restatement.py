@@ -24,16 +24,27 @@ from torch.nn import functional as F
 
 
 # --- activations: chemprop/nn/utils.py:43-55 ------------------------------------------------
-def activation(name: str):
+def activation(name, prelu_weight: Tensor | None = None):
+    """utils.py:19-55.  `name` may also be a callable (utils.py:37-42 passes modules through); "prelu" takes the
+    learnable slope (nn.PReLU: one parameter, initial value 0.25)."""
+    if callable(name):
+        return name
     name = name.lower()
     if name == "relu":
         return torch.relu
     if name == "leakyrelu":
         return lambda x: F.leaky_relu(x, 0.1)
+    if name == "prelu":
+        assert prelu_weight is not None, "prelu needs its weight"
+        return lambda x: F.prelu(x, prelu_weight)
     if name == "tanh":
         return torch.tanh
     if name == "elu":
         return F.elu
+    if name == "selu":
+        return F.selu
+    if name == "softplus":
+        return F.softplus
     raise KeyError(name)
 
 
@@ -87,23 +98,33 @@ def atom_message(H, E, edge_index, n_atoms):
     return _scatter_sum_rows(HE, edge_index[1], n_atoms)[edge_index[0]]
 
 
-def update(M_t, H_0, W_h, b_h, tau):
-    """base.py:135-141 (dropout p = 0)"""
-    return tau(H_0 + F.linear(M_t, W_h, b_h))
+def _no_dropout(H):
+    return H
 
 
-def finalize(M, V, W_o, b_o, tau, V_d=None, W_d=None, b_d=None):
-    """base.py:143-194 (dropout p = 0; note: no activation after W_d)"""
-    H = tau(F.linear(torch.cat((V, M), dim=1), W_o, b_o))
+def update(M_t, H_0, W_h, b_h, tau, dropout=_no_dropout):
+    """base.py:135-141"""
+    return dropout(tau(H_0 + F.linear(M_t, W_h, b_h)))
+
+
+def finalize(M, V, W_o, b_o, tau, V_d=None, W_d=None, b_d=None, dropout=_no_dropout):
+    """base.py:143-194 (note: no activation after W_d)"""
+    H = dropout(tau(F.linear(torch.cat((V, M), dim=1), W_o, b_o)))
     if V_d is not None:
-        H = F.linear(torch.cat((H, V_d), dim=1), W_d, b_d)
+        H = dropout(F.linear(torch.cat((H, V_d), dim=1), W_d, b_d))
     return H
 
 
 def message_passing_forward(kind, V, E, edge_index, rev_edge_index, W_i, b_i, W_h, b_h, W_o, b_o, depth, act="relu",
-                            undirected=False, V_d=None, W_d=None, b_d=None, return_intermediates=False):
-    """_MessagePassingBase.forward, base.py:196-212.  kind in {"bond", "atom"}."""
-    tau = activation(act)
+                            undirected=False, V_d=None, W_d=None, b_d=None, return_intermediates=False,
+                            prelu_weight=None, dropout_masks=None):
+    """_MessagePassingBase.forward, base.py:196-212.  kind in {"bond", "atom"}.
+    `dropout_masks`: training-mode dropout with the masks given explicitly -- a list of already scaled
+    (0 or 1/(1-p)) tensors consumed in call order (one E x h mask per depth step, base.py:139; one V x h mask after
+    W_o, base.py:182; one after W_d, base.py:188), so a run can be compared mask for mask."""
+    tau = activation(act, prelu_weight)
+    masks = list(dropout_masks) if dropout_masks is not None else None
+    dropout = _no_dropout if masks is None else (lambda H: H * masks.pop(0))
     n_atoms = V.shape[0]
     H_0 = bond_initialize(V, E, edge_index, W_i, b_i) if kind == "bond" else atom_initialize(V, edge_index, W_i, b_i)
     H = tau(H_0)                                                   # base.py:200
@@ -115,11 +136,11 @@ def message_passing_forward(kind, V, E, edge_index, rev_edge_index, W_i, b_i, W_
             M = bond_message(H, edge_index, rev_edge_index, n_atoms)
         else:
             M = atom_message(H, E, edge_index, n_atoms)
-        H = update(M, H_0, W_h, b_h, tau)                          # base.py:206
+        H = update(M, H_0, W_h, b_h, tau, dropout)                 # base.py:206
         inter["M"].append(M)
         inter["H"].append(H)
     M_v = _scatter_sum_rows(H, edge_index[1], n_atoms)             # base.py:208-211
-    out = finalize(M_v, V, W_o, b_o, tau, V_d, W_d, b_d)
+    out = finalize(M_v, V, W_o, b_o, tau, V_d, W_d, b_d, dropout)
     if return_intermediates:
         inter["M_v"] = M_v
         return out, inter

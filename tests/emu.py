@@ -1,0 +1,189 @@
+"""TEST INFRASTRUCTURE ONLY.  torch-CPU emulations of the libdmpnn kernels behind engine.py's op wrappers, written
+from the contracts in include/dmpnn.h, so that the HOST logic (the hand-written autograd mirrors in engine.py and the
+composed tier in composed.py: which op, which operand, which index table, in which order) can be checked against the
+golden vectors without a GPU.  `patch_engine(monkeypatch)` swaps the wrappers for these; nothing in the product
+imports this file, and a GPU run never touches it (the `-m gpu` tests call the real kernels through the C ABI).
+
+The emulation itself is validated by the fact that the GPU-verified monolithic f32 tier, run through it, reproduces
+every golden (tests/test_host_logic.py::test_monolithic_f32_tier_through_emulation)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from chemprop_b200 import _lib, engine
+from oracle import layout_np
+
+ACT_NONE, ACT_RELU, ACT_LEAKYRELU, ACT_TANH, ACT_ELU = (_lib.ACT_NONE, _lib.ACT_RELU, _lib.ACT_LEAKYRELU,
+                                                         _lib.ACT_TANH, _lib.ACT_ELU)
+
+
+def _act(x, act, p):
+    if act == ACT_NONE:
+        return x
+    if act == ACT_RELU:
+        return torch.relu(x)
+    if act == ACT_LEAKYRELU:
+        return torch.where(x > 0, x, x * p)
+    if act == ACT_TANH:
+        return torch.tanh(x)
+    if act == ACT_ELU:
+        return torch.where(x > 0, x, p * torch.expm1(x))
+    raise ValueError(act)
+
+
+def _dact(y, act, p, from_preact):
+    """tau' evaluated from the output y = tau(z) (from_preact False) or from z itself (dmpnn_act_bwd)."""
+    one = torch.ones_like(y)
+    if act == ACT_NONE:
+        return one
+    if act == ACT_RELU:
+        return (y > 0).to(y.dtype)
+    if act == ACT_LEAKYRELU:
+        return torch.where(y > 0, one, one * p)
+    if act == ACT_TANH:
+        t = torch.tanh(y) if from_preact else y
+        return 1 - t * t
+    if act == ACT_ELU:
+        return torch.where(y > 0, one, (p * torch.exp(y)) if from_preact else (y + p))
+    raise ValueError(act)
+
+
+def _rows(X, idx, R, K):
+    X = X.float()
+    return (X[:R, :K] if idx is None else X[idx[:R].long(), :K])
+
+
+def _cat(X1, K1, idx1, X2, K2, idx2, R):
+    A = _rows(X1, idx1, R, K1)
+    if K2:
+        A = torch.cat([A, _rows(X2, idx2, R, K2)], dim=1)
+    return A
+
+
+def linear_fwd(X1, K1, W, out, N, *, idx1=None, X2=None, K2=0, idx2=None, bias=None, res=None, act=ACT_NONE,
+               act_param=0.0, R=None, pad_to=None):
+    R = out.shape[0] if R is None else R
+    assert W.shape == (N, K1 + K2) and (K2 == 0 or X2 is not None) and out.shape[1] >= N
+    Y = _cat(X1, K1, idx1, X2, K2, idx2, R) @ W.float().t()
+    if bias is not None:
+        Y = Y + bias.float()
+    if res is not None:
+        Y = Y + res[:R, :N].float()
+    out[:R, :N] = _act(Y, act, act_param).to(out.dtype)
+    pad_to = min(out.stride(0), out.shape[1]) if pad_to is None else pad_to
+    if pad_to > N:
+        out[:R, N:pad_to] = 0
+
+
+def linear_wgrad(dY, X1, K1, dW, N, *, idx1=None, X2=None, K2=0, idx2=None, dbias=None, accumulate=False, R=None):
+    R = dY.shape[0] if R is None else R
+    g = dY[:R, :N].float()
+    upd = g.t() @ _cat(X1, K1, idx1, X2, K2, idx2, R)
+    if accumulate:
+        dW += upd
+    else:
+        dW.copy_(upd)
+    if dbias is not None:
+        if accumulate:
+            dbias += g.sum(0)
+        else:
+            dbias.copy_(g.sum(0))
+
+
+def _scale(ptr, s, mode, scale):
+    if mode == _lib.SCALE_INV_COUNT:
+        return float(ptr[s + 1] - ptr[s])
+    if mode == _lib.SCALE_DIV_CONST:
+        return float(scale)
+    return 1.0
+
+
+def segment_sum(X, ptr, n_seg, Ccols, out, *, idx=None, act=ACT_NONE, act_param=0.0, scale_mode=_lib.SCALE_NONE,
+                scale=1.0, pad_to=None):
+    p = ptr.tolist()
+    Xf = X.float()
+    for s in range(n_seg):
+        rows = torch.arange(p[s], p[s + 1])
+        if idx is not None:
+            rows = idx[rows].long()
+        acc = _act(Xf[rows, :Ccols], act, act_param).sum(0)
+        if p[s + 1] > p[s]:
+            acc = acc / _scale(p, s, scale_mode, scale)
+        out[s, :Ccols] = acc.to(out.dtype)     # empty segment -> zero row
+    pad_to = min(out.stride(0), out.shape[1]) if pad_to is None else pad_to
+    if pad_to > Ccols:
+        out[:n_seg, Ccols:pad_to] = 0
+
+
+def segment_bcast(G, seg_of_row, ptr, R, Ccols, out, *, scale_mode=_lib.SCALE_NONE, scale=1.0, n_seg=0):
+    if R == 0:
+        return
+    seg = seg_of_row[:R].long()
+    if ptr is not None and n_seg > 0:     # rows of segment s are [ptr[s], ptr[s+1])
+        cnt = (ptr[1:n_seg + 1] - ptr[:n_seg]).long()
+        assert int(cnt.sum()) == R
+        assert torch.equal(seg, torch.repeat_interleave(torch.arange(n_seg), cnt)), "ptr / seg_of_row disagree"
+    Y = G.float()[seg, :Ccols]
+    if scale_mode == _lib.SCALE_INV_COUNT:
+        Y = Y / (ptr[seg + 1] - ptr[seg]).float().unsqueeze(1)
+    elif scale_mode == _lib.SCALE_DIV_CONST:
+        Y = Y / scale
+    out[:R, :Ccols] = Y.to(out.dtype)
+
+
+def bond_message(X, lay, Ccols, out, *, act=ACT_NONE, act_param=0.0, permute_on_read=False):
+    if lay.E == 0:
+        return
+    rev = lay.rev_row.long()
+    dst = lay.dst_row.long()
+    f = _act(X.float()[: lay.E, :Ccols], act, act_param)
+    rd = f[rev] if permute_on_read else f                       # value read for in-edge row e'
+    s = torch.zeros((lay.V, Ccols)).index_add_(0, dst, rd)      # per destination atom
+    val = s[dst] - rd
+    if permute_on_read:
+        out[: lay.E, :Ccols] = val.to(out.dtype)
+    else:
+        out[rev, :Ccols] = val.to(out.dtype)
+
+
+def rev_average(X, lay, Ccols, out, *, act=ACT_NONE, act_param=0.0):
+    if lay.E == 0:
+        return
+    f = _act(X.float()[: lay.E, :Ccols], act, act_param)
+    out[: lay.E, :Ccols] = ((f + f[lay.rev_row.long()]) / 2).to(out.dtype)
+
+
+def act_bwd(G, Yact, R, Ccols, *, act, act_param=0.0, gidx=None, from_preact=False, dZ=None, acc=None):
+    if R == 0:
+        return
+    g = _rows(G, gidx, R, Ccols)
+    d = g * _dact(Yact.float()[:R, :Ccols], act, act_param, from_preact)
+    if dZ is not None:
+        dZ[:R, :Ccols] = d.to(dZ.dtype)
+        d = dZ[:R, :Ccols].float()          # the accumulator sees the rounded value, as in the kernel? (f32: identical)
+    if acc is not None:
+        acc[:R, :Ccols] += d.to(acc.dtype)
+
+
+def build_layout(edge_index, rev_edge_index, batch, n_mols):
+    L = layout_np.build_layout(edge_index.numpy(), rev_edge_index.numpy(), batch.numpy(), int(n_mols))
+    B = int(n_mols)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).astype(np.int32))
+    pad = lambda a: t(np.concatenate([a, np.zeros(B + 2 - len(a), np.int32)]))
+    meta = [0] * _lib.META_WORDS
+    meta[_lib.META_N_TILES], meta[_lib.META_FLAGS] = L["n_tiles"], L["flags"]
+    meta[_lib.META_MAX_INDEG], meta[_lib.META_MAX_TILE_ROWS] = L["max_indeg"], L["max_tile_rows"]
+    meta[_lib.META_MAX_TILE_ATOMS] = L["max_tile_atoms"]
+    return engine.Layout(int(batch.shape[0]), int(edge_index.shape[1]), B, t(L["perm"]), t(L["inv_perm"]), t(L["rowptr"]),
+                         t(L["src_row"]), t(L["dst_row"]), t(L["rev_row"]), t(L["mol_atom_ptr"]), t(L["mol_row_ptr"]),
+                         pad(L["tile_mol_ptr"]), pad(L["tile_row_ptr"]), pad(L["tile_atom_ptr"]),
+                         torch.tensor(meta, dtype=torch.int32), list(meta))
+
+
+def patch_engine(monkeypatch):
+    """Route engine.py's kernel wrappers to the emulations above (host-logic tests only)."""
+    for name in ("linear_fwd", "linear_wgrad", "segment_sum", "segment_bcast", "bond_message", "rev_average", "act_bwd",
+                 "build_layout"):
+        monkeypatch.setattr(engine, name, globals()[name])
+    monkeypatch.setattr(engine, "_require_cuda", lambda *ts: None)

@@ -6,12 +6,15 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import build_engine_module, golden_bmg, golden_names, load_golden, oracle_forward
+from tests.util import (COMPOSED_GOLDENS, build_engine_module, golden_bmg, golden_names, load_golden,
+                        oracle_forward)
 
 pytestmark = pytest.mark.gpu
 
 FP32_ATOL = 1e-5
 BF16_ATOL = 1e-2
+# goldens served by the monolithic (tau-fused) tiers; the composed-tier goldens run in tests/test_gpu_zcomposed.py
+MONOLITHIC_GOLDENS = [n for n in golden_names() if n not in COMPOSED_GOLDENS]
 
 
 def _engine_run(g, precision, fused=True):
@@ -48,7 +51,7 @@ def test_layout_bit_exact(name):
     assert lay.max_tile_rows == L["max_tile_rows"] and lay.max_tile_atoms == L["max_tile_atoms"]
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", MONOLITHIC_GOLDENS)
 def test_fp32_tier_matches_reference_golden(name):
     g = load_golden(name)
     mp, bmg, H, aggs, loss, grads = _engine_run(g, "fp32")
@@ -62,7 +65,7 @@ def test_fp32_tier_matches_reference_golden(name):
             np.testing.assert_allclose(got, v, rtol=1e-4, atol=FP32_ATOL, err_msg=k)
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", MONOLITHIC_GOLDENS)
 def test_bf16_tier_matches_reference_golden(name):
     g = load_golden(name)
     mp, bmg, H, aggs, loss, grads = _engine_run(g, "bf16")

@@ -1,0 +1,120 @@
+"""CPU tier: the HOST logic of the engine -- the hand-written autograd mirrors (engine.py) and the composed tier
+(composed.py) -- run with the kernel wrappers swapped for the torch emulations of tests/emu.py and compared with the
+golden vectors of the real reference.  What this pins without a GPU: which op is called on which operand with
+which index table, in which order, and that every gradient (incl. a learnable activation's) is wired through.  The
+kernels themselves are checked on the B200 by the `-m gpu` tests."""
+import numpy as np
+import pytest
+import torch
+
+from tests import emu
+from tests.util import COMPOSED_GOLDENS, build_engine_module, golden_bmg, golden_names, load_golden
+
+ATOL = 2e-6
+
+
+def _run(g, mp=None):
+    from chemprop_b200.nn import MeanAggregation, NormAggregation, SumAggregation
+
+    mp = build_engine_module(g, "cpu", "fp32") if mp is None else mp
+    bmg = golden_bmg(g, "cpu")
+    V_d = torch.from_numpy(g["V_d"]) if "V_d" in g else None
+    H = mp(bmg, V_d)
+    aggs = {n: a(H, bmg.batch) for n, a in (("mean", MeanAggregation()), ("sum", SumAggregation()),
+                                            ("norm", NormAggregation()))}
+    (aggs["mean"].float() * torch.from_numpy(g["G"])).sum().backward()
+    return mp, bmg, H, aggs
+
+
+def _check(g, mp, H, aggs):
+    np.testing.assert_allclose(H.detach().numpy(), g["H_v"], rtol=1e-5, atol=ATOL)
+    for n in ("mean", "sum", "norm"):
+        np.testing.assert_allclose(aggs[n].detach().numpy(), g[f"agg_{n}"], rtol=1e-5, atol=ATOL)
+    grads = {k: p.grad for k, p in mp.named_parameters()}
+    n_checked = 0
+    for k, v in g.items():
+        if k.startswith("grad."):
+            got = grads[k[len("grad."):]]
+            assert got is not None, k
+            np.testing.assert_allclose(got.numpy(), v, rtol=1e-4, atol=ATOL, err_msg=k)
+            n_checked += 1
+    assert n_checked >= 3
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n not in COMPOSED_GOLDENS])
+def test_monolithic_f32_tier_through_emulation(name, monkeypatch):
+    """engine.BondMPFunction / AtomMPFunction (generic mirror) on emulated kernels == reference golden.  Doubles as
+    the validation of the emulation: this host code is the one the GPU tests verify with the real kernels."""
+    emu.patch_engine(monkeypatch)
+    g = load_golden(name)
+    mp, bmg, H, aggs = _run(g)
+    assert not mp.uses_composed_tier()
+    _check(g, mp, H, aggs)
+
+
+@pytest.mark.parametrize("name", COMPOSED_GOLDENS)
+def test_composed_tier_matches_reference_golden(name, monkeypatch):
+    """PReLU (with its own gradient), SELU, a user module (Softplus), AtomMP undirected: composed.py == reference."""
+    emu.patch_engine(monkeypatch)
+    g = load_golden(name)
+    mp, bmg, H, aggs = _run(g)
+    assert mp.uses_composed_tier()
+    _check(g, mp, H, aggs)
+    if "prelu" in name:
+        assert "grad.tau.weight" in g and mp.tau.weight.grad is not None
+
+
+@pytest.mark.parametrize("name", ["bond_d3_relu", "bond_d2_bias", "bond_d3_undirected", "bond_d3_tanh", "bond_d3_mixed",
+                                  "bond_d3_noedges", "bond_d3_vd", "atom_d3_relu", "atom_d3_bias_tanh", "atom_d3_cgr",
+                                  "atom_d3_noedges", "atom_d1", "bond_d1"])
+def test_composed_tier_equals_monolithic_configurations(name, monkeypatch):
+    """The composed tier forced onto configurations the monolithic tier also serves: same goldens."""
+    emu.patch_engine(monkeypatch)
+    g = load_golden(name)
+    mp = build_engine_module(g, "cpu", "fp32")
+    monkeypatch.setattr(type(mp), "uses_composed_tier", lambda self: True)
+    mp, bmg, H, aggs = _run(g, mp)
+    _check(g, mp, H, aggs)
+
+
+@pytest.mark.parametrize("kind,undirected,act", [("bond", False, "relu"), ("bond", True, "tanh"), ("atom", False, "elu"),
+                                                 ("atom", True, "prelu")])
+def test_training_dropout_mask_for_mask(kind, undirected, act, monkeypatch):
+    """dropout > 0 in training (base.py:139, :182, :188): the composed tier applies the caller's dropout module at the
+    reference's three sites; with the masks it drew mapped back to the caller's edge order, the oracle reproduces the
+    run exactly (forward and every gradient)."""
+    from tests.util import dropout_mask_for_mask
+
+    emu.patch_engine(monkeypatch)
+    dropout_mask_for_mask(kind, undirected, act, "cpu")
+
+
+def test_eval_mode_with_dropout_configured_stays_monolithic(monkeypatch):
+    emu.patch_engine(monkeypatch)
+    g = load_golden("bond_d3_dropout_eval")
+    mp, bmg, H, aggs = _run(g)
+    assert mp.dropout.p == 0.3 and not mp.training and not mp.uses_composed_tier()
+    _check(g, mp, H, aggs)
+    mp.train()
+    assert mp.uses_composed_tier()
+
+
+def test_tier_selection():
+    from chemprop_b200.nn import AtomMessagePassing, BondMessagePassing
+
+    class MyReLU(torch.nn.ReLU):           # a subclass may override forward: not assumed to be ReLU
+        pass
+
+    assert not BondMessagePassing(d_h=8).uses_composed_tier()
+    assert not BondMessagePassing(d_h=8, undirected=True, activation="elu").uses_composed_tier()
+    assert BondMessagePassing(d_h=8, activation="prelu").uses_composed_tier()
+    assert BondMessagePassing(d_h=8, activation="selu").uses_composed_tier()
+    assert BondMessagePassing(d_h=8, activation=torch.nn.GELU()).uses_composed_tier()
+    assert BondMessagePassing(d_h=8, activation=MyReLU()).uses_composed_tier()
+    assert AtomMessagePassing(d_h=8, undirected=True).uses_composed_tier()
+    assert not AtomMessagePassing(d_h=8).uses_composed_tier()
+    mp = BondMessagePassing(d_h=8, dropout=0.1)
+    assert mp.uses_composed_tier() and not mp.eval().uses_composed_tier()
+    with pytest.raises(Exception, match="no CPU fallback|CUDA"):     # the composed tier has no CPU path either
+        from chemprop_b200.data import BatchMolGraph, make_molecules
+        BondMessagePassing(d_h=8, activation="prelu")(BatchMolGraph(make_molecules(2, seed=0)))

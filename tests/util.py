@@ -51,9 +51,22 @@ def oracle_forward(g: dict, dtype=torch.float32, requires_grad: bool = False):
     V_d = torch.from_numpy(g["V_d"]).to(dtype) if "V_d" in g else None
     H = R.message_passing_forward(
         cfg["kind"], V, E, ei, rev, P["W_i.weight"], P.get("W_i.bias"), P["W_h.weight"], P.get("W_h.bias"),
-        P["W_o.weight"], P.get("W_o.bias"), cfg["depth"], cfg.get("activation", "relu"),
-        cfg.get("undirected", False), V_d, P.get("W_d.weight"), P.get("W_d.bias"))
+        P["W_o.weight"], P.get("W_o.bias"), cfg["depth"], activation_name(cfg),
+        cfg.get("undirected", False), V_d, P.get("W_d.weight"), P.get("W_d.bias"), prelu_weight=P.get("tau.weight"))
     return H, P
+
+
+def activation_name(cfg: dict) -> str:
+    return cfg["activation_module"].lower() if cfg.get("activation_module") else cfg.get("activation", "relu")
+
+
+def activation_arg(cfg: dict):
+    """What the golden case handed to the module constructor: a name, or a module instance."""
+    return getattr(torch.nn, cfg["activation_module"])() if cfg.get("activation_module") else cfg.get("activation", "relu")
+
+
+COMPOSED_GOLDENS = ("bond_d3_prelu", "atom_d3_prelu_bias", "bond_d3_selu", "bond_d3_softplus", "atom_d3_undirected",
+                    "atom_d4_undir_elu", "bond_d3_undir_prelu", "atom_d3_noedges_prelu")
 
 
 def build_engine_module(g: dict, device="cuda", precision="fp32", fused=True):
@@ -67,12 +80,12 @@ def build_engine_module(g: dict, device="cuda", precision="fp32", fused=True):
                             ScaleTransform(g["gt_E_mean"][0], g["gt_E_scale"][0]))
     cls = BondMessagePassing if cfg["kind"] == "bond" else AtomMessagePassing
     mp = cls(d_v=cfg.get("d_v", 72), d_e=cfg.get("d_e", 14), d_h=cfg["d_h"], bias=cfg.get("bias", False),
-             depth=cfg["depth"], activation=cfg.get("activation", "relu"), undirected=cfg.get("undirected", False),
-             d_vd=cfg.get("d_vd"), graph_transform=gt, precision=precision)
+             depth=cfg["depth"], activation=activation_arg(cfg), undirected=cfg.get("undirected", False),
+             dropout=cfg.get("dropout", 0.0), d_vd=cfg.get("d_vd"), graph_transform=gt, precision=precision)
     mp.fused = fused
     mp.load_state_dict({k: v for k, v in params_of(g).items()}, strict=False)
     mp = mp.to(device)
-    if gt is not None:
+    if gt is not None or cfg.get("eval"):
         mp.eval()
     return mp
 
@@ -85,3 +98,60 @@ def golden_bmg(g: dict, device="cuda"):
         torch.from_numpy(g["rev_edge_index"]), torch.from_numpy(g["batch"]), int(g["n_mols"]))
     bmg.to(device)
     return bmg
+
+
+class RecordingDropout(torch.nn.Dropout):
+    """nn.Dropout that remembers the (scaled) masks it applied, in call order."""
+
+    def __init__(self, p):
+        super().__init__(p)
+        self.masks = []
+
+    def forward(self, x):
+        m = torch.nn.functional.dropout(torch.ones_like(x), self.p, self.training)
+        self.masks.append(m)
+        return x * m
+
+
+def dropout_mask_for_mask(kind: str, undirected: bool, act: str, device: str, n_mols: int = 12, d_h: int = 32):
+    """Training-mode dropout on the composed tier vs the oracle fed with the very masks the run drew (edge-level masks
+    mapped from the engine's dst-sorted row order back to the caller's edge order through `perm`)."""
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.engine import get_layout
+    from chemprop_b200.nn import AtomMessagePassing, BondMessagePassing, MeanAggregation
+    from oracle import restatement as R
+
+    torch.manual_seed(3)
+    bmg = BatchMolGraph(make_molecules(n_mols, seed=4, mean_atoms=10, std_atoms=4, shuffle_edges=True, min_atoms=1))
+    ref = BatchMolGraph(make_molecules(n_mols, seed=4, mean_atoms=10, std_atoms=4, shuffle_edges=True, min_atoms=1))
+    cls = BondMessagePassing if kind == "bond" else AtomMessagePassing
+    depth, d_vd = 3, 4
+    mp = cls(d_h=d_h, depth=depth, bias=True, dropout=0.4, activation=act, undirected=undirected, d_vd=d_vd)
+    mp.dropout = RecordingDropout(0.4)
+    mp.train()
+    assert mp.uses_composed_tier()
+    V_d = torch.randn(bmg.V.shape[0], d_vd)
+    P = {k: v.detach().double().requires_grad_(True) for k, v in mp.state_dict().items()}
+    mp = mp.to(device)
+    bmg.to(device)
+    H = mp(bmg, V_d.to(device))
+    a = MeanAggregation()(H, bmg.batch)
+    a.square().sum().backward()
+    masks = [m.cpu() for m in mp.dropout.masks]
+    assert len(masks) == (depth - 1) + 2 and 0.2 < float((masks[0] == 0).float().mean()) < 0.6
+    perm = get_layout(bmg).perm.long().cpu()
+    ref_masks = []
+    for m in masks[: depth - 1]:                  # edge-level masks were drawn in the internal (dst-sorted) row order
+        mm = torch.empty_like(m)
+        mm[perm] = m
+        ref_masks.append(mm.double())
+    ref_masks += [m.double() for m in masks[depth - 1:]]
+    H_ref = R.message_passing_forward(kind, ref.V.double(), ref.E.double(), ref.edge_index, ref.rev_edge_index,
+                                      P["W_i.weight"], P["W_i.bias"], P["W_h.weight"], P["W_h.bias"], P["W_o.weight"],
+                                      P["W_o.bias"], depth, act, undirected, V_d.double(), P["W_d.weight"], P["W_d.bias"],
+                                      prelu_weight=P.get("tau.weight"), dropout_masks=ref_masks)
+    R.aggregate(H_ref, ref.batch, "mean").square().sum().backward()
+    assert (H.detach().double().cpu() - H_ref.detach()).abs().max().item() <= 1e-5
+    for k, p in mp.named_parameters():
+        g = P[k].grad
+        assert p.grad is not None and (p.grad.double().cpu() - g).abs().max().item() <= 1e-4 * max(1.0, g.abs().max().item()), k
