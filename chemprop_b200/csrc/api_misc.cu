@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <atomic>
 #include <string.h>
+#include <vector>
 
 #include "common.cuh"
 
@@ -111,6 +112,71 @@ int dmpnn_collate_host_compact(int64_t n_mols, const int64_t* n_atoms, const int
     a0 += na;
     e0 += ne;
   }
+  return 0;
+}
+
+// The layout meta words of a batch (dmpnn_layout_build's `meta`), computed on the HOST from the batch's index arrays:
+// validity flags, max in-degree and the greedy molecule-aligned tile packing (tile count, largest tile).  A loader
+// calls this once per batch next to the collate, so the training step never has to read `meta` back from the device
+// (no host <-> device synchronisation inside the step).  Bit-exact w.r.t. oracle/layout_np.py for valid batches; for
+// an invalid batch only the flags are meaningful (the tile words are 0).
+int dmpnn_batch_meta_host(const int64_t* edge_index /*2 x E*/, const int64_t* rev, const int64_t* batch, int64_t V,
+                          int64_t E, int64_t B, int32_t* meta /*DMPNN_META_WORDS*/) {
+  DMPNN_CHECK_ARG(V >= 0 && E >= 0 && B >= 0 && meta, "batch_meta_host: bad sizes");
+  DMPNN_CHECK_ARG(E == 0 || (edge_index && rev), "batch_meta_host: null index array");
+  DMPNN_CHECK_ARG(V == 0 || batch, "batch_meta_host: null batch");
+  DMPNN_CHECK_ARG(V < (1LL << 31) && E < (1LL << 31) && B < (1LL << 31), "batch_meta_host: batch too large for int32");
+  for (int i = 0; i < DMPNN_META_WORDS; ++i) meta[i] = 0;
+  const int64_t* src = edge_index;
+  const int64_t* dst = edge_index + E;
+  bool in_range = true;
+  for (int64_t e = 0; e < E && in_range; ++e)
+    in_range = src[e] >= 0 && src[e] < V && dst[e] >= 0 && dst[e] < V && rev[e] >= 0 && rev[e] < E;
+  for (int64_t v = 0; v < V && in_range; ++v) in_range = batch[v] >= 0 && batch[v] < B;
+  if (!in_range) return 0;                                  // flags = 0: nothing else can be trusted
+  bool invol = true, sorted = true;
+  for (int64_t e = 0; e < E && invol; ++e) {
+    const int64_t r = rev[e];
+    invol = rev[r] == e && src[r] == dst[e] && dst[r] == src[e];
+  }
+  for (int64_t v = 1; v < V && sorted; ++v) sorted = batch[v] >= batch[v - 1];
+  for (int64_t e = 0; e < E && sorted; ++e) sorted = batch[src[e]] == batch[dst[e]];
+  meta[DMPNN_META_FLAGS] = DMPNN_FLAG_INDEX_IN_RANGE | (invol ? DMPNN_FLAG_REV_INVOLUTION : 0) |
+                           (sorted ? DMPNN_FLAG_BATCH_SORTED : 0);
+  std::vector<int32_t> deg((size_t)V, 0);
+  for (int64_t e = 0; e < E; ++e) ++deg[(size_t)dst[e]];
+  int32_t max_indeg = 0;
+  for (int64_t v = 0; v < V; ++v) max_indeg = deg[(size_t)v] > max_indeg ? deg[(size_t)v] : max_indeg;
+  meta[DMPNN_META_MAX_INDEG] = max_indeg;
+  if (!sorted || B == 0) return 0;
+  // molecule offsets: atoms of molecule m are [ap[m], ap[m+1]); its edge rows (edges are intra-molecule) [rp[m], rp[m+1])
+  std::vector<int64_t> ap((size_t)B + 1, 0), rp((size_t)B + 1, 0);
+  for (int64_t v = 0; v < V; ++v) {
+    ++ap[(size_t)batch[v] + 1];
+    rp[(size_t)batch[v] + 1] += deg[(size_t)v];
+  }
+  for (int64_t m = 0; m < B; ++m) {
+    ap[(size_t)m + 1] += ap[(size_t)m];
+    rp[(size_t)m + 1] += rp[(size_t)m];
+  }
+  // greedy packing, restarted every 1024 molecules (layout.cu: kTileChunk; oracle/layout_np.py: TILE_CHUNK)
+  const int64_t kRows = 128, kAtoms = 128, kChunk = 1024;
+  int64_t t_mol = 0, n_tiles = 0, max_rows = 0, max_atoms = 0;
+  for (int64_t m = 0; m < B; ++m) {
+    if (m > t_mol && (m % kChunk == 0 || rp[(size_t)m + 1] - rp[(size_t)t_mol] > kRows ||
+                      ap[(size_t)m + 1] - ap[(size_t)t_mol] > kAtoms)) {
+      ++n_tiles;
+      if (rp[(size_t)m] - rp[(size_t)t_mol] > max_rows) max_rows = rp[(size_t)m] - rp[(size_t)t_mol];
+      if (ap[(size_t)m] - ap[(size_t)t_mol] > max_atoms) max_atoms = ap[(size_t)m] - ap[(size_t)t_mol];
+      t_mol = m;
+    }
+  }
+  ++n_tiles;
+  if (rp[(size_t)B] - rp[(size_t)t_mol] > max_rows) max_rows = rp[(size_t)B] - rp[(size_t)t_mol];
+  if (ap[(size_t)B] - ap[(size_t)t_mol] > max_atoms) max_atoms = ap[(size_t)B] - ap[(size_t)t_mol];
+  meta[DMPNN_META_N_TILES] = (int32_t)n_tiles;
+  meta[DMPNN_META_MAX_TILE_ROWS] = (int32_t)max_rows;
+  meta[DMPNN_META_MAX_TILE_ATOMS] = (int32_t)max_atoms;
   return 0;
 }
 

@@ -47,8 +47,44 @@ def _collate_ext():
     return _EXT or None
 
 
+def host_meta(edge_index: Tensor, rev_edge_index: Tensor, batch: Tensor, n_mols: int) -> list | None:
+    """The layout meta words (flags, max in-degree, tile count, largest tile) of a batch whose int64 index tensors are
+    in host memory -- `dmpnn_batch_meta_host`, one C pass.  None when the tensors are not plain host int64."""
+    ts = (edge_index, rev_edge_index, batch)
+    if any(t.is_cuda or t.dtype != torch.int64 or not t.is_contiguous() for t in ts):
+        return None
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2 or rev_edge_index.shape[0] != edge_index.shape[1]:
+        return None
+    V, E = int(batch.shape[0]), int(edge_index.shape[1])
+    if max(V, E, n_mols) >= 2 ** 31:
+        return None
+    meta = np.zeros(_lib.META_WORDS, dtype=np.int32)
+    lib = _lib.load()
+    rc = lib.dmpnn_batch_meta_host(edge_index.data_ptr() if E else None, rev_edge_index.data_ptr() if E else None,
+                                   batch.data_ptr() if V else None, V, E, int(n_mols), meta.ctypes.data)
+    _lib.check(rc, "dmpnn_batch_meta_host")
+    return meta.tolist()
+
+
 class BatchMolGraph:
-    __slots__ = ("V", "E", "edge_index", "rev_edge_index", "batch", "_size", "_layout", "_xfer")
+    # the three index tensors sit behind properties: replacing one drops the cached device layout and host meta
+    __slots__ = ("V", "E", "_edge_index", "_rev_edge_index", "_batch", "_size", "_layout", "_xfer", "_meta_host")
+
+    def _index_property(name):  # noqa: N805
+        def get(self):
+            return getattr(self, name)
+
+        def set_(self, value):
+            setattr(self, name, value)
+            self._layout = None
+            self._meta_host = None
+
+        return property(get, set_)
+
+    edge_index = _index_property("_edge_index")
+    rev_edge_index = _index_property("_rev_edge_index")
+    batch = _index_property("_batch")
+    del _index_property
 
     def __init__(self, mgs: Sequence[MolGraph], pin_memory: bool = False, transfer_dtype: torch.dtype | None = None,
                  use_extension: bool = True):
@@ -60,6 +96,7 @@ class BatchMolGraph:
         self._size = len(mgs)
         self._layout = None
         self._xfer = None
+        self._meta_host = None
         if transfer_dtype is not None and transfer_dtype != torch.bfloat16:
             raise ValueError("transfer_dtype must be torch.bfloat16 or None")
         kw = dict(pin_memory=True) if pin_memory else {}
@@ -68,6 +105,8 @@ class BatchMolGraph:
             self._init_ext(ext, mgs, kw, transfer_dtype is not None)
         else:
             self._init_ctypes(mgs, kw, transfer_dtype is not None)
+        # flags / tile count of this batch, computed here in the loader so that the training step needs no device read-back
+        self._meta_host = host_meta(self._edge_index, self._rev_edge_index, self._batch, self._size)
 
     def _alloc(self, Vt: int, Et: int, d_v: int, d_e: int, kw: dict, compact: bool):
         self.V = torch.empty((Vt, d_v), dtype=torch.float32, **kw)
@@ -133,10 +172,11 @@ class BatchMolGraph:
                      size: int) -> "BatchMolGraph":
         """Wrap already-batched tensors (e.g. the five leaves of a reference BatchMolGraph)."""
         bmg = object.__new__(cls)
-        bmg.V, bmg.E, bmg.edge_index, bmg.rev_edge_index, bmg.batch = V, E, edge_index, rev_edge_index, batch
+        bmg.V, bmg.E, bmg._edge_index, bmg._rev_edge_index, bmg._batch = V, E, edge_index, rev_edge_index, batch
         bmg._size = int(size)
         bmg._layout = None
         bmg._xfer = None
+        bmg._meta_host = host_meta(edge_index, rev_edge_index, batch, int(size))   # None for device tensors
         return bmg
 
     def __len__(self) -> int:
@@ -158,15 +198,17 @@ class BatchMolGraph:
     def to(self, device, non_blocking: bool = False):
         """In place, returns None (chemprop/data/collate.py:68-73)."""
         dev = torch.device(device)
-        if self.V.device != dev:
-            self._layout = None
+        meta = self._meta_host                     # the index values do not change with the device
         self.V, self.E, self.edge_index, self.rev_edge_index, self.batch = self._moved(dev, non_blocking)
+        self._meta_host = meta
         if dev.type == "cuda":
             self._xfer = None
 
     def cuda_copy(self, device="cuda", non_blocking: bool = True) -> "BatchMolGraph":
         """A device-resident copy; this (pinned) host batch stays intact, e.g. for reuse by a loader."""
-        return BatchMolGraph.from_tensors(*self._moved(torch.device(device), non_blocking), self._size)
+        out = BatchMolGraph.from_tensors(*self._moved(torch.device(device), non_blocking), self._size)
+        out._meta_host = self._meta_host
+        return out
 
     def __copy__(self):
         # GraphTransform makes a shallow copy and replaces V / E (chemprop/nn/transforms.py:69-72);

@@ -20,6 +20,10 @@ from ._lib import (ACT_ELU, ACT_LEAKYRELU, ACT_NONE, ACT_RELU, ACT_TANH, BF16, F
 # False = the terms stay apart and the W_i gradient accumulates one GEMM per term (measured faster at depth 3)
 SUM_IN_EPILOGUE = False
 
+# True: a BatchMolGraph that carries host-computed layout meta words (our collate: dmpnn_batch_meta_host) is trusted
+# and the step never synchronises on the device copy; False: always read the device-computed words (one sync per batch)
+HOST_META = True
+
 HIDDEN_ALIGN = 64  # hidden row stride padded to 64 elements: bf16 rows start on 128-byte lines (one TMA request per box row)
 
 # Optional device-side timing of the depth step (bench.py's roofline): when a list, every depth step
@@ -127,20 +131,26 @@ class Layout:
         return self._host()[_lib.META_MAX_TILE_ATOMS]
 
     def validate(self):
-        f = self.flags
-        if not f & _lib.FLAG_INDEX_IN_RANGE:
-            raise DmpnnError("BatchMolGraph indices out of range (edge_index / rev_edge_index / batch)")
-        if not f & _lib.FLAG_BATCH_SORTED:
-            raise DmpnnError("BatchMolGraph.batch must be non-decreasing and edges must stay inside a molecule")
-        if not f & _lib.FLAG_REV_INVOLUTION:
-            raise DmpnnError(
-                "rev_edge_index is not a proper reverse-edge map (rev[rev[e]]==e with swapped endpoints); "
-                "the engine requires it (every featuriser-made graph satisfies it)"
-            )
+        check_flags(self.flags)
 
 
-def build_layout(edge_index: Tensor, rev_edge_index: Tensor, batch: Tensor, n_mols: int) -> Layout:
-    """dmpnn_layout_build on the current stream.  Inputs are the reference's int64 index tensors."""
+def check_flags(f: int):
+    if not f & _lib.FLAG_INDEX_IN_RANGE:
+        raise DmpnnError("BatchMolGraph indices out of range (edge_index / rev_edge_index / batch)")
+    if not f & _lib.FLAG_BATCH_SORTED:
+        raise DmpnnError("BatchMolGraph.batch must be non-decreasing and edges must stay inside a molecule")
+    if not f & _lib.FLAG_REV_INVOLUTION:
+        raise DmpnnError(
+            "rev_edge_index is not a proper reverse-edge map (rev[rev[e]]==e with swapped endpoints); "
+            "the engine requires it (every featuriser-made graph satisfies it)"
+        )
+
+
+def build_layout(edge_index: Tensor, rev_edge_index: Tensor, batch: Tensor, n_mols: int,
+                 meta_host: list | None = None) -> Layout:
+    """dmpnn_layout_build on the current stream.  Inputs are the reference's int64 index tensors.
+    `meta_host`: the meta words already computed on the host for this very batch (dmpnn_batch_meta_host, by our
+    collate): the layout then never reads `meta` back from the device -- no sync in the training step."""
     _require_cuda(edge_index, rev_edge_index, batch)
     lib = _lib.load()
     dev = edge_index.device
@@ -176,7 +186,8 @@ def build_layout(edge_index: Tensor, rev_edge_index: Tensor, batch: Tensor, n_mo
     )
     _lib.check(rc, "dmpnn_layout_build")
     return Layout(V, E, B, perm[:E], inv_perm[:E], rowptr, src_row[:E], dst_row[:E], rev_row[:E], mol_atom_ptr,
-                  mol_row_ptr, tile_mol_ptr, tile_row_ptr, tile_atom_ptr, meta)
+                  mol_row_ptr, tile_mol_ptr, tile_row_ptr, tile_atom_ptr, meta,
+                  None if meta_host is None else list(meta_host))
 
 
 def get_layout(bmg) -> Layout:
@@ -184,7 +195,12 @@ def get_layout(bmg) -> Layout:
     lay = getattr(bmg, "_layout", None)
     if lay is not None and lay.rowptr.device == bmg.edge_index.device:
         return lay
-    lay = build_layout(bmg.edge_index, bmg.rev_edge_index, bmg.batch, len(bmg))
+    meta_host = getattr(bmg, "_meta_host", None) if HOST_META else None
+    if meta_host is not None:
+        check_flags(meta_host[_lib.META_FLAGS])      # an invalid batch is refused before anything is launched
+        lay = build_layout(bmg.edge_index, bmg.rev_edge_index, bmg.batch, len(bmg), meta_host)
+    else:
+        lay = build_layout(bmg.edge_index, bmg.rev_edge_index, bmg.batch, len(bmg))
     lay.validate()
     try:
         bmg._layout = lay

@@ -98,6 +98,15 @@ int dmpnn_collate_host_compact(int64_t n_mols, const int64_t* n_atoms, const int
                                uint16_t* V_out, uint16_t* E_out, int32_t* edge_index_out /*2 x E_tot*/,
                                int32_t* rev_out, int32_t* batch_out);
 
+/* Layout meta words of a batch computed on the HOST (same DMPNN_META_* words dmpnn_layout_build writes on the
+ * device): validity flags, max in-degree, and the tile count / largest tile of the greedy molecule-aligned packing.
+ * A loader calls it next to the collate (the batch's int64 index arrays are in host memory there), so that the
+ * training step never reads `meta` back from the GPU: no host <-> device synchronisation inside the step.  The
+ * reference has the same kind of per-batch sync in agg.py:75 (`batch.max().int() + 1`).  Bit-exact w.r.t.
+ * oracle/layout_np.py; for an invalid batch only DMPNN_META_FLAGS is meaningful.  CPU code. */
+int dmpnn_batch_meta_host(const int64_t* edge_index /*2 x E*/, const int64_t* rev_edge_index, const int64_t* batch,
+                          int64_t V, int64_t E, int64_t B, int32_t* meta /*DMPNN_META_WORDS*/);
+
 /* ---------------------------------------------------------------------------------------
  * Device layout build.  Consumes the reference's BatchMolGraph index tensors
  * (chemprop/data/collate.py:24-33: edge_index int64 2xE, rev_edge_index int64 E, batch int64 V)

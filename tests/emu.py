@@ -166,7 +166,7 @@ def act_bwd(G, Yact, R, Ccols, *, act, act_param=0.0, gidx=None, from_preact=Fal
         acc[:R, :Ccols] += d.to(acc.dtype)
 
 
-def build_layout(edge_index, rev_edge_index, batch, n_mols):
+def build_layout(edge_index, rev_edge_index, batch, n_mols, meta_host=None):
     L = layout_np.build_layout(edge_index.numpy(), rev_edge_index.numpy(), batch.numpy(), int(n_mols))
     B = int(n_mols)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a).astype(np.int32))
@@ -175,6 +175,7 @@ def build_layout(edge_index, rev_edge_index, batch, n_mols):
     meta[_lib.META_N_TILES], meta[_lib.META_FLAGS] = L["n_tiles"], L["flags"]
     meta[_lib.META_MAX_INDEG], meta[_lib.META_MAX_TILE_ROWS] = L["max_indeg"], L["max_tile_rows"]
     meta[_lib.META_MAX_TILE_ATOMS] = L["max_tile_atoms"]
+    assert meta_host is None or list(meta_host) == meta, (meta_host, meta)
     return engine.Layout(int(batch.shape[0]), int(edge_index.shape[1]), B, t(L["perm"]), t(L["inv_perm"]), t(L["rowptr"]),
                          t(L["src_row"]), t(L["dst_row"]), t(L["rev_row"]), t(L["mol_atom_ptr"]), t(L["mol_row_ptr"]),
                          pad(L["tile_mol_ptr"]), pad(L["tile_row_ptr"]), pad(L["tile_atom_ptr"]),

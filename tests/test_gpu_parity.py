@@ -107,6 +107,23 @@ def test_layout_bit_exact_many_molecules(n_mols, min_atoms):
         L["flags"], L["max_indeg"], L["max_tile_rows"], L["max_tile_atoms"])
 
 
+@pytest.mark.parametrize("n_mols,kw", [(6, {}), (1500, dict(shuffle_edges=True, min_atoms=1)),
+                                        (40, dict(mean_atoms=90, std_atoms=20, max_atoms=150))])
+def test_host_meta_words_equal_device_meta_words(n_mols, kw):
+    """The meta words our collate computes on the host (dmpnn_batch_meta_host; they let the step skip the device
+    read-back) are the ones dmpnn_layout_build writes on the device."""
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.engine import get_layout
+
+    bmg = BatchMolGraph(make_molecules(n_mols, seed=n_mols, **kw))
+    host_words = list(bmg._meta_host)
+    bmg.to("cuda")
+    assert bmg._meta_host == host_words
+    lay = get_layout(bmg)
+    assert lay._meta_host == host_words                      # taken from the host, no read-back
+    assert lay.meta.tolist()[:5] == host_words[:5]           # and identical to the device's
+
+
 def test_inputs_not_mutated():
     """tests/integration/test_regression_mol.py:143-226 of the reference."""
     g = load_golden("bond_d3_graphtf")

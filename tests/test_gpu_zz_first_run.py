@@ -1,11 +1,14 @@
-"""GPU tier (B200): the composed tier (chemprop_b200/composed.py) -- PReLU / SELU / user activation modules, dropout
-> 0 in training, AtomMessagePassing(undirected=True) -- through the real kernels, against the golden vectors of the
-real reference and against the oracle.  Same tolerances as tests/test_gpu_parity.py.
+"""GPU tier (B200): tests of code that has not yet run on hardware.
+
+  * the composed tier (chemprop_b200/composed.py) -- PReLU / SELU / user activation modules, dropout > 0 in training,
+    AtomMessagePassing(undirected=True) -- through the real kernels, against the golden vectors of the real reference
+    and against the oracle; same tolerances as tests/test_gpu_parity.py;
+  * the sync-free training step (host-computed layout meta words, dmpnn_batch_meta_host).
 
 This file sorts last on purpose.  It was written after this round's GPU budget was spent: its first run on hardware
 is the round-end run, so it is marked xfail(strict=False) -- a pass is reported as XPASS, a failure does not mask the
 results of the hardware-verified tiers.  The host logic it exercises is covered on CPU by tests/test_host_logic.py
-(kernel wrappers emulated in torch); remove the marker once an XPASS has been seen."""
+(kernel wrappers emulated in torch) and tests/test_host.py; remove the marker once an XPASS has been seen."""
 import numpy as np
 import pytest
 import torch
@@ -13,8 +16,8 @@ import torch
 from tests.util import COMPOSED_GOLDENS, build_engine_module, dropout_mask_for_mask, golden_bmg, load_golden
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run of the composed tier (written after the "
-                                                      "round's GPU budget was spent); CPU host-logic tests cover the wiring")]
+              pytest.mark.xfail(strict=False, reason="first hardware run of this code (written after the round's "
+                                                      "GPU budget was spent); CPU host-logic tests cover the wiring")]
 
 FP32_ATOL = 1e-5
 BF16_ATOL = 1e-2
@@ -88,3 +91,32 @@ def test_composed_equals_fused_tier_on_a_shared_configuration(kind):
     for k in grads[0]:
         scale = max(1e-6, grads[0][k].abs().max().item())
         assert (grads[0][k] - grads[1][k]).abs().max().item() <= 2e-4 * scale, k
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_training_step_does_not_synchronise(precision):
+    """With the layout meta words computed by the collate on the host, a whole forward + backward of the hot path
+    issues no host <-> device synchronisation (torch's sync debug mode raises on any)."""
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.nn import BondMessagePassing, MeanAggregation
+
+    torch.manual_seed(0)
+    mp = BondMessagePassing(precision=precision).cuda()
+    agg = MeanAggregation()
+    host = BatchMolGraph(make_molecules(2000, seed=3), pin_memory=True)
+    assert host._meta_host is not None
+
+    def step():
+        bmg = host.cuda_copy("cuda", non_blocking=True)
+        loss = agg(mp(bmg), bmg.batch).float().square().mean()
+        loss.backward()
+        return loss
+
+    step()                                   # warm-up: lazy initialisation may synchronise
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        loss = step()
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    assert torch.isfinite(loss).item()

@@ -119,3 +119,57 @@ def test_collate_extension_and_ctypes_paths_agree():
     for ext in (True, False):
         with pytest.raises(ValueError, match="MolGraph.E has"):
             BatchMolGraph(bad, use_extension=ext)
+
+
+def _np_meta(bmg):
+    from chemprop_b200 import _lib
+    from oracle import layout_np
+
+    L = layout_np.build_layout(bmg.edge_index.numpy(), bmg.rev_edge_index.numpy(), bmg.batch.numpy(), len(bmg))
+    m = [0] * _lib.META_WORDS
+    m[_lib.META_N_TILES], m[_lib.META_FLAGS], m[_lib.META_MAX_INDEG] = L["n_tiles"], L["flags"], L["max_indeg"]
+    m[_lib.META_MAX_TILE_ROWS], m[_lib.META_MAX_TILE_ATOMS] = L["max_tile_rows"], L["max_tile_atoms"]
+    return m
+
+
+@pytest.mark.parametrize("n_mols,kw", [(0, {}), (1, {}), (7, dict(min_atoms=1)), (300, dict(shuffle_edges=True)),
+                                        (1024, {}), (1025, dict(min_atoms=1)), (3000, dict(shuffle_edges=True, min_atoms=1)),
+                                        (40, dict(mean_atoms=90, std_atoms=20, max_atoms=150))])
+def test_host_meta_bit_exact_vs_numpy_layout(n_mols, kw):
+    """dmpnn_batch_meta_host (what lets the training step skip the device read-back of the layout meta words) against
+    oracle/layout_np.py -- which the GPU tests in turn hold bit-exact against dmpnn_layout_build."""
+    bmg = BatchMolGraph(make_molecules(n_mols, seed=n_mols + 3, **kw))
+    assert bmg._meta_host == _np_meta(bmg)
+    moved = BatchMolGraph.from_tensors(bmg.V, bmg.E, bmg.edge_index, bmg.rev_edge_index, bmg.batch, len(bmg))
+    assert moved._meta_host == bmg._meta_host
+    c = copy.copy(bmg)
+    assert c._meta_host == bmg._meta_host
+    if n_mols >= 7:
+        assert bmg._meta_host[0] >= 1 and bmg._meta_host[1] == 7
+
+
+def test_host_meta_flags_on_invalid_batches_and_invalidation():
+    from chemprop_b200 import _lib
+    from chemprop_b200.data.collate import host_meta
+
+    bmg = BatchMolGraph(make_molecules(20, seed=8))
+    ei, rev, bt = bmg.edge_index.clone(), bmg.rev_edge_index.clone(), bmg.batch.clone()
+    bad_rev = rev.clone()
+    bad_rev[0] = 2                                                      # edge 0's reverse is edge 1
+    f = host_meta(ei, bad_rev, bt, 20)[_lib.META_FLAGS]
+    assert f & _lib.FLAG_INDEX_IN_RANGE and not f & _lib.FLAG_REV_INVOLUTION and f & _lib.FLAG_BATCH_SORTED
+    bad_bt = bt.clone()
+    bad_bt[0], bad_bt[-1] = bt[-1].item(), bt[0].item()
+    f = host_meta(ei, rev, bad_bt, 20)[_lib.META_FLAGS]
+    assert f & _lib.FLAG_INDEX_IN_RANGE and not f & _lib.FLAG_BATCH_SORTED
+    bad_ei = ei.clone()
+    bad_ei[0, 3] = bmg.V.shape[0]
+    assert host_meta(bad_ei, rev, bt, 20)[_lib.META_FLAGS] == 0
+    for bad in ((ei, bad_rev, bt), (ei, rev, bad_bt), (bad_ei, rev, bt)):
+        b = BatchMolGraph.from_tensors(bmg.V, bmg.E, *bad, 20)
+        assert b._meta_host == _np_meta(b) or b._meta_host[_lib.META_FLAGS] == _np_meta(b)[_lib.META_FLAGS] != 7
+    # replacing an index tensor drops the host words (and the cached layout): the engine re-derives them on the device
+    assert bmg._meta_host is not None
+    bmg.rev_edge_index = bad_rev
+    assert bmg._meta_host is None and bmg._layout is None
+    assert host_meta(ei.int(), rev, bt, 20) is None                     # not the reference's int64: no host words
