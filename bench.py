@@ -363,6 +363,37 @@ def main_gpu(args):
                     "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                     "first_step_ms": statistics.mean(by_tag.get(tag + "_first", [float("nan")]))}
 
+    # ---- resident data set: ids in, loss out -----------------------------------------------
+    # The data set's packed arrays live in HBM; a step uploads the molecule ids + output offsets (24 B / molecule),
+    # assembles its BatchMolGraph with one gather launch and runs the same fwd+bwd.  Extra figure, N = 1 only, measured
+    # last and guarded: it must never take the contract's numbers down with it.
+    resident_ds = None
+    if world == 1 and not args.no_dataset:
+        try:
+            from chemprop_b200.data import PackedMolGraphDataset, make_molecules
+
+            pool = 3 * n_mols
+            ds = PackedMolGraphDataset.from_molgraphs(make_molecules(pool, seed=7, mean_atoms=WORKLOAD["mean_atoms"])).to(dev)
+            rng = np.random.default_rng(0)
+            id_sets = [rng.permutation(pool)[:n_mols] for _ in range(4)]
+
+            def ds_loop(k):
+                losses = []
+                for i in range(k):
+                    loss = step(ds.batch(id_sets[i % len(id_sets)]))
+                    losses.append(loss.detach())
+                vals = torch.stack(losses).float().cpu()          # one D2H read of the k losses, inside the timed region
+                assert bool(torch.isfinite(vals).all())
+
+            ds_loop(3)
+            ms_ds = timed(lambda: ds_loop(args.steps), 1) / args.steps
+            resident_ds = {"value": n_mols / (ms_ds * 1e-3), "unit": "molecules/s", "ms_per_step": ms_ds,
+                           "h2d_bytes_per_step": 8 * (3 * n_mols + 2), "d2h_bytes_per_step": 4,
+                           "dataset_molecules": pool, "dataset_bytes_in_hbm": ds.nbytes(),
+                           "note": "batch assembled on the GPU from the HBM-resident packed data set (random ids per step)"}
+        except Exception as e:  # noqa: BLE001
+            resident_ds = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -394,6 +425,7 @@ def main_gpu(args):
                                 "tier rounds V/E to bf16 on the GPU anyway, results are bit-identical"
                                 if precision == "bf16" else "f32 features + int64 indices")},
         "e2e_f32_host": e2e_f32,
+        "resident_dataset": resident_ds,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -413,6 +445,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-fused", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dataset", action="store_true", help="skip the resident-data-set figure")
     args = ap.parse_args()
     if args.impl == "reference":
         main_reference(args)

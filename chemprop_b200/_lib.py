@@ -29,6 +29,11 @@ SIGNATURES = {
     "dmpnn_collate_host": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "dmpnn_collate_host_compact": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "dmpnn_batch_meta_host": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "dmpnn_dataset_batch_meta_host": (C.c_int, [_i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dmpnn_dataset_gather_host": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64]
+                                  + [_vp] * 10 + [_i32]),
+    "dmpnn_dataset_gather": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64,
+                                       _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "dmpnn_layout_workspace_bytes": (C.c_int, [_i64, _i64, _i64, C.POINTER(_sz)]),
     "dmpnn_layout_build": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64] + [_vp] * 12 + [_vp, _vp]),
     "dmpnn_sorted_index_to_ptr": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <atomic>
 #include <string.h>
+#include <functional>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -177,6 +179,158 @@ int dmpnn_batch_meta_host(const int64_t* edge_index /*2 x E*/, const int64_t* re
   meta[DMPNN_META_N_TILES] = (int32_t)n_tiles;
   meta[DMPNN_META_MAX_TILE_ROWS] = (int32_t)max_rows;
   meta[DMPNN_META_MAX_TILE_ATOMS] = (int32_t)max_atoms;
+  return 0;
+}
+
+// Tile packing words from per-molecule sizes: the O(B) form of dmpnn_batch_meta_host for batches assembled from a
+// packed dataset whose molecules were validated when the dataset was built (flags are then known to be all set).
+static void tiles_meta_from_sizes(int64_t B, const int64_t* n_atoms, const int64_t* n_edges, const int32_t* max_indeg,
+                                  int32_t* meta) {
+  for (int i = 0; i < DMPNN_META_WORDS; ++i) meta[i] = 0;
+  meta[DMPNN_META_FLAGS] = DMPNN_FLAG_INDEX_IN_RANGE | DMPNN_FLAG_REV_INVOLUTION | DMPNN_FLAG_BATCH_SORTED;
+  if (B == 0) return;
+  const int64_t kRows = 128, kAtoms = 128, kChunk = 1024;
+  int64_t rows = 0, atoms = 0, n_tiles = 0, max_rows = 0, max_atoms = 0, t_mol = 0;
+  int32_t mi = 0;
+  for (int64_t m = 0; m < B; ++m) {
+    if (m > t_mol && (m % kChunk == 0 || rows + n_edges[m] > kRows || atoms + n_atoms[m] > kAtoms)) {
+      ++n_tiles;
+      if (rows > max_rows) max_rows = rows;
+      if (atoms > max_atoms) max_atoms = atoms;
+      rows = 0;
+      atoms = 0;
+      t_mol = m;
+    }
+    rows += n_edges[m];
+    atoms += n_atoms[m];
+    if (max_indeg[m] > mi) mi = max_indeg[m];
+  }
+  ++n_tiles;
+  if (rows > max_rows) max_rows = rows;
+  if (atoms > max_atoms) max_atoms = atoms;
+  meta[DMPNN_META_N_TILES] = (int32_t)n_tiles;
+  meta[DMPNN_META_MAX_INDEG] = mi;
+  meta[DMPNN_META_MAX_TILE_ROWS] = (int32_t)max_rows;
+  meta[DMPNN_META_MAX_TILE_ATOMS] = (int32_t)max_atoms;
+}
+
+int dmpnn_dataset_batch_meta_host(int64_t n_sel, const int64_t* ids, int64_t n_total, const int64_t* atom_ptr,
+                                  const int64_t* edge_ptr, const int32_t* mol_max_indeg, int64_t* out_atom_ptr,
+                                  int64_t* out_edge_ptr, int32_t* meta) {
+  DMPNN_CHECK_ARG(n_sel >= 0 && n_total >= 0 && (n_sel == 0 || ids) && atom_ptr && edge_ptr && mol_max_indeg &&
+                      out_atom_ptr && out_edge_ptr && meta, "dataset_batch_meta_host: bad args");
+  std::vector<int64_t> na((size_t)n_sel), ne((size_t)n_sel);
+  std::vector<int32_t> mi((size_t)n_sel);
+  out_atom_ptr[0] = 0;
+  out_edge_ptr[0] = 0;
+  for (int64_t m = 0; m < n_sel; ++m) {
+    const int64_t id = ids[m];
+    DMPNN_CHECK_ARG(id >= 0 && id < n_total, "dataset_batch_meta_host: molecule id %lld out of range", (long long)id);
+    na[(size_t)m] = atom_ptr[id + 1] - atom_ptr[id];
+    ne[(size_t)m] = edge_ptr[id + 1] - edge_ptr[id];
+    mi[(size_t)m] = mol_max_indeg[id];
+    out_atom_ptr[m + 1] = out_atom_ptr[m] + na[(size_t)m];
+    out_edge_ptr[m + 1] = out_edge_ptr[m] + ne[(size_t)m];
+  }
+  DMPNN_CHECK_ARG(out_atom_ptr[n_sel] < (1LL << 31) && out_edge_ptr[n_sel] < (1LL << 31),
+                  "dataset_batch_meta_host: batch too large for int32 rows");
+  tiles_meta_from_sizes(n_sel, na.data(), ne.data(), mi.data(), meta);
+  return 0;
+}
+
+// Host-side batch assembly from a packed dataset: replaces `[dataset[i] for i in ids]` + collate_batch
+// (chemprop/data/datasets.py:222-244, collate.py:37-62) by contiguous copies of each selected molecule's rows.
+// Molecules are independent, so the selection is split over `n_threads` host threads (<= 0: one per 2048 molecules, at
+// most 8 and at most the hardware concurrency).
+struct GatherHostArgs {
+  const int64_t *ids, *out_atom_ptr, *out_edge_ptr, *atom_ptr, *edge_ptr;
+  const float *V_all, *E_all;
+  const int32_t *ei_local, *rev_local;
+  int64_t E_all_total, d_v, d_e, Et;
+  float *V_out, *E_out;
+  int64_t *ei_out, *rev_out, *batch_out;
+  uint16_t *Vb_out, *Eb_out;
+  int32_t *ei32_out, *rev32_out, *batch32_out;
+};
+
+static void gather_host_range(const GatherHostArgs& a, int64_t lo, int64_t hi) {
+  const bool compact = a.Vb_out || a.Eb_out || a.ei32_out || a.rev32_out || a.batch32_out;
+  const int64_t d_v = a.d_v, d_e = a.d_e, Et = a.Et;
+  for (int64_t m = lo; m < hi; ++m) {
+    const int64_t id = a.ids[m];
+    const int64_t sa = a.atom_ptr[id], se = a.edge_ptr[id];
+    const int64_t na = a.atom_ptr[id + 1] - sa, ne = a.edge_ptr[id + 1] - se;
+    const int64_t oa = a.out_atom_ptr[m], oe = a.out_edge_ptr[m];
+    if (a.V_out && na > 0 && d_v > 0) memcpy(a.V_out + oa * d_v, a.V_all + sa * d_v, sizeof(float) * na * d_v);
+    if (a.E_out && ne > 0 && d_e > 0) memcpy(a.E_out + oe * d_e, a.E_all + se * d_e, sizeof(float) * ne * d_e);
+    const int32_t* s0 = a.ei_local + se;
+    const int32_t* s1 = a.ei_local + a.E_all_total + se;
+    const int32_t* rv = a.rev_local + se;
+    if (a.ei_out)
+      for (int64_t j = 0; j < ne; ++j) {
+        a.ei_out[oe + j] = (int64_t)s0[j] + oa;            // collate.py:51
+        a.ei_out[Et + oe + j] = (int64_t)s1[j] + oa;
+        a.rev_out[oe + j] = (int64_t)rv[j] + oe;           // collate.py:52
+      }
+    if (a.batch_out)
+      for (int64_t j = 0; j < na; ++j) a.batch_out[oa + j] = m;   // collate.py:53
+    if (compact) {
+      const float* v = a.V_all + sa * d_v;
+      const float* e = a.E_all + se * d_e;
+      for (int64_t j = 0; j < na * d_v; ++j) a.Vb_out[oa * d_v + j] = f32_to_bf16_rne(v[j]);
+      for (int64_t j = 0; j < ne * d_e; ++j) a.Eb_out[oe * d_e + j] = f32_to_bf16_rne(e[j]);
+      for (int64_t j = 0; j < ne; ++j) {
+        a.ei32_out[oe + j] = (int32_t)(s0[j] + oa);
+        a.ei32_out[Et + oe + j] = (int32_t)(s1[j] + oa);
+        a.rev32_out[oe + j] = (int32_t)(rv[j] + oe);
+      }
+      for (int64_t j = 0; j < na; ++j) a.batch32_out[oa + j] = (int32_t)m;
+    }
+  }
+}
+
+int dmpnn_dataset_gather_host(int64_t n_sel, const int64_t* ids, const int64_t* out_atom_ptr, const int64_t* out_edge_ptr,
+                              const int64_t* atom_ptr, const int64_t* edge_ptr, const float* V_all, const float* E_all,
+                              const int32_t* ei_local, const int32_t* rev_local, int64_t E_all_total, int64_t d_v,
+                              int64_t d_e, float* V_out, float* E_out, int64_t* ei_out, int64_t* rev_out,
+                              int64_t* batch_out, uint16_t* Vb_out, uint16_t* Eb_out, int32_t* ei32_out,
+                              int32_t* rev32_out, int32_t* batch32_out, int n_threads) {
+  DMPNN_CHECK_ARG(n_sel >= 0 && d_v >= 0 && d_e >= 0 && E_all_total >= 0, "dataset_gather_host: bad sizes");
+  if (n_sel == 0) return 0;
+  DMPNN_CHECK_ARG(ids && out_atom_ptr && out_edge_ptr && atom_ptr && edge_ptr, "dataset_gather_host: null table");
+  const bool compact = Vb_out || Eb_out || ei32_out || rev32_out || batch32_out;
+  DMPNN_CHECK_ARG(!compact || (Vb_out && Eb_out && ei32_out && rev32_out && batch32_out),
+                  "dataset_gather_host: the compact copy needs all five outputs");
+  DMPNN_CHECK_ARG(!ei_out == !rev_out, "dataset_gather_host: edge_index and rev_edge_index go together");
+  GatherHostArgs a{ids, out_atom_ptr, out_edge_ptr, atom_ptr, edge_ptr, V_all, E_all, ei_local, rev_local, E_all_total,
+                   d_v, d_e, out_edge_ptr[n_sel], V_out, E_out, ei_out, rev_out, batch_out, Vb_out, Eb_out, ei32_out,
+                   rev32_out, batch32_out};
+  int T = n_threads;
+  if (T <= 0) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    T = (int)((n_sel + 2047) / 2048);
+    if (T > 8) T = 8;
+    if (hw > 0 && T > (int)hw) T = (int)hw;
+  }
+  if (T > n_sel) T = (int)n_sel;
+  if (T <= 1) {
+    gather_host_range(a, 0, n_sel);
+    return 0;
+  }
+  // split by output atoms (not by molecule count) so that threads copy similar byte counts
+  std::vector<std::thread> pool;
+  std::vector<int64_t> cut((size_t)T + 1, 0);
+  cut[(size_t)T] = n_sel;
+  const int64_t Vt = out_atom_ptr[n_sel];
+  int64_t m = 0;
+  for (int t = 1; t < T; ++t) {
+    const int64_t target = Vt * t / T;
+    while (m < n_sel && out_atom_ptr[m] < target) ++m;
+    cut[(size_t)t] = m;
+  }
+  for (int t = 1; t < T; ++t) pool.emplace_back(gather_host_range, std::cref(a), cut[(size_t)t], cut[(size_t)t + 1]);
+  gather_host_range(a, cut[0], cut[1]);
+  for (auto& th : pool) th.join();
   return 0;
 }
 

@@ -1,0 +1,105 @@
+// Device-resident packed dataset: assemble a BatchMolGraph for a list of molecule ids with ONE launch.
+//
+// Replaces, for pre-featurised data, `[dataset[i] for i in ids]` + collate_batch + the host -> device copy of the
+// batch (chemprop/data/datasets.py:222-244, chemprop/data/collate.py:37-97): the dataset's flat arrays stay in HBM
+// (1 M ~25-atom molecules: 7.2 GB of atom features, 3 GB of bond features, 0.8 GB of local indices -- of 180 GB), a
+// training step uploads only the ids and the output offsets (24 bytes per molecule) and this kernel copies each
+// selected molecule's rows to its place in the batch, turning molecule-local indices into batch-global ones.
+// Pure HBM streaming: 2 x (4 d_v V + 4 d_e E) + 40 E + 8 V bytes per batch, no reuse, no arithmetic beyond the offsets.
+#include "common.cuh"
+
+namespace {
+
+// copy n contiguous elements; W = elements per vector access (the caller guarantees both pointers are W-aligned)
+template <int W>
+__device__ __forceinline__ void copy_span(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  if constexpr (W == 4) {
+    const float4* s = reinterpret_cast<const float4*>(src);
+    float4* d = reinterpret_cast<float4*>(dst);
+    for (int64_t i = threadIdx.x; i < n / 4; i += blockDim.x) d[i] = s[i];
+  } else if constexpr (W == 2) {
+    const float2* s = reinterpret_cast<const float2*>(src);
+    float2* d = reinterpret_cast<float2*>(dst);
+    for (int64_t i = threadIdx.x; i < n / 2; i += blockDim.x) d[i] = s[i];
+  } else {
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  }
+}
+
+// one block per selected molecule
+template <int WV, int WE>
+__global__ void __launch_bounds__(128)
+k_dataset_gather(const int64_t* __restrict__ ids, const int64_t* __restrict__ out_atom_ptr,
+                 const int64_t* __restrict__ out_edge_ptr, const int64_t* __restrict__ atom_ptr,
+                 const int64_t* __restrict__ edge_ptr, const float* __restrict__ V_all, const float* __restrict__ E_all,
+                 const int32_t* __restrict__ ei_local, const int32_t* __restrict__ rev_local, int64_t E_all_total,
+                 int d_v, int d_e, float* __restrict__ V_out, float* __restrict__ E_out, int64_t* __restrict__ ei_out,
+                 int64_t* __restrict__ rev_out, int64_t* __restrict__ batch_out, int64_t E_out_total) {
+  const int64_t m = blockIdx.x;
+  const int64_t id = ids[m];
+  const int64_t sa = atom_ptr[id], se = edge_ptr[id];
+  const int64_t na = atom_ptr[id + 1] - sa, ne = edge_ptr[id + 1] - se;
+  const int64_t oa = out_atom_ptr[m], oe = out_edge_ptr[m];
+  if (d_v > 0) copy_span<WV>(V_all + sa * d_v, V_out + oa * d_v, na * d_v);
+  if (d_e > 0) copy_span<WE>(E_all + se * d_e, E_out + oe * d_e, ne * d_e);
+  const int32_t* s0 = ei_local + se;
+  const int32_t* s1 = ei_local + E_all_total + se;
+  const int32_t* rv = rev_local + se;
+  for (int64_t j = threadIdx.x; j < ne; j += blockDim.x) {
+    ei_out[oe + j] = (int64_t)s0[j] + oa;                  // collate.py:51
+    ei_out[E_out_total + oe + j] = (int64_t)s1[j] + oa;
+    rev_out[oe + j] = (int64_t)rv[j] + oe;                 // collate.py:52
+  }
+  for (int64_t j = threadIdx.x; j < na; j += blockDim.x) batch_out[oa + j] = m;   // collate.py:53
+}
+
+template <int WV>
+int launch_we(int we, dim3 grid, cudaStream_t st, const int64_t* ids, const int64_t* oap, const int64_t* oep,
+              const int64_t* ap, const int64_t* ep, const float* V_all, const float* E_all, const int32_t* ei,
+              const int32_t* rv, int64_t Eall, int d_v, int d_e, float* V_out, float* E_out, int64_t* ei_out,
+              int64_t* rev_out, int64_t* batch_out, int64_t Eout) {
+#define DMPNN_GATHER_LAUNCH(WE)                                                                                        \
+  k_dataset_gather<WV, WE><<<grid, 128, 0, st>>>(ids, oap, oep, ap, ep, V_all, E_all, ei, rv, Eall, d_v, d_e, V_out, \
+                                                 E_out, ei_out, rev_out, batch_out, Eout)
+  if (we == 4) DMPNN_GATHER_LAUNCH(4);
+  else if (we == 2) DMPNN_GATHER_LAUNCH(2);
+  else DMPNN_GATHER_LAUNCH(1);
+#undef DMPNN_GATHER_LAUNCH
+  return 0;
+}
+
+inline int vec_width(int64_t d, const void* a, const void* b) {
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b);
+  if (d % 4 == 0 && bits % 16 == 0) return 4;     // every row offset is then a multiple of 16 bytes
+  if (d % 2 == 0 && bits % 8 == 0) return 2;
+  return 1;
+}
+
+}  // namespace
+
+extern "C" int dmpnn_dataset_gather(const int64_t* ids, const int64_t* out_atom_ptr, const int64_t* out_edge_ptr,
+                                    int64_t n_sel, const int64_t* atom_ptr, const int64_t* edge_ptr, const float* V_all,
+                                    const float* E_all, const int32_t* ei_local, const int32_t* rev_local,
+                                    int64_t E_all_total, int64_t d_v, int64_t d_e, float* V_out, float* E_out,
+                                    int64_t* ei_out, int64_t* rev_out, int64_t* batch_out, int64_t E_out_total,
+                                    void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DMPNN_CHECK_ARG(n_sel >= 0 && d_v >= 0 && d_e >= 0 && E_all_total >= 0 && E_out_total >= 0 && n_sel < (1LL << 31),
+                  "dataset_gather: bad sizes");
+  if (n_sel == 0) return 0;
+  DMPNN_CHECK_ARG(ids && out_atom_ptr && out_edge_ptr && atom_ptr && edge_ptr && batch_out, "dataset_gather: null table");
+  DMPNN_CHECK_ARG((d_v == 0 || (V_all && V_out)) && (d_e == 0 || E_out_total == 0 || (E_all && E_out)),
+                  "dataset_gather: null feature array");
+  DMPNN_CHECK_ARG(E_out_total == 0 || (ei_local && rev_local && ei_out && rev_out), "dataset_gather: null index array");
+  const int wv = vec_width(d_v, V_all, V_out), we = vec_width(d_e, E_all, E_out);
+  dim3 grid((unsigned)n_sel);
+#define DMPNN_GATHER_WV(WV)                                                                                          \
+  launch_we<WV>(we, grid, st, ids, out_atom_ptr, out_edge_ptr, atom_ptr, edge_ptr, V_all, E_all, ei_local, rev_local, \
+                E_all_total, (int)d_v, (int)d_e, V_out, E_out, ei_out, rev_out, batch_out, E_out_total)
+  if (wv == 4) DMPNN_GATHER_WV(4);
+  else if (wv == 2) DMPNN_GATHER_WV(2);
+  else DMPNN_GATHER_WV(1);
+#undef DMPNN_GATHER_WV
+  DMPNN_CHECK_LAUNCH("dmpnn_dataset_gather", 1);
+  return 0;
+}

@@ -98,6 +98,40 @@ int dmpnn_collate_host_compact(int64_t n_mols, const int64_t* n_atoms, const int
                                uint16_t* V_out, uint16_t* E_out, int32_t* edge_index_out /*2 x E_tot*/,
                                int32_t* rev_out, int32_t* batch_out);
 
+/* ---------------------------------------------------------------------------------------
+ * Packed dataset: all molecules of a data set in flat arrays -- V_all (sum V x d_v f32), E_all
+ * (sum E x d_e f32), molecule-LOCAL edge_index (2 x sum E, int32) and rev_edge_index (sum E, int32), atom_ptr /
+ * edge_ptr (n + 1, int64) -- on the host or resident in HBM.  A batch for the molecule ids `ids` is one gather:
+ * replaces `[dataset[i] for i in ids]` + collate_batch (chemprop/data/datasets.py:222-244, collate.py:37-97) and,
+ * for the device-resident form, the host -> device copy of the batch.
+ *   dmpnn_dataset_batch_meta_host  output offsets of the selected molecules (out_atom_ptr / out_edge_ptr, n_sel + 1
+ *                                  each) and the batch's layout meta words in O(n_sel) from per-molecule sizes
+ *                                  (`mol_max_indeg`: max in-degree of each molecule; molecules are validated once,
+ *                                  when the data set is packed, so all three flags are set).  CPU code.
+ *   dmpnn_dataset_gather_host      the five public BatchMolGraph arrays (f32 / int64; any of V_out, E_out, ei_out +
+ *                                  rev_out, batch_out may be NULL to skip it) and, when the five compact pointers
+ *                                  are given, the bf16 / int32 transfer copy, in one pass, the selection split over host threads.
+ *                                  CPU code.
+ *   dmpnn_dataset_gather           the same five arrays on the device: one block per selected molecule, contiguous
+ *                                  row copies (16 / 8 / 4-byte accesses by feature width), indices offset on the fly.
+ *                                  All pointers are device pointers; ids / out_*_ptr are what the host computed with
+ *                                  dmpnn_dataset_batch_meta_host and uploaded (24 bytes per molecule).
+ * ------------------------------------------------------------------------------------- */
+int dmpnn_dataset_batch_meta_host(int64_t n_sel, const int64_t* ids, int64_t n_total, const int64_t* atom_ptr,
+                                  const int64_t* edge_ptr, const int32_t* mol_max_indeg, int64_t* out_atom_ptr,
+                                  int64_t* out_edge_ptr, int32_t* meta /*DMPNN_META_WORDS*/);
+int dmpnn_dataset_gather_host(int64_t n_sel, const int64_t* ids, const int64_t* out_atom_ptr, const int64_t* out_edge_ptr,
+                              const int64_t* atom_ptr, const int64_t* edge_ptr, const float* V_all, const float* E_all,
+                              const int32_t* ei_local, const int32_t* rev_local, int64_t E_all_total, int64_t d_v,
+                              int64_t d_e, float* V_out, float* E_out, int64_t* ei_out /*2 x E_out*/, int64_t* rev_out,
+                              int64_t* batch_out, uint16_t* Vb_out, uint16_t* Eb_out, int32_t* ei32_out,
+                              int32_t* rev32_out, int32_t* batch32_out, int n_threads /* <= 0: automatic */);
+int dmpnn_dataset_gather(const int64_t* ids, const int64_t* out_atom_ptr, const int64_t* out_edge_ptr, int64_t n_sel,
+                         const int64_t* atom_ptr, const int64_t* edge_ptr, const float* V_all, const float* E_all,
+                         const int32_t* ei_local, const int32_t* rev_local, int64_t E_all_total, int64_t d_v, int64_t d_e,
+                         float* V_out, float* E_out, int64_t* ei_out /*2 x E_out_total*/, int64_t* rev_out,
+                         int64_t* batch_out, int64_t E_out_total, void* stream);
+
 /* Layout meta words of a batch computed on the HOST (same DMPNN_META_* words dmpnn_layout_build writes on the
  * device): validity flags, max in-degree, and the tile count / largest tile of the greedy molecule-aligned packing.
  * A loader calls it next to the collate (the batch's int64 index arrays are in host memory there), so that the

@@ -3,7 +3,8 @@
   * the composed tier (chemprop_b200/composed.py) -- PReLU / SELU / user activation modules, dropout > 0 in training,
     AtomMessagePassing(undirected=True) -- through the real kernels, against the golden vectors of the real reference
     and against the oracle; same tolerances as tests/test_gpu_parity.py;
-  * the sync-free training step (host-computed layout meta words, dmpnn_batch_meta_host).
+  * the sync-free training step (host-computed layout meta words, dmpnn_batch_meta_host);
+  * the device-resident packed data set (dmpnn_dataset_gather).
 
 This file sorts last on purpose.  It was written after this round's GPU budget was spent: its first run on hardware
 is the round-end run, so it is marked xfail(strict=False) -- a pass is reported as XPASS, a failure does not mask the
@@ -120,3 +121,31 @@ def test_training_step_does_not_synchronise(precision):
     finally:
         torch.cuda.set_sync_debug_mode("default")
     assert torch.isfinite(loss).item()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(shuffle_edges=True, min_atoms=1), dict(d_v=106, d_e=28), dict(d_v=7, d_e=3)])
+def test_resident_dataset_batches_are_bit_identical_to_the_host_collate(kw):
+    """PackedMolGraphDataset on the GPU: `batch(ids)` (one dmpnn_dataset_gather launch) == the collate of the selected
+    molecules, every tensor bit for bit, and the module gives the same output on either batch."""
+    from chemprop_b200.data import BatchMolGraph, PackedMolGraphDataset, make_molecules
+    from chemprop_b200.nn import BondMessagePassing, MeanAggregation
+
+    mgs = make_molecules(3000, seed=17, **kw)
+    ds = PackedMolGraphDataset.from_molgraphs(mgs).to("cuda")
+    assert ds.device.type == "cuda" and len(ds) == 3000
+    rng = np.random.default_rng(2)
+    for ids in (rng.permutation(3000)[:2500], rng.integers(0, 3000, size=333), np.array([5]), np.arange(3000)):
+        got = ds.batch(ids)
+        ref = BatchMolGraph([mgs[i] for i in ids])
+        assert got.V.is_cuda and len(got) == len(ref) and got._meta_host == ref._meta_host
+        for k in ("V", "E", "edge_index", "rev_edge_index", "batch"):
+            x, y = getattr(got, k), getattr(ref, k)
+            assert x.dtype == y.dtype and x.shape == y.shape and torch.equal(x.cpu(), y), k
+    torch.manual_seed(0)
+    mp = BondMessagePassing(d_v=ds.d_v, d_e=ds.d_e, d_h=64, precision="fp32").cuda()
+    ids = rng.permutation(3000)[:1200]
+    a = ds.batch(ids)
+    b = BatchMolGraph([mgs[i] for i in ids])
+    b.to("cuda")
+    with torch.no_grad():
+        assert torch.equal(MeanAggregation()(mp(a), a.batch), MeanAggregation()(mp(b), b.batch))
