@@ -1,7 +1,8 @@
 from .collate import BatchMolGraph, Datum, TrainingBatch, collate_batch
 from .dataset import HostBatchBuffer, PackedMolGraphDataset
+from .loader import LoadedBatch, PackedBatchLoader
 from .molgraph import MolGraph
 from .synthetic import make_chain_graph, make_cgr_graphs, make_molecule, make_molecules
 
-__all__ = ["BatchMolGraph", "Datum", "TrainingBatch", "collate_batch", "MolGraph", "PackedMolGraphDataset", "HostBatchBuffer",
+__all__ = ["BatchMolGraph", "Datum", "TrainingBatch", "collate_batch", "MolGraph", "PackedMolGraphDataset", "HostBatchBuffer", "PackedBatchLoader", "LoadedBatch",
            "make_chain_graph", "make_cgr_graphs", "make_molecule", "make_molecules"]

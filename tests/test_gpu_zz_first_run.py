@@ -149,3 +149,27 @@ def test_resident_dataset_batches_are_bit_identical_to_the_host_collate(kw):
     b.to("cuda")
     with torch.no_grad():
         assert torch.equal(MeanAggregation()(mp(a), a.batch), MeanAggregation()(mp(b), b.batch))
+
+
+@pytest.mark.parametrize("resident", [False, True])
+def test_loader_feeds_the_gpu_with_the_batches_of_its_ids(resident):
+    """PackedBatchLoader: host data set -> pinned staging ring -> asynchronous H2D on a side stream, or the resident data
+    set gathered on the device; either way batch i is the collate of its ids."""
+    from chemprop_b200.data import BatchMolGraph, PackedBatchLoader, PackedMolGraphDataset, make_molecules
+
+    mgs = make_molecules(1200, seed=23, shuffle_edges=True, min_atoms=1)
+    ds = PackedMolGraphDataset.from_molgraphs(mgs)
+    if resident:
+        ds = ds.to("cuda")
+    Y = np.arange(1200, dtype=np.float32)
+    loader = PackedBatchLoader(ds, batch_size=256, shuffle=True, seed=11, device="cuda", arrays={"Y": Y},
+                               transfer_dtype=None)
+    n = 0
+    for b in loader:
+        assert b.bmg.V.is_cuda and b.extras["Y"].is_cuda
+        ref = BatchMolGraph([mgs[i] for i in b.ids])
+        for k in ("V", "E", "edge_index", "rev_edge_index", "batch"):
+            assert torch.equal(getattr(b.bmg, k).cpu(), getattr(ref, k)), k
+        assert b.bmg._meta_host == ref._meta_host and torch.equal(b.extras["Y"].cpu(), torch.from_numpy(Y[b.ids]))
+        n += len(b.ids)
+    assert n == 1200

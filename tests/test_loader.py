@@ -1,0 +1,109 @@
+"""CPU tier: PackedBatchLoader -- the reference's build_dataloader + SeededSampler + DistributedSampler semantics
+(chemprop/data/dataloader.py:24-96, samplers.py:8-27) over the packed data set."""
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from chemprop_b200.data import BatchMolGraph, PackedBatchLoader, PackedMolGraphDataset, make_molecules
+from chemprop_b200.data.loader import epoch_shard
+from oracle.ref_shim import reference_available
+
+N = 203
+
+
+@pytest.fixture(scope="module")
+def data():
+    mgs = make_molecules(N, seed=31, mean_atoms=9, std_atoms=3, shuffle_edges=True, min_atoms=1)
+    return mgs, PackedMolGraphDataset.from_molgraphs(mgs)
+
+
+def _check_batch(b, mgs):
+    ref = BatchMolGraph([mgs[i] for i in b.ids])
+    for k in ("V", "E", "edge_index", "rev_edge_index", "batch"):
+        assert torch.equal(getattr(b.bmg, k), getattr(ref, k)), k
+    assert b.bmg._meta_host == ref._meta_host and len(b.bmg) == len(b.ids)
+
+
+def test_seeded_order_is_the_references_seeded_sampler(data):
+    mgs, ds = data
+    loader = PackedBatchLoader(ds, batch_size=32, shuffle=True, seed=1234)
+    rg, idxs = np.random.default_rng(1234), np.arange(N)          # samplers.py:16-21, restated
+    for epoch in range(3):
+        rg.shuffle(idxs)
+        got = np.concatenate([b.ids for b in loader])
+        assert np.array_equal(got, idxs), epoch
+    assert len(loader) == 7                                        # 203 = 6 * 32 + 11
+    if reference_available():
+        from oracle.ref_shim import import_reference
+
+        import_reference()
+        from chemprop.data.samplers import SeededSampler
+
+        ref = SeededSampler(N, 99)
+        ours = PackedBatchLoader(ds, batch_size=50, shuffle=True, seed=99)
+        for _ in range(2):
+            assert np.array_equal(np.fromiter(iter(ref), dtype=np.int64), np.concatenate([b.ids for b in ours]))
+
+
+@pytest.mark.parametrize("prefetch,compact", [(2, False), (3, True)])
+def test_batches_are_the_collate_of_their_ids_even_with_a_slow_consumer(data, prefetch, compact):
+    mgs, ds = data
+    loader = PackedBatchLoader(ds, batch_size=24, shuffle=True, seed=5, prefetch=prefetch,
+                               transfer_dtype=torch.bfloat16 if compact else None)
+    seen = 0
+    for i, b in enumerate(loader):
+        if i % 3 == 0:
+            time.sleep(0.02)            # let the producer run ahead into the other staging buffers
+        _check_batch(b, mgs)
+        if compact:
+            assert torch.equal(b.bmg._xfer[0], b.bmg.V.bfloat16()) and b.bmg._xfer[2].dtype == torch.int32
+        seen += len(b.ids)
+    assert seen == N
+
+
+def test_drop_last_rule_and_unshuffled_order(data):
+    mgs, ds = data
+    assert [len(b.ids) for b in PackedBatchLoader(ds, batch_size=101, shuffle=False)] == [101, 101]      # 203 % 101 == 1
+    assert [len(b.ids) for b in PackedBatchLoader(ds, batch_size=101, shuffle=False, drop_last=False)] == [101, 101, 1]
+    assert [len(b.ids) for b in PackedBatchLoader(ds, batch_size=100, shuffle=False)] == [100, 100, 3]
+    assert len(PackedBatchLoader(ds, batch_size=101)) == 2 and len(PackedBatchLoader(ds, batch_size=100)) == 3
+    got = np.concatenate([b.ids for b in PackedBatchLoader(ds, batch_size=64, shuffle=False)])
+    assert np.array_equal(got, np.arange(N))
+    a = np.concatenate([b.ids for b in PackedBatchLoader(ds, batch_size=64, shuffle=True)])                # unseeded
+    assert np.array_equal(np.sort(a), np.arange(N))
+
+
+def test_ranks_partition_the_epoch_like_distributed_sampler(data):
+    mgs, ds = data
+    world = 4
+    per_rank = [np.concatenate([b.ids for b in PackedBatchLoader(ds, batch_size=16, shuffle=True, seed=7, rank=r, world=world)])
+                for r in range(world)]
+    assert {len(x) for x in per_rank} == {51}                                                              # ceil(203 / 4)
+    order = np.arange(N)
+    np.random.default_rng(7).shuffle(order)
+    padded = np.concatenate([order, order[:1]])
+    for r in range(world):
+        assert np.array_equal(per_rank[r], padded[r::world])
+    assert np.array_equal(epoch_shard(np.arange(5), 1, 2), [1, 3, 0]) and np.array_equal(epoch_shard(np.arange(5), 0, 1), np.arange(5))
+    torch_ds = torch.utils.data.distributed.DistributedSampler(list(range(N)), num_replicas=world, rank=2, shuffle=False)
+    ours = np.concatenate([b.ids for b in PackedBatchLoader(ds, batch_size=16, shuffle=False, rank=2, world=world)])
+    assert np.array_equal(ours, np.fromiter(iter(torch_ds), dtype=np.int64))
+
+
+def test_side_arrays_and_early_exit(data):
+    mgs, ds = data
+    Y = np.arange(N, dtype=np.float32)[:, None] * 2.0
+    w = np.ones(N, dtype=np.float32)
+    loader = PackedBatchLoader(ds, batch_size=20, shuffle=True, seed=3, arrays={"Y": Y, "w": w})
+    for i, b in enumerate(loader):
+        assert torch.equal(b.extras["Y"][:, 0], torch.from_numpy(b.ids.astype(np.float32) * 2.0)) and b.extras["w"].shape == (len(b.ids),)
+        if i == 2:
+            break                       # abandoning the iterator must not leave the producer thread hanging
+    t0 = time.time()
+    assert sum(len(b.ids) for b in loader) == N and time.time() - t0 < 10
+    with pytest.raises(ValueError):
+        PackedBatchLoader(ds, arrays={"Y": Y[:-1]})
+    with pytest.raises(ValueError):
+        PackedBatchLoader(ds, prefetch=1)
