@@ -175,16 +175,38 @@ class GatherBySrc(torch.autograd.Function):
         return dA, None
 
 
+class PermuteRows(torch.autograd.Function):
+    """out[r] = X[idx[r]] for a permutation `idx` with inverse `inv_idx` -- dmpnn_segment_bcast both ways.  Used to
+    hand per-edge results back in the caller's edge order (the engine's internal rows are sorted by destination)."""
+
+    @staticmethod
+    def forward(ctx, X, idx, inv_idx):
+        Xc = _c(X)
+        out = _buf(Xc.shape[0], Xc.shape[1], Xc)
+        if Xc.shape[0] > 0:
+            K.segment_bcast(Xc, idx, None, Xc.shape[0], Xc.shape[1], out)
+        ctx.inv_idx = inv_idx
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _c(g)
+        out = _buf(g.shape[0], g.shape[1], g)
+        if g.shape[0] > 0:
+            K.segment_bcast(g, ctx.inv_idx, None, g.shape[0], g.shape[1], out)
+        return out, None, None
+
+
 def _inputs(bmg):
     K._require_cuda(bmg.V, bmg.E)
     return bmg.V.contiguous().float(), bmg.E.contiguous().float()
 
 
-def bond_forward(mp, bmg, lay) -> Tensor:
-    """BondMessagePassing.forward up to and including dropout(tau(W_o(.))) (base.py:196-212, :180-182)."""
-    V, E = _inputs(bmg)
+def bond_edge_states(mp, V, E, lay) -> Tensor:
+    """The depth loop of BondMessagePassing (base.py:198-206): final directed-edge hidden states H^{T-1}, internal row
+    order.  A batch without edges (tests/integration/test_export.py:15-46) flows through as 0-row tensors, as in the
+    reference."""
     tau, drop = mp.tau, mp.dropout
-    # a batch without edges (tests/integration/test_export.py:15-46) flows through as 0-row tensors, as in the reference
     H0 = GatherLinear.apply(V, lay.src_row, E, lay.perm, mp.W_i.weight, mp.W_i.bias, None, lay.E)      # mixins.py:8-9
     H = tau(H0)                                                                                       # base.py:200
     for _ in range(1, int(mp.depth)):
@@ -193,15 +215,12 @@ def bond_forward(mp, bmg, lay) -> Tensor:
         M = BondMessage.apply(H, lay)                                                                 # mixins.py:11-18
         Z = GatherLinear.apply(M, None, None, None, mp.W_h.weight, mp.W_h.bias, H0, lay.E)            # base.py:137-138
         H = drop(tau(Z))                                                                              # base.py:138-139
-    Mv = SumByDst.apply(H, lay)                                                                       # base.py:208-211
-    Y = GatherLinear.apply(V, None, Mv, None, mp.W_o.weight, mp.W_o.bias, None, lay.V)                # base.py:180
-    return drop(tau(Y))                                                                               # base.py:181-182
+    return H
 
 
-def atom_forward(mp, bmg, lay) -> Tensor:
-    """AtomMessagePassing.forward, edge-granular as in the reference (mixins.py:22-30) so that `undirected`
+def atom_edge_states(mp, V, E, lay) -> Tensor:
+    """The depth loop of AtomMessagePassing, edge-granular as in the reference (mixins.py:22-30) so that `undirected`
     (base.py:202-203) keeps its meaning."""
-    V, E = _inputs(bmg)
     tau, drop = mp.tau, mp.dropout
     d_e = E.shape[1]
     H0 = GatherLinear.apply(V, lay.src_row, None, None, mp.W_i.weight, mp.W_i.bias, None, lay.E)       # mixins.py:22-23
@@ -220,6 +239,39 @@ def atom_forward(mp, bmg, lay) -> Tensor:
         Z = GatherLinear.apply(M, None, AE, lay.src_row if AE is not None else None, mp.W_h.weight, mp.W_h.bias,
                                H0, lay.E)                                                             # W_h([M_H || M_E]) + H_0
         H = drop(tau(Z))
+    return H
+
+
+def vertex_readout(mp, W_o, V, H, lay) -> Tensor:
+    """M_v = sum_{dst(e)=v} H[e] (base.py:208-211), then dropout(tau(W_o([V || M_v]))) (base.py:180-182)."""
     Mv = SumByDst.apply(H, lay)
-    Y = GatherLinear.apply(V, None, Mv, None, mp.W_o.weight, mp.W_o.bias, None, lay.V)
-    return drop(tau(Y))
+    Y = GatherLinear.apply(V, None, Mv, None, W_o.weight, W_o.bias, None, lay.V)
+    return mp.dropout(mp.tau(Y))
+
+
+def edge_readout(mp, W_eo, E, H, lay) -> Tensor:
+    """dropout(tau(W_eo([E || H]))) per directed edge, in the CALLER's edge order
+    (chemprop/nn/message_passing/mol_atom_bond.py `edge_finalize`)."""
+    Hc = PermuteRows.apply(H, lay.inv_perm, lay.perm)          # internal row of caller edge e is inv_perm[e]
+    Y = GatherLinear.apply(E, None, Hc, None, W_eo.weight, W_eo.bias, None, lay.E)
+    return mp.dropout(mp.tau(Y))
+
+
+def bond_forward(mp, bmg, lay) -> Tensor:
+    """BondMessagePassing.forward up to and including dropout(tau(W_o(.))) (base.py:196-212, :180-182)."""
+    V, E = _inputs(bmg)
+    return vertex_readout(mp, mp.W_o, V, bond_edge_states(mp, V, E, lay), lay)
+
+
+def atom_forward(mp, bmg, lay) -> Tensor:
+    V, E = _inputs(bmg)
+    return vertex_readout(mp, mp.W_o, V, atom_edge_states(mp, V, E, lay), lay)
+
+
+def mab_forward(mp, bmg, lay, kind: str):
+    """_MABMessagePassingBase.forward (mol_atom_bond.py): the same loop, then the vertex and / or the edge read-out."""
+    V, E = _inputs(bmg)
+    H = (bond_edge_states if kind == "bond" else atom_edge_states)(mp, V, E, lay)
+    H_v = vertex_readout(mp, mp.W_vo, V, H, lay) if mp.return_vertex_embeddings else None
+    H_e = edge_readout(mp, mp.W_eo, E, H, lay) if mp.return_edge_embeddings else None
+    return H_v, H_e

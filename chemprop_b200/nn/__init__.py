@@ -1,6 +1,9 @@
 from .agg import Aggregation, AggregationRegistry, MeanAggregation, NormAggregation, SumAggregation
 from .message_passing import AtomMessagePassing, BondMessagePassing
+from .mol_atom_bond import MABAtomMessagePassing, MABBondMessagePassing
+from .multi import MulticomponentMessagePassing
 from .transforms import GraphTransform, ScaleTransform
 
 __all__ = ["Aggregation", "AggregationRegistry", "MeanAggregation", "NormAggregation", "SumAggregation",
-           "AtomMessagePassing", "BondMessagePassing", "GraphTransform", "ScaleTransform"]
+           "AtomMessagePassing", "BondMessagePassing", "MABAtomMessagePassing", "MABBondMessagePassing",
+           "MulticomponentMessagePassing", "GraphTransform", "ScaleTransform"]

@@ -60,6 +60,12 @@ CASES = {
     "bond_d3_undir_prelu": dict(kind="bond", depth=3, d_h=64, undirected=True, activation="prelu", graph="mols6_shuffled"),
     "atom_d3_noedges_prelu": dict(kind="atom", depth=3, d_h=32, activation="prelu", graph="single_atoms4"),
     "bond_d3_dropout_eval": dict(kind="bond", depth=3, d_h=64, dropout=0.3, eval=True, graph="mols6"),
+    # mol-atom-bond variants (chemprop/nn/message_passing/mol_atom_bond.py): vertex AND per-edge embeddings
+    "mab_bond_d3":         dict(kind="mab_bond", depth=3, d_h=64, graph="mols6"),
+    "mab_atom_d3_desc":    dict(kind="mab_atom", depth=3, d_h=48, bias=True, d_vd=4, d_ed=3, activation="tanh", graph="mols6_shuffled"),
+    "mab_bond_edges_only": dict(kind="mab_bond", depth=3, d_h=40, undirected=True, activation="prelu", vertex=False, graph="mixed"),
+    "mab_atom_d2_vertex_only": dict(kind="mab_atom", depth=2, d_h=32, edge=False, graph="mols6"),
+    "mab_bond_noedges":    dict(kind="mab_bond", depth=3, d_h=32, graph="single_atoms4"),
 }
 
 
@@ -177,6 +183,54 @@ def run_case(name: str, cfg: dict, seed: int) -> dict:
     return out
 
 
+def run_mab_case(name: str, cfg: dict, seed: int) -> dict:
+    """MAB variants: outputs (H_v, H_e); loss = sum(mean_agg(H_v) * G) + sum(H_e * G_e)."""
+    import_reference()
+    from chemprop.data import BatchMolGraph
+    from chemprop.data.molgraph import MolGraph
+    from chemprop.nn import MeanAggregation
+    from chemprop.nn.message_passing import MABAtomMessagePassing, MABBondMessagePassing
+
+    d_v, d_e, d_h = cfg.get("d_v", 72), cfg.get("d_e", 14), cfg["d_h"]
+    mgs = make_batch(cfg["graph"], d_v, d_e, seed)
+    bmg = BatchMolGraph([MolGraph(m.V, m.E, m.edge_index, m.rev_edge_index) for m in mgs])
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed + 1)
+    cls = MABBondMessagePassing if cfg["kind"] == "mab_bond" else MABAtomMessagePassing
+    mp = cls(d_v=d_v, d_e=d_e, d_h=d_h, bias=cfg.get("bias", False), depth=cfg["depth"],
+             activation=cfg.get("activation", "relu"), undirected=cfg.get("undirected", False), d_vd=cfg.get("d_vd"),
+             d_ed=cfg.get("d_ed"), return_vertex_embeddings=cfg.get("vertex", True),
+             return_edge_embeddings=cfg.get("edge", True))
+    V_d = torch.from_numpy(rng.normal(size=(bmg.V.shape[0], cfg["d_vd"])).astype(np.float32)) if cfg.get("d_vd") else None
+    E_d = torch.from_numpy(rng.normal(size=(bmg.E.shape[0], cfg["d_ed"])).astype(np.float32)) if cfg.get("d_ed") else None
+    H_v, H_e = mp(bmg, V_d, E_d)
+    out = dict(V=bmg.V.numpy(), E=bmg.E.numpy(), edge_index=bmg.edge_index.numpy(),
+               rev_edge_index=bmg.rev_edge_index.numpy(), batch=bmg.batch.numpy(), n_mols=np.int64(len(bmg)),
+               config=np.array(json.dumps(cfg)))
+    loss = torch.zeros(())
+    if H_v is not None:
+        agg = MeanAggregation()(H_v, bmg.batch)
+        G = torch.from_numpy(rng.normal(size=tuple(agg.shape)).astype(np.float32))
+        loss = loss + (agg * G).sum()
+        out.update(H_v=H_v.detach().numpy(), agg_mean=agg.detach().numpy(), G=G.numpy())
+    if H_e is not None:
+        G_e = torch.from_numpy(rng.normal(size=tuple(H_e.shape)).astype(np.float32))
+        loss = loss + (H_e * G_e).sum()
+        out.update(H_e=H_e.detach().numpy(), G_e=G_e.numpy())
+    loss.backward()
+    out["loss"] = np.float64(loss.item())
+    if V_d is not None:
+        out["V_d"] = V_d.numpy()
+    if E_d is not None:
+        out["E_d"] = E_d.numpy()
+    for k, v in mp.state_dict().items():
+        out["param." + k] = v.detach().numpy()
+    for k, p in mp.named_parameters():
+        if p.grad is not None:
+            out["grad." + k] = p.grad.numpy()
+    return out
+
+
 def collate_case() -> dict:
     """The reference's collate fixture (tests/unit/data/test_dataloader.py:10-84) through the real collate."""
     import_reference()
@@ -206,10 +260,11 @@ def main():
     for i, (name, cfg) in enumerate(CASES.items()):
         if only and name not in only:
             continue
-        out = run_case(name, cfg, seed=100 + i)
+        out = (run_mab_case if cfg["kind"].startswith("mab_") else run_case)(name, cfg, seed=100 + i)
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"{name}.npz"), **out)
+        ref = out["H_v"] if "H_v" in out else out["H_e"]
         print(f"{name:24s} V={out['V'].shape[0]:4d} E={out['E'].shape[0]:4d} B={int(out['n_mols'])} "
-              f"|H_v|={np.abs(out['H_v']).mean():.4f} loss={float(out['loss']):+.5f}")
+              f"|H|={np.abs(ref).mean():.4f} loss={float(out['loss']):+.5f}")
     if not only:
         np.savez_compressed(os.path.join(GOLDEN_DIR, "collate_fixture.npz"), **collate_case())
         print("collate_fixture")

@@ -147,6 +147,29 @@ def message_passing_forward(kind, V, E, edge_index, rev_edge_index, W_i, b_i, W_
     return out
 
 
+def mab_forward(kind, V, E, edge_index, rev_edge_index, W_i, b_i, W_h, b_h, W_vo, b_vo, W_eo, b_eo, depth, act="relu",
+                undirected=False, V_d=None, W_vd=None, b_vd=None, E_d=None, W_ed=None, b_ed=None, prelu_weight=None,
+                return_vertex=True, return_edge=True):
+    """_MABMessagePassingBase.forward (chemprop/nn/message_passing/mol_atom_bond.py): the loop of base.py:196-206,
+    then vertex_finalize (same as `finalize`) and edge_finalize: tau(W_eo([E || H])) [-> W_ed([. || E_d])] per directed
+    edge.  kind in {"bond", "atom"}.  Returns (H_v | None, H_e | None)."""
+    tau = activation(act, prelu_weight)
+    if W_vo is None:   # edge embeddings only: the vertex read-out does not exist; run the loop with a dummy W_o
+        W_vo_, b_vo_ = torch.zeros(1, V.shape[1] + W_h.shape[0], dtype=V.dtype), None
+    else:
+        W_vo_, b_vo_ = W_vo, b_vo
+    H_v, inter = message_passing_forward(kind, V, E, edge_index, rev_edge_index, W_i, b_i, W_h, b_h, W_vo_, b_vo_, depth,
+                                         act, undirected, V_d if W_vo is not None else None, W_vd, b_vd,
+                                         return_intermediates=True, prelu_weight=prelu_weight)
+    H = inter["H"][-1]
+    H_e = None
+    if return_edge:
+        H_e = tau(F.linear(torch.cat((E, H), dim=1), W_eo, b_eo))
+        if E_d is not None:
+            H_e = F.linear(torch.cat((H_e, E_d), dim=1), W_ed, b_ed)
+    return (H_v if (return_vertex and W_vo is not None) else None), H_e
+
+
 # --- aggregation: chemprop/nn/agg.py:65-113 --------------------------------------------------
 def aggregate(H, batch, mode="mean", norm=100.0, n_mols=None):
     index_torch = batch.unsqueeze(1).repeat(1, H.shape[1])

@@ -32,7 +32,7 @@ def _engine_run(g, precision, fused=True):
     return mp, bmg, H, aggs, loss, grads
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", golden_names() + golden_names(mab=True))
 def test_layout_bit_exact(name):
     from chemprop_b200.engine import get_layout
     from oracle import layout_np

@@ -4,7 +4,8 @@
     AtomMessagePassing(undirected=True) -- through the real kernels, against the golden vectors of the real reference
     and against the oracle; same tolerances as tests/test_gpu_parity.py;
   * the sync-free training step (host-computed layout meta words, dmpnn_batch_meta_host);
-  * the device-resident packed data set (dmpnn_dataset_gather).
+  * the device-resident packed data set (dmpnn_dataset_gather) and the loader on top of it;
+  * the mol-atom-bond variants (MABBond / MABAtomMessagePassing), which run on the composed tier.
 
 This file sorts last on purpose.  It was written after this round's GPU budget was spent: its first run on hardware
 is the round-end run, so it is marked xfail(strict=False) -- a pass is reported as XPASS, a failure does not mask the
@@ -14,7 +15,8 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import COMPOSED_GOLDENS, build_engine_module, dropout_mask_for_mask, golden_bmg, load_golden
+from tests.util import (COMPOSED_GOLDENS, build_engine_module, check_mab_case, dropout_mask_for_mask, golden_bmg,
+                        golden_names, load_golden, run_mab_case)
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="first hardware run of this code (written after the round's "
@@ -173,3 +175,12 @@ def test_loader_feeds_the_gpu_with_the_batches_of_its_ids(resident):
         assert b.bmg._meta_host == ref._meta_host and torch.equal(b.extras["Y"].cpu(), torch.from_numpy(Y[b.ids]))
         n += len(b.ids)
     assert n == 1200
+
+
+@pytest.mark.parametrize("name", golden_names(mab=True))
+def test_mab_modules_match_reference_golden(name):
+    """MABBond / MABAtomMessagePassing through the real kernels: vertex embeddings, per-edge embeddings in the caller's
+    edge order, and every gradient, against the golden vectors of the reference's mol_atom_bond.py."""
+    g = load_golden(name)
+    mp, H_v, H_e = run_mab_case(g, "cuda")
+    check_mab_case(g, mp, H_v, H_e, FP32_ATOL)

@@ -8,7 +8,8 @@ import pytest
 import torch
 
 from tests import emu
-from tests.util import COMPOSED_GOLDENS, build_engine_module, golden_bmg, golden_names, load_golden
+from tests.util import (COMPOSED_GOLDENS, build_engine_module, check_mab_case, golden_bmg, golden_names, load_golden,
+                        run_mab_case)
 
 ATOL = 2e-6
 
@@ -87,6 +88,42 @@ def test_training_dropout_mask_for_mask(kind, undirected, act, monkeypatch):
 
     emu.patch_engine(monkeypatch)
     dropout_mask_for_mask(kind, undirected, act, "cpu")
+
+
+@pytest.mark.parametrize("name", golden_names(mab=True))
+def test_mab_modules_match_reference_golden(name, monkeypatch):
+    """MABBond / MABAtomMessagePassing (vertex + per-edge embeddings in the caller's edge order, extra atom / bond
+    descriptors, edges-only / vertex-only) on the composed tier == the reference, outputs and every gradient."""
+    emu.patch_engine(monkeypatch)
+    g = load_golden(name)
+    mp, H_v, H_e = run_mab_case(g, "cpu")
+    check_mab_case(g, mp, H_v, H_e, ATOL)
+
+
+def test_multicomponent_message_passing(monkeypatch):
+    """chemprop/nn/message_passing/multi.py:13-84: per-component blocks (or one shared block), list in, list out."""
+    from chemprop_b200.nn import BondMessagePassing, MulticomponentMessagePassing
+
+    emu.patch_engine(monkeypatch)
+    g1, g2 = load_golden("bond_d3_relu"), load_golden("bond_d3_tanh")
+    b1, b2 = build_engine_module(g1, "cpu"), build_engine_module(g2, "cpu")
+    mc = MulticomponentMessagePassing([b1, b2])
+    assert len(mc) == 2 and mc.output_dim == 128 and mc.hparams["blocks"][1]["activation"] == "tanh"
+    outs = mc([golden_bmg(g1, "cpu"), golden_bmg(g2, "cpu")])
+    np.testing.assert_allclose(outs[0].detach().numpy(), g1["H_v"], rtol=1e-5, atol=ATOL)
+    np.testing.assert_allclose(outs[1].detach().numpy(), g2["H_v"], rtol=1e-5, atol=ATOL)
+    shared = MulticomponentMessagePassing([b1], n_components=2, shared=True)
+    assert len(shared) == 2 and shared.blocks[0] is shared.blocks[1] and len(list(shared.parameters())) == len(list(b1.parameters()))
+    outs = shared([golden_bmg(g1, "cpu"), golden_bmg(g1, "cpu")], [None, None])
+    assert torch.equal(outs[0], outs[1])
+    with pytest.raises(ValueError):
+        MulticomponentMessagePassing([])
+    with pytest.raises(ValueError):
+        MulticomponentMessagePassing([b1], shared=True)
+    gv = load_golden("bond_d3_vd")
+    bv = build_engine_module(gv, "cpu")
+    out = MulticomponentMessagePassing([bv])([golden_bmg(gv, "cpu")], [torch.from_numpy(gv["V_d"])])[0]
+    np.testing.assert_allclose(out.detach().numpy(), gv["H_v"], rtol=1e-5, atol=ATOL)
 
 
 def test_eval_mode_with_dropout_configured_stays_monolithic(monkeypatch):

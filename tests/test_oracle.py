@@ -7,7 +7,7 @@ import torch
 
 from oracle import layout_np, restatement as R
 from oracle.ref_shim import reference_available
-from tests.util import golden_names, load_golden, oracle_forward
+from tests.util import golden_names, load_golden, mab_oracle_forward, oracle_forward
 
 TOL = dict(rtol=1e-5, atol=1e-6)  # same torch ops on the same machine: differences are summation-order only
 
@@ -30,6 +30,30 @@ def test_restatement_matches_golden(name):
             got = P[k[len("grad."):]].grad
             assert got is not None, k
             np.testing.assert_allclose(got.numpy(), v, rtol=1e-4, atol=2e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("name", golden_names(mab=True))
+def test_mab_restatement_matches_golden(name):
+    """mol_atom_bond.py variants: vertex and per-edge embeddings and every weight gradient."""
+    torch.set_num_threads(1)
+    g = load_golden(name)
+    H_v, H_e, P = mab_oracle_forward(g, torch.float32, requires_grad=True)
+    loss = torch.zeros(())
+    if "H_v" in g:
+        np.testing.assert_allclose(H_v.detach().numpy(), g["H_v"], **TOL)
+        loss = loss + (R.aggregate(H_v, torch.from_numpy(g["batch"]), "mean") * torch.from_numpy(g["G"])).sum()
+    else:
+        assert H_v is None
+    if "H_e" in g:
+        np.testing.assert_allclose(H_e.detach().numpy(), g["H_e"], **TOL)
+        loss = loss + (H_e * torch.from_numpy(g["G_e"])).sum()
+    else:
+        assert H_e is None
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * max(1.0, abs(float(g["loss"])))
+    loss.backward()
+    for k, v in g.items():
+        if k.startswith("grad."):
+            np.testing.assert_allclose(P[k[len("grad."):]].grad.numpy(), v, rtol=1e-4, atol=2e-6, err_msg=k)
 
 
 def test_restatement_fp64_close_to_fp32_golden():

@@ -11,9 +11,10 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_names(prefix: str = "") -> list[str]:
+def golden_names(prefix: str = "", mab: bool = False) -> list[str]:
+    """Golden cases of Bond / AtomMessagePassing (default) or of the mol-atom-bond variants (`mab=True`)."""
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if n != "collate_fixture" and n.startswith(prefix)]
+    return [n for n in names if n != "collate_fixture" and n.startswith(prefix) and n.startswith("mab_") == mab]
 
 
 def load_golden(name: str) -> dict:
@@ -155,3 +156,71 @@ def dropout_mask_for_mask(kind: str, undirected: bool, act: str, device: str, n_
     for k, p in mp.named_parameters():
         g = P[k].grad
         assert p.grad is not None and (p.grad.double().cpu() - g).abs().max().item() <= 1e-4 * max(1.0, g.abs().max().item()), k
+
+
+def mab_oracle_forward(g: dict, dtype=torch.float32, requires_grad: bool = False):
+    """oracle/restatement.mab_forward on a MAB golden case's inputs; returns (H_v | None, H_e | None, params)."""
+    from oracle import restatement as R
+
+    cfg = g["config"]
+    P = params_of(g, dtype)
+    if requires_grad:
+        for p in P.values():
+            p.requires_grad_(True)
+    t = lambda k: torch.from_numpy(g[k]).to(dtype) if k in g else None  # noqa: E731
+    H_v, H_e = R.mab_forward(
+        cfg["kind"][4:], t("V"), t("E"), torch.from_numpy(g["edge_index"]), torch.from_numpy(g["rev_edge_index"]),
+        P["W_i.weight"], P.get("W_i.bias"), P["W_h.weight"], P.get("W_h.bias"), P.get("W_vo.weight"), P.get("W_vo.bias"),
+        P.get("W_eo.weight"), P.get("W_eo.bias"), cfg["depth"], activation_name(cfg), cfg.get("undirected", False),
+        t("V_d"), P.get("W_vd.weight"), P.get("W_vd.bias"), t("E_d"), P.get("W_ed.weight"), P.get("W_ed.bias"),
+        prelu_weight=P.get("tau.weight"), return_vertex=cfg.get("vertex", True), return_edge=cfg.get("edge", True))
+    return H_v, H_e, P
+
+
+def build_mab_module(g: dict, device="cuda"):
+    from chemprop_b200.nn import MABAtomMessagePassing, MABBondMessagePassing
+
+    cfg = g["config"]
+    cls = MABBondMessagePassing if cfg["kind"] == "mab_bond" else MABAtomMessagePassing
+    mp = cls(d_v=cfg.get("d_v", 72), d_e=cfg.get("d_e", 14), d_h=cfg["d_h"], bias=cfg.get("bias", False),
+             depth=cfg["depth"], activation=activation_arg(cfg), undirected=cfg.get("undirected", False),
+             d_vd=cfg.get("d_vd"), d_ed=cfg.get("d_ed"), return_vertex_embeddings=cfg.get("vertex", True),
+             return_edge_embeddings=cfg.get("edge", True))
+    mp.load_state_dict(params_of(g), strict=True)      # the reference's state-dict keys, all of them
+    return mp.to(device)
+
+
+def run_mab_case(g: dict, device: str):
+    """Module forward + the golden's loss (sum(mean_agg(H_v) * G) + sum(H_e * G_e)) + backward; returns (mp, H_v, H_e)."""
+    from chemprop_b200.nn import MeanAggregation
+
+    mp = build_mab_module(g, device)
+    bmg = golden_bmg(g, device)
+    d = lambda k: torch.from_numpy(g[k]).to(device) if k in g else None  # noqa: E731
+    H_v, H_e = mp(bmg, d("V_d"), d("E_d"))
+    loss = 0.0
+    if H_v is not None:
+        loss = loss + (MeanAggregation()(H_v, bmg.batch) * d("G")).sum()
+    if H_e is not None:
+        loss = loss + (H_e * d("G_e")).sum()
+    loss.backward()
+    return mp, H_v, H_e
+
+
+def check_mab_case(g: dict, mp, H_v, H_e, atol: float, grad_rtol: float = 1e-4):
+    cfg = g["config"]
+    assert (H_v is None) == (not cfg.get("vertex", True)) and (H_e is None) == (not cfg.get("edge", True))
+    if H_v is not None:
+        np.testing.assert_allclose(H_v.detach().cpu().numpy(), g["H_v"], rtol=1e-5, atol=atol)
+    if H_e is not None:
+        assert tuple(H_e.shape) == g["H_e"].shape
+        np.testing.assert_allclose(H_e.detach().cpu().numpy(), g["H_e"], rtol=1e-5, atol=atol)   # caller's edge order
+    grads = {k: p.grad for k, p in mp.named_parameters()}
+    n = 0
+    for k, v in g.items():
+        if k.startswith("grad."):
+            got = grads[k[len("grad."):]]
+            assert got is not None, k
+            np.testing.assert_allclose(got.cpu().numpy(), v, rtol=grad_rtol, atol=10 * atol, err_msg=k)
+            n += 1
+    assert n >= 3
