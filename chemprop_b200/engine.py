@@ -1060,3 +1060,24 @@ class SegmentAggFunction(torch.autograd.Function):
         segment_bcast(g, ctx.atom_mol, ctx.ptr, ctx.nV, g.shape[1], dH, scale_mode=ctx.mode, scale=ctx.scale,
                       n_seg=g.shape[0])
         return dH, None, None, None, None, None
+
+
+class SegmentBcastFunction(torch.autograd.Function):
+    """rows <- their segment's row (`Z[batch]` of chemprop/nn/agg.py:127, nn/ffn.py:127): dmpnn_segment_bcast; the mirror
+    is the segment sum."""
+
+    @staticmethod
+    def forward(ctx, G, mol_atom_ptr, atom_mol, n_rows):
+        _require_cuda(G)
+        Gc = G if G.stride(1) == 1 else G.contiguous()
+        out = torch.empty((n_rows, G.shape[1]), dtype=G.dtype, device=G.device)
+        segment_bcast(Gc, atom_mol, mol_atom_ptr, n_rows, G.shape[1], out, n_seg=G.shape[0])
+        ctx.ptr, ctx.n_seg = mol_atom_ptr, G.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        dG = torch.empty((ctx.n_seg, g.shape[1]), dtype=g.dtype, device=g.device)
+        segment_sum(g, ctx.ptr, ctx.n_seg, g.shape[1], dG, pad_to=g.shape[1])
+        return dG, None, None, None

@@ -1,9 +1,10 @@
-from .agg import Aggregation, AggregationRegistry, MeanAggregation, NormAggregation, SumAggregation
+from .agg import (Aggregation, AggregationRegistry, AttentiveAggregation, MeanAggregation, NormAggregation,
+                  SumAggregation)
 from .message_passing import AtomMessagePassing, BondMessagePassing
 from .mol_atom_bond import MABAtomMessagePassing, MABBondMessagePassing
 from .multi import MulticomponentMessagePassing
 from .transforms import GraphTransform, ScaleTransform
 
-__all__ = ["Aggregation", "AggregationRegistry", "MeanAggregation", "NormAggregation", "SumAggregation",
+__all__ = ["Aggregation", "AggregationRegistry", "AttentiveAggregation", "MeanAggregation", "NormAggregation", "SumAggregation",
            "AtomMessagePassing", "BondMessagePassing", "MABAtomMessagePassing", "MABBondMessagePassing",
            "MulticomponentMessagePassing", "GraphTransform", "ScaleTransform"]

@@ -7,7 +7,8 @@ from __future__ import annotations
 from torch import Tensor, nn
 
 from .. import _lib
-from ..engine import SegmentAggFunction, segments_of
+from ..composed import GatherLinear
+from ..engine import SegmentAggFunction, SegmentBcastFunction, segments_of
 
 
 class Aggregation(nn.Module):
@@ -42,6 +43,27 @@ class NormAggregation(SumAggregation):
         self.norm = norm
         self._scale = norm
         self.hparams["norm"] = norm
+
+
+class AttentiveAggregation(Aggregation):
+    """chemprop/nn/agg.py:116-133: `alpha_v = exp(W h_v) / sum_{u in mol(v)} exp(W h_u)`, `h = sum_v alpha_v h_v` -- a
+    segmented softmax-weighted sum.  Composed from the engine's segment primitives: the `d -> 1` logit
+    layer (dmpnn_linear_fwd), the per-molecule sum of the exponentials (dmpnn_segment_sum), its broadcast back to the atoms
+    (dmpnn_segment_bcast) and the weighted per-molecule sum; exp / divide / multiply are torch elementwise ops in
+    between, exactly the reference's op sequence (no max-subtraction there either)."""
+
+    def __init__(self, dim: int = 0, *args, output_size: int, **kwargs):
+        super().__init__(dim, *args, **kwargs)
+        self.hparams["output_size"] = output_size
+        self.W = nn.Linear(output_size, 1)
+
+    def forward(self, H: Tensor, batch: Tensor) -> Tensor:
+        ptr, seg_of_row, B = segments_of(batch)
+        Hf = H.float()
+        logits = GatherLinear.apply(Hf, None, None, None, self.W.weight, self.W.bias, None, Hf.shape[0]).exp()   # agg.py:123
+        Z = SegmentAggFunction.apply(logits, ptr, seg_of_row, B, _lib.SCALE_NONE, 1.0)                            # agg.py:124-126
+        alphas = logits / SegmentBcastFunction.apply(Z, ptr, seg_of_row, Hf.shape[0])                             # agg.py:127
+        return SegmentAggFunction.apply(alphas * Hf, ptr, seg_of_row, B, _lib.SCALE_NONE, 1.0)                    # agg.py:128-131
 
 
 AggregationRegistry = {"mean": MeanAggregation, "sum": SumAggregation, "norm": NormAggregation}

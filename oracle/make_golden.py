@@ -250,12 +250,37 @@ def collate_case() -> dict:
     return out
 
 
+def attentive_case() -> dict:
+    """AttentiveAggregation (chemprop/nn/agg.py:116-133) of the real reference on seeded atom states."""
+    import_reference()
+    from chemprop.nn.agg import AttentiveAggregation
+
+    rng = np.random.default_rng(77)
+    sizes = [5, 1, 12, 7, 30, 2]
+    batch = torch.from_numpy(np.repeat(np.arange(len(sizes)), sizes))
+    H = torch.from_numpy(rng.normal(0, 0.5, size=(sum(sizes), 24)).astype(np.float32)).requires_grad_(True)
+    torch.manual_seed(77)
+    agg = AttentiveAggregation(output_size=24)
+    out = agg(H, batch)
+    G = torch.from_numpy(rng.normal(size=tuple(out.shape)).astype(np.float32))
+    (out * G).sum().backward()
+    return {"H": H.detach().numpy(), "batch": batch.numpy(), "out": out.detach().numpy(), "G": G.numpy(),
+            "param.W.weight": agg.W.weight.detach().numpy(), "param.W.bias": agg.W.bias.detach().numpy(),
+            "grad.H": H.grad.numpy(), "grad.W.weight": agg.W.weight.grad.numpy(), "grad.W.bias": agg.W.bias.grad.numpy()}
+
+
 def main():
     """`python -m oracle.make_golden [name ...]`: all cases, or only the named ones (a case's seed is its position in
     CASES, so adding cases at the end never changes the committed ones)."""
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)  # deterministic summation order
     only = set(sys.argv[1:])
+    if "fixture_attentive" in only or not only:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "fixture_attentive.npz"), **attentive_case())
+        print("fixture_attentive")
+        only.discard("fixture_attentive")
+        if not only and len(sys.argv) > 1:
+            return
     assert only <= set(CASES), only - set(CASES)
     for i, (name, cfg) in enumerate(CASES.items()):
         if only and name not in only:

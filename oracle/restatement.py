@@ -180,3 +180,15 @@ def aggregate(H, batch, mode="mean", norm=100.0, n_mols=None):
     if mode == "norm":
         out = out / norm                                             # agg.py:112-113
     return out
+
+
+def attentive_aggregate(H, batch, W, b, n_mols=None):
+    """AttentiveAggregation.forward, chemprop/nn/agg.py:121-133 (no max-subtraction, as in the reference)."""
+    dim_size = int(batch.max()) + 1 if n_mols is None else n_mols
+    logits = F.linear(H, W, b).exp()                                                        # agg.py:123
+    Z = torch.zeros(dim_size, 1, dtype=H.dtype).scatter_reduce_(0, batch.unsqueeze(1), logits, reduce="sum",
+                                                                include_self=False)         # agg.py:124-126
+    alphas = logits / Z[batch]                                                              # agg.py:127
+    index_torch = batch.unsqueeze(1).repeat(1, H.shape[1])
+    return torch.zeros(dim_size, H.shape[1], dtype=H.dtype).scatter_reduce_(0, index_torch, alphas * H, reduce="sum",
+                                                                            include_self=False)   # agg.py:128-131

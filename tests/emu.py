@@ -182,9 +182,25 @@ def build_layout(edge_index, rev_edge_index, batch, n_mols, meta_host=None):
                          torch.tensor(meta, dtype=torch.int32), list(meta))
 
 
+def segments_of(batch):
+    """engine.segments_of for a bare sorted `batch` (dmpnn_sorted_index_to_ptr): (ptr int32 [B + 1], seg_of_row int32, B)."""
+    seg = getattr(batch, "_dmpnn_seg", None)
+    if seg is not None:
+        return seg
+    b = batch.numpy()
+    assert np.all(np.diff(b) >= 0)
+    B = int(b.max()) + 1 if b.size else 0
+    ptr = np.searchsorted(b, np.arange(B + 1), side="left").astype(np.int32)
+    return torch.from_numpy(ptr), batch.to(torch.int32), B
+
+
 def patch_engine(monkeypatch):
     """Route engine.py's kernel wrappers to the emulations above (host-logic tests only)."""
     for name in ("linear_fwd", "linear_wgrad", "segment_sum", "segment_bcast", "bond_message", "rev_average", "act_bwd",
                  "build_layout"):
         monkeypatch.setattr(engine, name, globals()[name])
     monkeypatch.setattr(engine, "_require_cuda", lambda *ts: None)
+    import chemprop_b200.nn.agg as agg_mod
+
+    monkeypatch.setattr(engine, "segments_of", segments_of)
+    monkeypatch.setattr(agg_mod, "segments_of", segments_of)

@@ -184,3 +184,9 @@ def test_mab_modules_match_reference_golden(name):
     g = load_golden(name)
     mp, H_v, H_e = run_mab_case(g, "cuda")
     check_mab_case(g, mp, H_v, H_e, FP32_ATOL)
+
+
+def test_attentive_aggregation_matches_reference_fixture():
+    from tests.util import check_attentive
+
+    check_attentive("cuda", atol=FP32_ATOL)

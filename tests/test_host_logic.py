@@ -126,6 +126,13 @@ def test_multicomponent_message_passing(monkeypatch):
     np.testing.assert_allclose(out.detach().numpy(), gv["H_v"], rtol=1e-5, atol=ATOL)
 
 
+def test_attentive_aggregation_matches_reference_fixture(monkeypatch):
+    from tests.util import check_attentive
+
+    emu.patch_engine(monkeypatch)
+    check_attentive("cpu")
+
+
 def test_eval_mode_with_dropout_configured_stays_monolithic(monkeypatch):
     emu.patch_engine(monkeypatch)
     g = load_golden("bond_d3_dropout_eval")

@@ -56,6 +56,17 @@ def test_mab_restatement_matches_golden(name):
             np.testing.assert_allclose(P[k[len("grad."):]].grad.numpy(), v, rtol=1e-4, atol=2e-6, err_msg=k)
 
 
+def test_attentive_restatement_matches_reference_fixture():
+    g = load_golden("fixture_attentive")
+    H = torch.from_numpy(g["H"]).requires_grad_(True)
+    W, b = (torch.from_numpy(g[k]).requires_grad_(True) for k in ("param.W.weight", "param.W.bias"))
+    out = R.attentive_aggregate(H, torch.from_numpy(g["batch"]), W, b)
+    np.testing.assert_allclose(out.detach().numpy(), g["out"], **TOL)
+    (out * torch.from_numpy(g["G"])).sum().backward()
+    for t, k in ((H, "grad.H"), (W, "grad.W.weight"), (b, "grad.W.bias")):
+        np.testing.assert_allclose(t.grad.numpy(), g[k], rtol=1e-4, atol=2e-6, err_msg=k)
+
+
 def test_restatement_fp64_close_to_fp32_golden():
     g = load_golden("bond_d3_h300")
     H, _ = oracle_forward(g, torch.float64)

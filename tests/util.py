@@ -14,7 +14,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def golden_names(prefix: str = "", mab: bool = False) -> list[str]:
     """Golden cases of Bond / AtomMessagePassing (default) or of the mol-atom-bond variants (`mab=True`)."""
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if n != "collate_fixture" and n.startswith(prefix) and n.startswith("mab_") == mab]
+    return [n for n in names if n != "collate_fixture" and not n.startswith("fixture_") and n.startswith(prefix)
+            and n.startswith("mab_") == mab]
 
 
 def load_golden(name: str) -> dict:
@@ -224,3 +225,22 @@ def check_mab_case(g: dict, mp, H_v, H_e, atol: float, grad_rtol: float = 1e-4):
             np.testing.assert_allclose(got.cpu().numpy(), v, rtol=grad_rtol, atol=10 * atol, err_msg=k)
             n += 1
     assert n >= 3
+
+
+def check_attentive(device: str, atol: float = 2e-6):
+    """AttentiveAggregation against the reference's fixture (tests/golden/fixture_attentive.npz): output and the gradients
+    w.r.t. the atom states and the logit layer."""
+    from chemprop_b200.nn import AttentiveAggregation
+
+    g = load_golden("fixture_attentive")
+    agg = AttentiveAggregation(output_size=g["H"].shape[1])
+    agg.load_state_dict({"W.weight": torch.from_numpy(g["param.W.weight"]), "W.bias": torch.from_numpy(g["param.W.bias"])})
+    agg = agg.to(device)
+    H = torch.from_numpy(g["H"]).to(device).requires_grad_(True)
+    out = agg(H, torch.from_numpy(g["batch"]).to(device))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out"], rtol=1e-5, atol=atol)
+    (out * torch.from_numpy(g["G"]).to(device)).sum().backward()
+    np.testing.assert_allclose(H.grad.cpu().numpy(), g["grad.H"], rtol=1e-4, atol=atol)
+    np.testing.assert_allclose(agg.W.weight.grad.cpu().numpy(), g["grad.W.weight"], rtol=1e-4, atol=atol)
+    np.testing.assert_allclose(agg.W.bias.grad.cpu().numpy(), g["grad.W.bias"], rtol=1e-4, atol=atol)
+    assert agg.hparams == {"dim": 0, "cls": AttentiveAggregation, "output_size": g["H"].shape[1]}
