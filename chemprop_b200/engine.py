@@ -7,6 +7,7 @@ autograd graph; every arithmetic step on the path is a kernel of libdmpnn_sm100.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
@@ -22,7 +23,7 @@ SUM_IN_EPILOGUE = False
 
 # True: a BatchMolGraph that carries host-computed layout meta words (our collate: dmpnn_batch_meta_host) is trusted
 # and the step never synchronises on the device copy; False: always read the device-computed words (one sync per batch)
-HOST_META = True
+HOST_META = os.environ.get("DMPNN_HOST_META", "1") != "0"      # DMPNN_HOST_META=0: A/B switch for measurements
 
 HIDDEN_ALIGN = 64  # hidden row stride padded to 64 elements: bf16 rows start on 128-byte lines (one TMA request per box row)
 
