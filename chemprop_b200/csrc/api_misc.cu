@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <atomic>
 #include <string.h>
+#include <algorithm>
 #include <functional>
 #include <thread>
 #include <vector>
@@ -331,6 +332,60 @@ int dmpnn_dataset_gather_host(int64_t n_sel, const int64_t* ids, const int64_t* 
   for (int t = 1; t < T; ++t) pool.emplace_back(gather_host_range, std::cref(a), cut[(size_t)t], cut[(size_t)t + 1]);
   gather_host_range(a, cut[0], cut[1]);
   for (auto& th : pool) th.join();
+  return 0;
+}
+
+// Order the molecules of a batch so that the engine's greedy molecule-aligned tiles (<= 128 edge rows and <= 128 atoms of
+// CONSECUTIVE molecules, dmpnn_layout_build) come out nearly full: best-fit-decreasing bin packing on the edge counts.
+// The fused depth step spends the same time on a tile whatever its fill, so fewer, fuller tiles are a direct gain
+// (10 k ~25-atom molecules: 4856 tiles at 0.81 fill in arrival order -> 4186 tiles at 0.94).  A heuristic on the ORDER
+// only: tiles are always re-derived exactly from whatever order the batch ends up in, so correctness never depends on
+// it.  order_out receives a permutation of [0, n): bins in creation order, members in insertion order.
+int dmpnn_tile_pack_order(int64_t n, const int64_t* n_atoms, const int64_t* n_edges, int64_t* order_out) {
+  DMPNN_CHECK_ARG(n >= 0 && (n == 0 || (n_atoms && n_edges && order_out)), "tile_pack_order: bad args");
+  const int64_t kRows = 128, kAtoms = 128;
+  std::vector<int64_t> ids((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    DMPNN_CHECK_ARG(n_atoms[i] >= 0 && n_edges[i] >= 0, "tile_pack_order: negative molecule size");
+    ids[(size_t)i] = i;
+  }
+  std::stable_sort(ids.begin(), ids.end(), [&](int64_t a, int64_t b) { return n_edges[a] > n_edges[b]; });
+  struct Bin { int64_t rows, atoms, head, tail; };
+  std::vector<Bin> bins;
+  std::vector<int64_t> next((size_t)n, -1);
+  std::vector<std::vector<int64_t>> by_rem((size_t)kRows + 1);   // open bins by remaining row capacity
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t i = ids[(size_t)k], e = n_edges[i], a = n_atoms[i];
+    int64_t hit = -1;
+    if (e <= kRows && a <= kAtoms) {
+      for (int64_t r = e; r <= kRows && hit < 0; ++r) {           // best fit: the fullest bin that still takes it
+        auto& st = by_rem[(size_t)r];
+        for (size_t j = st.size(); j-- > 0;) {
+          if (bins[(size_t)st[j]].atoms + a <= kAtoms) {
+            hit = st[j];
+            st.erase(st.begin() + (std::ptrdiff_t)j);
+            break;
+          }
+        }
+      }
+    }
+    if (hit < 0) {
+      bins.push_back(Bin{e, a, i, i});
+      hit = (int64_t)bins.size() - 1;
+    } else {
+      Bin& b = bins[(size_t)hit];
+      next[(size_t)b.tail] = i;
+      b.tail = i;
+      b.rows += e;
+      b.atoms += a;
+    }
+    const Bin& b = bins[(size_t)hit];
+    if (b.rows <= kRows && b.atoms < kAtoms) by_rem[(size_t)(kRows - b.rows)].push_back(hit);   // still open
+  }
+  int64_t o = 0;
+  for (const Bin& b : bins)
+    for (int64_t i = b.head; i >= 0; i = next[(size_t)i]) order_out[o++] = i;
+  DMPNN_CHECK_ARG(o == n, "tile_pack_order: internal error");
   return 0;
 }
 

@@ -28,7 +28,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from .collate import BatchMolGraph
+from .collate import BatchMolGraph, tile_packing_order
 from .molgraph import MolGraph
 
 
@@ -172,6 +172,13 @@ class PackedMolGraphDataset:
             self._max_indeg_h.ctypes.data, plan[n:].ctypes.data, plan[2 * n + 1:].ctypes.data, meta.ctypes.data)
         _lib.check(rc, "dmpnn_dataset_batch_meta_host")
         return plan, n, int(plan[2 * n]), int(plan[3 * n + 1]), meta.tolist()
+
+    def packed_order(self, ids) -> np.ndarray:
+        """`ids` reordered so that the batch's tiles come out nearly full (see `tile_packing_order`)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        na = self._atom_ptr_h[ids + 1] - self._atom_ptr_h[ids]
+        ne = self._edge_ptr_h[ids + 1] - self._edge_ptr_h[ids]
+        return ids[tile_packing_order(na, ne)]
 
     def batch(self, ids, pin_memory: bool = False, transfer_dtype: torch.dtype | None = None,
               buffer: HostBatchBuffer | None = None, n_threads: int = 0) -> BatchMolGraph:

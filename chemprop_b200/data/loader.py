@@ -13,6 +13,10 @@ on top of a `PackedMolGraphDataset`:
     host -> device copy is issued asynchronously on a side stream and the consumer's stream waits on its event; a data
     set that is already resident in HBM is gathered directly on the device (one launch, no thread, no copy).
 
+  * `pack_tiles=True` (default): inside each batch the molecules are ordered by `dmpnn_tile_pack_order` so that the
+    engine's 128-row tiles come out ~0.94 full instead of ~0.81 (the fused depth step costs the same per tile whatever its
+    fill); batch membership is the sampler's, `LoadedBatch.ids` / `extras` follow the order used.
+
 Per-molecule side arrays (`Y`, `weights`, `X_d`, ... -- anything indexed by molecule) given as `arrays={name: ndarray}`
 come back gathered for the batch in `batch.extras[name]`.
 """
@@ -51,13 +55,14 @@ class PackedBatchLoader:
     def __init__(self, dataset: PackedMolGraphDataset, batch_size: int = 64, shuffle: bool = True,
                  seed: int | None = None, drop_last: bool | None = None, rank: int = 0, world: int = 1,
                  device: str | torch.device | None = None, prefetch: int = 3, transfer_dtype: torch.dtype | None = None,
-                 arrays: dict | None = None, n_threads: int = 0):
+                 arrays: dict | None = None, n_threads: int = 0, pack_tiles: bool = True):
         if batch_size <= 0 or world <= 0 or not 0 <= rank < world or prefetch < 2:
             raise ValueError("bad batch_size / rank / world / prefetch (prefetch >= 2)")
         self.dataset, self.batch_size, self.shuffle = dataset, int(batch_size), bool(shuffle)
         self.rank, self.world, self.prefetch, self.n_threads = int(rank), int(world), int(prefetch), int(n_threads)
         self.device = None if device is None else torch.device(device)
         self.transfer_dtype = transfer_dtype
+        self.pack_tiles = bool(pack_tiles)
         self.arrays = {k: np.asarray(v) for k, v in (arrays or {}).items()}
         n = len(dataset)
         for k, v in self.arrays.items():
@@ -91,6 +96,8 @@ class PackedBatchLoader:
         out = [order[i:i + self.batch_size] for i in range(0, order.shape[0], self.batch_size)]
         if out and self.drop_last and out[-1].shape[0] < self.batch_size:
             out.pop()
+        if self.pack_tiles:      # same molecules per batch, ordered for full tiles; `LoadedBatch.ids` reports the order
+            out = [self.dataset.packed_order(ids) for ids in out]
         return out
 
     def _extras(self, ids: np.ndarray) -> dict:

@@ -188,6 +188,42 @@ def test_medium_batch_vs_oracle(kind, precision, n_mols, d_h, depth):
         assert err <= (2e-4 if precision == "fp32" else 6e-2) * scale, (k, err, scale)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_tile_packed_molecule_order_vs_oracle(precision):
+    """bench.py's batch: molecules ordered by the loader's tile packing (dmpnn_tile_pack_order) -> nearly full 128-row
+    tiles, 3-4 molecules in many of them.  Same parity bar as any other order, forward and gradients."""
+    from chemprop_b200 import _lib
+    from chemprop_b200.data import BatchMolGraph, make_molecules, tile_packing_order_of
+    from chemprop_b200.nn import BondMessagePassing, MeanAggregation
+    from oracle import restatement as R
+
+    torch.manual_seed(0)
+    mgs = make_molecules(1500, seed=8)
+    plain_tiles = BatchMolGraph(mgs)._meta_host[_lib.META_N_TILES]
+    mgs = [mgs[i] for i in tile_packing_order_of(mgs)]
+    bmg = BatchMolGraph(mgs)
+    tiles = bmg._meta_host[_lib.META_N_TILES]
+    assert tiles < 0.9 * plain_tiles and bmg.E.shape[0] / (128 * tiles) > 0.9
+    mp = BondMessagePassing(d_h=300, depth=3, precision=precision)
+    P = {k: v.detach().double().requires_grad_(True) for k, v in mp.state_dict().items()}
+    H_ref = R.message_passing_forward("bond", bmg.V.double(), bmg.E.double(), bmg.edge_index, bmg.rev_edge_index,
+                                      P["W_i.weight"], None, P["W_h.weight"], None, P["W_o.weight"], P["W_o.bias"], 3)
+    a_ref = R.aggregate(H_ref, bmg.batch, "mean")
+    a_ref.square().sum().backward()
+    mp = mp.cuda()
+    bmg.to("cuda")
+    H = mp(bmg)
+    a = MeanAggregation()(H, bmg.batch)
+    a.float().square().sum().backward()
+    tol = FP32_ATOL if precision == "fp32" else BF16_ATOL * max(1.0, H_ref.detach().abs().max().item())
+    assert (H.detach().double().cpu() - H_ref.detach()).abs().max().item() <= tol
+    assert (a.detach().double().cpu() - a_ref.detach()).abs().max().item() <= tol
+    for k, p in mp.named_parameters():
+        ref = P[k].grad
+        scale = max(1e-6, ref.abs().max().item())
+        assert (p.grad.double().cpu() - ref).abs().max().item() <= (2e-4 if precision == "fp32" else 6e-2) * scale, k
+
+
 def test_aggregation_without_cached_segments():
     """Aggregation.forward(H, batch) called with a bare `batch` tensor (agg.py:39-59 contract)."""
     from chemprop_b200.nn import MeanAggregation, SumAggregation

@@ -28,7 +28,7 @@ def _check_batch(b, mgs):
 
 def test_seeded_order_is_the_references_seeded_sampler(data):
     mgs, ds = data
-    loader = PackedBatchLoader(ds, batch_size=32, shuffle=True, seed=1234)
+    loader = PackedBatchLoader(ds, batch_size=32, shuffle=True, seed=1234, pack_tiles=False)
     rg, idxs = np.random.default_rng(1234), np.arange(N)          # samplers.py:16-21, restated
     for epoch in range(3):
         rg.shuffle(idxs)
@@ -42,7 +42,7 @@ def test_seeded_order_is_the_references_seeded_sampler(data):
         from chemprop.data.samplers import SeededSampler
 
         ref = SeededSampler(N, 99)
-        ours = PackedBatchLoader(ds, batch_size=50, shuffle=True, seed=99)
+        ours = PackedBatchLoader(ds, batch_size=50, shuffle=True, seed=99, pack_tiles=False)
         for _ in range(2):
             assert np.array_equal(np.fromiter(iter(ref), dtype=np.int64), np.concatenate([b.ids for b in ours]))
 
@@ -69,7 +69,7 @@ def test_drop_last_rule_and_unshuffled_order(data):
     assert [len(b.ids) for b in PackedBatchLoader(ds, batch_size=101, shuffle=False, drop_last=False)] == [101, 101, 1]
     assert [len(b.ids) for b in PackedBatchLoader(ds, batch_size=100, shuffle=False)] == [100, 100, 3]
     assert len(PackedBatchLoader(ds, batch_size=101)) == 2 and len(PackedBatchLoader(ds, batch_size=100)) == 3
-    got = np.concatenate([b.ids for b in PackedBatchLoader(ds, batch_size=64, shuffle=False)])
+    got = np.concatenate([b.ids for b in PackedBatchLoader(ds, batch_size=64, shuffle=False, pack_tiles=False)])
     assert np.array_equal(got, np.arange(N))
     a = np.concatenate([b.ids for b in PackedBatchLoader(ds, batch_size=64, shuffle=True)])                # unseeded
     assert np.array_equal(np.sort(a), np.arange(N))
@@ -78,7 +78,8 @@ def test_drop_last_rule_and_unshuffled_order(data):
 def test_ranks_partition_the_epoch_like_distributed_sampler(data):
     mgs, ds = data
     world = 4
-    per_rank = [np.concatenate([b.ids for b in PackedBatchLoader(ds, batch_size=16, shuffle=True, seed=7, rank=r, world=world)])
+    per_rank = [np.concatenate([b.ids for b in PackedBatchLoader(ds, batch_size=16, shuffle=True, seed=7, rank=r, world=world,
+                                                                   pack_tiles=False)])
                 for r in range(world)]
     assert {len(x) for x in per_rank} == {51}                                                              # ceil(203 / 4)
     order = np.arange(N)
@@ -88,7 +89,8 @@ def test_ranks_partition_the_epoch_like_distributed_sampler(data):
         assert np.array_equal(per_rank[r], padded[r::world])
     assert np.array_equal(epoch_shard(np.arange(5), 1, 2), [1, 3, 0]) and np.array_equal(epoch_shard(np.arange(5), 0, 1), np.arange(5))
     torch_ds = torch.utils.data.distributed.DistributedSampler(list(range(N)), num_replicas=world, rank=2, shuffle=False)
-    ours = np.concatenate([b.ids for b in PackedBatchLoader(ds, batch_size=16, shuffle=False, rank=2, world=world)])
+    ours = np.concatenate([b.ids for b in PackedBatchLoader(ds, batch_size=16, shuffle=False, rank=2, world=world,
+                                                            pack_tiles=False)])
     assert np.array_equal(ours, np.fromiter(iter(torch_ds), dtype=np.int64))
 
 
@@ -107,3 +109,30 @@ def test_side_arrays_and_early_exit(data):
         PackedBatchLoader(ds, arrays={"Y": Y[:-1]})
     with pytest.raises(ValueError):
         PackedBatchLoader(ds, prefetch=1)
+
+
+def test_tile_packing_keeps_batch_membership_and_fills_tiles():
+    from chemprop_b200 import _lib
+    from chemprop_b200.data import tile_packing_order, tile_packing_order_of
+
+    mgs = make_molecules(4000, seed=1)
+    ds = PackedMolGraphDataset.from_molgraphs(mgs)
+    plain = PackedBatchLoader(ds, batch_size=2000, shuffle=True, seed=2, pack_tiles=False)
+    packed = PackedBatchLoader(ds, batch_size=2000, shuffle=True, seed=2)
+    for a, b in zip(plain, packed):
+        assert np.array_equal(np.sort(a.ids), np.sort(b.ids)) and not np.array_equal(a.ids, b.ids)
+        ta, tb = a.bmg._meta_host[_lib.META_N_TILES], b.bmg._meta_host[_lib.META_N_TILES]
+        rows = b.bmg.E.shape[0]
+        assert tb < 0.9 * ta and rows / (128 * tb) > 0.9, (ta, tb)
+        assert b.bmg._meta_host[_lib.META_MAX_TILE_ROWS] <= 128
+        _check_batch(b, mgs)
+    order = tile_packing_order_of(mgs[:500])
+    assert np.array_equal(np.sort(order), np.arange(500))
+    # degenerate inputs: empty, single-atom molecules (no edges: bounded by the 128-atom cap), an oversized molecule
+    assert tile_packing_order([], []).shape == (0,)
+    o = tile_packing_order([1] * 300, [0] * 300)
+    assert np.array_equal(np.sort(o), np.arange(300))
+    o = tile_packing_order([90, 10, 10, 70], [200, 20, 20, 108])
+    assert np.array_equal(np.sort(o), np.arange(4)) and o[0] == 0          # the oversized one sits alone, first
+    with pytest.raises(ValueError):
+        tile_packing_order([1, 2], [1])
