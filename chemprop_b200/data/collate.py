@@ -51,8 +51,9 @@ def host_meta(edge_index: Tensor, rev_edge_index: Tensor, batch: Tensor, n_mols:
     """The layout meta words (flags, max in-degree, tile count, largest tile) of a batch whose int64 index tensors are
     in host memory -- `dmpnn_batch_meta_host`, one C pass.  None when the tensors are not plain host int64."""
     ts = (edge_index, rev_edge_index, batch)
-    if any(t.is_cuda or t.dtype != torch.int64 or not t.is_contiguous() for t in ts):
+    if any(t.is_cuda or t.dtype != torch.int64 for t in ts):
         return None
+    edge_index, rev_edge_index, batch = (t.contiguous() for t in ts)
     if edge_index.dim() != 2 or edge_index.shape[0] != 2 or rev_edge_index.shape[0] != edge_index.shape[1]:
         return None
     V, E = int(batch.shape[0]), int(edge_index.shape[1])

@@ -4,8 +4,9 @@ composed tier in composed.py: which op, which operand, which index table, in whi
 golden vectors without a GPU.  `patch_engine(monkeypatch)` swaps the wrappers for these; nothing in the product
 imports this file, and a GPU run never touches it (the `-m gpu` tests call the real kernels through the C ABI).
 
-The emulation itself is validated by the fact that the GPU-verified monolithic f32 tier, run through it, reproduces
-every golden (tests/test_host_logic.py::test_monolithic_f32_tier_through_emulation)."""
+The emulation itself is validated by the fact that the GPU-verified monolithic tiers, run through it, reproduce every
+golden (tests/test_host_logic.py::test_monolithic_f32_tier_through_emulation, ::test_monolithic_bf16_tier_through_emulation:
+the bf16 emulations round where the kernels store bf16, so the tier's 1e-2 bound is checked for real)."""
 from __future__ import annotations
 
 import numpy as np
@@ -182,6 +183,110 @@ def build_layout(edge_index, rev_edge_index, batch, n_mols, meta_host=None):
                          torch.tensor(meta, dtype=torch.int32), list(meta))
 
 
+# ---- bf16 / tensor-core tier ------------------------------------------------------------------------------------
+def _bf(x):
+    """round to bf16, continue in f32 (what a bf16 store followed by a load does)"""
+    return x.to(torch.bfloat16).float()
+
+
+def pack_weight_tc(W, transpose=False):
+    """the 'packed' weight of the emulation is just B[n][k] (bf16-rounded) of C = A . B^T"""
+    return _bf(W.detach().float().t() if transpose else W.detach().float()).contiguous()
+
+
+def pack_weight_bf16(W):
+    return _bf(W.detach().float()).contiguous()
+
+
+def concat_bf16(X1, K1, out, R, *, idx1=None, X2=None, K2=0, idx2=None, width=None):
+    width = out.shape[1] if width is None else width
+    out[:R, :K1 + K2] = _cat(X1, K1, idx1, X2, K2, idx2, R).to(out.dtype)
+    if width > K1 + K2:
+        out[:R, K1 + K2:width] = 0
+
+
+def linear_tc(A, K, Wpk, N, out, *, bias=None, res=None, act=ACT_NONE, act_param=0.0, R=None):
+    R = out.shape[0] if R is None else R
+    assert A.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and Wpk.shape == (N, K)
+    Y = A[:R, :K].float() @ Wpk.t()
+    if bias is not None:
+        Y = Y + bias.float()
+    if res is not None:
+        Y = Y + res[:R, :N].float()
+    out[:R, :N] = _act(Y, act, act_param).to(out.dtype)
+    n16 = (N + 15) // 16 * 16
+    if n16 > N:
+        out[:R, N:n16] = 0
+
+
+def wgrad_tc(dY, X, R, N, K, dW, *, accumulate=False):
+    assert dY.dtype == torch.bfloat16 and X.dtype == torch.bfloat16 and dW.dtype == torch.float32
+    upd = dY[:R, :N].float().t() @ X[:R, :K].float()
+    if accumulate:
+        dW[:N, :K] += upd
+    else:
+        dW[:N, :K] = upd
+
+
+def column_sum(Y, R, N, out, *, accumulate=False):
+    v = Y[:R, :N].float().sum(0)
+    if accumulate:
+        out += v
+    else:
+        out.copy_(v)
+
+
+def bond_step_fused(H_prev, H0, H_next, h, Wpk, bias, lay, act, act_param, first_step, M_out=None):
+    """H_next[e] = tau(H_0[e] + b + W_h . M[e]),  M = message of g(H_prev), g = tau on the first step (include/dmpnn.h)."""
+    M = torch.zeros((lay.E, h))
+    bond_message(H_prev, lay, h, M, act=(act if first_step else ACT_NONE), act_param=act_param)
+    M = _bf(M)
+    Z = M @ Wpk.t() + H0[: lay.E, :h].float()
+    if bias is not None:
+        Z = Z + bias.float()
+    H_next[: lay.E, :h] = _act(Z, act, act_param).to(H_next.dtype)
+    H_next[: lay.E, h:(h + 15) // 16 * 16] = 0
+    if M_out is not None:
+        M_out[: lay.E, :h] = M.to(M_out.dtype)
+        M_out[: lay.E, h:(h + 15) // 16 * 16] = 0
+
+
+def bond_step_bwd_fused(dZ, Yact, dOut, h, WpkT, lay, act, act_param, G_out=None, y_is_preact=False, addends=()):
+    """dOut = ((S.P) dZ) . W_h [* tau'(Yact)] [+ addends];  G_out = (S.P) dZ   (WpkT holds B = W_h^T of A . B^T)."""
+    G = torch.zeros((lay.E, h))
+    bond_message(dZ, lay, h, G, permute_on_read=True)
+    G = _bf(G)
+    D = G @ WpkT.t()
+    if Yact is not None:
+        D = D * _dact(Yact[: lay.E, :h].float(), act, act_param, y_is_preact)
+    for a in addends:
+        D = D + a[: lay.E, :h].float()
+    dOut[: lay.E, :h] = D.to(dOut.dtype)
+    dOut[: lay.E, h:(h + 15) // 16 * 16] = 0
+    if G_out is not None:
+        G_out[: lay.E, :h] = G.to(G_out.dtype)
+        G_out[: lay.E, h:(h + 15) // 16 * 16] = 0
+
+
+def bond_message_bwd_masked(dM, Yact, lay, Ccols, out, *, act, act_param=0.0):
+    if lay.E == 0:
+        return
+    G = torch.zeros((lay.E, Ccols))
+    bond_message(dM, lay, Ccols, G, permute_on_read=True)
+    out[: lay.E, :Ccols] = (G * _dact(Yact[: lay.E, :Ccols].float(), act, act_param, False)).to(out.dtype)
+
+
+def sum_act_bwd(Zs, G, Ypre, out, R, Ccols, *, act, act_param=0.0):
+    if R == 0:
+        return
+    acc = torch.zeros((R, Ccols))
+    for z in Zs:
+        acc = acc + z[:R, :Ccols].float()
+    if G is not None:
+        acc = acc + G[:R, :Ccols].float() * _dact(Ypre[:R, :Ccols].float(), act, act_param, True)
+    out[:R, :Ccols] = acc.to(out.dtype)
+
+
 def segments_of(batch):
     """engine.segments_of for a bare sorted `batch` (dmpnn_sorted_index_to_ptr): (ptr int32 [B + 1], seg_of_row int32, B)."""
     seg = getattr(batch, "_dmpnn_seg", None)
@@ -197,7 +302,8 @@ def segments_of(batch):
 def patch_engine(monkeypatch):
     """Route engine.py's kernel wrappers to the emulations above (host-logic tests only)."""
     for name in ("linear_fwd", "linear_wgrad", "segment_sum", "segment_bcast", "bond_message", "rev_average", "act_bwd",
-                 "build_layout"):
+                 "build_layout", "pack_weight_tc", "pack_weight_bf16", "concat_bf16", "linear_tc", "wgrad_tc", "column_sum",
+                 "bond_step_fused", "bond_step_bwd_fused", "bond_message_bwd_masked", "sum_act_bwd"):
         monkeypatch.setattr(engine, name, globals()[name])
     monkeypatch.setattr(engine, "_require_cuda", lambda *ts: None)
     import chemprop_b200.nn.agg as agg_mod

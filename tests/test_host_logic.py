@@ -53,6 +53,40 @@ def test_monolithic_f32_tier_through_emulation(name, monkeypatch):
     _check(g, mp, H, aggs)
 
 
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name", [n for n in golden_names() if n not in COMPOSED_GOLDENS])
+def test_monolithic_bf16_tier_through_emulation(name, fused, monkeypatch):
+    """The bf16 / tensor-core tier's host logic (bond_forward tc path, bond_backward_tc with the fused-step mirror, the
+    atom tc path, and with `fused=False` the generic mirror on bf16 buffers) on emulated kernels, same bounds as
+    tests/test_gpu_parity.py::test_bf16_tier_matches_reference_golden."""
+    from chemprop_b200 import engine
+
+    emu.patch_engine(monkeypatch)
+    calls = {"fwd": 0, "bwd": 0}
+    f_fwd, f_bwd = engine.bond_step_fused, engine.bond_step_bwd_fused
+    monkeypatch.setattr(engine, "bond_step_fused", lambda *a, **k: (calls.__setitem__("fwd", calls["fwd"] + 1), f_fwd(*a, **k))[1])
+    monkeypatch.setattr(engine, "bond_step_bwd_fused", lambda *a, **k: (calls.__setitem__("bwd", calls["bwd"] + 1), f_bwd(*a, **k))[1])
+    g = load_golden(name)
+    mp = build_engine_module(g, "cpu", "bf16", fused)
+    mp, bmg, H, aggs = _run(g, mp)
+    cfg = g["config"]
+    expect_fused = (fused and cfg["kind"] == "bond" and cfg["depth"] > 1 and not cfg.get("undirected") and g["E"].shape[0] > 0
+                    and cfg["d_h"] % 4 == 0 and bmg._meta_host[3] <= 128)      # [3] = largest tile (rows)
+    assert (calls["fwd"], calls["bwd"]) == ((cfg["depth"] - 1,) * 2 if expect_fused else (0, 0)), calls
+    assert H.dtype == (torch.float32 if "V_d" in g else torch.bfloat16)      # W_d (torch, f32) follows the engine's part
+    np.testing.assert_allclose(H.detach().float().numpy(), g["H_v"], rtol=0, atol=1e-2)
+    np.testing.assert_allclose(aggs["mean"].detach().float().numpy(), g["agg_mean"], rtol=0, atol=1e-2)
+    smooth = g["config"].get("activation", "relu") in ("tanh", "elu")
+    grads = {k: p.grad for k, p in mp.named_parameters()}
+    for k, v in g.items():
+        if k.startswith("grad."):
+            got = grads[k[len("grad."):]].float().numpy()
+            scale = max(1e-3, float(np.abs(v).max()))
+            fro = float(np.linalg.norm(got - v) / max(1e-6, np.linalg.norm(v)))
+            lim = (2e-2, 2e-2) if smooth else (0.5, 0.2)
+            assert np.abs(got - v).max() <= lim[0] * scale and fro <= lim[1], (k, np.abs(got - v).max(), scale, fro)
+
+
 @pytest.mark.parametrize("name", COMPOSED_GOLDENS)
 def test_composed_tier_matches_reference_golden(name, monkeypatch):
     """PReLU (with its own gradient), SELU, a user module (Softplus), AtomMP undirected: composed.py == reference."""
