@@ -17,6 +17,8 @@ DMPNN_HOST_META=0 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu --n
 echo "bench(read-back) rc=$?"; cat gpurun_out/bench_readback.json
 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu --no-dataset --no-pack > gpurun_out/bench_nopack.json 2> gpurun_out/bench_nopack.err
 echo "bench(generator order, no tile packing) rc=$?"; cat gpurun_out/bench_nopack.json
+(PACK=0 timeout 120 python tools/time_step.py; PACK=1 timeout 120 python tools/time_step.py) > gpurun_out/time_step_pack.log 2>&1
+echo "fused step alone, generator vs tile-packed order:"; cat gpurun_out/time_step_pack.log
 timeout 300 python tools/time_loader.py > gpurun_out/time_loader.log 2>&1; echo "time_loader rc=$?"; cat gpurun_out/time_loader.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-dataset > gpurun_out/bench_under_ncu.log 2>&1
