@@ -173,6 +173,34 @@ def run_cpu(n_mols: int, steps: int, warmup: int):
     return n_mols / dt, dt
 
 
+def time_collate(n_mols: int = 4000):
+    """Host-side batch assembly, molecules/s (the reference collate is timed beside the path): the
+    reference's collate loop (oracle restatement of collate.py:37-62, numpy), our C collate of the same MolGraphs, and
+    the packed data set's gather into a reused staging buffer.  CPU only, bounded (a few seconds)."""
+    from oracle import restatement as R
+
+    from chemprop_b200.data import BatchMolGraph, HostBatchBuffer, PackedMolGraphDataset, make_molecules
+
+    mgs = make_molecules(n_mols, seed=3, mean_atoms=WORKLOAD["mean_atoms"])
+
+    def best(f, n=3):
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            f()
+            ts.append(time.perf_counter() - t0)
+        return n_mols / min(ts)
+
+    ds = PackedMolGraphDataset.from_molgraphs(mgs)
+    ids = np.random.default_rng(0).permutation(n_mols)
+    buf = HostBatchBuffer(ds.d_v, ds.d_e)
+    ds.batch(ids, buffer=buf)
+    return {"unit": "molecules/s", "sample": f"{n_mols} molecules, best of 3",
+            "reference_collate_port": best(lambda: R.collate_torch(mgs)),
+            "c_collate": best(lambda: BatchMolGraph(mgs)),
+            "packed_dataset_gather": best(lambda: ds.batch(ids, buffer=buf))}
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -416,6 +444,13 @@ def main_gpu(args):
                "sample": f"{sample} molecules x 3 steps (1 warm-up), oracle restatement on torch CPU, "
                          f"{torch.get_num_threads()} threads (fastest of 8/16/32/{os.cpu_count()})"}
 
+    host_assembly = None
+    if world == 1 and not args.no_cpu:
+        try:
+            host_assembly = time_collate()
+        except Exception as e:  # noqa: BLE001
+            host_assembly = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     line = {
         "metric": "molecules/sec fwd+bwd (h=300 d=3)", "value": value, "unit": "molecules/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -438,6 +473,7 @@ def main_gpu(args):
                                 if precision == "bf16" else "f32 features + int64 indices")},
         "e2e_f32_host": e2e_f32,
         "resident_dataset": resident_ds,
+        "host_batch_assembly": host_assembly,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -67,6 +67,25 @@ def collate(mgs):
             np.concatenate(batch).astype(np.int64))
 
 
+def collate_torch(mgs):
+    """collate.py:40-62 operation for operation (Python lists for `batch`, `torch.from_numpy(...).float()` / `.long()`
+    conversions): the version bench.py times as the reference's batch assembly."""
+    Vs, Es, edge_indexes, rev_edge_indexes, batch_indexes = [], [], [], [], []
+    num_nodes = 0
+    num_edges = 0
+    for i, mg in enumerate(mgs):
+        Vs.append(mg.V)
+        Es.append(mg.E)
+        edge_indexes.append(mg.edge_index + num_nodes)
+        rev_edge_indexes.append(mg.rev_edge_index + num_edges)
+        batch_indexes.append([i] * len(mg.V))
+        num_nodes += mg.V.shape[0]
+        num_edges += mg.edge_index.shape[1]
+    return (torch.from_numpy(np.concatenate(Vs)).float(), torch.from_numpy(np.concatenate(Es)).float(),
+            torch.from_numpy(np.hstack(edge_indexes)).long(), torch.from_numpy(np.concatenate(rev_edge_indexes)).long(),
+            torch.tensor(np.concatenate(batch_indexes)).long())
+
+
 # --- scatter-sum idiom: mixins.py:12-15, base.py:208-211 -----------------------------------
 def _scatter_sum_rows(H: Tensor, index: Tensor, n_rows: int) -> Tensor:
     index_torch = index.unsqueeze(1).repeat(1, H.shape[1])

@@ -82,6 +82,8 @@ def test_collate_restatement_matches_reference_fixture():
     V, E, ei, rev, batch = R.collate(mgs)
     for a, k in ((V, "V"), (E, "E"), (ei, "edge_index"), (rev, "rev_edge_index"), (batch, "batch")):
         assert a.dtype == g[k].dtype and np.array_equal(a, g[k]), k
+    for a, k in zip(R.collate_torch(mgs), ("V", "E", "edge_index", "rev_edge_index", "batch")):
+        assert np.array_equal(a.numpy(), g[k]) and a.dtype in (torch.float32, torch.int64), k
 
 
 def test_layout_restatement_properties():
