@@ -173,3 +173,13 @@ def test_host_meta_flags_on_invalid_batches_and_invalidation():
     bmg.rev_edge_index = bad_rev
     assert bmg._meta_host is None and bmg._layout is None
     assert host_meta(ei.int(), rev, bt, 20) is None                     # not the reference's int64: no host words
+
+
+def test_batchmolgraph_pickles_with_its_staging_copy_and_meta_words():
+    """DataLoader worker processes hand batches over by pickling (chemprop/cli/common.py:35 `num_workers`)."""
+    import pickle
+
+    b = BatchMolGraph(make_molecules(5, seed=0), transfer_dtype=torch.bfloat16)
+    c = pickle.loads(pickle.dumps(b))
+    assert len(c) == 5 and torch.equal(c.edge_index, b.edge_index) and torch.equal(c.V, b.V)
+    assert c._meta_host == b._meta_host and c._xfer is not None and c._layout is None
