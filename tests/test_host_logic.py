@@ -196,3 +196,47 @@ def test_tier_selection():
     with pytest.raises(Exception, match="no CPU fallback|CUDA"):     # the composed tier has no CPU path either
         from chemprop_b200.data import BatchMolGraph, make_molecules
         BondMessagePassing(d_h=8, activation="prelu")(BatchMolGraph(make_molecules(2, seed=0)))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_randomised_configurations_vs_oracle(seed, monkeypatch):
+    """Random module configuration x random batch (1-atom molecules, shuffled edge order, occasionally a > 128-edge
+    molecule or an edgeless batch): whichever tier serves it (monolithic f32 or composed) == the f64 oracle, forward
+    and every gradient."""
+    from chemprop_b200.data import BatchMolGraph, make_molecule, make_molecules
+    from chemprop_b200.nn import AtomMessagePassing, BondMessagePassing, MeanAggregation, NormAggregation, SumAggregation
+    from oracle import restatement as R
+
+    emu.patch_engine(monkeypatch)
+    rng = np.random.default_rng(1000 + seed)
+    kind = ("bond", "atom")[int(rng.integers(2))]
+    act = ("relu", "leakyrelu", "prelu", "tanh", "elu", "selu")[int(rng.integers(6))]
+    depth, bias, undirected = int(rng.integers(1, 6)), bool(rng.integers(2)), bool(rng.integers(2))
+    d_h, d_v, d_e = int(rng.choice([8, 20, 33, 64])), int(rng.choice([5, 72])), int(rng.choice([3, 14]))
+    shape = int(rng.integers(4))
+    if shape == 0:
+        mgs = [make_molecule(rng, 1, d_v, d_e) for _ in range(3)]                                   # no edges at all
+    elif shape == 1:
+        mgs = make_molecules(7, seed=seed, mean_atoms=8, std_atoms=4, min_atoms=1, d_v=d_v, d_e=d_e, shuffle_edges=True)
+    elif shape == 2:
+        mgs = [make_molecule(rng, 3, d_v, d_e), make_molecule(rng, 80, d_v, d_e), make_molecule(rng, 1, d_v, d_e)]
+    else:
+        mgs = make_molecules(1, seed=seed, mean_atoms=20, d_v=d_v, d_e=d_e)
+    torch.manual_seed(seed)
+    cls = BondMessagePassing if kind == "bond" else AtomMessagePassing
+    mp = cls(d_v=d_v, d_e=d_e, d_h=d_h, bias=bias, depth=depth, activation=act, undirected=undirected)
+    bmg = BatchMolGraph(mgs)
+    P = {k: v.detach().double().requires_grad_(True) for k, v in mp.state_dict().items()}
+    H_ref = R.message_passing_forward(kind, bmg.V.double(), bmg.E.double(), bmg.edge_index, bmg.rev_edge_index,
+                                      P["W_i.weight"], P.get("W_i.bias"), P["W_h.weight"], P.get("W_h.bias"),
+                                      P["W_o.weight"], P["W_o.bias"], depth, act, undirected, prelu_weight=P.get("tau.weight"))
+    agg_cls, mode = ((MeanAggregation, "mean"), (SumAggregation, "sum"), (NormAggregation, "norm"))[int(rng.integers(3))]
+    G = torch.from_numpy(rng.normal(size=(len(mgs), d_h)))
+    (R.aggregate(H_ref, bmg.batch, mode, n_mols=len(mgs)) * G).sum().backward()
+    H = mp(bmg)
+    (agg_cls()(H, bmg.batch) * G.float()).sum().backward()
+    assert (H.detach().double() - H_ref.detach()).abs().max().item() <= 2e-5
+    for k, p in mp.named_parameters():
+        ref = torch.zeros_like(P[k]) if P[k].grad is None else P[k].grad      # e.g. W_h at depth 1: unused
+        got = torch.zeros_like(ref) if p.grad is None else p.grad.double()
+        assert (got - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item()), (k, kind, act, depth, shape)
