@@ -261,8 +261,15 @@ class TrainingBatch(NamedTuple):
     gt_mask: Tensor | None
 
 
-def collate_batch(batch: Iterable[Datum]) -> TrainingBatch:
-    """Same contract as chemprop/data/collate.py:86-97."""
+def collate_batch(batch: Iterable[Datum], pack_tiles: bool = False) -> TrainingBatch:
+    """Same contract as chemprop/data/collate.py:86-97.  `pack_tiles=True` (training loaders:
+    `DataLoader(..., collate_fn=functools.partial(collate_batch, pack_tiles=True))`) reorders the data of the batch --
+    molecules, descriptors, targets, weights, masks, all alike -- by `tile_packing_order` so that the engine's tiles come
+    out nearly full; leave it off where the caller relies on the order inside a batch (prediction)."""
+    batch = list(batch)
+    if pack_tiles and len(batch) > 1:
+        order = tile_packing_order_of([d[0] for d in batch])
+        batch = [batch[i] for i in order]
     mgs, V_ds, x_ds, ys, weights, lt_masks, gt_masks = zip(*batch)
     return TrainingBatch(
         BatchMolGraph(mgs),

@@ -77,6 +77,23 @@ def test_collate_batch_contract():
     assert tb.lt_mask.dtype == torch.bool
 
 
+def test_collate_batch_tile_packing_reorders_every_field_alike():
+    from chemprop_b200 import _lib
+
+    mgs = make_molecules(600, seed=4)
+    data = [Datum(mg, np.full((mg.V.shape[0], 1), i, dtype=np.float32), np.array([float(i)]), np.array([float(i)]), float(i),
+                  None, None) for i, mg in enumerate(mgs)]
+    plain, packed = collate_batch(data), collate_batch(data, pack_tiles=True)
+    order = packed.Y[:, 0].long()
+    assert torch.equal(torch.sort(order).values, torch.arange(600)) and not torch.equal(order, torch.arange(600))
+    assert torch.equal(packed.w[:, 0].long(), order) and torch.equal(packed.X_d[:, 0].long(), order)
+    ref = BatchMolGraph([mgs[i] for i in order.tolist()])
+    assert torch.equal(packed.bmg.V, ref.V) and torch.equal(packed.bmg.edge_index, ref.edge_index)
+    assert torch.equal(packed.V_d[:, 0].long(), order[packed.bmg.batch])            # per-atom descriptors follow their molecule
+    assert packed.bmg._meta_host[_lib.META_N_TILES] < 0.9 * plain.bmg._meta_host[_lib.META_N_TILES]
+    assert torch.equal(plain.Y[:, 0].long(), torch.arange(600))
+
+
 def test_compact_transfer_staging_is_the_rounded_batch():
     """transfer_dtype=bfloat16 stages bf16 features / int32 indices next to the public f32 / int64 view."""
     mgs = make_molecules(40, seed=3)
