@@ -28,6 +28,7 @@ SIGNATURES = {
     "dmpnn_launch_count": (C.c_longlong, []),
     "dmpnn_collate_host": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "dmpnn_collate_host_compact": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "dmpnn_scale_mask": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _f32, _vp]),
     "dmpnn_tile_pack_order": (C.c_int, [_i64, _vp, _vp, _vp]),
     "dmpnn_batch_meta_host": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "dmpnn_dataset_batch_meta_host": (C.c_int, [_i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -103,3 +103,53 @@ extern "C" int dmpnn_dataset_gather(const int64_t* ids, const int64_t* out_atom_
   DMPNN_CHECK_LAUNCH("dmpnn_dataset_gather", 1);
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Dropout application (base.py:139, :182): OUT = X * M * scale over a flat, contiguous buffer of n elements (the hidden
+// matrix including its zero padding columns), M a {0, 1} keep mask of the same element type drawn by the caller's RNG.
+// In place allowed (OUT == X).  The product is formed in f32 with the exact scale 1 / (1 - p) and rounded once.
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) k_scale_mask(const T* __restrict__ X, const T* __restrict__ M, T* OUT, int64_t n,
+                                                    float scale, int vec) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    const int64_t n4 = n / 4;
+    for (int64_t q = i; q < n4; q += stride) {
+      float x[4], m[4];
+      dmpnn::ld4(X + 4 * q, x);
+      dmpnn::ld4(M + 4 * q, m);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] = x[k] * m[k] * scale;
+      dmpnn::st4(OUT + 4 * q, x);
+    }
+    for (int64_t j = 4 * n4 + i; j < n; j += stride)
+      dmpnn::st_from_float(OUT + j, dmpnn::ld_as_float(X + j) * dmpnn::ld_as_float(M + j) * scale);
+  } else {
+    for (int64_t j = i; j < n; j += stride)
+      dmpnn::st_from_float(OUT + j, dmpnn::ld_as_float(X + j) * dmpnn::ld_as_float(M + j) * scale);
+  }
+}
+}  // namespace
+
+extern "C" int dmpnn_scale_mask(const void* X, const void* M, void* OUT, int dtype, int64_t n, float scale, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DMPNN_CHECK_ARG(n >= 0 && (n == 0 || (X && M && OUT)), "scale_mask: bad args");
+  DMPNN_CHECK_ARG(dtype == DMPNN_F32 || dtype == DMPNN_BF16, "scale_mask: bad dtype");
+  if (n == 0) return 0;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == DMPNN_F32) {
+    const int vec = dmpnn::vec4_ok<float>(X, 4) && dmpnn::vec4_ok<float>(M, 4) && dmpnn::vec4_ok<float>(OUT, 4);
+    k_scale_mask<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)X, (const float*)M, (float*)OUT, n, scale, vec);
+  } else {
+    const int vec = dmpnn::vec4_ok<__nv_bfloat16>(X, 4) && dmpnn::vec4_ok<__nv_bfloat16>(M, 4) &&
+                    dmpnn::vec4_ok<__nv_bfloat16>(OUT, 4);
+    k_scale_mask<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)X, (const __nv_bfloat16*)M,
+                                                                   (__nv_bfloat16*)OUT, n, scale, vec);
+  }
+  DMPNN_CHECK_LAUNCH("dmpnn_scale_mask", 1);
+  return 0;
+}

@@ -346,6 +346,8 @@ class MPConfig:
     undirected: bool
     hidden_dtype: torch.dtype  # torch.float32 (<=1e-5 tier) or torch.bfloat16 (<=1e-2 tier)
     fused: bool = True         # use the tcgen05 fused depth-step kernel when applicable
+    dropout_p: float = 0.0     # > 0: training-mode dropout on the fused bf16 / ReLU path (dropout_fused_ok)
+    mask_fn: object = None     # keep-mask source `f(like) -> {0,1} tensor like `like``; None = torch's bernoulli_
 
 
 def _hidden(rows: int, hp: int, dtype, dev) -> Tensor:
@@ -497,6 +499,30 @@ def _empty_hidden(rows: int, hp: int, dtype, dev) -> Tensor:
     return torch.empty((max(rows, 1), hp), dtype=dtype, device=dev)
 
 
+def scale_mask_(X: Tensor, M: Tensor, scale: float):
+    """X <- X * M * scale in place over the whole (contiguous) buffer -- dmpnn_scale_mask."""
+    lib = _lib.load()
+    assert X.is_contiguous() and M.is_contiguous() and X.shape == M.shape and X.dtype == M.dtype
+    rc = lib.dmpnn_scale_mask(X.data_ptr(), M.data_ptr(), X.data_ptr(), _dt(X), X.numel(), float(scale), _stream())
+    _lib.check(rc, "dmpnn_scale_mask")
+
+
+def _dropout_(X: Tensor, cfg: MPConfig):
+    """nn.Dropout(p) in training mode on a hidden buffer (base.py:139, :182): keep mask from torch's RNG stream (so
+    torch.manual_seed governs it, as in the reference), applied with the exact f32 scale 1 / (1 - p)."""
+    keep = 1.0 - cfg.dropout_p
+    M = cfg.mask_fn(X) if cfg.mask_fn is not None else torch.empty_like(X).bernoulli_(keep)
+    scale_mask_(X, M, 1.0 / keep)
+
+
+def dropout_fused_ok(cfg: MPConfig, lay: Layout, h: int, d_v: int, d_e: int) -> bool:
+    """Training-mode dropout can stay on the fused bf16 path: ReLU (tau' of the post-dropout state is the keep mask times
+    tau' of the pre-dropout one, so no mask is stored and the scale 1 / (1 - p) folds into the packed weights of the
+    mirror), directed bonds, every GEMM on the tensor-core kernels and every depth step on the fused kernel."""
+    return (cfg.act == ACT_RELU and not cfg.undirected and lay.E > 0 and h % 4 == 0 and _tc_ok(cfg, h, d_v + d_e, d_v + h)
+            and (cfg.depth == 1 or _fused_step_ok(cfg, lay, h)))
+
+
 def bond_step_bwd_fused(dZ: Tensor, Yact: Tensor | None, dOut: Tensor, h: int, WpkT: Tensor, lay: Layout, act: int,
                         act_param: float, G_out: Tensor | None = None, y_is_preact: bool = False,
                         addends: tuple = ()):
@@ -547,8 +573,12 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
             M1 = _empty_hidden(nE, hp, T, dev) if (first and for_backward) else None
             with _StepTimer("fused_first" if first else "fused"):
                 bond_step_fused(Hprev, H0, Hn, h, Wpk, bh, lay, a, ap, first, M_out=M1)
+            if cfg.dropout_p > 0:
+                _dropout_(Hn, cfg)                                                 # base.py:139
             Ms.append(M1)
         else:
+            if cfg.dropout_p > 0:
+                raise DmpnnError("dropout on the monolithic tier needs the fused depth step (see dropout_fused_ok)")
             src_in, fa = Hprev, (a if first else ACT_NONE)
             if cfg.undirected:  # H = (H + H[rev]) / 2   (base.py:202-203)
                 Hbar = _hidden(nE, hp, T, dev)
@@ -574,8 +604,12 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
                     pad_to=(hc if d_v + hc <= ko else h))
         Hvp = torch.empty((max(nV, 1), pad_hidden(h)), dtype=T, device=dev)
         linear_tc(XO, d_v + h, pack_weight_tc(Wo), h, Hvp, bias=bo, act=a, act_param=ap, R=nV)
+        if cfg.dropout_p > 0:
+            _dropout_(Hvp, cfg)                                                    # base.py:182
         Hv = Hvp[:nV, :h]
     else:
+        if cfg.dropout_p > 0:
+            raise DmpnnError("dropout on the monolithic tier needs the tensor-core path (see dropout_fused_ok)")
         XO = None
         # M_v = sum_{dst(e)=v} H[e]   (base.py:208-211)
         Mv = _hidden(nV, hp, T, dev)
@@ -702,22 +736,38 @@ def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
     dbo = torch.zeros(h, **f32) if need_bias[2] else None
     if gHv.stride(1) != 1:
         gHv = gHv.contiguous()
+    # Training-mode dropout (cfg.dropout_p > 0; ReLU only, dropout_fused_ok): a gradient that crosses a dropout site is
+    # multiplied by the keep mask and by s = 1 / (1 - p).  With ReLU the mask is already in tau' of the stored POST-dropout
+    # state ([H_post > 0] = mask * [H_pre > 0]), and s, a scalar, folds into the packed weight of the GEMM that produces
+    # the gradient arriving at the site (or, for W_o's own gradient, into the result).
+    s_drop = 1.0 / (1.0 - cfg.dropout_p) if cfg.dropout_p > 0 else 1.0
+    s_v = s_drop                                      # site after W_o (base.py:182)
+    s_e = s_drop if cfg.depth > 1 else 1.0            # site on H^{T-1} (base.py:139); H^0 = tau(H_0) has none
     dY = _empty_hidden(nV, hp, T, dev)
-    act_bwd(gHv, Hv, nV, h, act=a, act_param=ap, dZ=dY)
+    act_bwd(gHv, Hv, nV, h, act=a, act_param=ap, dZ=dY)      # dY / s_v
     wgrad_tc(dY, saved["XO"], nV, h, d_v + h, dWo)
     if dbo is not None:
         column_sum(dY, nV, h, dbo)
+    if s_v != 1.0:
+        dWo.mul_(s_v)
+        if dbo is not None:
+            dbo.mul_(s_v)
     if nE == 0:
         return dWi, dbi, dWh, dbh, dWo, dbo
     dMv = _empty_hidden(nV, hp, T, dev)
-    linear_tc(dY, h, pack_weight_tc(Wo[:, d_v:], transpose=True), h, dMv, R=nV)
+    Wo_m = Wo[:, d_v:] if s_v * s_e == 1.0 else Wo[:, d_v:] * (s_v * s_e)
+    linear_tc(dY, h, pack_weight_tc(Wo_m, transpose=True), h, dMv, R=nV)
     dH0b = _empty_hidden(nE, hp, T, dev)
     if cfg.depth == 1:
         act_bwd(dMv, H0, nE, hc, act=a, act_param=ap, gidx=lay.dst_row, from_preact=True, dZ=dH0b)
     else:
         fused_bwd = _fused_step_ok(cfg, lay, h)      # the depth step's mirror on the same fused tcgen05 kernel
+        if s_drop != 1.0 and not fused_bwd:
+            raise DmpnnError("dropout on the monolithic tier needs the fused depth step (see dropout_fused_ok)")
         WhT_pk = None if fused_bwd else pack_weight_tc(Wh, transpose=True)
         WhT_pkf = pack_weight_bf16(Wh.t().contiguous()) if fused_bwd else None
+        # mirror steps whose result arrives at a dropout site (every one but the last, which lands on H^0) carry s
+        WhT_pkf_s = WhT_pkf if s_drop == 1.0 else pack_weight_bf16((Wh * s_drop).t().contiguous())
         dZ = _empty_hidden(nE, hp, T, dev)
         act_bwd(dMv, Hs[-1], nE, hc, act=a, act_param=ap, gidx=lay.dst_row, dZ=dZ)    # dZ^{T-1}
         dZs, dH_first, fused_sum, dH0_terms = [dZ], None, False, None
@@ -753,7 +803,7 @@ def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
                 else:
                     dZn = _empty_hidden(nE, hp, T, dev)
                     G = _empty_hidden(nE, hp, T, dev)
-                    bond_step_bwd_fused(dZ, Hin, dZn, h, WhT_pkf, lay, a, ap, G_out=G)
+                    bond_step_bwd_fused(dZ, Hin, dZn, h, WhT_pkf_s, lay, a, ap, G_out=G)
                     wgrad_tc(G, Hin, nE, h, h, dWh, accumulate=True)
                     dZ = dZn
                     dZs.append(dZ)

@@ -17,7 +17,7 @@ import torch
 from torch import Tensor, nn
 
 from .. import _lib, composed
-from ..engine import AtomMPFunction, BondMPFunction, MPConfig, get_layout
+from ..engine import AtomMPFunction, BondMPFunction, MPConfig, dropout_fused_ok, get_layout
 from ..exceptions import InvalidShapeError
 
 DEFAULT_ATOM_FDIM, DEFAULT_BOND_FDIM, DEFAULT_HIDDEN_DIM = 72, 14, 300  # chemprop/conf.py
@@ -102,21 +102,34 @@ class _MessagePassingBase(nn.Module):
                         hidden_dtype=torch.bfloat16 if self.precision == "bf16" else torch.float32,
                         fused=bool(self.fused))
 
-    def uses_composed_tier(self) -> bool:
-        """True when this call cannot run on the monolithic functions (see the module docstring)."""
-        return not is_fused_activation(self.tau) or (self.training and self.dropout.p > 0)
+    def _dropout_on_fused_path(self, lay) -> bool:
+        """Training-mode dropout that can stay on the fused bf16 path for this batch (BondMessagePassing only)."""
+        return False
+
+    def uses_composed_tier(self, lay=None) -> bool:
+        """True when this call cannot run on the monolithic functions (see the module docstring).  Training-mode
+        dropout stays monolithic only on the fused bf16 / ReLU path, which depends on the batch's layout `lay`."""
+        if not is_fused_activation(self.tau):
+            return True
+        if self.training and self.dropout.p > 0:
+            return not (lay is not None and self._dropout_on_fused_path(lay))
+        return False
 
     def forward(self, bmg, V_d: Tensor | None = None) -> Tensor:
         bmg = self.graph_transform(bmg)
         lay = get_layout(bmg)
-        if self.uses_composed_tier():
+        if self.uses_composed_tier(lay):
             H = type(self)._composed_forward(self, bmg, lay)
             if self.precision == "bf16":
                 H = H.to(torch.bfloat16)     # same output dtype as the fused bf16 tier (computed in f32)
         else:
+            cfg = self._config()
+            if self.training and self.dropout.p > 0:
+                cfg.dropout_p = float(self.dropout.p)
+                cfg.mask_fn = getattr(self, "_mask_fn", None)      # test hook: where the keep masks come from
             H = type(self)._function.apply(
                 bmg.V, bmg.E, self.W_i.weight, self.W_i.bias, self.W_h.weight, self.W_h.bias,
-                self.W_o.weight, self.W_o.bias, lay, self._config(),
+                self.W_o.weight, self.W_o.bias, lay, cfg,
             )
         return self.finalize_descriptors(H, V_d)
 
@@ -138,6 +151,12 @@ class BondMessagePassing(_MessagePassingBase):
     _function = BondMPFunction
     _composed_forward = staticmethod(composed.bond_forward)
 
+    def _dropout_on_fused_path(self, lay) -> bool:
+        h = self.W_h.out_features
+        d_v = self.W_o.in_features - h
+        return (self.precision == "bf16" and 0.0 < self.dropout.p < 1.0 and is_fused_activation(self.tau)
+                and dropout_fused_ok(self._config(), lay, h, d_v, self.W_i.in_features - d_v))
+
     def setup(self, d_v=DEFAULT_ATOM_FDIM, d_e=DEFAULT_BOND_FDIM, d_h=DEFAULT_HIDDEN_DIM, d_vd=None, bias=False):
         W_i = nn.Linear(d_v + d_e, d_h, bias)
         W_h = nn.Linear(d_h, d_h, bias)
@@ -158,6 +177,6 @@ class AtomMessagePassing(_MessagePassingBase):
         W_d = nn.Linear(d_h + d_vd, d_h + d_vd) if d_vd else None
         return W_i, W_h, W_o, W_d
 
-    def uses_composed_tier(self) -> bool:
+    def uses_composed_tier(self, lay=None) -> bool:
         # undirected averaging (base.py:202-203) breaks the atom-granular restatement the monolithic tier relies on
-        return bool(self.undirected) or super().uses_composed_tier()
+        return bool(self.undirected) or super().uses_composed_tier(lay)

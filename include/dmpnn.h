@@ -132,6 +132,12 @@ int dmpnn_dataset_gather(const int64_t* ids, const int64_t* out_atom_ptr, const 
                          float* V_out, float* E_out, int64_t* ei_out /*2 x E_out_total*/, int64_t* rev_out,
                          int64_t* batch_out, int64_t E_out_total, void* stream);
 
+/* Dropout application (chemprop/nn/message_passing/base.py:139, :182; nn.Dropout): OUT[i] = X[i] * M[i] * scale over a flat
+ * contiguous buffer of n elements of type `dtype` (a hidden matrix with its padding columns), M a {0, 1} keep mask of the same
+ * element type drawn by the caller's RNG (torch's Philox stream, so `torch.manual_seed` governs it as in the reference),
+ * scale = 1 / (1 - p) applied in f32 with one rounding.  In place allowed (OUT == X). */
+int dmpnn_scale_mask(const void* X, const void* M, void* OUT, int dtype, int64_t n, float scale, void* stream);
+
 /* Loader-side molecule order for full tiles: a permutation of the batch's molecules (best-fit-decreasing bin packing of
  * their edge counts into the 128-row / 128-atom tiles of dmpnn_layout_build) under which the greedy tile packing of
  * CONSECUTIVE molecules comes out ~0.94 full instead of ~0.81 for ~25-atom molecules in arrival order.  The order of

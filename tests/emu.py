@@ -236,6 +236,11 @@ def column_sum(Y, R, N, out, *, accumulate=False):
         out.copy_(v)
 
 
+def scale_mask_(X, M, scale):
+    assert X.is_contiguous() and M.is_contiguous() and X.shape == M.shape and X.dtype == M.dtype
+    X.copy_((X.float() * M.float() * scale).to(X.dtype))
+
+
 def bond_step_fused(H_prev, H0, H_next, h, Wpk, bias, lay, act, act_param, first_step, M_out=None):
     """H_next[e] = tau(H_0[e] + b + W_h . M[e]),  M = message of g(H_prev), g = tau on the first step (include/dmpnn.h)."""
     M = torch.zeros((lay.E, h))
@@ -303,7 +308,7 @@ def patch_engine(monkeypatch):
     """Route engine.py's kernel wrappers to the emulations above (host-logic tests only)."""
     for name in ("linear_fwd", "linear_wgrad", "segment_sum", "segment_bcast", "bond_message", "rev_average", "act_bwd",
                  "build_layout", "pack_weight_tc", "pack_weight_bf16", "concat_bf16", "linear_tc", "wgrad_tc", "column_sum",
-                 "bond_step_fused", "bond_step_bwd_fused", "bond_message_bwd_masked", "sum_act_bwd"):
+                 "bond_step_fused", "bond_step_bwd_fused", "bond_message_bwd_masked", "sum_act_bwd", "scale_mask_"):
         monkeypatch.setattr(engine, name, globals()[name])
     monkeypatch.setattr(engine, "_require_cuda", lambda *ts: None)
     import chemprop_b200.nn.agg as agg_mod

@@ -5,6 +5,7 @@
     and against the oracle; same tolerances as tests/test_gpu_parity.py;
   * the sync-free training step (host-computed layout meta words, dmpnn_batch_meta_host);
   * the device-resident packed data set (dmpnn_dataset_gather) and the loader on top of it;
+  * training-mode dropout on the fused bf16 / ReLU path (dmpnn_scale_mask + scale factors folded into the mirror's weights);
   * the mol-atom-bond variants (MABBond / MABAtomMessagePassing), which run on the composed tier.
 
 This file sorts last on purpose.  It was written after this round's GPU budget was spent: its first run on hardware
@@ -84,7 +85,7 @@ def test_composed_equals_fused_tier_on_a_shared_configuration(kind):
         bmg = BatchMolGraph(make_molecules(1500, seed=5, shuffle_edges=True))
         bmg.to("cuda")
         if composed:
-            mp.uses_composed_tier = lambda: True
+            mp.uses_composed_tier = lambda lay=None: True
         mp.zero_grad()
         H = mp(bmg)
         H.square().mean().backward()
@@ -190,3 +191,11 @@ def test_attentive_aggregation_matches_reference_fixture():
     from tests.util import check_attentive
 
     check_attentive("cuda", atol=FP32_ATOL)
+
+
+@pytest.mark.parametrize("depth,bias,d_h", [(3, False, 300), (1, True, 64), (4, True, 128)])
+def test_training_dropout_on_the_fused_bf16_path(depth, bias, d_h):
+    """ReLU + dropout in training stays on the fused tcgen05 path; mask for mask against the oracle."""
+    from tests.util import fused_dropout_vs_oracle
+
+    fused_dropout_vs_oracle("cuda", depth=depth, bias=bias, d_h=d_h, n_mols=400)

@@ -107,7 +107,7 @@ def test_composed_tier_equals_monolithic_configurations(name, monkeypatch):
     emu.patch_engine(monkeypatch)
     g = load_golden(name)
     mp = build_engine_module(g, "cpu", "fp32")
-    monkeypatch.setattr(type(mp), "uses_composed_tier", lambda self: True)
+    monkeypatch.setattr(type(mp), "uses_composed_tier", lambda self, lay=None: True)
     mp, bmg, H, aggs = _run(g, mp)
     _check(g, mp, H, aggs)
 
@@ -165,6 +165,21 @@ def test_attentive_aggregation_matches_reference_fixture(monkeypatch):
 
     emu.patch_engine(monkeypatch)
     check_attentive("cpu")
+
+
+@pytest.mark.parametrize("depth,bias", [(3, True), (1, False), (2, False), (5, True)])
+def test_training_dropout_on_the_fused_bf16_path(depth, bias, monkeypatch):
+    """ReLU + dropout in training keeps the fused bf16 path (no 10x cliff onto the composed tier): masks are not stored,
+    1 / (1 - p) is folded into the packed weights of the mirror -- checked mask for mask against the oracle."""
+    from chemprop_b200 import engine
+    from tests.util import fused_dropout_vs_oracle
+
+    emu.patch_engine(monkeypatch)
+    calls = {"n": 0}
+    f = engine.bond_step_fused
+    monkeypatch.setattr(engine, "bond_step_fused", lambda *a, **k: (calls.__setitem__("n", calls["n"] + 1), f(*a, **k))[1])
+    fused_dropout_vs_oracle("cpu", depth=depth, bias=bias)
+    assert calls["n"] == depth - 1
 
 
 def test_eval_mode_with_dropout_configured_stays_monolithic(monkeypatch):

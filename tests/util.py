@@ -244,3 +244,55 @@ def check_attentive(device: str, atol: float = 2e-6):
     np.testing.assert_allclose(agg.W.weight.grad.cpu().numpy(), g["grad.W.weight"], rtol=1e-4, atol=atol)
     np.testing.assert_allclose(agg.W.bias.grad.cpu().numpy(), g["grad.W.bias"], rtol=1e-4, atol=atol)
     assert agg.hparams == {"dim": 0, "cls": AttentiveAggregation, "output_size": g["H"].shape[1]}
+
+
+def fused_dropout_vs_oracle(device: str, depth: int = 3, bias: bool = True, d_h: int = 64, n_mols: int = 60, p: float = 0.3):
+    """Training-mode dropout on the fused bf16 / ReLU path (engine.dropout_fused_ok) vs the oracle fed with the very keep
+    masks the run drew (mapped from the engine's row order to the caller's edge order): hidden states within the bf16
+    bound, gradients within a bound that a wrong 1 / (1 - p) factor anywhere in the mirror would break."""
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.engine import get_layout
+    from chemprop_b200.nn import BondMessagePassing, MeanAggregation
+    from oracle import restatement as R
+
+    torch.manual_seed(11)
+    mgs = make_molecules(n_mols, seed=6, mean_atoms=12, std_atoms=4, shuffle_edges=True)
+    bmg, ref = BatchMolGraph(mgs), BatchMolGraph(mgs)
+    mp = BondMessagePassing(d_h=d_h, depth=depth, bias=bias, dropout=p, precision="bf16")
+    P = {k: v.detach().double().requires_grad_(True) for k, v in mp.state_dict().items()}
+    masks = []
+
+    def mask_fn(like):
+        m = torch.empty_like(like).bernoulli_(1.0 - p)
+        masks.append(m)
+        return m
+
+    mp._mask_fn = mask_fn
+    mp = mp.to(device).train()
+    bmg.to(device)
+    lay = get_layout(bmg)
+    assert not mp.uses_composed_tier(lay) and mp.uses_composed_tier()          # monolithic for THIS batch
+    H = mp(bmg)
+    MeanAggregation()(H, bmg.batch).float().square().sum().backward()
+    assert len(masks) == depth and all(m.dtype == torch.bfloat16 for m in masks)          # depth - 1 edge sites + read-out
+    nE, nV, perm = ref.E.shape[0], ref.V.shape[0], lay.perm.long().cpu()
+    keep = 1.0 - p
+    ref_masks = []
+    for m in masks[:-1]:
+        mm = torch.empty((nE, d_h), dtype=torch.float64)
+        mm[perm] = m[:nE, :d_h].double().cpu() / keep
+        ref_masks.append(mm)
+    ref_masks.append(masks[-1][:nV, :d_h].double().cpu() / keep)
+    H_ref = R.message_passing_forward("bond", ref.V.double(), ref.E.double(), ref.edge_index, ref.rev_edge_index,
+                                      P["W_i.weight"], P.get("W_i.bias"), P["W_h.weight"], P.get("W_h.bias"), P["W_o.weight"],
+                                      P["W_o.bias"], depth, "relu", False, dropout_masks=ref_masks)
+    R.aggregate(H_ref, ref.batch, "mean").square().sum().backward()
+    frac0 = float((H_ref == 0).double().mean())
+    assert frac0 > p * 0.8                                                      # dropout really happened
+    tol = 1e-2 * max(1.0, H_ref.detach().abs().max().item())
+    assert (H.detach().double().cpu() - H_ref.detach()).abs().max().item() <= tol
+    for k, prm in mp.named_parameters():
+        g = P[k].grad if P[k].grad is not None else torch.zeros_like(P[k])
+        got = prm.grad.double().cpu()
+        fro = float((got - g).norm() / max(1e-9, g.norm()))
+        assert fro <= 0.12, (k, fro)              # a missing / doubled 1/(1-p) = 1.43 would show as >= 0.3
