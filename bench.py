@@ -396,6 +396,8 @@ def main_gpu(args):
         roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "kernel": f"bond depth step t>=2 ({tag})", "launch_ms": dur_ms,
                     "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                    "traffic_source": ("profiles/fused_step_traffic.json: ncu --set full capture of round 1 (same rows, "
+                                       "generator molecule order)") if traffic is not None else None,
                     "first_step_ms": statistics.mean(by_tag.get(tag + "_first", [float("nan")]))}
 
     # ---- resident data set: ids in, loss out -----------------------------------------------
