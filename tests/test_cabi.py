@@ -77,6 +77,33 @@ def test_bad_arguments_fail_loudly():
         _lib.check(lib.dmpnn_linear_wgrad_workspace_bytes(1, 0, 1, ctypes.byref(n)), "wgrad_workspace_bytes")
 
 
+def test_new_entry_points_validate_their_arguments_before_touching_the_device():
+    """Argument checks of the device-side entry points added for the packed data set / dropout run on the host, before
+    any CUDA call: they are callable (and must fail cleanly) without a GPU."""
+    lib = _lib.load()
+    assert lib.dmpnn_dataset_gather(None, None, None, -1, None, None, None, None, None, None, 0, 72, 14,
+                                    None, None, None, None, None, 0, None) != 0
+    assert b"dataset_gather" in lib.dmpnn_last_error()
+    assert lib.dmpnn_dataset_gather(None, None, None, 0, None, None, None, None, None, None, 0, 72, 14,
+                                    None, None, None, None, None, 0, None) == 0            # empty selection: nothing to do
+    assert lib.dmpnn_dataset_gather(None, None, None, 3, None, None, None, None, None, None, 0, 72, 14,
+                                    None, None, None, None, None, 0, None) != 0            # null tables
+    assert lib.dmpnn_scale_mask(None, None, None, _lib.F32, 5, 1.0, None) != 0 and b"scale_mask" in lib.dmpnn_last_error()
+    assert lib.dmpnn_scale_mask(None, None, None, 7, 0, 1.0, None) != 0                     # unknown dtype
+    assert lib.dmpnn_scale_mask(None, None, None, _lib.BF16, 0, 1.0, None) == 0
+    meta = np.zeros(_lib.META_WORDS, dtype=np.int32)
+    assert lib.dmpnn_batch_meta_host(None, None, None, 0, 0, 0, meta.ctypes.data) == 0 and meta[_lib.META_FLAGS] == 7
+    assert lib.dmpnn_batch_meta_host(None, None, None, 3, 0, 1, meta.ctypes.data) != 0      # atoms without a batch array
+    ids = np.array([5], dtype=np.int64)
+    ptr = np.array([0, 2], dtype=np.int64)
+    out = np.zeros(2, dtype=np.int64)
+    mi = np.zeros(1, dtype=np.int32)
+    assert lib.dmpnn_dataset_batch_meta_host(1, ids.ctypes.data, 1, ptr.ctypes.data, ptr.ctypes.data, mi.ctypes.data,
+                                             out.ctypes.data, out.ctypes.data, meta.ctypes.data) != 0
+    assert b"out of range" in lib.dmpnn_last_error()
+    assert lib.dmpnn_tile_pack_order(-1, None, None, None) != 0
+
+
 def test_collate_host_matches_oracle_and_reference_fixture():
     from chemprop_b200.data import BatchMolGraph, MolGraph, make_molecules
     from oracle import restatement as R

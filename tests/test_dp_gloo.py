@@ -48,6 +48,50 @@ def test_flat_grad_allreduce_world2():
     assert res[0][3] == res[1][3] == 4 * sum(p.numel() for p in __import__("chemprop_b200").nn.BondMessagePassing(d_h=16).parameters())
 
 
+def _loader_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+
+    from chemprop_b200.data import BatchMolGraph, PackedBatchLoader, PackedMolGraphDataset, make_molecules
+
+    mgs = make_molecules(101, seed=5, mean_atoms=8, std_atoms=3, min_atoms=1)            # every rank packs the same data set
+    ds = PackedMolGraphDataset.from_molgraphs(mgs)
+    loader = PackedBatchLoader(ds, batch_size=16, shuffle=True, seed=42, rank=rank, world=world)
+    ok, mine = True, []
+    for epoch in range(2):
+        ids = []
+        for b in loader:
+            ref = BatchMolGraph([mgs[i] for i in b.ids])
+            ok = ok and torch.equal(b.bmg.V, ref.V) and torch.equal(b.bmg.edge_index, ref.edge_index)
+            ids.append(b.ids)
+        mine.append(np.concatenate(ids))
+    # the ranks' shards of an epoch: equal sizes, together the whole (padded) epoch
+    for e in range(2):
+        t = torch.from_numpy(mine[e].copy())
+        gathered = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        allids = torch.cat(gathered).numpy()
+        ok = ok and len(t) == 51 and set(allids.tolist()) == set(range(101)) and len(allids) == 102
+    ok = ok and not np.array_equal(np.sort(mine[0]), np.sort(mine[1]))                    # reshuffled between epochs
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_loader_shards_the_epoch_across_ranks_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_loader_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
+
+
 def test_single_process_is_noop():
     from chemprop_b200.parallel import FlatGradAllReducer
 
