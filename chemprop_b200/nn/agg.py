@@ -4,11 +4,17 @@ segmented reduction over the (contiguous) atom range of each molecule instead of
 `index.repeat()` + `scatter_reduce_` (agg.py:74-78)."""
 from __future__ import annotations
 
+import torch
 from torch import Tensor, nn
 
 from .. import _lib
 from ..composed import GatherLinear
 from ..engine import SegmentAggFunction, SegmentBcastFunction, segments_of
+
+try:
+    from .. import export as _export
+except Exception:  # noqa: BLE001
+    _export = None
 
 
 class Aggregation(nn.Module):
@@ -23,6 +29,8 @@ class Aggregation(nn.Module):
     _scale = 1.0
 
     def forward(self, H: Tensor, batch: Tensor) -> Tensor:
+        if _export is not None and _export.is_tracing():      # torch.export: one custom op (chemprop_b200/export.py)
+            return torch.ops.dmpnn.segment_agg(H, batch, int(self._mode), float(self._scale))
         ptr, seg_of_row, B = segments_of(batch)
         return SegmentAggFunction.apply(H, ptr, seg_of_row, B, self._mode, float(self._scale))
 

@@ -20,6 +20,11 @@ from .. import _lib, composed
 from ..engine import AtomMPFunction, BondMPFunction, MPConfig, dropout_fused_ok, get_layout
 from ..exceptions import InvalidShapeError
 
+try:                                   # custom-op registration for torch.export (inference); optional
+    from .. import export as _export
+except Exception:  # noqa: BLE001 -- an old torch without torch.library.custom_op: export support is simply absent
+    _export = None
+
 DEFAULT_ATOM_FDIM, DEFAULT_BOND_FDIM, DEFAULT_HIDDEN_DIM = 72, 14, 300  # chemprop/conf.py
 
 _ACT_NAMES = {"relu": nn.ReLU, "leakyrelu": lambda: nn.LeakyReLU(0.1), "prelu": nn.PReLU, "tanh": nn.Tanh,
@@ -115,8 +120,23 @@ class _MessagePassingBase(nn.Module):
             return not (lay is not None and self._dropout_on_fused_path(lay))
         return False
 
+    _kind = 0
+
+    def _traced_forward(self, bmg) -> Tensor:
+        """Under torch.export: the whole forward as ONE custom op (chemprop_b200/export.py), inference only."""
+        if self.uses_composed_tier():
+            raise NotImplementedError("torch.export covers the monolithic tiers (ReLU / LeakyReLU / Tanh / ELU, no "
+                                      "training-mode dropout, AtomMessagePassing directed)")
+        cfg = self._config()
+        return torch.ops.dmpnn.mp_forward(
+            bmg.V, bmg.E, bmg.edge_index, bmg.rev_edge_index, bmg.batch, self.W_i.weight, self.W_i.bias, self.W_h.weight,
+            self.W_h.bias, self.W_o.weight, self.W_o.bias, type(self)._kind, cfg.depth, cfg.act, cfg.act_param,
+            cfg.undirected, self.precision == "bf16", bool(self.fused))
+
     def forward(self, bmg, V_d: Tensor | None = None) -> Tensor:
         bmg = self.graph_transform(bmg)
+        if _export is not None and _export.is_tracing():
+            return self.finalize_descriptors(self._traced_forward(bmg), V_d)
         lay = get_layout(bmg)
         if self.uses_composed_tier(lay):
             H = type(self)._composed_forward(self, bmg, lay)
@@ -169,6 +189,7 @@ class AtomMessagePassing(_MessagePassingBase):
     """Atom message passing (chemprop/nn/message_passing/base.py:254-289)."""
     _function = AtomMPFunction
     _composed_forward = staticmethod(composed.atom_forward)
+    _kind = 1
 
     def setup(self, d_v=DEFAULT_ATOM_FDIM, d_e=DEFAULT_BOND_FDIM, d_h=DEFAULT_HIDDEN_DIM, d_vd=None, bias=False):
         W_i = nn.Linear(d_v, d_h, bias)

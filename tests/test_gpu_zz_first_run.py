@@ -6,6 +6,7 @@
   * the sync-free training step (host-computed layout meta words, dmpnn_batch_meta_host);
   * the device-resident packed data set (dmpnn_dataset_gather) and the loader on top of it;
   * training-mode dropout on the fused bf16 / ReLU path (dmpnn_scale_mask + scale factors folded into the mirror's weights);
+  * torch.export of a model on the engine's modules (custom ops dmpnn::mp_forward / dmpnn::segment_agg);
   * the mol-atom-bond variants (MABBond / MABAtomMessagePassing), which run on the composed tier.
 
 This file sorts last on purpose.  It was written after this round's GPU budget was spent: its first run on hardware
@@ -199,3 +200,38 @@ def test_training_dropout_on_the_fused_bf16_path(depth, bias, d_h):
     from tests.util import fused_dropout_vs_oracle
 
     fused_dropout_vs_oracle("cuda", depth=depth, bias=bias, d_h=d_h, n_mols=400)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_exported_model_runs_on_the_gpu(precision):
+    """tests/integration/test_export.py:15-46 of the reference on the engine: export with dynamic atom / edge counts, run
+    the exported program on other batches incl. one without edges; equal to the eager module."""
+    from chemprop_b200.data import BatchMolGraph, make_molecule, make_molecules
+    from chemprop_b200.export import register_batch_mol_graph_pytree
+    from chemprop_b200.nn import BondMessagePassing, SumAggregation
+
+    register_batch_mol_graph_pytree()
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.message_passing, self.agg = BondMessagePassing(precision=precision), SumAggregation()
+            self.head = torch.nn.Linear(300, 1)
+
+        def forward(self, bmg):
+            return self.head(self.agg(self.message_passing(bmg), bmg.batch).float())
+
+    torch.manual_seed(0)
+    model = Model().cuda().eval()
+    rng = np.random.default_rng(0)
+    graphs = [BatchMolGraph(make_molecules(4, seed=1, mean_atoms=6, std_atoms=2)),
+              BatchMolGraph([make_molecule(rng, 1) for _ in range(4)]),
+              BatchMolGraph(make_molecules(4, seed=2, mean_atoms=30, std_atoms=5, shuffle_edges=True))]
+    for g in graphs:
+        g.to("cuda")
+    na, ne = torch.export.Dim("num_atoms"), torch.export.Dim("num_edges")
+    exported = torch.export.export(model, (graphs[0],), strict=False,
+                                   dynamic_shapes={"bmg": [{0: na}, {0: ne}, {1: ne}, {0: ne}, {0: na}]})
+    for g in graphs:
+        with torch.inference_mode():
+            torch.testing.assert_close(exported.module()(g), model(g))
