@@ -61,6 +61,11 @@ class _Metric(nn.Module):
         else:
             setattr(self, name, default)
 
+    def clone(self):
+        import copy
+
+        return copy.deepcopy(self)
+
 
 class _HyperparametersMixin:
     """Stand-in for lightning.pytorch.core.mixins.HyperparametersMixin (ctor-kwarg capture)."""

@@ -1,0 +1,75 @@
+"""CPU tier, reference tree required (skipped on the GPU box): the north-star claim "drops into the existing MPNN /
+Lightning model as-is", checked literally.  The reference's own `chemprop.models.MPNN` (unmodified, imported through
+oracle/ref_shim.py) is built twice on the same weights -- once with the reference's BondMessagePassing + MeanAggregation,
+once with the engine's modules plugged into the same constructor -- and fed the reference's own BatchMolGraph; the
+engine side runs with the kernel wrappers emulated (tests/emu.py).  Predictions, the training loss and every gradient
+must agree, and the reference state dict must load into the drop-in model unchanged."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.ref_shim import reference_available
+from tests import emu
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not reachable (GPU box)")
+
+
+@pytest.mark.parametrize("kind,agg,act,undirected", [("bond", "mean", "relu", False), ("atom", "sum", "tanh", False),
+                                                     ("bond", "norm", "prelu", True)])
+def test_engine_modules_inside_the_reference_mpnn(kind, agg, act, undirected, monkeypatch):
+    from oracle.ref_shim import import_reference
+
+    import_reference()
+    import chemprop.nn as ref_nn
+    from chemprop.data import BatchMolGraph as RefBMG
+    from chemprop.data.molgraph import MolGraph as RefMG
+    from chemprop.models import MPNN
+
+    import chemprop_b200.nn as ours
+    from chemprop_b200.data import make_molecules
+    from chemprop_b200.integrate import register_with_chemprop
+
+    emu.patch_engine(monkeypatch)
+    torch.manual_seed(0)
+    mgs = make_molecules(16, seed=3, mean_atoms=9, std_atoms=3, shuffle_edges=True, min_atoms=1)
+    bmg = RefBMG([RefMG(*m) for m in mgs])                                   # the REFERENCE's batch object
+    targets = torch.from_numpy(np.random.default_rng(0).normal(size=(16, 1)).astype(np.float32))
+    kw = dict(d_h=48, depth=3, bias=True, activation=act, undirected=undirected)
+    ref_mp = (ref_nn.BondMessagePassing if kind == "bond" else ref_nn.AtomMessagePassing)(**kw)
+    ref_agg = {"mean": ref_nn.MeanAggregation, "sum": ref_nn.SumAggregation, "norm": ref_nn.NormAggregation}[agg]()
+    ref = MPNN(ref_mp, ref_agg, ref_nn.RegressionFFN(input_dim=48), batch_norm=True)
+    our_mp = (ours.BondMessagePassing if kind == "bond" else ours.AtomMessagePassing)(**kw)
+    our_agg = ours.AggregationRegistry[agg]()
+    drop = MPNN(our_mp, our_agg, copy.deepcopy(ref.predictor), batch_norm=True)          # same constructor, engine modules
+    assert set(drop.state_dict()) == set(ref.state_dict())
+    drop.load_state_dict(ref.state_dict())                                             # strict: keys and shapes identical
+    reg = register_with_chemprop()
+    assert isinstance(our_mp, type(ref_mp)) and isinstance(our_agg, ref_nn.Aggregation) and len(reg) >= 9
+    assert isinstance(our_mp, ref_nn.BondMessagePassing) == (kind == "bond")           # chemprop/cli/predict.py:256
+    rebuilt = our_mp.hparams["cls"](**{k: v for k, v in our_mp.hparams.items() if k != "cls"})   # models/model.py:267-271
+    assert type(rebuilt) is type(our_mp) and rebuilt.output_dim == drop.message_passing.output_dim == 48
+    before = [t.clone() for t in (bmg.V, bmg.E, bmg.edge_index, bmg.rev_edge_index, bmg.batch)]
+    for model in (ref, drop):
+        model.train()
+    outs, grads = [], []
+    for model in (ref, drop):
+        model.zero_grad()
+        Z = model.fingerprint(bmg)                                                     # message passing + agg + batch norm
+        preds = model.predictor.train_step(Z)
+        loss = torch.nn.functional.mse_loss(preds, targets)
+        loss.backward()
+        outs.append((Z.detach(), preds.detach(), loss.detach()))
+        grads.append({k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    for a, b in zip(outs[0], outs[1]):
+        torch.testing.assert_close(b, a, rtol=1e-4, atol=1e-5)
+    assert set(grads[0]) == set(grads[1])
+    for k in grads[0]:
+        torch.testing.assert_close(grads[1][k], grads[0][k], rtol=2e-3, atol=2e-5, msg=k)
+    for a, b in zip(before, (bmg.V, bmg.E, bmg.edge_index, bmg.rev_edge_index, bmg.batch)):
+        assert torch.equal(a, b)                                                       # the caller's batch is untouched
+    for model in (ref, drop):
+        model.eval()
+    with torch.inference_mode():
+        torch.testing.assert_close(drop(bmg), ref(bmg), rtol=1e-4, atol=1e-5)
