@@ -73,3 +73,47 @@ def test_engine_modules_inside_the_reference_mpnn(kind, agg, act, undirected, mo
         model.eval()
     with torch.inference_mode():
         torch.testing.assert_close(drop(bmg), ref(bmg), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_engine_blocks_inside_the_reference_multicomponent_mpnn(shared, monkeypatch):
+    """chemprop.models.MulticomponentMPNN (models/multi.py) with the engine's MulticomponentMessagePassing of engine
+    blocks: two components (e.g. solute / solvent), per-component or shared encoder."""
+    from oracle.ref_shim import import_reference
+
+    import_reference()
+    import chemprop.nn as ref_nn
+    from chemprop.data import BatchMolGraph as RefBMG
+    from chemprop.data.molgraph import MolGraph as RefMG
+    from chemprop.models import MulticomponentMPNN
+
+    import chemprop_b200.nn as ours
+    from chemprop_b200.data import make_molecules
+
+    emu.patch_engine(monkeypatch)
+    torch.manual_seed(1)
+    bmgs = [RefBMG([RefMG(*m) for m in make_molecules(10, seed=s, mean_atoms=7, std_atoms=2, min_atoms=1)]) for s in (4, 5)]
+    targets = torch.from_numpy(np.random.default_rng(1).normal(size=(10, 1)).astype(np.float32))
+    if shared:
+        ref_blocks, our_blocks = [ref_nn.BondMessagePassing(d_h=24)], [ours.BondMessagePassing(d_h=24)]
+    else:
+        ref_blocks = [ref_nn.BondMessagePassing(d_h=24), ref_nn.AtomMessagePassing(d_h=16, activation="elu")]
+        our_blocks = [ours.BondMessagePassing(d_h=24), ours.AtomMessagePassing(d_h=16, activation="elu")]
+    ref_mc = ref_nn.MulticomponentMessagePassing(ref_blocks, n_components=2, shared=shared)
+    our_mc = ours.MulticomponentMessagePassing(our_blocks, n_components=2, shared=shared)
+    assert our_mc.output_dim == ref_mc.output_dim and len(our_mc) == len(ref_mc) == 2
+    ref = MulticomponentMPNN(ref_mc, ref_nn.MeanAggregation(), ref_nn.RegressionFFN(input_dim=ref_mc.output_dim), batch_norm=True)
+    drop = MulticomponentMPNN(our_mc, ours.MeanAggregation(), copy.deepcopy(ref.predictor), batch_norm=True)
+    drop.load_state_dict(ref.state_dict())
+    results = []
+    for model in (ref, drop):
+        model.train()
+        model.zero_grad()
+        preds = model.predictor.train_step(model.fingerprint(bmgs))
+        loss = torch.nn.functional.mse_loss(preds, targets)
+        loss.backward()
+        results.append((preds.detach(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}))
+    torch.testing.assert_close(results[1][0], results[0][0], rtol=1e-4, atol=1e-5)
+    assert set(results[0][1]) == set(results[1][1])
+    for k in results[0][1]:
+        torch.testing.assert_close(results[1][1][k], results[0][1][k], rtol=2e-3, atol=2e-5, msg=k)
