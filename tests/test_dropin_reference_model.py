@@ -117,3 +117,29 @@ def test_engine_blocks_inside_the_reference_multicomponent_mpnn(shared, monkeypa
     assert set(results[0][1]) == set(results[1][1])
     for k in results[0][1]:
         torch.testing.assert_close(results[1][1][k], results[0][1][k], rtol=2e-3, atol=2e-5, msg=k)
+
+
+def test_reference_checkpoint_round_trip_rebuilds_the_engine_modules(tmp_path):
+    """chemprop.models.utils.save_model / load_model (hparams["cls"](**hparams), models/model.py:267-271): a model saved
+    with the engine's modules comes back with the engine's modules -- `precision` and `norm` included."""
+    from oracle.ref_shim import import_reference
+
+    import_reference()
+    import chemprop.nn as ref_nn
+    from chemprop.models import MPNN
+    from chemprop.models.utils import load_model, save_model
+
+    import chemprop_b200.nn as ours
+
+    torch.manual_seed(2)
+    model = MPNN(ours.BondMessagePassing(d_h=16, depth=4, precision="bf16", activation="tanh", bias=True, d_vd=3),
+                 ours.NormAggregation(norm=50.0), ref_nn.RegressionFFN(input_dim=19))
+    path = tmp_path / "model.pt"
+    save_model(path, model)
+    back = load_model(path)
+    mp = back.message_passing
+    assert type(mp) is ours.BondMessagePassing and mp.precision == "bf16" and mp.depth == 4 and isinstance(mp.tau, torch.nn.Tanh)
+    assert mp.W_d is not None and mp.output_dim == 19 and mp.W_i.bias is not None
+    assert type(back.agg) is ours.NormAggregation and back.agg.norm == 50.0
+    for (ka, a), (kb, b) in zip(model.state_dict().items(), back.state_dict().items()):
+        assert ka == kb and torch.equal(a, b)
