@@ -143,3 +143,49 @@ def test_reference_checkpoint_round_trip_rebuilds_the_engine_modules(tmp_path):
     assert type(back.agg) is ours.NormAggregation and back.agg.norm == 50.0
     for (ka, a), (kb, b) in zip(model.state_dict().items(), back.state_dict().items()):
         assert ka == kb and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("kind", ["bond", "atom"])
+def test_engine_mab_modules_inside_the_reference_mol_atom_bond_mpnn(kind, monkeypatch):
+    """chemprop.models.MolAtomBondMPNN (models/mol_atom_bond.py:215-238) with the engine's MAB message passing: the
+    molecule-, atom- and bond-level fingerprints (the last one pairs every directed edge with its reverse, so the
+    per-edge embeddings must come back in the caller's edge order) and the gradients of a loss on all three."""
+    from oracle.ref_shim import import_reference
+
+    import_reference()
+    import chemprop.nn as ref_nn
+    from chemprop.data.collate import BatchMolAtomBondGraph
+    from chemprop.data.molgraph import MolGraph as RefMG
+    from chemprop.models import MolAtomBondMPNN
+    from chemprop.nn.message_passing import MABAtomMessagePassing, MABBondMessagePassing
+
+    import chemprop_b200.nn as ours
+    from chemprop_b200.data import make_molecules
+
+    emu.patch_engine(monkeypatch)
+    torch.manual_seed(4)
+    bmg = BatchMolAtomBondGraph([RefMG(*m) for m in make_molecules(9, seed=6, mean_atoms=8, std_atoms=3, shuffle_edges=True)])
+    kw = dict(d_h=32, depth=3, bias=True, activation="elu")
+    ref_mp = (MABBondMessagePassing if kind == "bond" else MABAtomMessagePassing)(**kw)
+    our_mp = (ours.MABBondMessagePassing if kind == "bond" else ours.MABAtomMessagePassing)(**kw)
+    preds = lambda: dict(mol_predictor=ref_nn.RegressionFFN(input_dim=32), atom_predictor=ref_nn.RegressionFFN(input_dim=32),  # noqa: E731
+                         bond_predictor=ref_nn.RegressionFFN(input_dim=64))
+    ref = MolAtomBondMPNN(ref_mp, ref_nn.SumAggregation(), batch_norm=True, **preds())
+    drop = MolAtomBondMPNN(our_mp, ours.SumAggregation(), batch_norm=True, **preds())
+    assert set(drop.state_dict()) == set(ref.state_dict())
+    drop.load_state_dict(ref.state_dict())
+    results = []
+    for model in (ref, drop):
+        model.train()
+        model.zero_grad()
+        H_g, H_v, H_e = model.fingerprint(bmg)
+        assert H_e.shape == (bmg.E.shape[0], 64) and H_v.shape == (bmg.V.shape[0], 32) and H_g.shape == (9, 32)
+        loss = H_g.square().mean() + H_v.tanh().mean() + (H_e * torch.linspace(-1, 1, 64)).mean()
+        loss.backward()
+        results.append(([t.detach() for t in (H_g, H_v, H_e)],
+                        {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}))
+    for a, b in zip(results[0][0], results[1][0]):
+        torch.testing.assert_close(b, a, rtol=1e-4, atol=1e-5)
+    assert set(results[0][1]) == set(results[1][1])
+    for k in results[0][1]:
+        torch.testing.assert_close(results[1][1][k], results[0][1][k], rtol=2e-3, atol=2e-5, msg=k)
