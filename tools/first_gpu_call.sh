@@ -20,6 +20,7 @@ echo "bench(generator order, no tile packing) rc=$?"; cat gpurun_out/bench_nopac
 (PACK=0 timeout 120 python tools/time_step.py; PACK=1 timeout 120 python tools/time_step.py) > gpurun_out/time_step_pack.log 2>&1
 echo "fused step alone, generator vs tile-packed order:"; cat gpurun_out/time_step_pack.log
 timeout 300 python tools/time_loader.py > gpurun_out/time_loader.log 2>&1; echo "time_loader rc=$?"; cat gpurun_out/time_loader.log
+timeout 400 python tools/bench_configs.py C4 C2a C3 --steps 3 > gpurun_out/bench_configs.log 2>&1; echo "other configs rc=$?"; cat gpurun_out/bench_configs.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-dataset > gpurun_out/bench_under_ncu.log 2>&1
 echo "ncu rc=$?"
