@@ -66,6 +66,10 @@ CASES = {
     "mab_bond_edges_only": dict(kind="mab_bond", depth=3, d_h=40, undirected=True, activation="prelu", vertex=False, graph="mixed"),
     "mab_atom_d2_vertex_only": dict(kind="mab_atom", depth=2, d_h=32, edge=False, graph="mols6"),
     "mab_bond_noedges":    dict(kind="mab_bond", depth=3, d_h=32, graph="single_atoms4"),
+    # BASELINE config 1: the reference's own CPU case -- tests/data/regression.csv (SMILES topology through
+    # oracle/smiles_topology.py), BondMessagePassing h = 300 depth 3, batch = 50; and all 500 molecules at h = 64
+    "config1_regression_b50": dict(kind="bond", depth=3, d_h=300, graph="regression_csv:0:50"),
+    "config1_regression_all500": dict(kind="bond", depth=3, d_h=64, graph="regression_csv:0:500"),
 }
 
 
@@ -73,6 +77,15 @@ def make_batch(spec: str, d_v: int, d_e: int, seed: int):
     from chemprop_b200.data.synthetic import make_chain_graph, make_molecule, make_molecules
 
     rng = np.random.default_rng(seed)
+    if spec.startswith("regression_csv:"):
+        import csv
+
+        from oracle.smiles_topology import to_molgraph
+
+        _, lo, hi = spec.split(":")
+        with open(os.path.join(REFERENCE_ROOT, "tests", "data", "regression.csv")) as f:
+            rows = list(csv.DictReader(f))
+        return [to_molgraph(r["smiles"], d_v, d_e) for r in rows[int(lo):int(hi)]]
     if spec == "mols6":
         return make_molecules(6, seed=seed, mean_atoms=12, std_atoms=5, d_v=d_v, d_e=d_e)
     if spec == "mols6_shuffled":

@@ -67,6 +67,28 @@ def test_attentive_restatement_matches_reference_fixture():
         np.testing.assert_allclose(t.grad.numpy(), g[k], rtol=1e-4, atol=2e-6, err_msg=k)
 
 
+def test_smiles_topology_parser_of_config1():
+    """oracle/smiles_topology.py (BASELINE config 1 graphs): atoms / bonds of hand-checked SMILES, featuriser edge order."""
+    from oracle.smiles_topology import parse, to_molgraph
+
+    atoms, bonds = parse("Cc1occc1C(=O)Nc2ccccc2")                      # 2-methyl-3-furanilide: 15 heavy atoms, 2 rings
+    assert len(atoms) == 15 and len(bonds) == 16 and (6, 7, 1) in bonds and (1, 5, 3) in bonds and (9, 14, 3) in bonds
+    atoms, bonds = parse("c1ccc2[nH]ccc2c1")                            # indole
+    assert len(atoms) == 9 and len(bonds) == 10 and atoms[4] == ("N", True, 1)
+    atoms, bonds = parse("ClC(Br)(F)C#N")
+    assert [a[0] for a in atoms] == ["Cl", "C", "Br", "F", "C", "N"] and (4, 5, 2) in bonds and len(bonds) == 5
+    assert len(parse("CC.O")[1]) == 1 and len(parse("C1CC1")[1]) == 3 and len(parse("F/C=C/F")[1]) == 3
+    for bad in ("C1CC", "C(C", "C*C"):
+        with pytest.raises(ValueError):
+            parse(bad)
+    mg = to_molgraph("CC(=O)O")
+    assert mg.V.shape == (4, 72) and mg.E.shape == (6, 14) and mg.edge_index.tolist() == [[0, 1, 1, 2, 1, 3], [1, 0, 2, 1, 3, 1]]
+    assert mg.rev_edge_index.tolist() == [1, 0, 3, 2, 5, 4] and np.array_equal(mg.E[0], mg.E[1]) and mg.E[2, 1] == 1
+    g = load_golden("config1_regression_b50")                           # the committed graphs of config 1: 50 molecules
+    assert int(g["n_mols"]) == 50 and g["config"]["d_h"] == 300 and g["V"].shape[1] == 72 and g["E"].shape[1] == 14
+    assert np.array_equal(g["rev_edge_index"], np.arange(g["E"].shape[0]) ^ 1)
+
+
 def test_restatement_fp64_close_to_fp32_golden():
     g = load_golden("bond_d3_h300")
     H, _ = oracle_forward(g, torch.float64)
