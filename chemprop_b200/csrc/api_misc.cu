@@ -386,6 +386,26 @@ int dmpnn_tile_pack_order(int64_t n, const int64_t* n_atoms, const int64_t* n_ed
   for (const Bin& b : bins)
     for (int64_t i = b.head; i >= 0; i = next[(size_t)i]) order_out[o++] = i;
   DMPNN_CHECK_ARG(o == n, "tile_pack_order: internal error");
+  // safety net: the engine packs CONSECUTIVE molecules greedily (restarting every 1024); keep the arrival order
+  // whenever the bin-packed one would not give fewer tiles under that exact rule
+  auto greedy_tiles = [&](bool packed) {
+    const int64_t kChunk = 1024;
+    int64_t rows = 0, atoms = 0, tiles = n > 0 ? 1 : 0, t_mol = 0;
+    for (int64_t m = 0; m < n; ++m) {
+      const int64_t i = packed ? order_out[m] : m;
+      if (m > t_mol && (m % kChunk == 0 || rows + n_edges[i] > kRows || atoms + n_atoms[i] > kAtoms)) {
+        ++tiles;
+        rows = 0;
+        atoms = 0;
+        t_mol = m;
+      }
+      rows += n_edges[i];
+      atoms += n_atoms[i];
+    }
+    return tiles;
+  };
+  if (greedy_tiles(true) >= greedy_tiles(false))
+    for (int64_t i = 0; i < n; ++i) order_out[i] = i;
   return 0;
 }
 
