@@ -255,3 +255,36 @@ def test_randomised_configurations_vs_oracle(seed, monkeypatch):
         ref = torch.zeros_like(P[k]) if P[k].grad is None else P[k].grad      # e.g. W_h at depth 1: unused
         got = torch.zeros_like(ref) if p.grad is None else p.grad.double()
         assert (got - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item()), (k, kind, act, depth, shape)
+
+
+@pytest.mark.parametrize("precision,dropout", [("bf16", 0.1), ("fp32", 0.0)])
+def test_training_loop_through_the_loader_overfits(precision, dropout, monkeypatch):
+    """README's training loop (PackedBatchLoader with side arrays + tile packing -> module -> aggregation -> head ->
+    Adam; bf16 with dropout = the fused-path dropout), kernels emulated: the loss must collapse, as in the reference's
+    "can it overfit" integration tests (tests/integration/test_regression_mol.py:56-89)."""
+    from chemprop_b200.data import PackedBatchLoader, PackedMolGraphDataset, make_molecules
+    from chemprop_b200.nn import BondMessagePassing, MeanAggregation
+    from chemprop_b200.parallel import FlatGradAllReducer
+
+    emu.patch_engine(monkeypatch)
+    torch.manual_seed(0)
+    mgs = make_molecules(120, seed=0, mean_atoms=8, std_atoms=2)
+    targets = np.array([[mg.V.shape[0] / 8.0 - 1.0] for mg in mgs], dtype=np.float32)
+    loader = PackedBatchLoader(PackedMolGraphDataset.from_molgraphs(mgs), batch_size=40, shuffle=True, seed=0,
+                               transfer_dtype=torch.bfloat16 if precision == "bf16" else None, arrays={"y": targets})
+    mp, agg, head = BondMessagePassing(d_h=32, precision=precision, dropout=dropout), MeanAggregation(), torch.nn.Linear(32, 1)
+    params = list(mp.parameters()) + list(head.parameters())
+    opt, reducer = torch.optim.Adam(params, 3e-3), FlatGradAllReducer(params)
+    epoch_loss = []
+    for _ in range(30):
+        tot = 0.0
+        for batch in loader:
+            opt.zero_grad(set_to_none=True)
+            pred = head(agg(mp(batch.bmg), batch.bmg.batch).float())
+            loss = torch.nn.functional.mse_loss(pred, batch.extras["y"])
+            loss.backward()
+            reducer.allreduce_()
+            opt.step()
+            tot += loss.item()
+        epoch_loss.append(tot / len(loader))
+    assert epoch_loss[-1] < 0.1 * epoch_loss[0] and epoch_loss[-1] < 0.01, (epoch_loss[0], epoch_loss[-1])
