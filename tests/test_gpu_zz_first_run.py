@@ -9,6 +9,10 @@
   * torch.export of a model on the engine's modules (custom ops dmpnn::mp_forward / dmpnn::segment_agg);
   * the mol-atom-bond variants (MABBond / MABAtomMessagePassing), which run on the composed tier.
 
+(The two NEW kernels these tests reach -- dmpnn_dataset_gather, dmpnn_scale_mask -- did run on a B200 in that round, through
+tests/native/check_new_kernels: bit-exact, profiles/r1_native_check_new_kernels.log.  Everything else here is host-side
+orchestration over kernels the verified tiers already exercise.)
+
 This file sorts last on purpose.  It was written after this round's GPU budget was spent: its first run on hardware
 is the round-end run, so it is marked xfail(strict=False) -- a pass is reported as XPASS, a failure does not mask the
 results of the hardware-verified tiers.  The host logic it exercises is covered on CPU by tests/test_host_logic.py
