@@ -7,6 +7,7 @@
 set -u
 mkdir -p gpurun_out
 ./tests/native/check_new_kernels 2>&1 | tee gpurun_out/native_check.log
+./tests/native/fused_step_harness 10000 300 2 2>&1 | tee gpurun_out/native_fused_step.log     # tile packing A/B, no Python
 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
 timeout 900 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_zz_first_run.py > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest(verified tiers) rc=$?"; tail -3 gpurun_out/pytest_gpu.log
