@@ -32,6 +32,12 @@ def register_with_chemprop() -> dict:
         ours.AttentiveAggregation: ref_nn.AttentiveAggregation,
         ours.Aggregation: ref_nn.Aggregation,
     }
+    try:
+        from chemprop.nn.ffn import ConstrainerFFN as ref_constrainer
+
+        pairs[ours.ConstrainerFFN] = ref_constrainer
+    except Exception:  # noqa: BLE001 -- older chemprop without the mol-atom-bond models
+        pass
     done = {}
     for mine, theirs in pairs.items():
         reg = getattr(theirs, "register", None)

@@ -1,10 +1,11 @@
 from .agg import (Aggregation, AggregationRegistry, AttentiveAggregation, MeanAggregation, NormAggregation,
                   SumAggregation)
+from .constrainer import ConstrainerFFN
 from .message_passing import AtomMessagePassing, BondMessagePassing
 from .mol_atom_bond import MABAtomMessagePassing, MABBondMessagePassing
 from .multi import MulticomponentMessagePassing
 from .transforms import GraphTransform, ScaleTransform
 
 __all__ = ["Aggregation", "AggregationRegistry", "AttentiveAggregation", "MeanAggregation", "NormAggregation", "SumAggregation",
-           "AtomMessagePassing", "BondMessagePassing", "MABAtomMessagePassing", "MABBondMessagePassing",
+           "AtomMessagePassing", "BondMessagePassing", "ConstrainerFFN", "MABAtomMessagePassing", "MABBondMessagePassing",
            "MulticomponentMessagePassing", "GraphTransform", "ScaleTransform"]

@@ -282,6 +282,34 @@ def attentive_case() -> dict:
             "grad.H": H.grad.numpy(), "grad.W.weight": agg.W.weight.grad.numpy(), "grad.W.bias": agg.W.bias.grad.numpy()}
 
 
+def constrainer_case() -> dict:
+    """ConstrainerFFN (chemprop/nn/ffn.py:70-145) of the real reference: 2 constrained columns of 3, 2-layer tanh MLP."""
+    import_reference()
+    from chemprop.nn.ffn import ConstrainerFFN
+
+    rng = np.random.default_rng(88)
+    sizes = [3, 1, 9, 4, 22]
+    batch = torch.from_numpy(np.repeat(np.arange(len(sizes)), sizes))
+    n = sum(sizes)
+    torch.manual_seed(88)
+    mod = ConstrainerFFN(n_constraints=2, fp_dim=20, hidden_dim=16, n_layers=2, activation="tanh")
+    fp = torch.from_numpy(rng.normal(0, 0.7, size=(n, 20)).astype(np.float32)).requires_grad_(True)
+    preds = torch.from_numpy(rng.normal(size=(n, 3)).astype(np.float32)).requires_grad_(True)
+    cons = rng.normal(size=(len(sizes), 3)).astype(np.float32)
+    cons[:, 1] = np.nan                                              # column 1 is unconstrained (ffn.py:136)
+    constraints = torch.from_numpy(cons)
+    out = mod(fp, preds, batch, constraints)
+    G = torch.from_numpy(rng.normal(size=tuple(out.shape)).astype(np.float32))
+    (out * G).sum().backward()
+    d = {"fp": fp.detach().numpy(), "preds": preds.detach().numpy(), "batch": batch.numpy(), "constraints": cons,
+         "out": out.detach().numpy(), "G": G.numpy(), "grad.fp": fp.grad.numpy(), "grad.preds": preds.grad.numpy()}
+    for k, v in mod.state_dict().items():
+        d["param." + k] = v.detach().numpy()
+    for k, p in mod.named_parameters():
+        d["grad." + k] = p.grad.numpy()
+    return d
+
+
 def main():
     """`python -m oracle.make_golden [name ...]`: all cases, or only the named ones (a case's seed is its position in
     CASES, so adding cases at the end never changes the committed ones)."""
@@ -292,6 +320,12 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN_DIR, "fixture_attentive.npz"), **attentive_case())
         print("fixture_attentive")
         only.discard("fixture_attentive")
+        if not only and len(sys.argv) > 1:
+            return
+    if "fixture_constrainer" in only or not only:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "fixture_constrainer.npz"), **constrainer_case())
+        print("fixture_constrainer")
+        only.discard("fixture_constrainer")
         if not only and len(sys.argv) > 1:
             return
     assert only <= set(CASES), only - set(CASES)

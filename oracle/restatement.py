@@ -211,3 +211,22 @@ def attentive_aggregate(H, batch, W, b, n_mols=None):
     index_torch = batch.unsqueeze(1).repeat(1, H.shape[1])
     return torch.zeros(dim_size, H.shape[1], dtype=H.dtype).scatter_reduce_(0, index_torch, alphas * H, reduce="sum",
                                                                             include_self=False)   # agg.py:128-131
+
+
+def constrain(k, preds, batch, constraints):
+    """ConstrainerFFN.forward after its MLP (chemprop/nn/ffn.py:120-142): k = ffn(fp)."""
+    expk = k.exp()
+    n_mols = constraints.shape[0]
+    idx = batch.unsqueeze(1).repeat(1, k.shape[1])
+    per_mol_sum_expk = torch.zeros(n_mols, expk.shape[1], dtype=expk.dtype).scatter_reduce_(0, idx, expk, reduce="sum",
+                                                                                           include_self=False)
+    w = expk / per_mol_sum_expk[batch]
+    idx = batch.unsqueeze(1).repeat(1, preds.shape[1])
+    per_mol_preds = torch.zeros(n_mols, preds.shape[1], dtype=preds.dtype).scatter_reduce_(0, idx, preds, reduce="sum",
+                                                                                          include_self=False)
+    has = ~torch.isnan(constraints)[0]
+    deviation = constraints[:, has] - per_mol_preds[:, has]
+    corrections = w * deviation[batch]
+    cor = torch.zeros_like(preds)
+    cor[:, has] = corrections
+    return preds + cor

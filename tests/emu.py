@@ -312,6 +312,8 @@ def patch_engine(monkeypatch):
         monkeypatch.setattr(engine, name, globals()[name])
     monkeypatch.setattr(engine, "_require_cuda", lambda *ts: None)
     import chemprop_b200.nn.agg as agg_mod
+    import chemprop_b200.nn.constrainer as con_mod
 
     monkeypatch.setattr(engine, "segments_of", segments_of)
     monkeypatch.setattr(agg_mod, "segments_of", segments_of)
+    monkeypatch.setattr(con_mod, "segments_of", segments_of)

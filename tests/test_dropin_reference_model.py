@@ -189,3 +189,41 @@ def test_engine_mab_modules_inside_the_reference_mol_atom_bond_mpnn(kind, monkey
     assert set(results[0][1]) == set(results[1][1])
     for k in results[0][1]:
         torch.testing.assert_close(results[1][1][k], results[0][1][k], rtol=2e-3, atol=2e-5, msg=k)
+
+
+def test_engine_constrainer_inside_the_reference_mol_atom_bond_mpnn(monkeypatch):
+    """MolAtomBondMPNN.forward with an atom constrainer (models/mol_atom_bond.py:255-290): the engine's ConstrainerFFN in
+    the reference model == the reference's own, and the constrained atom predictions sum to the constraint per molecule."""
+    from oracle.ref_shim import import_reference
+
+    import_reference()
+    import chemprop.nn as ref_nn
+    from chemprop.data.collate import BatchMolAtomBondGraph
+    from chemprop.data.molgraph import MolGraph as RefMG
+    from chemprop.models import MolAtomBondMPNN
+    from chemprop.nn.ffn import ConstrainerFFN as RefConstrainer
+    from chemprop.nn.message_passing import MABBondMessagePassing
+
+    import chemprop_b200.nn as ours
+    from chemprop_b200.data import make_molecules
+    from chemprop_b200.integrate import register_with_chemprop
+
+    emu.patch_engine(monkeypatch)
+    torch.manual_seed(5)
+    bmg = BatchMolAtomBondGraph([RefMG(*m) for m in make_molecules(7, seed=9, mean_atoms=7, std_atoms=2)])
+    constraints = [torch.from_numpy(np.random.default_rng(2).normal(size=(7, 1)).astype(np.float32)), None]
+    ref = MolAtomBondMPNN(MABBondMessagePassing(d_h=32), ref_nn.SumAggregation(), atom_predictor=ref_nn.RegressionFFN(input_dim=32),
+                          atom_constrainer=RefConstrainer(n_constraints=1, fp_dim=32, hidden_dim=16))
+    drop = MolAtomBondMPNN(ours.MABBondMessagePassing(d_h=32), ours.SumAggregation(), atom_predictor=ref_nn.RegressionFFN(input_dim=32),
+                           atom_constrainer=ours.ConstrainerFFN(n_constraints=1, fp_dim=32, hidden_dim=16))
+    assert set(drop.state_dict()) == set(ref.state_dict())
+    drop.load_state_dict(ref.state_dict())
+    assert isinstance(drop.atom_constrainer, RefConstrainer) or register_with_chemprop() and isinstance(drop.atom_constrainer, RefConstrainer)
+    for model in (ref, drop):
+        model.eval()
+    with torch.no_grad():
+        a = ref(bmg, constraints=constraints)[1]
+        b = drop(bmg, constraints=constraints)[1]
+    torch.testing.assert_close(b, a, rtol=1e-4, atol=1e-5)
+    sums = torch.zeros(7, 1).index_add_(0, bmg.batch, b)
+    torch.testing.assert_close(sums, constraints[0], rtol=1e-4, atol=1e-4)

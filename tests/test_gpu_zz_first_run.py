@@ -7,7 +7,8 @@
   * the device-resident packed data set (dmpnn_dataset_gather) and the loader on top of it;
   * training-mode dropout on the fused bf16 / ReLU path (dmpnn_scale_mask + scale factors folded into the mirror's weights);
   * torch.export of a model on the engine's modules (custom ops dmpnn::mp_forward / dmpnn::segment_agg);
-  * the mol-atom-bond variants (MABBond / MABAtomMessagePassing), which run on the composed tier.
+  * the mol-atom-bond variants (MABBond / MABAtomMessagePassing), which run on the composed tier, AttentiveAggregation and
+    ConstrainerFFN (segment primitives + torch elementwise ops).
 
 (The two NEW kernels these tests reach -- dmpnn_dataset_gather, dmpnn_scale_mask -- did run on a B200 in that round, through
 tests/native/check_new_kernels: bit-exact, profiles/r1_native_check_new_kernels.log.  Everything else here is host-side
@@ -239,3 +240,9 @@ def test_exported_model_runs_on_the_gpu(precision):
     for g in graphs:
         with torch.inference_mode():
             torch.testing.assert_close(exported.module()(g), model(g))
+
+
+def test_constrainer_ffn_matches_reference_fixture():
+    from tests.util import check_constrainer
+
+    check_constrainer("cuda", atol=FP32_ATOL)

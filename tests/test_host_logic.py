@@ -182,6 +182,13 @@ def test_training_dropout_on_the_fused_bf16_path(depth, bias, monkeypatch):
     assert calls["n"] == depth - 1
 
 
+def test_constrainer_ffn_matches_reference_fixture(monkeypatch):
+    from tests.util import check_constrainer
+
+    emu.patch_engine(monkeypatch)
+    check_constrainer("cpu")
+
+
 def test_eval_mode_with_dropout_configured_stays_monolithic(monkeypatch):
     emu.patch_engine(monkeypatch)
     g = load_golden("bond_d3_dropout_eval")

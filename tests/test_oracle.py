@@ -89,6 +89,16 @@ def test_smiles_topology_parser_of_config1():
     assert np.array_equal(g["rev_edge_index"], np.arange(g["E"].shape[0]) ^ 1)
 
 
+def test_constrain_restatement_matches_reference_fixture():
+    g = load_golden("fixture_constrainer")
+    t = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    h = torch.tanh(torch.nn.functional.linear(t("fp"), t("param.ffn.0.0.weight"), t("param.ffn.0.0.bias")))
+    h = torch.tanh(torch.nn.functional.linear(h, t("param.ffn.1.2.weight"), t("param.ffn.1.2.bias")))
+    k = torch.nn.functional.linear(h, t("param.ffn.2.2.weight"), t("param.ffn.2.2.bias"))
+    out = R.constrain(k, t("preds"), t("batch"), t("constraints"))
+    np.testing.assert_allclose(out.numpy(), g["out"], **TOL)
+
+
 def test_restatement_fp64_close_to_fp32_golden():
     g = load_golden("bond_d3_h300")
     H, _ = oracle_forward(g, torch.float64)

@@ -296,3 +296,27 @@ def fused_dropout_vs_oracle(device: str, depth: int = 3, bias: bool = True, d_h:
         got = prm.grad.double().cpu()
         fro = float((got - g).norm() / max(1e-9, g.norm()))
         assert fro <= 0.12, (k, fro)              # a missing / doubled 1/(1-p) = 1.43 would show as >= 0.3
+
+
+def check_constrainer(device: str, atol: float = 2e-6):
+    """ConstrainerFFN against the reference's fixture (tests/golden/fixture_constrainer.npz): adjusted predictions, the
+    constraint itself, and the gradients w.r.t. fingerprints, predictions and the MLP."""
+    from chemprop_b200.nn import ConstrainerFFN
+
+    g = load_golden("fixture_constrainer")
+    mod = ConstrainerFFN(n_constraints=2, fp_dim=20, hidden_dim=16, n_layers=2, activation="tanh")
+    mod.load_state_dict({k[len("param."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")})   # strict
+    mod = mod.to(device)
+    fp = torch.from_numpy(g["fp"]).to(device).requires_grad_(True)
+    preds = torch.from_numpy(g["preds"]).to(device).requires_grad_(True)
+    batch, cons = torch.from_numpy(g["batch"]).to(device), torch.from_numpy(g["constraints"]).to(device)
+    out = mod(fp, preds, batch, cons)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out"], rtol=1e-5, atol=atol)
+    sums = torch.zeros(cons.shape, device=device).index_add_(0, batch, out.detach())
+    assert (sums[:, [0, 2]] - cons[:, [0, 2]]).abs().max().item() <= 1e-4           # the constrained columns sum to the constraint
+    (out * torch.from_numpy(g["G"]).to(device)).sum().backward()
+    np.testing.assert_allclose(fp.grad.cpu().numpy(), g["grad.fp"], rtol=1e-4, atol=atol)
+    np.testing.assert_allclose(preds.grad.cpu().numpy(), g["grad.preds"], rtol=1e-4, atol=atol)
+    for k, p in mod.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), g["grad." + k], rtol=1e-4, atol=atol, err_msg=k)
+    assert mod.hparams["cls"] is ConstrainerFFN and mod.hparams["n_constraints"] == 2
