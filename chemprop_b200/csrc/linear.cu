@@ -177,13 +177,22 @@ k_wgrad_partial(const TY* __restrict__ dY, int64_t lddy, ASrc a, float* __restri
   const int64_t r_end = min(R, r_begin + rows_per_split);
   const int lr = tid >> 4, lc = (tid & 15) * 4;  // loader: row lr, 4 consecutive columns at lc
 
-  float acc[4][4];
+  // Two-level sum: a WR-row block is accumulated from zero (fmaf chain of 16 terms), the block sums are added with
+  // Kahan compensation.  A plain chain over the ~1000 rows of a split has an error of ~sqrt(rows) ulps of sum|terms|,
+  // which on weight gradients with heavy cancellation (reference config 1, all 500 molecules: |dW_o| up to 63, an
+  // element of 0.96) exceeded the fp32 tier's 1e-4 relative bound; this keeps it at a few ulps of sum|terms|.
+  float tot[4][4], comp[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) { tot[i][j] = 0.f; comp[i][j] = 0.f; }
 
   for (int64_t rb = r_begin; rb < r_end; rb += WR) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const int64_t r = rb + lr;
     float yv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
     if (r < r_end) {
@@ -218,6 +227,15 @@ k_wgrad_partial(const TY* __restrict__ dY, int64_t lddy, ASrc a, float* __restri
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(yr[i], xr[j], acc[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                 // Kahan: tot += acc, rounding error carried in comp
+        const float y = __fsub_rn(acc[i][j], comp[i][j]);
+        const float t = __fadd_rn(tot[i][j], y);
+        comp[i][j] = __fsub_rn(__fsub_rn(t, tot[i][j]), y);
+        tot[i][j] = t;
+      }
   }
   float* P = part + (int64_t)blockIdx.z * N * K;
 #pragma unroll
@@ -227,7 +245,7 @@ k_wgrad_partial(const TY* __restrict__ dY, int64_t lddy, ASrc a, float* __restri
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int k = k0 + tx * 4 + j;
-      if (k < K) P[(int64_t)n * K + k] = acc[i][j];
+      if (k < K) P[(int64_t)n * K + k] = tot[i][j];
     }
   }
 }
@@ -239,8 +257,13 @@ __global__ void k_colsum_partial(const TY* __restrict__ dY, int64_t lddy, float*
   if (n >= N) return;
   const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
   const int64_t r_end = min(R, r_begin + rows_per_split);
-  float s = 0.f;
-  for (int64_t r = r_begin; r < r_end; ++r) s += ld_as_float(dY + r * lddy + n);
+  float s = 0.f, c = 0.f;                           // Kahan (see k_wgrad_partial)
+  for (int64_t r = r_begin; r < r_end; ++r) {
+    const float y = __fsub_rn(ld_as_float(dY + r * lddy + n), c);
+    const float t = __fadd_rn(s, y);
+    c = __fsub_rn(__fsub_rn(t, s), y);
+    s = t;
+  }
   part[(int64_t)blockIdx.y * N + n] = s;
 }
 
@@ -292,8 +315,13 @@ __global__ void k_reduce_splits(const float* __restrict__ part, int S, int64_t c
   // out[(i / inner) * ld_out + i % inner] (+)= sum_s part[s*count + i]
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= count) return;
-  float s = 0.f;
-  for (int k = 0; k < S; ++k) s += part[(int64_t)k * count + i];
+  float s = 0.f, c = 0.f;                           // Kahan over the splits (fixed order: deterministic)
+  for (int k = 0; k < S; ++k) {
+    const float y = __fsub_rn(part[(int64_t)k * count + i], c);
+    const float t = __fadd_rn(s, y);
+    c = __fsub_rn(__fsub_rn(t, s), y);
+    s = t;
+  }
   float* o = out + (i / inner) * ld_out + (i % inner);
   *o = accumulate ? (*o + s) : s;
 }

@@ -113,61 +113,6 @@ __device__ __forceinline__ void trace_ev(const Params& p, int it, int ev) {
   }
 }
 
-// One (atom, 16-byte column chunk): rows r0 .. r0+d-1 of the slab-swizzled A buffer are replaced by
-// the sum of the OTHER rows of the atom (= sum of all in-edge states minus the row's own, i.e. the
-// message M[rev(row)] of mixins.py:11-18).  d <= 4 (every organic atom) is done as explicit sums of
-// the others in packed bf16x2 -- at most two roundings per output; larger d falls back to an f32
-// sum-minus-self.
-template <int ACT, bool FIRST>
-__device__ __forceinline__ void message_atom_chunk(uint32_t abuf, int r0, int d, int c, float ap) {
-  const uint32_t cbase = abuf + (uint32_t)(c >> 3) * kSlabBytes;
-  const int cc = c & 7;
-  const uint32_t a0 = cbase + sw128_off(r0, cc);
-  if (d == 1) {
-    sts128(a0, make_uint4(0u, 0u, 0u, 0u));
-  } else if (d == 2) {
-    const uint32_t a1 = cbase + sw128_off(r0 + 1, cc);
-    const uint4 x0 = s_load<ACT, FIRST>(a0, ap), x1 = s_load<ACT, FIRST>(a1, ap);
-    sts128(a0, x1);
-    sts128(a1, x0);
-  } else if (d == 3) {
-    const uint32_t a1 = cbase + sw128_off(r0 + 1, cc), a2 = cbase + sw128_off(r0 + 2, cc);
-    const uint4 x0 = s_load<ACT, FIRST>(a0, ap), x1 = s_load<ACT, FIRST>(a1, ap), x2 = s_load<ACT, FIRST>(a2, ap);
-    sts128(a0, add4(x1, x2));
-    sts128(a1, add4(x0, x2));
-    sts128(a2, add4(x0, x1));
-  } else if (d == 4) {
-    const uint32_t a1 = cbase + sw128_off(r0 + 1, cc), a2 = cbase + sw128_off(r0 + 2, cc),
-                   a3 = cbase + sw128_off(r0 + 3, cc);
-    const uint4 x0 = s_load<ACT, FIRST>(a0, ap), x1 = s_load<ACT, FIRST>(a1, ap), x2 = s_load<ACT, FIRST>(a2, ap),
-                x3 = s_load<ACT, FIRST>(a3, ap);
-    const uint4 p = add4(x0, x1), q = add4(x2, x3);
-    sts128(a0, add4(x1, q));
-    sts128(a1, add4(x0, q));
-    sts128(a2, add4(p, x3));
-    sts128(a3, add4(p, x2));
-  } else {
-    float acc[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-    for (int r = r0; r < r0 + d; ++r) {
-      const uint4 u = s_load<ACT, FIRST>(cbase + sw128_off(r, cc), ap);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { acc[2 * q] += bf_lo(w[q]); acc[2 * q + 1] += bf_hi(w[q]); }
-    }
-    for (int r = r0; r < r0 + d; ++r) {
-      const uint32_t addr = cbase + sw128_off(r, cc);
-      const uint4 u = s_load<ACT, FIRST>(addr, ap);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-      uint32_t o[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) o[q] = pack_bf2(acc[2 * q] - bf_lo(w[q]), acc[2 * q + 1] - bf_hi(w[q]));
-      sts128(addr, make_uint4(o[0], o[1], o[2], o[3]));
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // MODE 0: forward step (message of H, epilogue tau(H_0[rev] + bias + acc) written to row rev(e'))
 // MODE 1: autograd mirror, masked:  A row e' = sum of dZ[rev(x)] over the siblings x of e';  out[e'] = acc * tau'(Y[e'])

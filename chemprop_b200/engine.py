@@ -215,27 +215,36 @@ def get_layout(bmg) -> Layout:
     return lay
 
 
-def segments_of(batch: Tensor):
-    """(ptr int32 [B+1], seg_of_row int32 [V], B) for a sorted int64 `batch` (agg.py:74-75)."""
+def segments_of(batch: Tensor, n_seg: int | None = None):
+    """(ptr int32 [B+1], seg_of_row int32 [V], B) for a sorted int64 `batch` (agg.py:74-75).  `n_seg`: the segment count
+    is given by the caller (nn/ffn.py:123 sizes by the constraints' rows): trailing segments without rows come out empty
+    (`ptr[s] == ptr[s+1]`), an index >= n_seg is an error."""
     seg = getattr(batch, "_dmpnn_seg", None)
-    if seg is not None and seg[0].device == batch.device:
+    if seg is not None and seg[0].device == batch.device and (n_seg is None or seg[2] == n_seg):
         return seg
     _require_cuda(batch)
     lib = _lib.load()
     n = int(batch.shape[0])
-    B = int(batch.max().item()) + 1 if n > 0 else 0   # same device sync as the reference (agg.py:75)
+    if n_seg is None:
+        B = int(batch.max().item()) + 1 if n > 0 else 0   # same device sync as the reference (agg.py:75)
+    else:
+        B = int(n_seg)
     ptr = torch.zeros(B + 1, dtype=torch.int32, device=batch.device)
     status = torch.zeros(1, dtype=torch.int32, device=batch.device)
     bc = batch.contiguous()
     _lib.check(lib.dmpnn_sorted_index_to_ptr(bc.data_ptr(), n, B, ptr.data_ptr(), status.data_ptr(), _stream()),
                "dmpnn_sorted_index_to_ptr")
-    if int(status.item()) != 0:
+    st = int(status.item())
+    if st & 1:       # V_RANGE of csrc/layout.cu
+        raise DmpnnError(f"`batch` holds a molecule index outside [0, {B})")
+    if st != 0:
         raise DmpnnError("Aggregation: `batch` must be non-decreasing (atoms of a molecule contiguous)")
     seg = (ptr, bc.to(torch.int32), B)
-    try:
-        batch._dmpnn_seg = seg
-    except Exception:
-        pass
+    if n_seg is None:
+        try:
+            batch._dmpnn_seg = seg
+        except Exception:
+            pass
     return seg
 
 
@@ -834,10 +843,21 @@ def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
     return dWi, dbi, dWh, dbh, dWo, dbo
 
 
+def _refuse_feature_grads(ctx):
+    """The hand-written mirrors produce the six parameter gradients only.  chemprop never asks for d/dV or d/dE (features
+    come out of the featuriser), but a caller who does (learned atom embeddings, input saliency) must not get a silent
+    `None` where the reference's autograd would deliver a gradient."""
+    if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+        raise DmpnnError(
+            "bmg.V / bmg.E require grad: the engine's hand-written backward produces parameter gradients only "
+            "(d/dV, d/dE are not implemented); detach the features, or use the reference module for input attribution")
+
+
 class BondMPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, V, E, Wi, bi, Wh, bh, Wo, bo, lay, cfg):
         _require_cuda(V, E, Wi, Wh, Wo)
+        _refuse_feature_grads(ctx)
         V = V.contiguous().float()
         E = E.contiguous().float()
         Wi_, Wh_, Wo_ = Wi.detach().contiguous().float(), Wh.detach().contiguous().float(), Wo.detach().contiguous().float()
@@ -859,7 +879,7 @@ class BondMPFunction(torch.autograd.Function):
         bwd = bond_backward_tc if (ctx.saved.get("tc") and not ctx.cfg.undirected and ctx.saved.get("X0") is not None
                                    and h_is_mult4(Wh)) else bond_backward
         dWi, dbi, dWh, dbh, dWo, dbo = bwd(ctx.lay, V, E, Wi, Wh, Wo, ctx.cfg, ctx.saved, gHv, ctx.has_bias)
-        ctx.saved = None
+        # ctx.saved stays until autograd frees the node: a second backward (retain_graph=True) works like torch's own
         d0, d1, d2 = ctx.wdtypes
         cast = lambda g, d: None if g is None else g.to(d)
         return (None, None, cast(dWi, d0), cast(dbi, d0), cast(dWh, d1), cast(dbh, d1), cast(dWo, d2),
@@ -1059,6 +1079,7 @@ class AtomMPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, V, E, Wi, bi, Wh, bh, Wo, bo, lay, cfg):
         _require_cuda(V, E, Wi, Wh, Wo)
+        _refuse_feature_grads(ctx)
         V = V.contiguous().float()
         E = E.contiguous().float()
         Wi_, Wh_, Wo_ = Wi.detach().contiguous().float(), Wh.detach().contiguous().float(), Wo.detach().contiguous().float()
@@ -1080,7 +1101,7 @@ class AtomMPFunction(torch.autograd.Function):
         Wi, Wh, Wo = ctx.W
         bwd = atom_backward_tc if ctx.saved.get("tc") else atom_backward
         dWi, dbi, dWh, dbh, dWo, dbo = bwd(ctx.lay, V, E, Wi, Wh, Wo, ctx.cfg, ctx.saved, gHv, ctx.has_bias)
-        ctx.saved = None
+        # ctx.saved stays until autograd frees the node: a second backward (retain_graph=True) works like torch's own
         d0, d1, d2 = ctx.wdtypes
         cast = lambda g, d: None if g is None else g.to(d)
         return (None, None, cast(dWi, d0), cast(dbi, d0), cast(dWh, d1), cast(dbh, d1), cast(dWo, d2),
@@ -1097,17 +1118,21 @@ class SegmentAggFunction(torch.autograd.Function):
     def forward(ctx, H, mol_atom_ptr, atom_mol, n_mols, scale_mode, scale):
         _require_cuda(H)
         Hc = H if H.stride(1) == 1 else H.contiguous()
-        out = torch.empty((n_mols, H.shape[1]), dtype=H.dtype, device=H.device)
+        # molecule-level output is always f32 (b x d is tiny): whatever follows -- the reference's BatchNorm / FFN heads
+        # (models/model.py:126-161) -- holds f32 parameters, so a bf16-tier encoder drops in without a cast by the caller
+        out = torch.empty((n_mols, H.shape[1]), dtype=torch.float32, device=H.device)
         segment_sum(Hc, mol_atom_ptr, n_mols, H.shape[1], out, scale_mode=scale_mode, scale=scale,
                     pad_to=H.shape[1])
         ctx.ptr, ctx.atom_mol, ctx.mode, ctx.scale = mol_atom_ptr, atom_mol, scale_mode, scale
-        ctx.nV = H.shape[0]
+        ctx.nV, ctx.in_dtype = H.shape[0], H.dtype
         return out
 
     @staticmethod
     def backward(ctx, g):
         g = g.contiguous()
-        dH = torch.empty((ctx.nV, g.shape[1]), dtype=g.dtype, device=g.device)
+        if g.dtype not in (torch.float32, torch.bfloat16):
+            g = g.float()
+        dH = torch.empty((ctx.nV, g.shape[1]), dtype=ctx.in_dtype, device=g.device)
         segment_bcast(g, ctx.atom_mol, ctx.ptr, ctx.nV, g.shape[1], dH, scale_mode=ctx.mode, scale=ctx.scale,
                       n_seg=g.shape[0])
         return dH, None, None, None, None, None

@@ -23,7 +23,6 @@ def register_with_chemprop() -> dict:
     pairs = {
         ours.BondMessagePassing: ref_nn.BondMessagePassing,
         ours.AtomMessagePassing: ref_nn.AtomMessagePassing,
-        ours.MulticomponentMessagePassing: ref_nn.MulticomponentMessagePassing,
         ours.MABBondMessagePassing: ref_mab.MABBondMessagePassing,
         ours.MABAtomMessagePassing: ref_mab.MABAtomMessagePassing,
         ours.MeanAggregation: ref_nn.MeanAggregation,

@@ -3,9 +3,8 @@ from .agg import (Aggregation, AggregationRegistry, AttentiveAggregation, MeanAg
 from .constrainer import ConstrainerFFN
 from .message_passing import AtomMessagePassing, BondMessagePassing
 from .mol_atom_bond import MABAtomMessagePassing, MABBondMessagePassing
-from .multi import MulticomponentMessagePassing
 from .transforms import GraphTransform, ScaleTransform
 
 __all__ = ["Aggregation", "AggregationRegistry", "AttentiveAggregation", "MeanAggregation", "NormAggregation", "SumAggregation",
            "AtomMessagePassing", "BondMessagePassing", "ConstrainerFFN", "MABAtomMessagePassing", "MABBondMessagePassing",
-           "MulticomponentMessagePassing", "GraphTransform", "ScaleTransform"]
+           "GraphTransform", "ScaleTransform"]

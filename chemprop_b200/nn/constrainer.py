@@ -38,15 +38,18 @@ class ConstrainerFFN(nn.Module):
     def forward(self, fp: Tensor, preds: Tensor, batch: Tensor, constraints: Tensor) -> Tensor:
         """fp: b x h fingerprints; preds: b x t; batch: b (molecule of each atom / bond, sorted); constraints: m x t (NaN in
         row 0 marks an unconstrained column, ffn.py:137).  Returns the adjusted b x t predictions."""
-        ptr, seg, n_mols = segments_of(batch)
-        if n_mols != constraints.shape[0]:              # ffn.py:123 sizes everything by the constraints' row count
-            raise ValueError(f"`batch` holds {n_mols} molecules but `constraints` has {constraints.shape[0]} rows")
+        # ffn.py:123 sizes everything by the constraints' row count: molecules without an atom / bond row (a trailing
+        # single-heavy-atom SMILES has no bond) are empty segments, not an error
+        n_mols = int(constraints.shape[0])
+        ptr, seg, _ = segments_of(batch, n_seg=n_mols)
         rows = preds.shape[0]
+        has = ~torch.isnan(constraints)[0]                                                           # ffn.py:136
+        if rows == 0 or not bool(has.any()):             # nothing to adjust (the segment kernels need >= 1 column)
+            return preds + torch.zeros_like(preds)
         expk = self.ffn(fp).exp()                                                                  # ffn.py:120-121
         Z = SegmentAggFunction.apply(expk.float(), ptr, seg, n_mols, _lib.SCALE_NONE, 1.0)           # ffn.py:124-127
         w = expk / SegmentBcastFunction.apply(Z, ptr, seg, rows)                                     # ffn.py:128-129
         per_mol = SegmentAggFunction.apply(preds.float(), ptr, seg, n_mols, _lib.SCALE_NONE, 1.0)    # ffn.py:131-134
-        has = ~torch.isnan(constraints)[0]                                                           # ffn.py:136
         deviation = (constraints[:, has] - per_mol[:, has]).contiguous()                             # ffn.py:137
         corrections = w * SegmentBcastFunction.apply(deviation, ptr, seg, rows)                      # ffn.py:139
         out = torch.zeros_like(preds)

@@ -75,15 +75,18 @@ class _MessagePassingBase(nn.Module):
     def __init__(self, d_v: int = DEFAULT_ATOM_FDIM, d_e: int = DEFAULT_BOND_FDIM, d_h: int = DEFAULT_HIDDEN_DIM,
                  bias: bool = False, depth: int = 3, dropout: float = 0.0, activation="relu",
                  undirected: bool = False, d_vd: int | None = None, V_d_transform: nn.Module | None = None,
-                 graph_transform: nn.Module | None = None, precision: str = "fp32"):
+                 graph_transform: nn.Module | None = None, precision: str = "fp32",
+                 output_dtype: torch.dtype | None = None):
         super().__init__()
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
+        if output_dtype not in (None, torch.float32, torch.bfloat16):
+            raise ValueError("output_dtype must be None, torch.float32 or torch.bfloat16")
         # same keys as the reference's save_hyperparameters() result (base.py:70-80)
         self.hparams = dict(d_v=d_v, d_e=d_e, d_h=d_h, bias=bias, depth=depth, dropout=dropout,
                             activation=activation, undirected=undirected, d_vd=d_vd,
                             V_d_transform=V_d_transform, graph_transform=graph_transform,
-                            precision=precision, cls=self.__class__)
+                            precision=precision, output_dtype=output_dtype, cls=self.__class__)
         self.W_i, self.W_h, self.W_o, self.W_d = self.setup(d_v, d_e, d_h, d_vd, bias)
         self.depth = depth
         self.undirected = undirected
@@ -92,6 +95,10 @@ class _MessagePassingBase(nn.Module):
         self.V_d_transform = V_d_transform if V_d_transform is not None else nn.Identity()
         self.graph_transform = graph_transform if graph_transform is not None else nn.Identity()
         self.precision = precision
+        # dtype of the atom-level output H_v.  None = the tier's storage type (bf16 for precision="bf16": what the engine's
+        # Aggregation consumes without a pass over V x h; the aggregation itself always returns f32).  Heads that read H_v
+        # directly with f32 parameters (atom-level predictors of the mol-atom-bond models) want torch.float32.
+        self.output_dtype = output_dtype
         self.fused = True
 
     @property
@@ -138,10 +145,9 @@ class _MessagePassingBase(nn.Module):
         if _export is not None and _export.is_tracing():
             return self.finalize_descriptors(self._traced_forward(bmg), V_d)
         lay = get_layout(bmg)
+        out_dtype = self.output_dtype or (torch.bfloat16 if self.precision == "bf16" else torch.float32)
         if self.uses_composed_tier(lay):
-            H = type(self)._composed_forward(self, bmg, lay)
-            if self.precision == "bf16":
-                H = H.to(torch.bfloat16)     # same output dtype as the fused bf16 tier (computed in f32)
+            H = type(self)._composed_forward(self, bmg, lay)          # computed in f32 on this tier
         else:
             cfg = self._config()
             if self.training and self.dropout.p > 0:
@@ -151,6 +157,8 @@ class _MessagePassingBase(nn.Module):
                 bmg.V, bmg.E, self.W_i.weight, self.W_i.bias, self.W_h.weight, self.W_h.bias,
                 self.W_o.weight, self.W_o.bias, lay, cfg,
             )
+        if H.dtype != out_dtype:
+            H = H.to(out_dtype)
         return self.finalize_descriptors(H, V_d)
 
     def finalize_descriptors(self, H: Tensor, V_d: Tensor | None) -> Tensor:

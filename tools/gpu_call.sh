@@ -1,0 +1,40 @@
+#!/usr/bin/env bash
+# One GPU call of round 2 as ONE gpurun command (everything lands in gpurun_out/<tag>/):
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_call.sh <tag> [steps...]'
+# steps: tests bench launches ncu_fused ncu_gemm native  (default: tests bench launches)
+set -u
+TAG=${1:-call}; shift || true
+STEPS=${*:-tests bench launches}
+OUT=gpurun_out/$TAG
+mkdir -p "$OUT"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$OUT/gpu.txt" 2>&1
+for s in $STEPS; do
+  case $s in
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider -rfEX --durations=15 > "$OUT/pytest_gpu.log" 2>&1
+      echo "pytest rc=$?"; tail -40 "$OUT/pytest_gpu.log" ;;
+    testsx)
+      timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > "$OUT/pytest_gpu_x.log" 2>&1
+      echo "pytest -x rc=$?"; tail -5 "$OUT/pytest_gpu_x.log" ;;
+    smoke)
+      python __graft_entry__.py --smoke > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?"; tail -3 "$OUT/smoke.log" ;;
+    bench)
+      timeout 600 python bench.py --steps 20 --warmup 5 > "$OUT/bench.json" 2> "$OUT/bench.err"
+      echo "bench rc=$?"; cat "$OUT/bench.json"; tail -5 "$OUT/bench.err" ;;
+    launches)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file "$OUT/launches.csv" \
+        python bench.py --steps 2 --warmup 3 --no-cpu --no-dataset > "$OUT/bench_under_ncu.log" 2>&1
+      echo "ncu launches rc=$?" ;;
+    ncu_fused)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bond_step_fused -s 12 -c 4 \
+        -o "$OUT/fused_step" -f python bench.py --steps 1 --warmup 3 --no-cpu --no-dataset > "$OUT/ncu_fused.log" 2>&1
+      echo "ncu fused rc=$?" ;;
+    ncu_gemm)
+      timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_linear_tc|k_wgrad_tc" -s 18 -c 6 \
+        -o "$OUT/gemm" -f python bench.py --steps 1 --warmup 3 --no-cpu --no-dataset > "$OUT/ncu_gemm.log" 2>&1
+      echo "ncu gemm rc=$?" ;;
+    native)
+      ./tests/native/fused_step_harness 10000 300 2 2>&1 | tee "$OUT/native_fused_step.log" ;;
+    *) echo "unknown step $s" ;;
+  esac
+done
