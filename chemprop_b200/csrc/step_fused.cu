@@ -120,7 +120,6 @@ __device__ __forceinline__ void trace_ev(const Params& p, int it, int ev) {
 // MODE_BWD_LAST: mask from the PRE-activation (Y = H_0) and up to two row-aligned addends summed into the output:
 // the t = 1 step then produces dH_0 = dZ^{T-1} + ... + dZ^1 + dH^0 * tau'(H_0) directly.
 enum { MODE_FWD = 0, MODE_BWD_MASK = 1, MODE_BWD_COPY = 2, MODE_BWD_LAST = 3 };
-constexpr int kAddBatch = 4;   // 16-byte chunks per thread whose addend loads are in flight together
 
 template <int ACT, bool FIRST, bool HAS_BIAS, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -294,11 +293,13 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       }
     }
   } else if (warp < 12) {
-    // ===================== epilogue (2 groups x 4 warps; thread == TMEM lane == A row e') ==========
-    // Row e' of the accumulator is the update of edge rev(e'): it needs H_0 row rev(e') and produces
-    // H_next row rev(e'), both inside this tile -> staged through a shared-memory slab that TMA fills
-    // with H_0 and that is written back with coalesced 16-byte stores.  Group g owns the 64-column
-    // slabs s = g, g+2, ... and staging buffer g, so the two groups drain the accumulator concurrently.
+    // ===================== epilogue (2 groups x 4 warps; thread == TMEM lane == GEMM row == OUTPUT row) ==========
+    // The message warps build A row r as the message of edge r itself (they gather through the tile-local rev() table),
+    // so accumulator row r is the update of edge r: it needs H_0 row r -- read from the TMA-staged slab at the thread's own
+    // row, which is bank-conflict free under the 128-byte swizzle -- and produces output row r, written straight from
+    // registers to global memory, one 32-byte sector per thread and 16-column block (STG.256; the four sectors of a
+    // 128-byte line merge in L2).  The staging slab is read-only: no staging writes, no group barrier, no copy-out pass.
+    // Group g owns the 64-column slabs s = g, g+2, ... so the two groups drain the accumulator concurrently.
     const int eg = (warp - 4) >> 2;
     const int et = threadIdx.x - 128 - eg * 128;  // 0..127 inside the group
     const int r = et;                              // TMEM lane (warp & 3 selects the 32-lane quadrant)
@@ -307,21 +308,21 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
     uint32_t hcnt = 0;                             // slabs this group has consumed
     int it = 0;
     int t = blockIdx.x;
-    int row0 = 0, nrows = 0, lr = 0;
+    int row0 = 0, nrows = 0;
     if (t < p.n_tiles) {
       row0 = __ldg(p.tile_row_ptr + t);
       nrows = __ldg(p.tile_row_ptr + t + 1) - row0;
-      lr = (MODE == MODE_FWD && r < nrows) ? (__ldg(p.rev_row + row0 + r) - row0) : r;
     }
     for (; t < p.n_tiles; t += gridDim.x, ++it) {
       // prefetch the next tile's metadata (hides the dependent global loads behind this tile's work)
       const int tn = t + gridDim.x;
-      int row0n = 0, nrowsn = 0, lrn = 0;
+      int row0n = 0, nrowsn = 0;
       if (tn < p.n_tiles) {
         row0n = __ldg(p.tile_row_ptr + tn);
         nrowsn = __ldg(p.tile_row_ptr + tn + 1) - row0n;
-        lrn = (MODE == MODE_FWD && r < nrowsn) ? __ldg(p.rev_row + row0n + r) : (row0n + r);
       }
+      const bool rvalid = r < nrows;
+      __nv_bfloat16* orow = p.Hn + (int64_t)(row0 + r) * p.ld;
       int cready = -1;                             // highest accumulator chunk already waited for
       // group g takes the slabs s with (s + it) % 2 == g when the slab count is odd (5 at h = 300): the group that
       // got three slabs of this tile gets two of the next, so both drain the accumulator in the same average time.
@@ -341,11 +342,20 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
             cready = c;
           }
           uint32_t v[16];
-          if (!(p.exp_flags & 512)) tmem_ld16(taddr + j * 16, v);
-          const uint32_t a_lo = hbuf + sw128_off(lr, 2 * jj), a_hi = hbuf + sw128_off(lr, 2 * jj + 1);
+          tmem_ld16(taddr + j * 16, v);
           uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
-          if (MODE != MODE_BWD_COPY && !(p.exp_flags & 1024)) { h0 = lds128(a_lo); h1 = lds128(a_hi); }
-          if (!(p.exp_flags & 512)) tmem_wait_ld();
+          if (MODE != MODE_BWD_COPY) { h0 = lds128(hbuf + sw128_off(r, 2 * jj)); h1 = lds128(hbuf + sw128_off(r, 2 * jj + 1)); }
+          uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+          if (MODE == MODE_BWD_LAST && p.add0 != nullptr && rvalid) {
+            // dH_0 = (this step's masked gradient) + the earlier steps' dZ rows (L2 hits: prefetched by the staging warp)
+            const uint4* ap = reinterpret_cast<const uint4*>(p.add0 + (int64_t)(row0 + r) * p.ld + j * 16);
+            a0 = __ldg(ap); a1 = __ldg(ap + 1);
+            if (p.add1 != nullptr) {
+              const uint4* bp = reinterpret_cast<const uint4*>(p.add1 + (int64_t)(row0 + r) * p.ld + j * 16);
+              b0 = __ldg(bp); b1 = __ldg(bp + 1);
+            }
+          }
+          tmem_wait_ld();
           const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
           uint32_t o[8];
 #pragma unroll
@@ -359,7 +369,14 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
                                                      : act_grad_from_out(ACT, p.act_param, bf_lo(hw[qq]));
               const float g1 = MODE == MODE_BWD_LAST ? act_grad_from_pre(ACT, p.act_param, bf_hi(hw[qq]))
                                                      : act_grad_from_out(ACT, p.act_param, bf_hi(hw[qq]));
-              o[qq] = pack_bf2(__uint_as_float(v[2 * qq]) * g0, __uint_as_float(v[2 * qq + 1]) * g1);
+              float z0 = __uint_as_float(v[2 * qq]) * g0, z1 = __uint_as_float(v[2 * qq + 1]) * g1;
+              if constexpr (MODE == MODE_BWD_LAST) {
+                const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                z0 += bf_lo(aw[qq]) + bf_lo(bw[qq]);
+                z1 += bf_hi(aw[qq]) + bf_hi(bw[qq]);
+              }
+              o[qq] = pack_bf2(z0, z1);
               continue;
             }
             float z0 = __uint_as_float(v[2 * qq]) + bf_lo(hw[qq]);
@@ -371,10 +388,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
             if constexpr (ACT == DMPNN_ACT_RELU) o[qq] = act_word<ACT>(pack_bf2(z0, z1), 0.f);  // max after rounding == rounding after max
             else o[qq] = pack_bf2(act_t<ACT>(p.act_param, z0), act_t<ACT>(p.act_param, z1));
           }
-          if (!(p.exp_flags & 128)) {
-            sts128(a_lo, make_uint4(o[0], o[1], o[2], o[3]));
-            sts128(a_hi, make_uint4(o[4], o[5], o[6], o[7]));
-          }
+          if (rvalid) st_global_256(orow + j * 16, o);
           // release accumulator chunk c once this group has read its last column block of it
           const int jn = (jj + 1 < njj) ? j + 1 : 4 * (s + kEpiGroups);   // next block this group will read
           if (jn >= nj || jn / 5 != c) {
@@ -382,62 +396,12 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
             mbar_arrive(bar(B_ACCFREE + c));
           }
         }
-        // all 128 rows of this slab are final -> coalesced copy-out of the valid rows
-        if (eg == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
-        else asm volatile("bar.sync 3, 128;" ::: "memory");
-        const int ncc = 2 * njj;  // valid 16-byte chunks per row in this slab
-        if (MODE == MODE_BWD_LAST && p.add0 != nullptr) {
-          // dH_0 = (this step's masked gradient) + the earlier steps' dZ: coalesced 16-byte loads of the addends
-          // at the output position (L2 hits: prefetched by the staging warp), f32 sum, one rounding.
-#pragma unroll
-          for (int kb = 0; kb < 8; kb += kAddBatch) {
-            uint4 a0[kAddBatch], a1[kAddBatch];
-#pragma unroll
-            for (int k = 0; k < kAddBatch; ++k) {
-              const int pidx = et + 128 * (kb + k);
-              const int rr = pidx >> 3, cc = pidx & 7;
-              a0[k] = make_uint4(0, 0, 0, 0); a1[k] = make_uint4(0, 0, 0, 0);
-              if (rr < nrows && cc < ncc) {
-                const int64_t off = (int64_t)(row0 + rr) * p.ld + s * 64 + cc * 8;
-                a0[k] = __ldg(reinterpret_cast<const uint4*>(p.add0 + off));
-                if (p.add1 != nullptr) a1[k] = __ldg(reinterpret_cast<const uint4*>(p.add1 + off));
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < kAddBatch; ++k) {
-              const int pidx = et + 128 * (kb + k);
-              const int rr = pidx >> 3, cc = pidx & 7;
-              if (rr < nrows && cc < ncc) {
-                const uint4 val = lds128(hbuf + sw128_off(rr, cc));
-                const uint32_t vw[4] = {val.x, val.y, val.z, val.w};
-                const uint32_t w0[4] = {a0[k].x, a0[k].y, a0[k].z, a0[k].w};
-                const uint32_t w1[4] = {a1[k].x, a1[k].y, a1[k].z, a1[k].w};
-                uint32_t ow[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  ow[q] = pack_bf2(bf_lo(vw[q]) + bf_lo(w0[q]) + bf_lo(w1[q]), bf_hi(vw[q]) + bf_hi(w0[q]) + bf_hi(w1[q]));
-                *reinterpret_cast<uint4*>(p.Hn + (int64_t)(row0 + rr) * p.ld + s * 64 + cc * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-              }
-            }
-          }
-        } else if (!(p.exp_flags & 256)) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int pidx = et + 128 * k;
-            const int rr = pidx >> 3, cc = pidx & 7;
-            if (rr < nrows && cc < ncc) {
-              const uint4 val = lds128(hbuf + sw128_off(rr, cc));
-              *reinterpret_cast<uint4*>(p.Hn + (int64_t)(row0 + rr) * p.ld + s * 64 + cc * 8) = val;
-            }
-          }
-        }
-        fence_proxy_async();
+        // this thread has read its H_0 row of the slab: the staging buffer may be refilled
         if (MODE != MODE_BWD_COPY) mbar_arrive(bar(B_HFREE + q));
       }
       if (et == 0) trace_ev(p, it, 8 + eg);
       row0 = row0n;
       nrows = nrowsn;
-      lr = lrn - row0n;
     }
   } else {
     // ===================== message (warps 12..19): thread == tile row == TMEM lane ==================
@@ -453,7 +417,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
     const uint32_t at_base = tmem_base + kTmemAOff + ((uint32_t)(sq * 32) << 16);
     const int nj = p.hp >> 4;
     constexpr bool kCanEmit = FIRST || MODE != MODE_FWD;   // variants that may also write the gathered operand out
-    constexpr bool kNeedRev = MODE != MODE_FWD || FIRST;    // ... and those that need the tile-local rev() table
+    constexpr bool kNeedRev = true;    // every mode gathers through the tile-local rev() table
     int it = 0;
     int t = blockIdx.x;
     int row0 = 0, atom0 = 0, natoms = 0;
@@ -485,26 +449,31 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         const int nrn = __ldg(p.tile_row_ptr + tn + 1) - row0n;
         if (tS < nrn) rvn = __ldg(p.rev_row + row0n + tS) - row0n;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // rp[] (and rvl[]) of this tile are complete
-      // segment (atom) of row r: largest a with rp[a] <= r
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // rp[] and rvl[] of this tile are complete
+      // Forward: A row r is the message of edge r ITSELF = sum over the in-edges of src(r) other than rev(r), i.e. the
+      // siblings of rs = rev(r) inside rs's destination segment, read directly.  Autograd mirror: A row r = sum over the
+      // siblings x of r of dZ[rev(x)].  Either way the row the epilogue produces from accumulator row r is output row r.
+      const bool rin = r < rp[natoms];
+      const int rs = (MODE == MODE_FWD && rin) ? (int)rvl[r] : r;
+      // segment (atom) of row rs: largest a with rp[a] <= rs
       int g0 = 0, d = 0;
-      if (r < rp[natoms]) {
-        int lo = 0, hi = natoms;          // invariant: rp[lo] <= r < rp[hi]
+      if (rin) {
+        int lo = 0, hi = natoms;          // invariant: rp[lo] <= rs < rp[hi]
         while (hi - lo > 1) {
           const int mid = (lo + hi) >> 1;
-          if (rp[mid] <= r) lo = mid; else hi = mid;
+          if (rp[mid] <= rs) lo = mid; else hi = mid;
         }
         g0 = rp[lo];
         d = rp[lo + 1] - g0;
       }
-      // up to three siblings (in-degree <= 4); slot k is row g0+k, skipping r itself
+      // up to three siblings (in-degree <= 4); slot k is row g0+k, skipping rs itself
       uint32_t soff[3];
       int sxr[3];
       bool sval[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         int x = g0 + k;
-        if (x >= r) ++x;
+        if (x >= rs) ++x;
         sval[k] = (k < d - 1) && d <= 4;
         if (!sval[k]) x = r;               // harmless in-bounds address for the predicated-off slot
         if (MODE != MODE_FWD) x = rvl[x];  // autograd mirror: the sibling contributes the row of its reverse edge
@@ -513,8 +482,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       }
       __nv_bfloat16* gout = nullptr;
       if constexpr (kCanEmit) {
-        if (p.G != nullptr && r < rp[natoms])
-          gout = p.G + (int64_t)(row0 + (MODE == MODE_FWD ? (int)rvl[r] : r)) * p.ld;
+        if (p.G != nullptr && rin) gout = p.G + (int64_t)(row0 + r) * p.ld;
       }
       int cur_slab = -1;                              // slab whose AFULL this thread has waited for
       uint32_t left = (1u << p.nslab) - 1u;           // slabs this thread still has to release
@@ -569,7 +537,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
 #pragma unroll
           for (int q = 0; q < 16; ++q) acc[q] = 0.f;
           for (int xx = g0; xx < g0 + d; ++xx) {
-            if (xx == r) continue;
+            if (xx == rs) continue;
             const int x = (MODE != MODE_FWD) ? (int)rvl[xx] : xx;
             const uint4 u0 = s_load<ACT, FIRST>(sbase + sw128_off(x, c0), p.act_param);
             const uint4 u1 = s_load<ACT, FIRST>(sbase + sw128_off(x, c0 + 1), p.act_param);
@@ -582,7 +550,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         }
         tmem_st8(at_base + (uint32_t)(j * 8), o);
         if constexpr (kCanEmit) {
-          // forward: A row r is M[rev(r)] (mixins.py:11-18); backward: A row r is ((S.P) dZ)[r].  One 32-byte
+          // forward: A row r is M[r] (mixins.py:11-18); backward: A row r is ((S.P) dZ)[r].  One 32-byte
           // sector per thread and block (STG.256), consumed by the W_h weight-gradient GEMM.
           if (gout != nullptr) st_global_256(gout + j * 16, o);
         }
@@ -724,12 +692,12 @@ static int launch_step(const char* what, const void* H_prev, const void* H_0, vo
                   "%s: null pointer", what);
   DMPNN_CHECK_ARG(h > 0 && h <= kMaxHp, "%s: h=%lld unsupported (max %d)", what, (long long)h, kMaxHp);
   const int hp = (int)((h + 15) / 16 * 16);
-  DMPNN_CHECK_ARG(ld >= hp && ld % 8 == 0, "%s: ld=%lld must be >= %d and a multiple of 8", what, (long long)ld, hp);
+  DMPNN_CHECK_ARG(ld >= hp && ld % 16 == 0, "%s: ld=%lld must be >= %d and a multiple of 16 (rows are written as 32-byte sectors)", what, (long long)ld, hp);
   DMPNN_CHECK_ARG(n_rows_alloc > 0 && n_tiles >= 0, "%s: bad sizes", what);
   DMPNN_CHECK_ARG(act >= DMPNN_ACT_NONE && act <= DMPNN_ACT_ELU, "%s: bad activation %d", what, act);
   DMPNN_CHECK_ARG((reinterpret_cast<uintptr_t>(H_prev) & 15) == 0 && (reinterpret_cast<uintptr_t>(H_0) & 15) == 0 &&
-                      (reinterpret_cast<uintptr_t>(H_next) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wpk) & 15) == 0,
-                  "%s: buffers must be 16-byte aligned", what);
+                      (reinterpret_cast<uintptr_t>(H_next) & 31) == 0 && (reinterpret_cast<uintptr_t>(Wpk) & 15) == 0,
+                  "%s: inputs must be 16-byte aligned, the output 32-byte aligned", what);
   DMPNN_CHECK_ARG(H_next != H_prev && H_next != H_0, "%s: in-place update not supported", what);
   if (n_tiles == 0) return 0;
   EncodeTiledFn enc = get_encode_fn();

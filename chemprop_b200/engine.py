@@ -257,7 +257,7 @@ def linear_fwd(X1: Tensor, K1: int, W: Tensor, out: Tensor, N: int, *, idx1: Ten
                pad_to: int | None = None):
     lib = _lib.load()
     R = out.shape[0] if R is None else R
-    assert W.dtype == torch.float32 and W.stride(1) == 1 and W.shape[0] == N and W.shape[1] == K1 + K2
+    assert W.dtype == torch.float32 and (W.stride(1) == 1 or W.shape[1] == 1) and W.shape[0] == N and W.shape[1] == K1 + K2
     rc = lib.dmpnn_linear_fwd(
         X1.data_ptr(), _dt(X1), _ld(X1), _ptr(idx1), K1,
         _ptr(X2), _dt(X2) if X2 is not None else F32, _ld(X2) if X2 is not None else 0, _ptr(idx2), K2,
@@ -431,6 +431,59 @@ def wgrad_tc(dY: Tensor, X: Tensor, R: int, N: int, K: int, dW: Tensor, *, accum
     _lib.check(rc, "dmpnn_wgrad_tc_bf16")
 
 
+# ---- fp32-accurate tensor-core GEMMs (3xTF32, csrc/gemm_x3.cu) -------------------------------------------------
+X3_ENABLED = os.environ.get("DMPNN_X3", "1") != "0"          # DMPNN_X3=0: A/B switch (fp32 tier on the SIMT f32 GEMMs)
+
+
+def _x3_ok(cfg: "MPConfig", *dims: int) -> bool:
+    """fp32 tier on the tensor cores: f32 hidden states, fused kernels enabled, every GEMM dimension a multiple of 4
+    (16-byte operand rows)."""
+    return (X3_ENABLED and cfg.fused and cfg.hidden_dtype == torch.float32 and all(d % 4 == 0 and 0 < d <= 4096 for d in dims)
+            and _fused_available())
+
+
+def pack_weight_x3(W: Tensor, transpose: bool = False) -> Tensor:
+    """nn.Linear weight (N x K; with transpose: a K x N matrix used as B[n][k] = W[k][n]) split into tf32 hi / lo parts and
+    laid out for dmpnn_linear_x3."""
+    lib = _lib.load()
+    Wc = W.detach()
+    if Wc.dtype != torch.float32 or Wc.stride(1) != 1:
+        Wc = Wc.float().contiguous()
+    N, K = (Wc.shape[1], Wc.shape[0]) if transpose else (Wc.shape[0], Wc.shape[1])
+    n = C.c_size_t(0)
+    _lib.check(lib.dmpnn_pack_weight_x3_bytes(N, K, C.byref(n)), "dmpnn_pack_weight_x3_bytes")
+    out = torch.empty(n.value, dtype=torch.uint8, device=W.device)
+    _lib.check(lib.dmpnn_pack_weight_x3(Wc.data_ptr(), Wc.stride(0), N, K, 1 if transpose else 0, out.data_ptr(), _stream()),
+               "dmpnn_pack_weight_x3")
+    return out
+
+
+def linear_x3(A: Tensor, K: int, Wpk: Tensor, N: int, out: Tensor, *, idx: Tensor | None = None, bias: Tensor | None = None,
+              res: Tensor | None = None, act: int = ACT_NONE, act_param: float = 0.0, R: int | None = None,
+              pad_to: int | None = None):
+    """out[:, :N] = act(A[idx][:, :K] . W^T + bias + res) with f32 accuracy on the tensor cores; columns [N, pad_to) zeroed."""
+    lib = _lib.load()
+    R = out.shape[0] if R is None else R
+    assert A.dtype == torch.float32 and out.dtype == torch.float32 and (res is None or res.dtype == torch.float32)
+    pad_to = min(_ld(out), out.shape[1]) if pad_to is None else pad_to
+    rc = lib.dmpnn_linear_x3(A.data_ptr(), _ld(A), _ptr(idx), R, K, Wpk.data_ptr(), N, _ptr(bias), _ptr(res),
+                             _ld(res) if res is not None else 0, act, float(act_param), out.data_ptr(), _ld(out),
+                             max(N, min(pad_to, (N + 15) // 16 * 16)), _stream())
+    _lib.check(rc, "dmpnn_linear_x3")
+
+
+def wgrad_x3(dY: Tensor, X: Tensor, R: int, N: int, K: int, dW: Tensor, *, accumulate: bool = False):
+    """dW[n, :K] (+)= sum_r dY[r, n] X[r, :K] with f32 accuracy on the tensor cores."""
+    lib = _lib.load()
+    assert dY.dtype == torch.float32 and X.dtype == torch.float32 and dW.dtype == torch.float32
+    n = C.c_size_t(0)
+    _lib.check(lib.dmpnn_wgrad_x3_workspace_bytes(N, K, C.byref(n)), "dmpnn_wgrad_x3_workspace_bytes")
+    ws = torch.empty(n.value, dtype=torch.uint8, device=dW.device)
+    rc = lib.dmpnn_wgrad_x3(dY.data_ptr(), _ld(dY), X.data_ptr(), _ld(X), R, N, K, dW.data_ptr(), dW.stride(0),
+                            1 if accumulate else 0, ws.data_ptr(), _stream())
+    _lib.check(rc, "dmpnn_wgrad_x3")
+
+
 def column_sum(Y: Tensor, R: int, N: int, out: Tensor, *, accumulate: bool = False):
     lib = _lib.load()
     n = C.c_size_t(0)
@@ -574,6 +627,8 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
     Hprev, first = H0, True  # H^0 = tau(H_0) is applied on load (base.py:200)
     use_fused = cfg.depth > 1 and _fused_step_ok(cfg, lay, h)
     Wpk = pack_weight_bf16(Wh) if use_fused else None
+    x3 = _x3_ok(cfg, h, d_v + h)          # fp32 tier: W_h / W_o GEMMs as 3xTF32 on the tensor cores (f32-accurate)
+    Wh_x3 = pack_weight_x3(Wh) if (x3 and cfg.depth > 1 and nE > 0) else None
     for _ in range(1, cfg.depth):
         if use_fused:
             Hn = _empty_hidden(nE, hp, T, dev)
@@ -598,7 +653,11 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
             Hn = _hidden(nE, hp, T, dev)
             with _StepTimer("unfused_first" if first else "unfused"):
                 bond_message(src_in, lay, h, M, act=fa, act_param=ap)           # mixins.py:11-18
-                linear_fwd(M, h, Wh, Hn, h, bias=bh, res=H0, act=a, act_param=ap, R=nE, pad_to=hp)  # base.py:135-141
+                if Wh_x3 is not None:
+                    with _StepTimer("x3_gemm"):
+                        linear_x3(M, h, Wh_x3, h, Hn, bias=bh, res=H0, act=a, act_param=ap, R=nE, pad_to=hp)
+                else:
+                    linear_fwd(M, h, Wh, Hn, h, bias=bh, res=H0, act=a, act_param=ap, R=nE, pad_to=hp)  # base.py:135-141
             Ms.append(M)
         Hs.append(Hn)
         Hprev, first = Hn, False
@@ -620,13 +679,22 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
         if cfg.dropout_p > 0:
             raise DmpnnError("dropout on the monolithic tier needs the tensor-core path (see dropout_fused_ok)")
         XO = None
-        # M_v = sum_{dst(e)=v} H[e]   (base.py:208-211)
-        Mv = _hidden(nV, hp, T, dev)
-        segment_sum(Hprev, lay.rowptr, nV, h, Mv, act=(a if first else ACT_NONE), act_param=ap, pad_to=hp)
-        # H_v = tau(W_o([V || M_v]))   (base.py:180-182)
-        Hv = torch.empty((nV, h), dtype=T, device=dev)
-        linear_fwd(V, d_v, Wo, Hv, h, X2=Mv, K2=h, bias=bo, act=a, act_param=ap, R=nV, pad_to=h)
-    saved = dict(H0=H0, Hs=Hs, Ms=Ms, Hbars=Hbars, Mv=Mv, Hv=Hv, X0=X0, XO=XO, tc=tc)
+        if x3 and nV > 0:
+            # [V || M_v] assembled once in f32 (torch.cat of base.py:180): V copied in, M_v written in place by the segment sum
+            XO = torch.empty((nV, d_v + h), dtype=T, device=dev)
+            XO[:, :d_v].copy_(V)
+            Mv = XO[:, d_v:]
+            segment_sum(Hprev, lay.rowptr, nV, h, Mv, act=(a if first else ACT_NONE), act_param=ap, pad_to=h)
+            Hv = torch.empty((nV, h), dtype=T, device=dev)
+            linear_x3(XO, d_v + h, pack_weight_x3(Wo), h, Hv, bias=bo, act=a, act_param=ap, R=nV, pad_to=h)
+        else:
+            # M_v = sum_{dst(e)=v} H[e]   (base.py:208-211)
+            Mv = _hidden(nV, hp, T, dev)
+            segment_sum(Hprev, lay.rowptr, nV, h, Mv, act=(a if first else ACT_NONE), act_param=ap, pad_to=hp)
+            # H_v = tau(W_o([V || M_v]))   (base.py:180-182)
+            Hv = torch.empty((nV, h), dtype=T, device=dev)
+            linear_fwd(V, d_v, Wo, Hv, h, X2=Mv, K2=h, bias=bo, act=a, act_param=ap, R=nV, pad_to=h)
+    saved = dict(H0=H0, Hs=Hs, Ms=Ms, Hbars=Hbars, Mv=Mv, Hv=Hv, X0=X0, XO=XO, tc=tc, x3=x3)
     return Hv, saved
 
 
@@ -650,6 +718,7 @@ def bond_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo:
     dbh = torch.zeros(h, **f32) if need_bias[1] else None
     dbo = torch.zeros(h, **f32) if need_bias[2] else None
     tc = bool(saved.get("tc"))
+    x3 = bool(saved.get("x3")) and saved.get("XO") is not None
     if gHv.stride(1) != 1:
         gHv = gHv.contiguous()
     # readout: dY = g * tau'(Y); dW_o = dY^T [V || M_v]; dM_v = dY . W_o[:, d_v:]
@@ -659,11 +728,18 @@ def bond_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo:
         wgrad_tc(dY, saved["XO"], nV, h, d_v + h, dWo)
         if dbo is not None:
             column_sum(dY, nV, h, dbo)
+    elif x3:
+        wgrad_x3(dY, saved["XO"], nV, h, d_v + h, dWo)
+        if dbo is not None:
+            column_sum(dY, nV, h, dbo)
     else:
         linear_wgrad(dY, V, d_v, dWo, h, X2=Mv, K2=h, dbias=dbo, R=nV)
     if tc:
         dMv = _empty_hidden(nV, hp, T, dev)
         linear_tc(dY, h, pack_weight_tc(Wo[:, d_v:], transpose=True), h, dMv, R=nV)
+    elif x3:
+        dMv = _hidden(nV, hp, T, dev)
+        linear_x3(dY, h, pack_weight_x3(Wo[:, d_v:], transpose=True), h, dMv, R=nV, pad_to=hp)
     else:
         WoT = Wo[:, d_v:].t().contiguous()
         dMv = _hidden(nV, hp, T, dev)
@@ -674,8 +750,9 @@ def bond_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo:
             # dH^0[e] = dM_v[dst(e)];  dH_0 = dH^0 * tau'(H_0)
             act_bwd(dMv, H0, nE, h, act=a, act_param=ap, gidx=lay.dst_row, from_preact=True, acc=dH0)
         else:
-            WhT = None if tc else Wh.t().contiguous()
+            WhT = None if (tc or x3) else Wh.t().contiguous()
             WhT_pk = pack_weight_tc(Wh, transpose=True) if tc else None
+            WhT_x3 = pack_weight_x3(Wh, transpose=True) if x3 else None
             dZ = _hidden(nE, hp, T, dev)
             act_bwd(dMv, Hs[-1], nE, h, act=a, act_param=ap, gidx=lay.dst_row, dZ=dZ, acc=dH0)
             for t in range(cfg.depth - 1, 0, -1):
@@ -690,11 +767,18 @@ def bond_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo:
                     wgrad_tc(dZ, M, nE, h, h, dWh, accumulate=True)
                     if dbh is not None:
                         column_sum(dZ, nE, h, dbh, accumulate=True)
+                elif x3:
+                    wgrad_x3(dZ, M, nE, h, h, dWh, accumulate=True)
+                    if dbh is not None:
+                        column_sum(dZ, nE, h, dbh, accumulate=True)
                 else:
                     linear_wgrad(dZ, M, h, dWh, h, dbias=dbh, accumulate=True, R=nE)
                 if tc:
                     dM = _empty_hidden(nE, hp, T, dev)
                     linear_tc(dZ, h, WhT_pk, h, dM, R=nE)
+                elif x3:
+                    dM = _hidden(nE, hp, T, dev)
+                    linear_x3(dZ, h, WhT_x3, h, dM, R=nE, pad_to=hp)
                 else:
                     dM = _hidden(nE, hp, T, dev)
                     linear_fwd(dZ, h, WhT, dM, h, R=nE, pad_to=hp)
@@ -865,6 +949,10 @@ class BondMPFunction(torch.autograd.Function):
         bh_ = None if bh is None else bh.detach().contiguous().float()
         bo_ = None if bo is None else bo.detach().contiguous().float()
         Hv, saved = bond_forward(lay, V, E, Wi_, bi_, Wh_, bh_, Wo_, bo_, cfg, for_backward=any(ctx.needs_input_grad))
+        # `Hv` is the tensor autograd turns into this node's output: keeping THAT object in ctx.saved would be a reference
+        # cycle (node -> saved -> Hv -> grad_fn = node) and the step's activations would live until Python's cyclic GC
+        # runs (GBs per step, cudaMalloc on every step); a detached alias shares the storage without the back edge
+        saved["Hv"] = Hv.detach()
         ctx.lay, ctx.cfg, ctx.saved = lay, cfg, saved
         ctx.VE = (V, E)
         ctx.W = (Wi_, Wh_, Wo_)
@@ -1088,6 +1176,10 @@ class AtomMPFunction(torch.autograd.Function):
         bo_ = None if bo is None else bo.detach().contiguous().float()
         fwd = atom_forward_tc if (_atom_tc_ok(cfg, Wi_.shape[0], V.shape[1], E.shape[1]) and lay.V > 0) else atom_forward
         Hv, saved = fwd(lay, V, E, Wi_, bi_, Wh_, bh_, Wo_, bo_, cfg)
+        # `Hv` is the tensor autograd turns into this node's output: keeping THAT object in ctx.saved would be a reference
+        # cycle (node -> saved -> Hv -> grad_fn = node) and the step's activations would live until Python's cyclic GC
+        # runs (GBs per step, cudaMalloc on every step); a detached alias shares the storage without the back edge
+        saved["Hv"] = Hv.detach()
         ctx.lay, ctx.cfg, ctx.saved = lay, cfg, saved
         ctx.VE = (V, E)
         ctx.W = (Wi_, Wh_, Wo_)

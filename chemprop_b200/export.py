@@ -63,7 +63,7 @@ def segment_agg(H: Tensor, batch: Tensor, scale_mode: int, scale: float) -> Tens
     """Mean / Sum / Norm aggregation (chemprop/nn/agg.py:73-78, 90-95, 112-113), inference only."""
     ptr, _, B = engine.segments_of(batch)
     Hc = H if H.stride(1) == 1 else H.contiguous()
-    out = torch.empty((B, H.shape[1]), dtype=H.dtype, device=H.device)
+    out = torch.empty((B, H.shape[1]), dtype=torch.float32, device=H.device)     # molecule level: always f32 (engine.SegmentAggFunction)
     engine.segment_sum(Hc, ptr, B, H.shape[1], out, scale_mode=int(scale_mode), scale=float(scale), pad_to=H.shape[1])
     return out
 
@@ -71,7 +71,7 @@ def segment_agg(H: Tensor, batch: Tensor, scale_mode: int, scale: float) -> Tens
 @segment_agg.register_fake
 def _segment_agg_fake(H, batch, scale_mode, scale):
     n_mols = torch.library.get_ctx().new_dynamic_size()               # batch.max() + 1: data dependent (agg.py:75)
-    return H.new_empty((n_mols, H.shape[1]))
+    return H.new_empty((n_mols, H.shape[1]), dtype=torch.float32)
 
 
 _PYTREE_DONE = False

@@ -283,7 +283,7 @@ int dmpnn_act_bwd(const void* G, int g_dtype, int64_t ldg, const int32_t* gidx,
  * i.e. message (mixins.py:11-18) + update (base.py:135-141) in ONE launch, one CTA per SM,
  * molecule-aligned 128-row tiles from dmpnn_layout_build.  g = tau when first_step!=0
  * (H_prev = H_0 and H^0 = tau(H_0) is recomputed on load), identity otherwise.
- * Wpk is W_h packed by dmpnn_pack_weight_bf16.  Requires ld % 8 == 0, h <= 304, all tiles
+ * Wpk is W_h packed by dmpnn_pack_weight_bf16.  Requires ld % 16 == 0, a 32-byte aligned H_next, h <= 304, all tiles
  * <= 128 rows, DMPNN_FLAG_REV_INVOLUTION.  Returns <0 (and does nothing) otherwise.
  * M_out (nullable; first_step only; bf16, same ld, 32-byte aligned, ld % 16 == 0): also stores the message
  * M^1[e] (mixins.py:11-18) that the step consumed, saved for the W_h gradient instead of being recomputed.
@@ -344,6 +344,28 @@ int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, void* H_next
                                const int32_t* rowptr, const int32_t* rev_row,
                                const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
                                int act, float act_param, int first_step, void* M_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * fp32-ACCURATE tensor-core GEMMs of the fp32 tier (csrc/gemm_x3.cu): every product is three
+ * tcgen05.mma.kind::tf32 passes over an error-free hi / lo split of both operands, f32 accumulation in TMEM --
+ * the accuracy of an f32 FMA chain (the reference's ATen sgemm on base.py:135-141, 180-182) at tensor-core
+ * speed; hidden size up to 4096 (BASELINE config 3: h = 600, depth 6).
+ *   dmpnn_pack_weight_x3  nn.Linear weight W (N x K f32, row stride ldw; transpose != 0: B[n][k] = W[k][n]) ->
+ *                         pre-split {hi, lo} shared-memory images per (128-column pass, 32-wide k slab)
+ *   dmpnn_linear_x3       C[r, 0:N] = act(A[row_idx ? row_idx[r] : r, 0:K] . B^T + bias + res[r, 0:N]);  A, C, res f32
+ *                         row-major; K % 4 == 0, lda / ldc / ldres % 4 == 0, 16-byte aligned bases;
+ *                         C columns [N, min(ldc_pad, pad16(N))) are written as zeros.
+ *   dmpnn_wgrad_x3        dW[n, 0:K] (+)= sum_r dY[r, n] * X[r, 0:K];  dY: R x N, X: R x K f32 row-major, N, K, lddy,
+ *                         ldx % 4 == 0; deterministic two-pass reduction; workspace from dmpnn_wgrad_x3_workspace_bytes.
+ * ------------------------------------------------------------------------------------- */
+int dmpnn_pack_weight_x3_bytes(int64_t N, int64_t K, size_t* bytes);
+int dmpnn_pack_weight_x3(const float* W, int64_t ldw, int64_t N, int64_t K, int transpose, void* Wpk, void* stream);
+int dmpnn_linear_x3(const float* A, int64_t lda, const int32_t* row_idx, int64_t R, int64_t K, const void* Wpk,
+                    int64_t N, const float* bias, const float* res, int64_t ldres, int act, float act_param,
+                    float* C, int64_t ldc, int64_t ldc_pad, void* stream);
+int dmpnn_wgrad_x3_workspace_bytes(int64_t N, int64_t K, size_t* bytes);
+int dmpnn_wgrad_x3(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t R, int64_t N, int64_t K,
+                   float* dW, int64_t lddw, int accumulate, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,7 @@ _GPU_ORDER = (
                             "test_multi_tile")),
     ("test_gpu_training.py", ("",)),
     ("test_gpu_head.py", ("",)),
+    ("test_gpu_x3.py", ("",)),
     ("test_gpu_fused_step.py", ("",)),
     ("test_gpu_linear_tc.py", ("",)),
     ("test_gpu_parity.py", ("",)),

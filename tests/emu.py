@@ -228,6 +228,36 @@ def wgrad_tc(dY, X, R, N, K, dW, *, accumulate=False):
         dW[:N, :K] = upd
 
 
+def pack_weight_x3(W, transpose=False):
+    """fp32-accurate tier: the 'packed' weight of the emulation is B[n][k] in f32 (the hi / lo split is exact to 2^-22)"""
+    W = W.detach().float()
+    return (W.t() if transpose else W).contiguous()
+
+
+def linear_x3(A, K, Wpk, N, out, *, idx=None, bias=None, res=None, act=ACT_NONE, act_param=0.0, R=None, pad_to=None):
+    R = out.shape[0] if R is None else R
+    assert A.dtype == torch.float32 and out.dtype == torch.float32 and Wpk.shape == (N, K) and K % 4 == 0
+    Y = _rows(A, idx, R, K) @ Wpk.t()
+    if bias is not None:
+        Y = Y + bias.float()
+    if res is not None:
+        Y = Y + res[:R, :N].float()
+    out[:R, :N] = _act(Y, act, act_param)
+    pad_to = min(out.stride(0), out.shape[1]) if pad_to is None else pad_to
+    pad_to = max(N, min(pad_to, (N + 15) // 16 * 16))
+    if pad_to > N:
+        out[:R, N:pad_to] = 0
+
+
+def wgrad_x3(dY, X, R, N, K, dW, *, accumulate=False):
+    assert dY.dtype == torch.float32 and X.dtype == torch.float32 and N % 4 == 0 and K % 4 == 0
+    upd = dY[:R, :N].t() @ X[:R, :K]
+    if accumulate:
+        dW[:N, :K] += upd
+    else:
+        dW[:N, :K] = upd
+
+
 def column_sum(Y, R, N, out, *, accumulate=False):
     v = Y[:R, :N].float().sum(0)
     if accumulate:
@@ -338,9 +368,11 @@ def patch_engine(monkeypatch):
     """Route engine.py's kernel wrappers to the emulations above (host-logic tests only)."""
     for name in ("linear_fwd", "linear_wgrad", "segment_sum", "segment_bcast", "bond_message", "rev_average", "act_bwd",
                  "build_layout", "pack_weight_tc", "pack_weight_bf16", "concat_bf16", "linear_tc", "wgrad_tc", "column_sum",
+                 "pack_weight_x3", "linear_x3", "wgrad_x3",
                  "bond_step_fused", "bond_step_bwd_fused", "bond_message_bwd_masked", "sum_act_bwd", "scale_mask_"):
         monkeypatch.setattr(engine, name, globals()[name])
     monkeypatch.setattr(engine, "_require_cuda", lambda *ts: None)
+    monkeypatch.setattr(engine, "_fused_available", lambda: True)
     import chemprop_b200.nn.agg as agg_mod
     import chemprop_b200.nn.constrainer as con_mod
 
