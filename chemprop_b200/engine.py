@@ -1087,12 +1087,13 @@ def atom_forward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tenso
     Hprev, first = H0, True
     for _ in range(1, cfg.depth):
         XA = torch.empty((rows, ka), dtype=T, device=dev)   # [sum_{u in N(v)} Ha[u] || sum_in E]   (mixins.py:25-30)
-        segment_sum(Hprev, lay.rowptr, nV, h, XA[:, :h], idx=lay.src_row, act=(a if first else ACT_NONE), act_param=ap,
-                    pad_to=h)
-        if d_e > 0:
-            concat_bf16(SE, d_e, XA[:, h:], nV, width=d_e)
-        Hn = _empty_hidden(nV, hp, T, dev)
-        linear_tc(XA, h + d_e, Whpk, h, Hn, bias=bh, res=H0, act=a, act_param=ap, R=nV)       # base.py:135-141
+        with _StepTimer("atom_step_first" if first else "atom_step"):
+            segment_sum(Hprev, lay.rowptr, nV, h, XA[:, :h], idx=lay.src_row, act=(a if first else ACT_NONE), act_param=ap,
+                        pad_to=h)
+            if d_e > 0:
+                concat_bf16(SE, d_e, XA[:, h:], nV, width=d_e)
+            Hn = _empty_hidden(nV, hp, T, dev)
+            linear_tc(XA, h + d_e, Whpk, h, Hn, bias=bh, res=H0, act=a, act_param=ap, R=nV)   # base.py:135-141
         Hs.append(Hn)
         XAs.append(XA)
         Hprev, first = Hn, False

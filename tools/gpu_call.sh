@@ -33,6 +33,30 @@ for s in $STEPS; do
       timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_linear_tc|k_wgrad_tc" -s 18 -c 6 \
         -o "$OUT/gemm" -f python bench.py --steps 1 --warmup 3 --no-cpu --no-dataset > "$OUT/ncu_gemm.log" 2>&1
       echo "ncu gemm rc=$?" ;;
+    x3)
+      for k in linear_x3_vs_f64 transposed wgrad_x3_vs_f64 deterministic; do
+        timeout 600 python -m pytest tests/test_gpu_x3.py -m gpu -q -x -p no:cacheprovider -k "$k" > "$OUT/pytest_x3_$k.log" 2>&1
+        echo "x3[$k] rc=$?"; tail -4 "$OUT/pytest_x3_$k.log"
+      done ;;
+    x3san)
+      timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_x3.py -m gpu -q -x -p no:cacheprovider \
+        -k "linear_x3_vs_f64 and 300-300-300" > "$OUT/san_linear.log" 2>&1
+      echo "san linear rc=$?"; grep -m 30 -A12 "Invalid\|Error\|error" "$OUT/san_linear.log" | head -80
+      timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_x3.py -m gpu -q -x -p no:cacheprovider \
+        -k "wgrad_x3_vs_f64 and 31-300-372" > "$OUT/san_wgrad.log" 2>&1
+      echo "san wgrad rc=$?"; grep -m 30 -A12 "Invalid\|Error\|error" "$OUT/san_wgrad.log" | head -80 ;;
+    tests_nox3)
+      DMPNN_X3=0 timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider -rfEX --deselect tests/test_gpu_x3.py > "$OUT/pytest_gpu_nox3.log" 2>&1
+      echo "pytest (DMPNN_X3=0) rc=$?"; tail -30 "$OUT/pytest_gpu_nox3.log" ;;
+    bench_c4)
+      timeout 600 python bench.py --config C4 --steps 10 --warmup 3 > "$OUT/bench_c4.json" 2> "$OUT/bench_c4.err"
+      echo "bench C4 rc=$?"; cat "$OUT/bench_c4.json"; tail -5 "$OUT/bench_c4.err" ;;
+    bench_c3)
+      timeout 900 python bench.py --config C3 --steps 3 --warmup 3 > "$OUT/bench_c3.json" 2> "$OUT/bench_c3.err"
+      echo "bench C3 rc=$?"; cat "$OUT/bench_c3.json"; tail -5 "$OUT/bench_c3.err" ;;
+    bench_c5)
+      timeout 900 python bench.py --config C5 --steps 3 --warmup 3 > "$OUT/bench_c5.json" 2> "$OUT/bench_c5.err"
+      echo "bench C5 rc=$?"; cat "$OUT/bench_c5.json"; tail -5 "$OUT/bench_c5.err" ;;
     native)
       ./tests/native/fused_step_harness 10000 300 2 2>&1 | tee "$OUT/native_fused_step.log" ;;
     *) echo "unknown step $s" ;;
