@@ -23,8 +23,8 @@
 // the kernel on the tensor pipe rather than on L2 bandwidth (the pipe needs ~100 flop / L2 byte at 3 passes of tf32).
 //
 // k_wgrad_x3 -- CTA (n tile of 128, k tile of <= 256, row slot): D[128 x 256] (TMEM) += dY_blk^T . X_blk over 32-row
-// blocks; both operands are MN-major (the contraction runs over rows), written by the producers into the canonical
-// MN-major SWIZZLE_128B atom layout; partial sums per CTA, fixed-order reduce (deterministic).
+// blocks; both operands are MN-major (the contraction runs over rows), written by the producers into the one layout the
+// tensor core transposes 32-bit operands from (SWIZZLE_128B_BASE32B); partial sums per CTA, fixed-order reduce (deterministic).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -68,15 +68,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
-// MN-major SWIZZLE_128B operand: 8 contraction rows x 128 B per atom, atoms along MN `lbo` bytes apart, 8-row groups
-// along K 1024 B apart
-__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr, uint32_t lbo) {
+// MN-major tf32 operand.  32-bit operands transposed by the tensor core exist in ONE shared-memory layout only,
+// SWIZZLE_128B_BASE32B (descriptor layout type 1): rows of the contraction index at a 128-byte pitch (32 tf32 along MN),
+// atoms of FOUR rows (512 B) inside which the 32-byte chunk index is XORed with (row & 3) -- Swizzle<2,5,2> on byte
+// addresses; atoms along K `sbo` = 512 B apart, 32-element blocks along MN `lbo` bytes apart.  One k step of the
+// instruction (8 tf32) covers two atoms.
+__device__ __forceinline__ uint64_t desc_mn_sw128_32b(uint32_t saddr, uint32_t lbo) {
   uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(512 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;
   return d;
+}
+// byte offset of 16-byte chunk `c` (0..7) of contraction row `r` inside one 32-element MN block of that layout
+__device__ __forceinline__ uint32_t mn32b_off(int r, int c) {
+  return (uint32_t)(r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4)));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -401,8 +408,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_x3(Params p) {
         const uint32_t stg = sbase + st * kStageBytes;
 #pragma unroll
         for (int kk = 0; kk < kRows / 8; ++kk) {        // k step = 8 contraction rows = one 1024-byte group of every atom
-          const uint64_t ahi = desc_mn_sw128(stg + kOffAhi + kk * 1024, kAtomBytes), alo = desc_mn_sw128(stg + kOffAlo + kk * 1024, kAtomBytes);
-          const uint64_t bhi = desc_mn_sw128(stg + kOffBhi + kk * 1024, kAtomBytes), blo = desc_mn_sw128(stg + kOffBlo + kk * 1024, kAtomBytes);
+          const uint64_t ahi = desc_mn_sw128_32b(stg + kOffAhi + kk * 1024, kAtomBytes), alo = desc_mn_sw128_32b(stg + kOffAlo + kk * 1024, kAtomBytes);
+          const uint64_t bhi = desc_mn_sw128_32b(stg + kOffBhi + kk * 1024, kAtomBytes), blo = desc_mn_sw128_32b(stg + kOffBlo + kk * 1024, kAtomBytes);
           umma_tf32(tmem_base, alo, bhi, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
           umma_tf32(tmem_base, ahi, blo, idesc, 1u);
           umma_tf32(tmem_base, ahi, bhi, idesc, 1u);
@@ -467,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_x3(Params p) {
         uint4 hi, lo;
         split4(x[i], hi, lo);
         const int cb = cc < 32 ? cc : cc - 32;            // 16-byte chunk along MN inside the operand
-        const uint32_t off = (uint32_t)(cb >> 3) * kAtomBytes + sw128_off(rr, cb & 7);
+        const uint32_t off = (uint32_t)(cb >> 3) * kAtomBytes + mn32b_off(rr, cb & 7);
         if (cc < 32) {
           sts128(stg + kOffAhi + off, hi);
           sts128(stg + kOffAlo + off, lo);

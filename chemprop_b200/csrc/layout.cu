@@ -348,6 +348,75 @@ extern "C" int dmpnn_layout_build(const int64_t* edge_index, const int64_t* rev_
   return 0;
 }
 
+// Work table of the fused depth step for batches holding molecules of more than 128 directed edges: every tile of the
+// layout with <= 128 rows becomes one work item (flag 0), every larger tile -- one oversized molecule -- is cut into
+// ceil(rows / 128) windows of <= 128 consecutive rows (flag 1: siblings / reverse edges may lie in another window, the
+// kernel gathers them from global memory).  One block; tiles are scanned in chunks of 1024 (fixed order).
+__global__ void __launch_bounds__(1024)
+k_work_table(const int32_t* __restrict__ tile_row_ptr, const int32_t* __restrict__ tile_atom_ptr, int n_tiles,
+             int32_t* __restrict__ work_row_ptr, int32_t* __restrict__ work_atom_ptr, int8_t* __restrict__ work_flag,
+             int32_t* __restrict__ n_work) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < n_tiles; t0 += 1024) {
+    const int t = t0 + tid;
+    int r0 = 0, nr = 0, cnt = 0;
+    if (t < n_tiles) {
+      r0 = tile_row_ptr[t];
+      nr = tile_row_ptr[t + 1] - r0;
+      cnt = nr > 128 ? (nr + 127) >> 7 : 1;
+    }
+    int incl = cnt;                                   // inclusive scan inside the warp
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += v;
+      }
+      s_warp[lane] = w;                               // inclusive totals of the warps
+    }
+    __syncthreads();
+    const int base = s_base + (warp > 0 ? s_warp[warp - 1] : 0) + incl - cnt;
+    if (t < n_tiles) {
+      const int a0 = tile_atom_ptr[t];
+      for (int k = 0; k < cnt; ++k) {
+        work_row_ptr[base + k] = r0 + 128 * k;
+        work_atom_ptr[base + k] = a0;
+        work_flag[base + k] = cnt > 1 ? 1 : 0;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_base += s_warp[31];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int n = s_base;
+    work_row_ptr[n] = n_tiles > 0 ? tile_row_ptr[n_tiles] : 0;
+    work_atom_ptr[n] = n_tiles > 0 ? tile_atom_ptr[n_tiles] : 0;
+    n_work[0] = n;
+  }
+}
+
+extern "C" int dmpnn_work_table_build(const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
+                                      int32_t* work_row_ptr, int32_t* work_atom_ptr, int8_t* work_flag, int32_t* n_work,
+                                      void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DMPNN_CHECK_ARG(tile_row_ptr && tile_atom_ptr && work_row_ptr && work_atom_ptr && work_flag && n_work && n_tiles >= 0,
+                  "work_table_build: bad args");
+  k_work_table<<<1, 1024, 0, st>>>(tile_row_ptr, tile_atom_ptr, (int)n_tiles, work_row_ptr, work_atom_ptr, work_flag, n_work);
+  DMPNN_CHECK_LAUNCH("work_table_build", 1);
+  return 0;
+}
+
 extern "C" int dmpnn_sorted_index_to_ptr(const int64_t* index, int64_t n, int64_t n_seg, int32_t* ptr,
                                          int32_t* status, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;

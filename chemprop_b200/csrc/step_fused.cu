@@ -68,8 +68,12 @@ struct Params {
   const float* bias;
   const int32_t* rowptr;
   const int32_t* rev_row;
-  const int32_t* tile_row_ptr;
-  const int32_t* tile_atom_ptr;
+  const int32_t* tile_row_ptr;   // work items: the layout's tiles, or (work_flag != nullptr) the work table in which
+  const int32_t* tile_atom_ptr;  // every tile of more than 128 rows is cut into 128-row windows
+  const int8_t* work_flag;       // nullable; 1 = window of a multi-window molecule: siblings / rev() partners may lie outside
+  const int32_t* n_work_dev;     // nullable; number of work items when the work table is in use (device scalar)
+  const int32_t* dst_row;        // destination atom of every row (needed by the non-local windows only)
+  const __nv_bfloat16* Hprev;    // the H tile's matrix again, for the non-local windows' global gathers
   int n_tiles, h, hp, nslab, ksteps_last, nchunks;
   float act_param;
   int exp_flags;  // timing experiments only (DMPNN_EXP env var); 0 in production
@@ -168,14 +172,15 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   const bool alt_groups = p.nslab >= 3 && (p.nslab & 1);   // alternate the epilogue groups' slab parity per tile
+  const int n_items = p.n_work_dev ? __ldg(p.n_work_dev) : p.n_tiles;   // work items of this launch (uniform over the grid)
 
   if (warp == 0) {
     // ===================== TMA producer: H_prev tile -> shared memory (single buffer) =====================
     int it = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x; t < n_items; t += gridDim.x, ++it) {
       const int row0 = __ldg(p.tile_row_ptr + t);
       const int t2 = t + gridDim.x;
-      const int row2 = (t2 < p.n_tiles && !(p.exp_flags & 2048)) ? __ldg(p.tile_row_ptr + t2) : -1;
+      const int row2 = (t2 < n_items && !(p.exp_flags & 2048)) ? __ldg(p.tile_row_ptr + t2) : -1;
       // slab s of this tile is loaded as soon as the message warps have left slab s of the previous tile: the load
       // of the leading slabs overlaps the gather of the trailing ones (one shared-memory tile, no exposed latency)
       for (int s = 0; s < p.nslab; ++s) {
@@ -195,7 +200,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
     // ===================== TMA producer: W_h stages (pre-packed smem images) =====================
     // a stage = the W_h rows of one 80-column output chunk for k slabs {0,1,2} or {3,4} (contiguous in the image)
     uint32_t ws = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
       for (int s0 = 0; s0 < p.nslab; s0 += kWHalfSlabs) {         // k half (outer) ...
         const int ns = min(kWHalfSlabs, p.nslab - s0);
         for (int c = 0; c < p.nchunks; ++c, ++ws) {               // ... x 80-column output chunk (inner)
@@ -217,7 +222,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
     // D[128 x hp] (TMEM cols 0..) += A (TMEM cols kTmemAOff.., written by the message warps) . W_h^T (smem ring)
     uint32_t ws = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x; t < n_items; t += gridDim.x, ++it) {
       int half = 0;
       for (int s0 = 0; s0 < p.nslab; s0 += kWHalfSlabs, ++half) {     // pass over one k half of the A tile
         const int ns = min(kWHalfSlabs, p.nslab - s0);
@@ -261,10 +266,10 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
     // ===================== TMA producer: H_0 slabs -> staging buffers (two per epilogue group) ==========
     uint32_t cnt[2] = {0u, 0u};   // slabs handed to each group so far
     int it = 0;
-    for (int t = blockIdx.x; MODE != MODE_BWD_COPY && t < p.n_tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x; MODE != MODE_BWD_COPY && t < n_items; t += gridDim.x, ++it) {
       const int row0 = __ldg(p.tile_row_ptr + t);
       const int tn = t + gridDim.x;
-      const int rown = (tn < p.n_tiles && !(p.exp_flags & 2048)) ? __ldg(p.tile_row_ptr + tn) : -1;
+      const int rown = (tn < n_items && !(p.exp_flags & 2048)) ? __ldg(p.tile_row_ptr + tn) : -1;
       if (rown >= 0 && elect_one())
         for (int s = 0; s < p.nslab; ++s) tma_prefetch_2d(&tmapH0, s * 64, rown);
       __syncwarp();
@@ -309,15 +314,15 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
     int it = 0;
     int t = blockIdx.x;
     int row0 = 0, nrows = 0;
-    if (t < p.n_tiles) {
+    if (t < n_items) {
       row0 = __ldg(p.tile_row_ptr + t);
       nrows = __ldg(p.tile_row_ptr + t + 1) - row0;
     }
-    for (; t < p.n_tiles; t += gridDim.x, ++it) {
+    for (; t < n_items; t += gridDim.x, ++it) {
       // prefetch the next tile's metadata (hides the dependent global loads behind this tile's work)
       const int tn = t + gridDim.x;
       int row0n = 0, nrowsn = 0;
-      if (tn < p.n_tiles) {
+      if (tn < n_items) {
         row0n = __ldg(p.tile_row_ptr + tn);
         nrowsn = __ldg(p.tile_row_ptr + tn + 1) - row0n;
       }
@@ -421,31 +426,37 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
     int it = 0;
     int t = blockIdx.x;
     int row0 = 0, atom0 = 0, natoms = 0;
-    if (t < p.n_tiles) {
+    bool far = false;                        // this work item is a window of a multi-window molecule
+    if (t < n_items) {
       row0 = __ldg(p.tile_row_ptr + t);
       atom0 = __ldg(p.tile_atom_ptr + t);
       natoms = __ldg(p.tile_atom_ptr + t + 1) - atom0;
+      far = p.work_flag != nullptr && __ldg(p.work_flag + t) != 0;
+      if (far) natoms = 0;
       if (tS <= natoms) s_rowptr[tS] = __ldg(p.rowptr + atom0 + tS) - row0;
       if (kNeedRev && tS < 128) {
         const int nr = __ldg(p.tile_row_ptr + t + 1) - row0;
         s_revl[tS] = (int16_t)(tS < nr ? __ldg(p.rev_row + row0 + tS) - row0 : tS);
       }
     }
-    for (; t < p.n_tiles; t += gridDim.x, ++it) {
+    for (; t < n_items; t += gridDim.x, ++it) {
       const int b = it & 1;
       const int32_t* rp = s_rowptr + b * 132;
       const int16_t* rvl = s_revl + b * 128;
       // prefetch next tile's rowptr slice into a register
       const int tn = t + gridDim.x;
       int row0n = 0, atom0n = 0, natomsn = 0, rpn = 0;
-      if (tn < p.n_tiles) {
+      bool farn = false;
+      if (tn < n_items) {
         row0n = __ldg(p.tile_row_ptr + tn);
         atom0n = __ldg(p.tile_atom_ptr + tn);
         natomsn = __ldg(p.tile_atom_ptr + tn + 1) - atom0n;
+        farn = p.work_flag != nullptr && __ldg(p.work_flag + tn) != 0;
+        if (farn) natomsn = 0;
         if (tS <= natomsn) rpn = __ldg(p.rowptr + atom0n + tS) - row0n;
       }
       int rvn = tS;
-      if (kNeedRev && tn < p.n_tiles && tS < 128) {
+      if (kNeedRev && tn < n_items && tS < 128) {
         const int nrn = __ldg(p.tile_row_ptr + tn + 1) - row0n;
         if (tS < nrn) rvn = __ldg(p.rev_row + row0n + tS) - row0n;
       }
@@ -453,11 +464,23 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       // Forward: A row r is the message of edge r ITSELF = sum over the in-edges of src(r) other than rev(r), i.e. the
       // siblings of rs = rev(r) inside rs's destination segment, read directly.  Autograd mirror: A row r = sum over the
       // siblings x of r of dZ[rev(x)].  Either way the row the epilogue produces from accumulator row r is output row r.
-      const bool rin = r < rp[natoms];
-      const int rs = (MODE == MODE_FWD && rin) ? (int)rvl[r] : r;
+      // A window of a molecule with more than 128 rows ("far"): the segment of rs and the rows it needs may lie outside the
+      // window, so everything is looked up in ABSOLUTE rows (rev_row / dst_row / rowptr) and gathered from global memory
+      // (L2 hits: the molecule's other windows are in flight on neighbouring CTAs); the shared-memory tile is not read.
+      const int wrows = far ? (__ldg(p.tile_row_ptr + t + 1) - row0) : 0;
+      const bool rin = far ? (r < wrows) : (r < rp[natoms]);
+      int rs = (MODE == MODE_FWD && rin && !far) ? (int)rvl[r] : r;
       // segment (atom) of row rs: largest a with rp[a] <= rs
       int g0 = 0, d = 0;
-      if (rin) {
+      const __nv_bfloat16* fsrc[3] = {p.Hprev, p.Hprev, p.Hprev};   // far: the (<= 3) sibling rows in global memory
+      int g0a = 0, rsa = 0;                                          // far: absolute segment start / skipped row
+      if (far && rin) {
+        rsa = row0 + r;
+        if (MODE == MODE_FWD) rsa = __ldg(p.rev_row + rsa);
+        const int v = __ldg(p.dst_row + rsa);
+        g0a = __ldg(p.rowptr + v);
+        d = __ldg(p.rowptr + v + 1) - g0a;
+      } else if (rin) {
         int lo = 0, hi = natoms;          // invariant: rp[lo] <= rs < rp[hi]
         while (hi - lo > 1) {
           const int mid = (lo + hi) >> 1;
@@ -475,8 +498,17 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         int x = g0 + k;
         if (x >= rs) ++x;
         sval[k] = (k < d - 1) && d <= 4;
+        if (far) {
+          int xa = g0a + k;
+          if (xa >= rsa) ++xa;
+          if (sval[k]) {
+            if (MODE != MODE_FWD) xa = __ldg(p.rev_row + xa);
+            fsrc[k] = p.Hprev + (int64_t)xa * p.ld;
+          }
+          x = r;
+        }
         if (!sval[k]) x = r;               // harmless in-bounds address for the predicated-off slot
-        if (MODE != MODE_FWD) x = rvl[x];  // autograd mirror: the sibling contributes the row of its reverse edge
+        if (MODE != MODE_FWD && !far) x = rvl[x];  // autograd mirror: the sibling contributes the row of its reverse edge
         soff[k] = (uint32_t)((x >> 3) * 1024 + (x & 7) * 128);
         sxr[k] = x & 7;
       }
@@ -517,8 +549,14 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
             u[k][0] = make_uint4(0, 0, 0, 0);
             u[k][1] = make_uint4(0, 0, 0, 0);
             if (sval[k]) {
-              u[k][0] = s_load<ACT, FIRST>(sbase + soff[k] + (uint32_t)((c0 ^ sxr[k]) << 4), p.act_param);
-              u[k][1] = s_load<ACT, FIRST>(sbase + soff[k] + (uint32_t)(((c0 + 1) ^ sxr[k]) << 4), p.act_param);
+              if (far) {
+                const uint4* gp = reinterpret_cast<const uint4*>(fsrc[k] + j * 16);
+                u[k][0] = g_load<ACT, FIRST>(gp, p.act_param);
+                u[k][1] = g_load<ACT, FIRST>(gp + 1, p.act_param);
+              } else {
+                u[k][0] = s_load<ACT, FIRST>(sbase + soff[k] + (uint32_t)((c0 ^ sxr[k]) << 4), p.act_param);
+                u[k][1] = s_load<ACT, FIRST>(sbase + soff[k] + (uint32_t)(((c0 + 1) ^ sxr[k]) << 4), p.act_param);
+              }
             }
           }
 #pragma unroll
@@ -536,11 +574,19 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
           float acc[16];
 #pragma unroll
           for (int q = 0; q < 16; ++q) acc[q] = 0.f;
-          for (int xx = g0; xx < g0 + d; ++xx) {
-            if (xx == rs) continue;
-            const int x = (MODE != MODE_FWD) ? (int)rvl[xx] : xx;
-            const uint4 u0 = s_load<ACT, FIRST>(sbase + sw128_off(x, c0), p.act_param);
-            const uint4 u1 = s_load<ACT, FIRST>(sbase + sw128_off(x, c0 + 1), p.act_param);
+          for (int xx = (far ? g0a : g0); xx < (far ? g0a : g0) + d; ++xx) {
+            if (xx == (far ? rsa : rs)) continue;
+            uint4 u0, u1;
+            if (far) {
+              const int xa = (MODE != MODE_FWD) ? __ldg(p.rev_row + xx) : xx;
+              const uint4* gp = reinterpret_cast<const uint4*>(p.Hprev + (int64_t)xa * p.ld + j * 16);
+              u0 = g_load<ACT, FIRST>(gp, p.act_param);
+              u1 = g_load<ACT, FIRST>(gp + 1, p.act_param);
+            } else {
+              const int x = (MODE != MODE_FWD) ? (int)rvl[xx] : xx;
+              u0 = s_load<ACT, FIRST>(sbase + sw128_off(x, c0), p.act_param);
+              u1 = s_load<ACT, FIRST>(sbase + sw128_off(x, c0 + 1), p.act_param);
+            }
             const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
             for (int q = 0; q < 8; ++q) { acc[2 * q] += bf_lo(w[q]); acc[2 * q + 1] += bf_hi(w[q]); }
@@ -563,9 +609,9 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       for (int q = cur_pass; q < npass; ++q) mbar_arrive(bar(B_AREADY + q));   // every thread arrives once per pass
       if (tS == 0) trace_ev(p, it, 2);
       // publish the next tile's rowptr slice (other buffer; readers of it finished a tile ago)
-      if (tn < p.n_tiles && tS <= natomsn) s_rowptr[(b ^ 1) * 132 + tS] = rpn;
-      if (kNeedRev && tn < p.n_tiles && tS < 128) s_revl[(b ^ 1) * 128 + tS] = (int16_t)rvn;
-      row0 = row0n; atom0 = atom0n; natoms = natomsn;
+      if (tn < n_items && tS <= natomsn) s_rowptr[(b ^ 1) * 132 + tS] = rpn;
+      if (kNeedRev && tn < n_items && tS < 128) s_revl[(b ^ 1) * 128 + tS] = (int16_t)rvn;
+      row0 = row0n; atom0 = atom0n; natoms = natomsn; far = farn;
     }
   }
 
@@ -678,7 +724,10 @@ extern "C" int dmpnn_pack_weight_bf16(const float* W, int64_t ldw, int64_t N, in
 static int launch_step(const char* what, const void* H_prev, const void* H_0, void* H_next, int64_t ld, int64_t n_rows_alloc,
                        int64_t h, const void* Wpk, const float* bias, const int32_t* rowptr, const int32_t* rev_row,
                        const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles, int act, float act_param,
-                       int first_step, int mode, void* gather_out, const void* add0, const void* add1, cudaStream_t st) {
+                       int first_step, int mode, void* gather_out, const void* add0, const void* add1,
+                       const int8_t* work_flag, const int32_t* n_work_dev, const int32_t* dst_row, cudaStream_t st) {
+  DMPNN_CHECK_ARG((work_flag == nullptr) == (n_work_dev == nullptr) && (work_flag == nullptr || dst_row != nullptr),
+                  "%s: work_flag, n_work_dev and dst_row come together (dmpnn_work_table_build)", what);
   DMPNN_CHECK_ARG((add0 == nullptr && add1 == nullptr) || (mode == MODE_BWD_LAST && add0 != nullptr),
                   "%s: addends need y_is_preact (and add0 before add1)", what);
   DMPNN_CHECK_ARG(((reinterpret_cast<uintptr_t>(add0) | reinterpret_cast<uintptr_t>(add1)) & 15) == 0,
@@ -721,6 +770,10 @@ static int launch_step(const char* what, const void* H_prev, const void* H_0, vo
   p.rev_row = rev_row;
   p.tile_row_ptr = tile_row_ptr;
   p.tile_atom_ptr = tile_atom_ptr;
+  p.work_flag = work_flag;
+  p.n_work_dev = n_work_dev;
+  p.dst_row = dst_row;
+  p.Hprev = (const __nv_bfloat16*)H_prev;
   p.n_tiles = (int)n_tiles;
   p.h = (int)h;
   p.hp = hp;
@@ -746,7 +799,7 @@ static int launch_step(const char* what, const void* H_prev, const void* H_0, vo
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
+  const int grid = (work_flag != nullptr || n_tiles >= sm_count) ? sm_count : (int)n_tiles;
   cudaError_t e = cudaErrorInvalidValue;
   if (mode == MODE_FWD) {
 #define DMPNN_LAUNCH_ACT(A)                                                          \
@@ -790,19 +843,22 @@ extern "C" int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, v
                                           int64_t n_rows_alloc, int64_t h, const void* Wpk, const float* bias,
                                           const int32_t* rowptr, const int32_t* rev_row, const int32_t* tile_row_ptr,
                                           const int32_t* tile_atom_ptr, int64_t n_tiles, int act, float act_param,
-                                          int first_step, void* M_out, void* stream_) {
+                                          int first_step, void* M_out, const int8_t* work_flag, const int32_t* n_work_dev,
+                                          const int32_t* dst_row, void* stream_) {
   return launch_step("bond_step_fused", H_prev, H_0, H_next, ld, n_rows_alloc, h, Wpk, bias, rowptr, rev_row, tile_row_ptr,
-                     tile_atom_ptr, n_tiles, act, act_param, first_step, MODE_FWD, M_out, nullptr, nullptr, (cudaStream_t)stream_);
+                     tile_atom_ptr, n_tiles, act, act_param, first_step, MODE_FWD, M_out, nullptr, nullptr, work_flag, n_work_dev,
+                     dst_row, (cudaStream_t)stream_);
 }
 
 extern "C" int dmpnn_bond_step_bwd_fused_bf16(const void* dZ, const void* Yact, void* dOut, int64_t ld, int64_t n_rows_alloc,
                                               int64_t h, const void* WpkT, const int32_t* rowptr, const int32_t* rev_row,
                                               const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
                                               int act, float act_param, int y_is_preact, const void* add0,
-                                              const void* add1, void* G_out, void* stream_) {
+                                              const void* add1, void* G_out, const int8_t* work_flag,
+                                              const int32_t* n_work_dev, const int32_t* dst_row, void* stream_) {
   DMPNN_CHECK_ARG(!y_is_preact || Yact, "bond_step_bwd_fused: y_is_preact needs Yact");
   return launch_step("bond_step_bwd_fused", dZ, Yact, dOut, ld, n_rows_alloc, h, WpkT, nullptr, rowptr, rev_row, tile_row_ptr,
                      tile_atom_ptr, n_tiles, act, act_param, 0,
-                     Yact ? (y_is_preact ? MODE_BWD_LAST : MODE_BWD_MASK) : MODE_BWD_COPY, G_out, add0, add1,
-                     (cudaStream_t)stream_);
+                     Yact ? (y_is_preact ? MODE_BWD_LAST : MODE_BWD_MASK) : MODE_BWD_COPY, G_out, add0, add1, work_flag,
+                     n_work_dev, dst_row, (cudaStream_t)stream_);
 }

@@ -197,5 +197,16 @@ __device__ __forceinline__ uint4 s_load(uint32_t addr, float ap) {
 }
 
 
+// the same 16-byte load from global memory (windows of molecules larger than a tile gather from L2)
+template <int ACT, bool FIRST>
+__device__ __forceinline__ uint4 g_load(const uint4* ptr, float ap) {
+  uint4 u = __ldg(ptr);
+  if constexpr (FIRST) {
+    u.x = act_word<ACT>(u.x, ap); u.y = act_word<ACT>(u.y, ap);
+    u.z = act_word<ACT>(u.z, ap); u.w = act_word<ACT>(u.w, ap);
+  }
+  return u;
+}
+
 }  // namespace tc
 }  // namespace dmpnn

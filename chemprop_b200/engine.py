@@ -105,6 +105,7 @@ class Layout:
     tile_atom_ptr: Tensor
     meta: Tensor
     _meta_host: list | None = None
+    _work: tuple | None = None
 
     def _host(self):
         if self._meta_host is None:
@@ -133,6 +134,28 @@ class Layout:
 
     def validate(self):
         check_flags(self.flags)
+
+    def step_tables(self):
+        """(tile_row_ptr, tile_atom_ptr, n_tiles, work_flag, n_work_dev, dst_row) for the fused depth step.  Batches whose
+        molecules all fit a 128-row tile pass the layout's tile tables as they are; a batch with larger molecules (condensed
+        reaction graphs) gets the work table of dmpnn_work_table_build: oversized tiles cut into 128-row windows, built once
+        per batch on the device (no host read-back: the kernel reads the window count from device memory)."""
+        if self.max_tile_rows <= 128:
+            return self.tile_row_ptr, self.tile_atom_ptr, self.n_tiles, None, None, None
+        if self._work is None:
+            lib = _lib.load()
+            dev = self.rowptr.device
+            cap = self.n_tiles + self.E // 128 + 2
+            wr = torch.empty(cap + 1, dtype=torch.int32, device=dev)
+            wa = torch.empty(cap + 1, dtype=torch.int32, device=dev)
+            wf = torch.zeros(cap + 1, dtype=torch.int8, device=dev)
+            nw = torch.zeros(1, dtype=torch.int32, device=dev)
+            _lib.check(lib.dmpnn_work_table_build(self.tile_row_ptr.data_ptr(), self.tile_atom_ptr.data_ptr(), self.n_tiles,
+                                                  wr.data_ptr(), wa.data_ptr(), wf.data_ptr(), nw.data_ptr(), _stream()),
+                       "dmpnn_work_table_build")
+            self._work = (wr, wa, wf, nw)
+        wr, wa, wf, nw = self._work
+        return wr, wa, self.n_tiles, wf, nw, self.dst_row
 
 
 def check_flags(f: int):
@@ -364,8 +387,26 @@ def _hidden(rows: int, hp: int, dtype, dev) -> Tensor:
 
 
 def _fused_step_ok(cfg: MPConfig, lay: Layout, h: int) -> bool:
-    return (cfg.fused and cfg.hidden_dtype == torch.bfloat16 and not cfg.undirected and h <= 304
-            and lay.E > 0 and lay.max_tile_rows <= 128 and _fused_available())
+    """The fused tcgen05 depth step applies: bf16 tier, directed bonds, h <= 304.  Molecules of any size: those with more
+    than 128 directed edges run as 128-row windows of the same kernel (Layout.step_tables)."""
+    ok = (cfg.fused and cfg.hidden_dtype == torch.bfloat16 and not cfg.undirected and h <= 304 and lay.E > 0
+          and _fused_available())
+    if not ok and cfg.fused and cfg.hidden_dtype == torch.bfloat16 and lay.E > 0:
+        _warn_once("unfused", "chemprop_b200: this batch leaves the fused depth-step kernel (" +
+                   ("undirected=True" if cfg.undirected else f"d_h = {h} > 304" if h > 304 else "kernel unavailable") +
+                   "): the depth loop runs as separate message + GEMM launches")
+    return ok
+
+
+_WARNED: set = set()
+
+
+def _warn_once(key: str, msg: str):
+    if key not in _WARNED:
+        _WARNED.add(key)
+        import warnings
+
+        warnings.warn(msg, RuntimeWarning, stacklevel=3)
 
 
 _FUSED_STATE: dict = {}
@@ -484,6 +525,33 @@ def wgrad_x3(dY: Tensor, X: Tensor, R: int, N: int, K: int, dW: Tensor, *, accum
     _lib.check(rc, "dmpnn_wgrad_x3")
 
 
+# ---- molecule-level head (csrc/head.cu) ------------------------------------------------------------------------
+def bn_train_fwd(X: Tensor, gamma, beta, running_mean, running_var, eps: float, momentum: float, Y: Tensor, Xhat: Tensor,
+                 mean: Tensor, invstd: Tensor):
+    lib = _lib.load()
+    B, d = X.shape
+    rc = lib.dmpnn_bn_train_fwd(X.data_ptr(), X.stride(0), B, d, _ptr(gamma), _ptr(beta), float(eps), float(momentum),
+                                _ptr(running_mean), _ptr(running_var), Y.data_ptr(), Y.stride(0), Xhat.data_ptr(),
+                                Xhat.stride(0), mean.data_ptr(), invstd.data_ptr(), _stream())
+    _lib.check(rc, "dmpnn_bn_train_fwd")
+
+
+def bn_bwd(dY: Tensor, Xhat: Tensor, gamma, invstd: Tensor, dX: Tensor, dgamma, dbeta):
+    lib = _lib.load()
+    B, d = dY.shape
+    rc = lib.dmpnn_bn_bwd(dY.data_ptr(), dY.stride(0), Xhat.data_ptr(), Xhat.stride(0), B, d, _ptr(gamma), invstd.data_ptr(),
+                          dX.data_ptr(), dX.stride(0), _ptr(dgamma), _ptr(dbeta), _stream())
+    _lib.check(rc, "dmpnn_bn_bwd")
+
+
+def mse_loss(P: Tensor, Y: Tensor, w, tw, loss: Tensor, dP: Tensor):
+    lib = _lib.load()
+    B, T = P.shape
+    rc = lib.dmpnn_mse_loss(P.data_ptr(), P.stride(0) if B else T, Y.data_ptr(), Y.stride(0) if B else T, _ptr(w), _ptr(tw), B, T,
+                            loss.data_ptr(), dP.data_ptr(), dP.stride(0) if B else T, _stream())
+    _lib.check(rc, "dmpnn_mse_loss")
+
+
 def column_sum(Y: Tensor, R: int, N: int, out: Tensor, *, accumulate: bool = False):
     lib = _lib.load()
     n = C.c_size_t(0)
@@ -538,10 +606,11 @@ def bond_step_fused(H_prev: Tensor, H0: Tensor, H_next: Tensor, h: int, Wpk: Ten
                     lay: Layout, act: int, act_param: float, first_step: bool, M_out: Tensor | None = None):
     """One fused depth step; M_out (first step only) also receives the message M^1 the step consumed."""
     lib = _lib.load()
+    trp, tap, nt, wf, nw, dr = lay.step_tables()
     rc = lib.dmpnn_bond_step_fused_bf16(
         H_prev.data_ptr(), H0.data_ptr(), H_next.data_ptr(), _ld(H0), H0.shape[0], h, Wpk.data_ptr(), _ptr(bias),
-        lay.rowptr.data_ptr(), lay.rev_row.data_ptr(), lay.tile_row_ptr.data_ptr(), lay.tile_atom_ptr.data_ptr(),
-        lay.n_tiles, act, float(act_param), 1 if first_step else 0, _ptr(M_out), _stream(),
+        lay.rowptr.data_ptr(), lay.rev_row.data_ptr(), trp.data_ptr(), tap.data_ptr(),
+        nt, act, float(act_param), 1 if first_step else 0, _ptr(M_out), _ptr(wf), _ptr(nw), _ptr(dr), _stream(),
     )
     _lib.check(rc, "dmpnn_bond_step_fused_bf16")
 
@@ -591,12 +660,13 @@ def bond_step_bwd_fused(dZ: Tensor, Yact: Tensor | None, dOut: Tensor, h: int, W
     """dOut = (S.P)(dZ . W_h) [* tau'(Yact)] in one fused launch (WpkT = pack_weight_bf16(W_h.t()));
     G_out also receives (S.P) dZ, the left operand of this step's W_h gradient."""
     lib = _lib.load()
+    trp, tap, nt, wf, nw, dr = lay.step_tables()
     rc = lib.dmpnn_bond_step_bwd_fused_bf16(
         dZ.data_ptr(), _ptr(Yact), dOut.data_ptr(), _ld(dZ), dZ.shape[0], h, WpkT.data_ptr(),
-        lay.rowptr.data_ptr(), lay.rev_row.data_ptr(), lay.tile_row_ptr.data_ptr(), lay.tile_atom_ptr.data_ptr(),
-        lay.n_tiles, act, float(act_param), 1 if y_is_preact else 0,
+        lay.rowptr.data_ptr(), lay.rev_row.data_ptr(), trp.data_ptr(), tap.data_ptr(),
+        nt, act, float(act_param), 1 if y_is_preact else 0,
         addends[0].data_ptr() if len(addends) > 0 else None, addends[1].data_ptr() if len(addends) > 1 else None,
-        _ptr(G_out), _stream())
+        _ptr(G_out), _ptr(wf), _ptr(nw), _ptr(dr), _stream())
     _lib.check(rc, "dmpnn_bond_step_bwd_fused_bf16")
 
 

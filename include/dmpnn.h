@@ -321,7 +321,8 @@ int dmpnn_bond_step_bwd_fused_bf16(const void* dZ, const void* Yact, void* dOut,
                                    int64_t h, const void* WpkT, const int32_t* rowptr, const int32_t* rev_row,
                                    const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
                                    int act, float act_param, int y_is_preact, const void* add0, const void* add1,
-                                   void* G_out, void* stream);
+                                   void* G_out, const int8_t* work_flag, const int32_t* n_work_dev, const int32_t* dst_row,
+                                   void* stream);
 
 /* Tensor-core weight gradient (bf16 operands, f32 accumulate, deterministic two-pass reduction):
  *   dW[n, 0:K] (+)= sum_r dY[r, n] * X[r, 0:K]      dY: R x N (ld lddy), X: R x K (ld ldx), both bf16 row-major
@@ -343,7 +344,17 @@ int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, void* H_next
                                const void* Wpk, const float* bias,
                                const int32_t* rowptr, const int32_t* rev_row,
                                const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
-                               int act, float act_param, int first_step, void* M_out, void* stream);
+                               int act, float act_param, int first_step, void* M_out,
+                               const int8_t* work_flag, const int32_t* n_work_dev, const int32_t* dst_row, void* stream);
+
+/* Work table for batches with molecules of MORE than 128 directed edges (condensed reaction graphs, BASELINE config 4 with
+ * BondMessagePassing): the layout's tiles, with every tile of > 128 rows (one oversized molecule) cut into windows of <= 128
+ * consecutive rows.  Outputs: work_row_ptr / work_atom_ptr (n_work + 1 entries; capacity n_tiles + E / 128 + 2), work_flag
+ * (1 = window of a cut molecule) and the device scalar n_work.  Pass work_row_ptr / work_atom_ptr as the tile tables of the
+ * fused step together with work_flag, n_work and the layout's dst_row (all three NULL for batches without such molecules):
+ * a flagged window gathers its sibling / reverse-edge rows from global memory instead of its shared-memory tile. */
+int dmpnn_work_table_build(const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
+                           int32_t* work_row_ptr, int32_t* work_atom_ptr, int8_t* work_flag, int32_t* n_work, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * fp32-ACCURATE tensor-core GEMMs of the fp32 tier (csrc/gemm_x3.cu): every product is three
@@ -366,6 +377,25 @@ int dmpnn_linear_x3(const float* A, int64_t lda, const int32_t* row_idx, int64_t
 int dmpnn_wgrad_x3_workspace_bytes(int64_t N, int64_t K, size_t* bytes);
 int dmpnn_wgrad_x3(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t R, int64_t N, int64_t K,
                    float* dW, int64_t lddw, int accumulate, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Molecule-level head of the training step (csrc/head.cu; chemprop/models/model.py:126-161):
+ *   dmpnn_bn_train_fwd  nn.BatchNorm1d in training mode on X (B x d f32): Y = (X - mean) * invstd * gamma + beta with the
+ *                       batch mean / biased variance; running_mean / running_var (nullable) are updated in place with
+ *                       `momentum` and the unbiased variance; Xhat, save_mean, save_invstd are kept for the mirror.
+ *   dmpnn_bn_bwd        dX (and dgamma, dbeta when non-null) from dY, Xhat, invstd.
+ *   dmpnn_mse_loss      chemprop's MSE criterion (nn/metrics.py:78-123, 139-141): loss[0] = sum_{b,t} w[b] tw[t] m (P - Y)^2
+ *                       / sum m with m = isfinite(Y) (NaN target = masked, model.py:140-141); dP (nullable) = dloss/dP.
+ * All reductions run in a fixed order (deterministic); no host synchronisation.
+ * ------------------------------------------------------------------------------------- */
+int dmpnn_bn_train_fwd(const float* X, int64_t ldx, int64_t B, int64_t d, const float* gamma, const float* beta,
+                       float eps, float momentum, float* running_mean, float* running_var, float* Y, int64_t ldy,
+                       float* Xhat, int64_t ldh, float* save_mean, float* save_invstd, void* stream);
+int dmpnn_bn_bwd(const float* dY, int64_t lddy, const float* Xhat, int64_t ldh, int64_t B, int64_t d,
+                 const float* gamma, const float* invstd, float* dX, int64_t lddx, float* dgamma, float* dbeta,
+                 void* stream);
+int dmpnn_mse_loss(const float* P, int64_t ldp, const float* Y, int64_t ldy, const float* weights,
+                   const float* task_weights, int64_t B, int64_t T, float* loss, float* dP, int64_t lddp, void* stream);
 
 #ifdef __cplusplus
 }

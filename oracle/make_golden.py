@@ -310,6 +310,58 @@ def constrainer_case() -> dict:
     return d
 
 
+def mpnn_head_case() -> dict:
+    """The reference's own training step (chemprop/models/model.py:134-147): `MPNN(BondMessagePassing, MeanAggregation,
+    RegressionFFN(n_tasks = 2, 2 layers), batch_norm = True).training_step(batch)` on a seeded batch with a NaN target and
+    per-molecule weights: loss, predictions, every gradient, and the batch-norm running statistics after the step."""
+    import_reference()
+    import chemprop.nn as ref_nn
+    from chemprop.data import BatchMolGraph as RefBMG
+    from chemprop.data.molgraph import MolGraph as RefMG
+    from chemprop.models import MPNN
+
+    from chemprop_b200.data.synthetic import make_molecules
+
+    rng = np.random.default_rng(97)
+    torch.manual_seed(97)
+    mgs = make_molecules(14, seed=97, mean_atoms=9, std_atoms=3, min_atoms=1)
+    bmg = RefBMG([RefMG(*m) for m in mgs])
+    mp = ref_nn.BondMessagePassing(d_h=40, depth=3)
+    model = MPNN(mp, ref_nn.MeanAggregation(), ref_nn.RegressionFFN(n_tasks=2, input_dim=40, hidden_dim=24, n_layers=2),
+                 batch_norm=True)
+    model.log = lambda *a, **k: None                     # Lightning's logger is not part of the path
+    with torch.no_grad():                                # non-trivial affine / running statistics
+        model.bn.weight.uniform_(0.5, 1.5)
+        model.bn.bias.normal_(0, 0.2)
+        model.bn.running_mean.normal_(0, 0.1)
+        model.bn.running_var.uniform_(0.5, 2.0)
+    state0 = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
+    Y = rng.normal(size=(14, 2)).astype(np.float32)
+    Y[3, 1] = np.nan
+    Y[9, 0] = np.nan
+    w = rng.uniform(0.5, 2.0, size=(14,)).astype(np.float32)
+    model.train()
+    batch = (bmg, None, None, torch.from_numpy(Y), torch.from_numpy(w), None, None)
+    loss = model.training_step(batch, 0)
+    loss.backward()
+    with torch.no_grad():
+        model.eval()
+        preds_eval = model(bmg)
+    d = {"V": bmg.V.numpy(), "E": bmg.E.numpy(), "edge_index": bmg.edge_index.numpy(),
+         "rev_edge_index": bmg.rev_edge_index.numpy(), "batch": bmg.batch.numpy(), "n_mols": np.int64(14), "Y": Y, "w": w,
+         "loss": loss.detach().numpy(), "preds_eval": preds_eval.numpy()}
+    for k, v in state0.items():
+        if not k.startswith("metrics."):
+            d["param." + k] = v
+    for k, v in model.state_dict().items():
+        if k.startswith("bn.running") or k == "bn.num_batches_tracked":
+            d["after." + k] = v.detach().numpy()
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            d["grad." + k] = p.grad.numpy()
+    return d
+
+
 def main():
     """`python -m oracle.make_golden [name ...]`: all cases, or only the named ones (a case's seed is its position in
     CASES, so adding cases at the end never changes the committed ones)."""
@@ -320,6 +372,12 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN_DIR, "fixture_attentive.npz"), **attentive_case())
         print("fixture_attentive")
         only.discard("fixture_attentive")
+        if not only and len(sys.argv) > 1:
+            return
+    if "fixture_mpnn_head" in only or not only:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "fixture_mpnn_head.npz"), **mpnn_head_case())
+        print("fixture_mpnn_head")
+        only.discard("fixture_mpnn_head")
         if not only and len(sys.argv) > 1:
             return
     if "fixture_constrainer" in only or not only:

@@ -58,8 +58,22 @@ class _Metric(nn.Module):
     def add_state(self, name, default, dist_reduce_fx=None):
         if isinstance(default, torch.Tensor):
             self.register_buffer(name, default)
+            self.__dict__.setdefault("_state_defaults", {})[name] = default.clone()
         else:
             setattr(self, name, default)
+
+    def forward(self, *a, **k):
+        """torchmetrics.Metric.forward for `full_state_update = False` (chemprop's metrics, nn/metrics.py:62): the value of
+        THIS batch -- the states are reset, updated with the batch, computed -- while the global states keep accumulating."""
+        defaults = self.__dict__.get("_state_defaults", {})
+        glob = {n: getattr(self, n).detach().clone() for n in defaults}
+        for n, d in defaults.items():
+            setattr(self, n, d.clone().to(getattr(self, n).device))
+        self.update(*a, **k)
+        val = self.compute()
+        for n in defaults:
+            setattr(self, n, glob[n] + getattr(self, n).detach())
+        return val
 
     def clone(self):
         import copy

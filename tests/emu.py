@@ -258,6 +258,39 @@ def wgrad_x3(dY, X, R, N, K, dW, *, accumulate=False):
         dW[:N, :K] = upd
 
 
+def bn_train_fwd(X, gamma, beta, running_mean, running_var, eps, momentum, Y, Xhat, mean, invstd):
+    B = X.shape[0]
+    mu, var = X.mean(0), X.var(0, unbiased=False)
+    mean.copy_(mu)
+    invstd.copy_(torch.rsqrt(var + eps))
+    Xhat.copy_((X - mu) * invstd)
+    Y.copy_(Xhat * (gamma if gamma is not None else 1.0) + (beta if beta is not None else 0.0))
+    if running_mean is not None:
+        running_mean.mul_(1 - momentum).add_(momentum * mu)
+    if running_var is not None:
+        running_var.mul_(1 - momentum).add_(momentum * (X.var(0, unbiased=True) if B > 1 else var))
+
+
+def bn_bwd(dY, Xhat, gamma, invstd, dX, dgamma, dbeta):
+    B = dY.shape[0]
+    sdy, sdyx = dY.sum(0), (dY * Xhat).sum(0)
+    if dbeta is not None:
+        dbeta.copy_(sdy)
+    if dgamma is not None:
+        dgamma.copy_(sdyx)
+    g = gamma if gamma is not None else 1.0
+    dX.copy_(g * invstd / B * (B * dY - sdy - Xhat * sdyx))
+
+
+def mse_loss(P, Y, w, tw, loss, dP):
+    m = torch.isfinite(Y)
+    e = torch.where(m, P - torch.nan_to_num(Y), torch.zeros_like(P))
+    ww = (w.view(-1, 1) if w is not None else 1.0) * (tw.view(1, -1) if tw is not None else 1.0) * m
+    n = m.sum().clamp(min=1)
+    loss.copy_(((ww * e * e).sum() / n).reshape(1))
+    dP.copy_(2 * ww * e / n)
+
+
 def column_sum(Y, R, N, out, *, accumulate=False):
     v = Y[:R, :N].float().sum(0)
     if accumulate:
@@ -368,7 +401,7 @@ def patch_engine(monkeypatch):
     """Route engine.py's kernel wrappers to the emulations above (host-logic tests only)."""
     for name in ("linear_fwd", "linear_wgrad", "segment_sum", "segment_bcast", "bond_message", "rev_average", "act_bwd",
                  "build_layout", "pack_weight_tc", "pack_weight_bf16", "concat_bf16", "linear_tc", "wgrad_tc", "column_sum",
-                 "pack_weight_x3", "linear_x3", "wgrad_x3",
+                 "pack_weight_x3", "linear_x3", "wgrad_x3", "bn_train_fwd", "bn_bwd", "mse_loss",
                  "bond_step_fused", "bond_step_bwd_fused", "bond_message_bwd_masked", "sum_act_bwd", "scale_mask_"):
         monkeypatch.setattr(engine, name, globals()[name])
     monkeypatch.setattr(engine, "_require_cuda", lambda *ts: None)

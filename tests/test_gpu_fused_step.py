@@ -8,11 +8,17 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _setup(n_mols, h, seed, shuffle=True, min_atoms=2):
+def _setup(n_mols, h, seed, shuffle=True, min_atoms=2, big=0):
     from chemprop_b200.data import BatchMolGraph, make_molecules
     from chemprop_b200.engine import get_layout, pad_hidden
 
     mgs = make_molecules(n_mols, seed=seed, shuffle_edges=shuffle, min_atoms=min_atoms)
+    if big:        # molecules of ~130 .. 400 directed edges scattered through the batch: more rows than one 128-row tile
+        bigs = make_molecules(big, seed=seed + 1, mean_atoms=110.0, std_atoms=40.0, min_atoms=66, max_atoms=200,
+                              shuffle_edges=shuffle)
+        step = max(1, len(mgs) // big)
+        for i, m in enumerate(bigs):
+            mgs.insert(min(len(mgs), i * step + 1), m)
     bmg = BatchMolGraph(mgs)
     bmg.to("cuda")
     lay = get_layout(bmg)
@@ -184,3 +190,58 @@ def test_fused_backward_last_step_masks_from_preactivation_and_sums(h, act, n_ad
     assert pad16 == h or float(out[:, h:pad16].float().abs().max()) == 0.0
     with pytest.raises(Exception):                  # addends are a property of the pre-activation (last) mode
         bond_step_bwd_fused(dZ, Hp, out, h, pack_weight_bf16(W.t().contiguous()), lay, code, 0.0, addends=(dZ,))
+
+
+@pytest.mark.parametrize("h,first,act", [(300, False, "relu"), (300, True, "relu"), (64, False, "tanh")])
+def test_fused_step_molecules_larger_than_a_tile(h, first, act):
+    """Molecules with more than 128 directed edges (condensed reaction graphs): their tiles run as 128-row windows of the
+    same kernel, siblings / reverse edges outside the window gathered from global memory (Layout.step_tables)."""
+    from chemprop_b200 import _lib
+    from chemprop_b200.engine import bond_step_fused, pack_weight_bf16
+
+    lay, H0, Hp, W, b, hp = _setup(300, h, seed=41 + h, big=25)
+    assert lay.max_tile_rows > 128
+    trp, tap, nt, wf, nw, dr = lay.step_tables()
+    n_work = int(nw.item())
+    rows = trp[: n_work + 1].cpu().numpy()
+    assert n_work > nt and (np.diff(rows) <= 128).all() and (np.diff(rows) >= 0).all() and rows[-1] == lay.E
+    assert int(wf[:n_work].sum()) >= 2 * 25 - 5
+    Hin = H0 if first else Hp
+    code = {"relu": _lib.ACT_RELU, "tanh": _lib.ACT_TANH}[act]
+    Hn = torch.zeros_like(H0)
+    Hn[:, :h] = float("nan")
+    M1 = torch.full_like(H0, float("nan")) if first else None
+    bond_step_fused(Hin, H0, Hn, h, pack_weight_bf16(W), b, lay, code, 0.0, first, M_out=M1)
+    torch.cuda.synchronize()
+    ref = _torch_reference(lay, Hin, H0, W, b, h, act, first)
+    assert torch.isfinite(Hn.float()).all(), "rows/columns left unwritten"
+    torch.testing.assert_close(Hn.float(), ref.float(), rtol=2 ** -6, atol=2e-2)
+    if first:
+        tau = {"relu": torch.relu, "tanh": torch.tanh}[act]
+        X, dst, rev = tau(H0[:, :h].float()), lay.dst_row.long(), lay.rev_row.long()
+        Mref = torch.zeros(lay.V, h, device="cuda").index_add_(0, dst, X)[dst[rev]] - X[rev]
+        torch.testing.assert_close(M1[:, :h].float(), Mref.bfloat16().float(), rtol=2 ** -6, atol=2e-2)
+
+
+def test_fused_backward_step_molecules_larger_than_a_tile():
+    from chemprop_b200 import _lib
+    from chemprop_b200.engine import bond_step_bwd_fused, pack_weight_bf16
+
+    h = 300
+    lay, H0, Hp, W, b, hp = _setup(300, h, seed=77, big=25)
+    assert lay.max_tile_rows > 128
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dZ = torch.zeros_like(H0)
+    dZ[:, :h] = torch.randn(lay.E, h, device="cuda", generator=g).bfloat16()
+    out = torch.zeros_like(H0)
+    out[:, :h] = float("nan")
+    Gk = torch.full_like(H0, float("nan"))
+    bond_step_bwd_fused(dZ, Hp, out, h, pack_weight_bf16(W.t().contiguous()), lay, _lib.ACT_RELU, 0.0, G_out=Gk)
+    torch.cuda.synchronize()
+    rev, dst = lay.rev_row.long(), lay.dst_row.long()
+    X = dZ[:, :h].float()[rev]
+    A = torch.zeros(lay.V, h, device="cuda").index_add_(0, dst, X)
+    torch.testing.assert_close(Gk[:, :h].float(), (A[dst] - X).bfloat16().float(), rtol=2 ** -6, atol=2e-2)
+    G = ((A[dst] - X).bfloat16().float() @ W.bfloat16().float()) * (Hp[:, :h].float() > 0).float()
+    assert torch.isfinite(out.float()).all()
+    torch.testing.assert_close(out[:, :h].float(), G.bfloat16().float(), rtol=2 ** -6, atol=2e-2)

@@ -71,7 +71,7 @@ def test_monolithic_bf16_tier_through_emulation(name, fused, monkeypatch):
     mp, bmg, H, aggs = _run(g, mp)
     cfg = g["config"]
     expect_fused = (fused and cfg["kind"] == "bond" and cfg["depth"] > 1 and not cfg.get("undirected") and g["E"].shape[0] > 0
-                    and cfg["d_h"] % 4 == 0 and bmg._meta_host[3] <= 128)      # [3] = largest tile (rows)
+                    and cfg["d_h"] % 4 == 0)      # molecules larger than a 128-row tile stay on the fused kernel too
     assert (calls["fwd"], calls["bwd"]) == ((cfg["depth"] - 1,) * 2 if expect_fused else (0, 0)), calls
     assert H.dtype == (torch.float32 if "V_d" in g else torch.bfloat16)      # W_d (torch, f32) follows the engine's part
     np.testing.assert_allclose(H.detach().float().numpy(), g["H_v"], rtol=0, atol=1e-2)
@@ -168,6 +168,14 @@ def test_constrainer_ffn_trailing_molecules_without_rows(monkeypatch):
 
     emu.patch_engine(monkeypatch)
     check_constrainer_empty_trailing("cpu")
+
+
+def test_engine_mpnn_head_matches_reference_training_step(monkeypatch):
+    """agg -> batch norm -> FFN -> MSE on the engine == chemprop's MPNN.training_step (loss, gradients, running stats)."""
+    from tests.util import check_mpnn_head
+
+    emu.patch_engine(monkeypatch)
+    check_mpnn_head("cpu")
 
 
 def test_eval_mode_with_dropout_configured_stays_monolithic(monkeypatch):

@@ -346,3 +346,52 @@ def check_constrainer_empty_trailing(device: str, atol: float = 2e-6):
     from chemprop_b200 import DmpnnError
     with _pt.raises(DmpnnError):
         mod(fp.to(device), preds.to(device), batch.to(device), cons[:3].to(device))       # index 3 >= 3 rows
+
+
+def check_mpnn_head(device: str, rtol: float = 2e-4, atol: float = 2e-6, graph: bool = False):
+    """EngineMPNN.training_loss (encoder -> aggregation -> batch norm -> FFN -> masked / weighted MSE, every step on libdmpnn)
+    against the reference's own `MPNN.training_step` (tests/golden/fixture_mpnn_head.npz: loss, every gradient, the batch-norm
+    running statistics after the step, eval-mode predictions).  `graph`: the step runs as a captured CUDA graph."""
+    import chemprop_b200.nn as N
+
+    g = load_golden("fixture_mpnn_head")
+    model = N.EngineMPNN(N.BondMessagePassing(d_h=40, depth=3), N.MeanAggregation(),
+                         N.EngineRegressionFFN(n_tasks=2, input_dim=40, hidden_dim=24, n_layers=2), batch_norm=True)
+    state = {k[len("param."):]: torch.from_numpy(np.asarray(v)) for k, v in g.items() if k.startswith("param.")}
+    missing = model.load_state_dict({k: v for k, v in state.items() if not k.endswith(("total_loss", "num_samples"))}, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model = model.to(device)
+    model.train()
+    bmg = golden_bmg(g, device)
+    Y, w = torch.from_numpy(g["Y"]).to(device), torch.from_numpy(g["w"]).to(device)
+    if graph:
+        from chemprop_b200.graph import CudaGraphStep
+
+        for p in model.parameters():
+            p.grad = torch.zeros_like(p)
+        rm0, rv0, nb0 = model.bn.running_mean.clone(), model.bn.running_var.clone(), model.bn.num_batches_tracked.clone()
+
+        def fn(b):
+            for p in model.parameters():
+                p.grad.zero_()
+            loss = model.training_loss(b, Y, w)
+            loss.backward()
+            return loss
+
+        step = CudaGraphStep(fn)
+        loss = step(bmg)                    # warm-up (2 eager steps) + capture + first replay: 4 updates of the running statistics
+        # one more replay from the fixture's initial running statistics: this is the step the reference took
+        model.bn.running_mean.copy_(rm0); model.bn.running_var.copy_(rv0); model.bn.num_batches_tracked.copy_(nb0)
+        loss = step(bmg).clone()
+        assert step.captures == 1 and step.replays == 2
+    else:
+        loss = model.training_loss(bmg, Y, w)
+        loss.backward()
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), g["loss"], rtol=rtol, atol=atol)
+    for k, p in model.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), g["grad." + k], rtol=rtol, atol=atol, err_msg=k)
+    for k in ("running_mean", "running_var", "num_batches_tracked"):
+        np.testing.assert_allclose(getattr(model.bn, k).cpu().numpy(), g["after.bn." + k], rtol=1e-5, atol=1e-6, err_msg=k)
+    model.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(model(bmg).cpu().numpy(), g["preds_eval"], rtol=rtol, atol=1e-5)
