@@ -283,7 +283,17 @@ def main_gpu(args):
     agg = MeanAggregation()
     params = list(mp.parameters())
     reducer = FlatGradAllReducer(params)
+    if world > 1:
+        reducer.attach()           # p.grad = views of the flat bucket; NCCL AVG on a side stream behind the backward
     strong = cfg["scaling"] == "strong"
+
+    def zero_grads():
+        if world > 1:
+            reducer.wait()         # the previous step's all-reduce has to be done before its bucket is cleared
+            reducer.zero_()
+        else:
+            for p in params:
+                p.grad = None
 
     # ---- data: a packed data set resident in HBM + the loader over it -------------------------------------------
     if strong:
@@ -323,8 +333,7 @@ def main_gpu(args):
         return loss
 
     def step_resident():
-        for p in params:
-            p.grad = None
+        zero_grads()
         loss = None
         for _ in range(micro_per_step):
             loss = fwd_bwd(resident)
@@ -342,6 +351,7 @@ def main_gpu(args):
         e0.record()
         for _ in range(steps):
             fn()
+        reducer.wait()             # the last step's gradient all-reduce is part of the timed region
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -352,6 +362,10 @@ def main_gpu(args):
         return ms
 
     # ---- device-resident throughput --------------------------------------------------------
+    # Eager first (per-kernel CUDA events for the roofline), then -- the product's way to run a fixed-signature batch -- the
+    # same step as ONE CUDA graph (chemprop_b200.graph.CudaGraphStep: layout build + forward + loss + backward captured once,
+    # replayed per step; the gradient all-reduce stays outside the graph on its side stream).  `value` is the graph figure
+    # when the capture works (it does wherever the step is sync-free), the eager one otherwise; both are reported.
     W = max(args.warmup, 3)
     for _ in range(W):
         step_resident()
@@ -363,6 +377,51 @@ def main_gpu(args):
     step_events, engine.STEP_EVENTS = engine.STEP_EVENTS, None
     ms_per_step = ms / args.steps
     value = mols_per_step / (ms_per_step * 1e-3)
+    eager = {"value": value, "ms_per_step": ms_per_step, "gpu_launches": int(launches)}
+    graph_info = {"used": False}
+    if not args.no_graph:
+        try:
+            from chemprop_b200.graph import CudaGraphStep
+
+            if world == 1:
+                for p in params:
+                    p.grad = torch.zeros_like(p)
+
+            def graph_body(b):
+                if world > 1:
+                    reducer.zero_()
+                else:
+                    for p in params:
+                        p.grad.zero_()
+                loss = None
+                for _ in range(micro_per_step):
+                    loss = fwd_bwd(b)
+                return loss
+
+            gstep = CudaGraphStep(graph_body)
+
+            def step_graph():
+                reducer.wait()
+                loss = gstep(resident)
+                reducer.allreduce_()
+                return loss
+
+            for _ in range(W):
+                step_graph()
+            with ClockSampler(local) as clocks_g:
+                ms_g = timed(step_graph, args.steps)
+            if gstep.captures == 1 and ms_g > 0:
+                ms_per_step = ms_g / args.steps
+                value = mols_per_step / (ms_per_step * 1e-3)
+                launches = gstep.last_launches * args.steps
+                clocks = clocks_g
+                graph_info = {"used": True, "kernels_per_replay": gstep.last_launches, "graph_launches_per_step": 1}
+            if world == 1:
+                for p in params:
+                    p.grad = None
+        except Exception as e:  # noqa: BLE001 -- the eager figures stand
+            graph_info = {"used": False, "error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.synchronize()
 
     # ---- end to end through the loader: ids in (pinned host -> device), loss out ---------------------------------
     loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
@@ -374,8 +433,7 @@ def main_gpu(args):
         # from the loader (ids uploaded, batch gathered on the device) and all k losses are read inside the timed region.
         pending, losses = None, []
         for i in range(k):
-            for p in params:
-                p.grad = None
+            zero_grads()
             loss = None
             for _ in range(micro_per_step):
                 loss = fwd_bwd(next(stream_it).bmg)
@@ -423,8 +481,7 @@ def main_gpu(args):
                     t.record_stream(torch.cuda.current_stream())
                 if i + 1 < k:
                     nxt = issue_copy()
-                for p in params:
-                    p.grad = None
+                zero_grads()
                 loss = fwd_bwd(bmg)
                 reducer.allreduce_()
                 slot = loss_host[i & 1:(i & 1) + 1]
@@ -536,6 +593,8 @@ def main_gpu(args):
                         "output offsets go host -> device from pinned memory, one gather launch assembles the BatchMolGraph, "
                         "the loss comes back to the host"},
         "e2e_host_batch": e2e_host,
+        "eager": eager,
+        "cuda_graph": graph_info,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -559,6 +618,7 @@ def main():
     ap.add_argument("--no-host-batch", action="store_true", help="skip the complete-host-batch e2e figure (C2)")
     ap.add_argument("--no-dataset", action="store_true", help="(kept for old command lines; no effect)")
     ap.add_argument("--no-pack", action="store_true", help="keep the sampler's molecule order (no tile packing)")
+    ap.add_argument("--no-graph", action="store_true", help="do not run the resident step as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         main_reference(args)

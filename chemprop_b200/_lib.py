@@ -67,7 +67,8 @@ SIGNATURES = {
     "dmpnn_pack_weight_bf16_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
     "dmpnn_pack_weight_bf16": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "dmpnn_bond_step_fused_bf16": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
-                                             _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
+                                             _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _vp]),
+    "dmpnn_dropout_bits": (C.c_int, [_vp, _i64, _i64, _f32, C.c_uint64, C.c_uint64, _vp]),
     "dmpnn_pack_weight_x3_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
     "dmpnn_pack_weight_x3": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp]),
     "dmpnn_linear_x3": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _f32, _vp, _i64, _i64, _vp]),

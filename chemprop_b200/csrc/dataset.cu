@@ -133,6 +133,56 @@ __global__ void __launch_bounds__(256) k_scale_mask(const T* __restrict__ X, con
 }
 }  // namespace
 
+// ---- dropout keep bits (Philox4x32-10, the counter-based generator torch's CUDA stream uses) -----------------------
+// One thread = one (row, 16-column block): 16 keep bits, bit q = [u16_q >= thr], u16_q = 16 random bits of the block's
+// 256-bit Philox output (2 counters), thr = round(p * 65536): P(drop) = thr / 65536.  Counter = (word index, offset);
+// key = seed: the same (seed, offset) gives the same bits on every launch, whatever the grid.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t ctr_lo, uint64_t ctr_hi, uint32_t (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)ctr_lo, (uint32_t)(ctr_lo >> 32), (uint32_t)ctr_hi, (uint32_t)(ctr_hi >> 32)};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+__global__ void k_dropout_bits(uint16_t* __restrict__ bits, int64_t n_words, uint64_t seed, uint64_t offset, uint32_t thr) {
+  const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  uint32_t a[4], b[4];
+  philox4x32_10(seed, (uint64_t)(2 * w), offset, a);
+  philox4x32_10(seed, (uint64_t)(2 * w + 1), offset, b);
+  const uint32_t u[8] = {a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3]};
+  uint32_t m = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    m |= ((u[q] & 0xffffu) >= thr ? 1u : 0u) << (2 * q);
+    m |= ((u[q] >> 16) >= thr ? 1u : 0u) << (2 * q + 1);
+  }
+  bits[w] = (uint16_t)m;
+}
+
+extern "C" int dmpnn_dropout_bits(void* bits, int64_t n_rows, int64_t words_per_row, float p, uint64_t seed, uint64_t offset,
+                                  void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DMPNN_CHECK_ARG(bits && n_rows >= 0 && words_per_row > 0 && p >= 0.f && p < 1.f, "dropout_bits: bad args (0 <= p < 1)");
+  const int64_t n = n_rows * words_per_row;
+  if (n == 0) return 0;
+  const uint32_t thr = (uint32_t)(p * 65536.0f + 0.5f);
+  k_dropout_bits<<<dmpnn::ceil_div_i64(n, 256), 256, 0, st>>>((uint16_t*)bits, n, seed, offset, thr);
+  DMPNN_CHECK_LAUNCH("dropout_bits", 1);
+  return 0;
+}
+
 extern "C" int dmpnn_scale_mask(const void* X, const void* M, void* OUT, int dtype, int64_t n, float scale, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   DMPNN_CHECK_ARG(n >= 0 && (n == 0 || (X && M && OUT)), "scale_mask: bad args");

@@ -526,7 +526,8 @@ static Geom geom(int64_t R, int64_t N, int64_t K) {
   Geom g;
   g.n_mt = (int)((N + kMT - 1) / kMT);
   g.n_kt = (int)((K + kKT - 1) / kKT);
-  g.n_blocks = (int)((R + kRows - 1) / kRows);
+  const int64_t nb = (R + kRows - 1) / kRows;
+  g.n_blocks = nb > 0x7fffffff ? 0x7fffffff : (int)nb;
   int slots = sm_count / (g.n_mt * g.n_kt);
   if (slots < 1) slots = 1;
   if (slots > g.n_blocks) slots = g.n_blocks > 0 ? g.n_blocks : 1;
@@ -536,7 +537,7 @@ static Geom geom(int64_t R, int64_t N, int64_t K) {
 }
 // the workspace must not depend on R (callers size it once): slots <= SM count / tiles
 static size_t workspace_bytes(int64_t N, int64_t K) {
-  Geom g = geom((int64_t)1 << 40, N, K);
+  Geom g = geom((int64_t)1 << 30, N, K);     // any R large enough to give every tile its full set of row slots
   return (size_t)g.grid * kMT * kKT * sizeof(float);
 }
 }  // namespace wg

@@ -74,6 +74,8 @@ struct Params {
   const int32_t* n_work_dev;     // nullable; number of work items when the work table is in use (device scalar)
   const int32_t* dst_row;        // destination atom of every row (needed by the non-local windows only)
   const __nv_bfloat16* Hprev;    // the H tile's matrix again, for the non-local windows' global gathers
+  const uint16_t* drop_bits;     // nullable (forward): 16 keep bits per (row, 16-column block), dmpnn_dropout_bits
+  float drop_scale;              // 1 / (1 - p)
   int n_tiles, h, hp, nslab, ksteps_last, nchunks;
   float act_param;
   int exp_flags;  // timing experiments only (DMPNN_EXP env var); 0 in production
@@ -360,6 +362,8 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
               b0 = __ldg(bp); b1 = __ldg(bp + 1);
             }
           }
+          uint32_t kb = 0xffffu;
+          if (MODE == MODE_FWD && p.drop_bits != nullptr && rvalid) kb = __ldg(p.drop_bits + (int64_t)(row0 + r) * nj + j);
           tmem_wait_ld();
           const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
           uint32_t o[8];
@@ -389,6 +393,15 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
             if constexpr (HAS_BIAS) {
               z0 += s_bias[j * 16 + 2 * qq];
               z1 += s_bias[j * 16 + 2 * qq + 1];
+            }
+            if constexpr (MODE == MODE_FWD) {
+              if (p.drop_bits != nullptr) {
+                // nn.Dropout of base.py:139 in the epilogue: tau in f32, keep bit, exact f32 scale 1 / (1 - p), one rounding
+                z0 = ((kb >> (2 * qq)) & 1u) ? act_t<ACT>(p.act_param, z0) * p.drop_scale : 0.f;
+                z1 = ((kb >> (2 * qq + 1)) & 1u) ? act_t<ACT>(p.act_param, z1) * p.drop_scale : 0.f;
+                o[qq] = pack_bf2(z0, z1);
+                continue;
+              }
             }
             if constexpr (ACT == DMPNN_ACT_RELU) o[qq] = act_word<ACT>(pack_bf2(z0, z1), 0.f);  // max after rounding == rounding after max
             else o[qq] = pack_bf2(act_t<ACT>(p.act_param, z0), act_t<ACT>(p.act_param, z1));
@@ -725,7 +738,9 @@ static int launch_step(const char* what, const void* H_prev, const void* H_0, vo
                        int64_t h, const void* Wpk, const float* bias, const int32_t* rowptr, const int32_t* rev_row,
                        const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles, int act, float act_param,
                        int first_step, int mode, void* gather_out, const void* add0, const void* add1,
-                       const int8_t* work_flag, const int32_t* n_work_dev, const int32_t* dst_row, cudaStream_t st) {
+                       const int8_t* work_flag, const int32_t* n_work_dev, const int32_t* dst_row, const uint16_t* drop_bits,
+                       float drop_scale, cudaStream_t st) {
+  DMPNN_CHECK_ARG(drop_bits == nullptr || mode == MODE_FWD, "%s: keep bits apply to the forward step", what);
   DMPNN_CHECK_ARG((work_flag == nullptr) == (n_work_dev == nullptr) && (work_flag == nullptr || dst_row != nullptr),
                   "%s: work_flag, n_work_dev and dst_row come together (dmpnn_work_table_build)", what);
   DMPNN_CHECK_ARG((add0 == nullptr && add1 == nullptr) || (mode == MODE_BWD_LAST && add0 != nullptr),
@@ -774,6 +789,8 @@ static int launch_step(const char* what, const void* H_prev, const void* H_0, vo
   p.n_work_dev = n_work_dev;
   p.dst_row = dst_row;
   p.Hprev = (const __nv_bfloat16*)H_prev;
+  p.drop_bits = drop_bits;
+  p.drop_scale = drop_scale;
   p.n_tiles = (int)n_tiles;
   p.h = (int)h;
   p.hp = hp;
@@ -844,10 +861,10 @@ extern "C" int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, v
                                           const int32_t* rowptr, const int32_t* rev_row, const int32_t* tile_row_ptr,
                                           const int32_t* tile_atom_ptr, int64_t n_tiles, int act, float act_param,
                                           int first_step, void* M_out, const int8_t* work_flag, const int32_t* n_work_dev,
-                                          const int32_t* dst_row, void* stream_) {
+                                          const int32_t* dst_row, const void* drop_bits, float drop_scale, void* stream_) {
   return launch_step("bond_step_fused", H_prev, H_0, H_next, ld, n_rows_alloc, h, Wpk, bias, rowptr, rev_row, tile_row_ptr,
                      tile_atom_ptr, n_tiles, act, act_param, first_step, MODE_FWD, M_out, nullptr, nullptr, work_flag, n_work_dev,
-                     dst_row, (cudaStream_t)stream_);
+                     dst_row, (const uint16_t*)drop_bits, drop_scale, (cudaStream_t)stream_);
 }
 
 extern "C" int dmpnn_bond_step_bwd_fused_bf16(const void* dZ, const void* Yact, void* dOut, int64_t ld, int64_t n_rows_alloc,
@@ -860,5 +877,5 @@ extern "C" int dmpnn_bond_step_bwd_fused_bf16(const void* dZ, const void* Yact, 
   return launch_step("bond_step_bwd_fused", dZ, Yact, dOut, ld, n_rows_alloc, h, WpkT, nullptr, rowptr, rev_row, tile_row_ptr,
                      tile_atom_ptr, n_tiles, act, act_param, 0,
                      Yact ? (y_is_preact ? MODE_BWD_LAST : MODE_BWD_MASK) : MODE_BWD_COPY, G_out, add0, add1, work_flag,
-                     n_work_dev, dst_row, (cudaStream_t)stream_);
+                     n_work_dev, dst_row, nullptr, 1.f, (cudaStream_t)stream_);
 }

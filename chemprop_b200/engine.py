@@ -602,15 +602,39 @@ def concat_bf16(X1: Tensor, K1: int, out: Tensor, R: int, *, idx1: Tensor | None
     _lib.check(rc, "dmpnn_concat_bf16")
 
 
+def dropout_keep_bits(rows: int, h: int, cfg: "MPConfig", like: Tensor) -> Tensor:
+    """uint16 [rows, pad16(h) / 16] keep bits for one dropout site of the fused path (dmpnn_dropout_bits: Philox4x32-10 keyed
+    by the device generator's seed and current offset, so `torch.manual_seed` governs the masks as in the reference; the
+    offset is then advanced).  `cfg.mask_fn` (test hook) supplies a {0, 1} tensor instead, which is packed into the same words."""
+    nj = (h + 15) // 16
+    dev = like.device
+    if cfg.mask_fn is not None:
+        M = cfg.mask_fn(like)[:rows, : nj * 16].to(torch.int32).reshape(rows, nj, 16)
+        w = (M << torch.arange(16, device=dev, dtype=torch.int32)).sum(-1)
+        return w.to(torch.uint16).contiguous()
+    if torch.cuda.is_current_stream_capturing():
+        raise DmpnnError("training-mode dropout inside a captured CUDA graph is not supported (the Philox offset is host state)")
+    lib = _lib.load()
+    gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+    seed, off = int(gen.initial_seed()) & (2 ** 64 - 1), int(gen.get_offset())
+    gen.set_offset(off + 4)
+    bits = torch.empty((max(rows, 1), nj), dtype=torch.uint16, device=dev)
+    _lib.check(lib.dmpnn_dropout_bits(bits.data_ptr(), rows, nj, float(cfg.dropout_p), seed, off, _stream()), "dmpnn_dropout_bits")
+    return bits
+
+
 def bond_step_fused(H_prev: Tensor, H0: Tensor, H_next: Tensor, h: int, Wpk: Tensor, bias: Tensor | None,
-                    lay: Layout, act: int, act_param: float, first_step: bool, M_out: Tensor | None = None):
-    """One fused depth step; M_out (first step only) also receives the message M^1 the step consumed."""
+                    lay: Layout, act: int, act_param: float, first_step: bool, M_out: Tensor | None = None,
+                    drop_bits: Tensor | None = None, drop_scale: float = 1.0):
+    """One fused depth step; M_out (first step only) also receives the message M^1 the step consumed; `drop_bits`
+    (dropout_keep_bits) applies training-mode dropout with scale `drop_scale` in the epilogue."""
     lib = _lib.load()
     trp, tap, nt, wf, nw, dr = lay.step_tables()
     rc = lib.dmpnn_bond_step_fused_bf16(
         H_prev.data_ptr(), H0.data_ptr(), H_next.data_ptr(), _ld(H0), H0.shape[0], h, Wpk.data_ptr(), _ptr(bias),
         lay.rowptr.data_ptr(), lay.rev_row.data_ptr(), trp.data_ptr(), tap.data_ptr(),
-        nt, act, float(act_param), 1 if first_step else 0, _ptr(M_out), _ptr(wf), _ptr(nw), _ptr(dr), _stream(),
+        nt, act, float(act_param), 1 if first_step else 0, _ptr(M_out), _ptr(wf), _ptr(nw), _ptr(dr), _ptr(drop_bits),
+        float(drop_scale), _stream(),
     )
     _lib.check(rc, "dmpnn_bond_step_fused_bf16")
 
@@ -705,10 +729,11 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
             # training: the first step also stores M^1 (it is tau(H_0)-gathered, which no later kernel can rebuild
             # from a stored activation); the later steps' W_h gradients use (S.P) dZ from the backward kernel instead
             M1 = _empty_hidden(nE, hp, T, dev) if (first and for_backward) else None
+            # base.py:139 (training-mode dropout): keep bits from Philox, applied in the step's epilogue -- no pass over E x h
+            bits = dropout_keep_bits(nE, h, cfg, Hn) if cfg.dropout_p > 0 else None
             with _StepTimer("fused_first" if first else "fused"):
-                bond_step_fused(Hprev, H0, Hn, h, Wpk, bh, lay, a, ap, first, M_out=M1)
-            if cfg.dropout_p > 0:
-                _dropout_(Hn, cfg)                                                 # base.py:139
+                bond_step_fused(Hprev, H0, Hn, h, Wpk, bh, lay, a, ap, first, M_out=M1, drop_bits=bits,
+                                drop_scale=1.0 / (1.0 - cfg.dropout_p) if bits is not None else 1.0)
             Ms.append(M1)
         else:
             if cfg.dropout_p > 0:

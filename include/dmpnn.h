@@ -345,7 +345,15 @@ int dmpnn_bond_step_fused_bf16(const void* H_prev, const void* H_0, void* H_next
                                const int32_t* rowptr, const int32_t* rev_row,
                                const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles,
                                int act, float act_param, int first_step, void* M_out,
-                               const int8_t* work_flag, const int32_t* n_work_dev, const int32_t* dst_row, void* stream);
+                               const int8_t* work_flag, const int32_t* n_work_dev, const int32_t* dst_row,
+                               const void* drop_bits, float drop_scale, void* stream);
+
+/* Training-mode dropout of base.py:139 INSIDE the fused step: `drop_bits` (nullable) holds 16 keep bits per (row, 16-column
+ * block) -- uint16 [n_rows][pad16(h) / 16], bit q of word j = column 16 j + q -- and the epilogue writes
+ * keep ? tau(z) * drop_scale : 0 with one rounding (drop_scale = 1 / (1 - p)); no mask pass over the E x h matrix.
+ * dmpnn_dropout_bits fills such an array from Philox4x32-10 (key = seed, counter = (word index, offset)): bit = [u16 >= round(p *
+ * 65536)], i.e. P(drop) = p to 2^-16; the same (seed, offset) always gives the same bits. */
+int dmpnn_dropout_bits(void* bits, int64_t n_rows, int64_t words_per_row, float p, uint64_t seed, uint64_t offset, void* stream);
 
 /* Work table for batches with molecules of MORE than 128 directed edges (condensed reaction graphs, BASELINE config 4 with
  * BondMessagePassing): the layout's tiles, with every tile of > 128 rows (one oversized molecule) cut into windows of <= 128

@@ -331,7 +331,8 @@ def _sibling_sum_packed(f, lay, through_rev):
     return small
 
 
-def bond_step_fused(H_prev, H0, H_next, h, Wpk, bias, lay, act, act_param, first_step, M_out=None):
+def bond_step_fused(H_prev, H0, H_next, h, Wpk, bias, lay, act, act_param, first_step, M_out=None, drop_bits=None,
+                    drop_scale=1.0):
     """H_next[e] = tau(H_0[e] + b + W_h . M[e]),  M = message of g(H_prev), g = tau on the first step (include/dmpnn.h)."""
     f = _act(H_prev.float()[: lay.E, :h], act if first_step else ACT_NONE, act_param)
     if first_step:
@@ -342,7 +343,12 @@ def bond_step_fused(H_prev, H0, H_next, h, Wpk, bias, lay, act, act_param, first
     Z = M @ Wpk.t() + H0[: lay.E, :h].float()
     if bias is not None:
         Z = Z + bias.float()
-    H_next[: lay.E, :h] = _act(Z, act, act_param).to(H_next.dtype)
+    Y = _act(Z, act, act_param)
+    if drop_bits is not None:           # keep ? tau(z) * scale : 0 in f32, one rounding (the kernel's epilogue)
+        nj = (h + 15) // 16
+        keep = ((drop_bits[: lay.E].to(torch.int32).unsqueeze(-1) >> torch.arange(16, dtype=torch.int32)) & 1).reshape(lay.E, nj * 16)
+        Y = Y * keep[:, :h].float() * drop_scale
+    H_next[: lay.E, :h] = Y.to(H_next.dtype)
     H_next[: lay.E, h:(h + 15) // 16 * 16] = 0
     if M_out is not None:
         M_out[: lay.E, :h] = M.to(M_out.dtype)

@@ -27,6 +27,16 @@ def _worker(rank, world, port, q):
     ok = abs(params[0].grad.mean().item() - exp0) < 1e-6
     for i, p in enumerate(params[1:], start=1):
         ok = ok and abs(p.grad.mean().item() - (1 + 2) * (i + 1) / 2) < 1e-6
+    # attached mode: p.grad are views of the bucket, no copies; zero_() is one memset
+    red2 = FlatGradAllReducer(params).attach()
+    red2.zero_()
+    for i, p in enumerate(params):
+        p.grad.add_(float(rank + 1) * (i + 2))                      # what autograd's in-place accumulation does
+        ok = ok and p.grad.data_ptr() == red2.views[i].data_ptr()
+    red2.allreduce_()
+    red2.wait()
+    for i, p in enumerate(params):
+        ok = ok and abs(p.grad.mean().item() - (1 + 2) * (i + 2) / 2) < 1e-6
     shards = list(shard_indices(11, rank, world))
     q.put((rank, ok, shards, red.nbytes))
     dist.destroy_process_group()

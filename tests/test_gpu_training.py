@@ -80,3 +80,63 @@ def test_compact_transfer_is_bit_identical_for_the_bf16_tier():
     assert torch.equal(outs[0][0], outs[1][0])
     for g0, g1 in zip(outs[0][1], outs[1][1]):
         assert torch.equal(g0, g1)
+
+
+def test_dropout_keep_bits_statistics_and_determinism():
+    """dmpnn_dropout_bits (Philox4x32-10): P(drop) = p, bits independent of position, reproducible from (seed, offset)."""
+    import ctypes as C
+
+    from chemprop_b200 import _lib
+
+    lib = _lib.load()
+    rows, nj, p = 6000, 19, 0.3
+
+    def draw(seed, off):
+        b = torch.empty((rows, nj), dtype=torch.uint16, device="cuda")
+        _lib.check(lib.dmpnn_dropout_bits(b.data_ptr(), rows, nj, p, seed, off, torch.cuda.current_stream().cuda_stream), "bits")
+        return b
+
+    a, a2, b, c = draw(7, 0), draw(7, 0), draw(7, 4), draw(8, 0)
+    assert torch.equal(a, a2) and not torch.equal(a, b) and not torch.equal(a, c)
+    keep = ((a.to(torch.int32).unsqueeze(-1) >> torch.arange(16, device="cuda", dtype=torch.int32)) & 1).float()   # rows x nj x 16
+    n = keep.numel()
+    sigma = (p * (1 - p) / n) ** 0.5
+    assert abs(keep.mean().item() - (1 - p)) <= 5 * sigma
+    per_pos = keep.mean(0).reshape(-1)                                  # every (word, bit) position over the rows
+    assert (per_pos - (1 - p)).abs().max().item() <= 5.5 * (p * (1 - p) / rows) ** 0.5
+    x, y = keep[:, :, :8].reshape(-1), keep[:, :, 8:].reshape(-1)        # the two 16-bit halves of a Philox word: uncorrelated
+    assert abs(((x - x.mean()) * (y - y.mean())).mean().item()) <= 5 * p * (1 - p) / x.numel() ** 0.5
+
+
+def test_fused_path_dropout_is_seeded_and_unbiased():
+    """Training-mode dropout inside the fused depth step (keep bits in the epilogue): governed by torch.manual_seed like the
+    reference's nn.Dropout, E[output] = the no-dropout output, and the zero fraction of H_v matches p x ReLU sparsity."""
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.engine import get_layout
+    from chemprop_b200.nn import BondMessagePassing
+
+    torch.manual_seed(0)
+    bmg = BatchMolGraph(make_molecules(400, seed=12))
+    bmg.to("cuda")
+    mp = BondMessagePassing(d_h=300, depth=3, dropout=0.25, precision="bf16").cuda().train()
+    assert not mp.uses_composed_tier(get_layout(bmg))
+
+    def run(seed):
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            return mp(bmg).float()
+
+    h1, h1b, h2 = run(1), run(1), run(2)
+    assert torch.equal(h1, h1b) and not torch.equal(h1, h2)
+    mp.eval()
+    with torch.no_grad():
+        ref = mp(bmg).float()
+    mp.train()
+    acc = torch.zeros_like(ref)
+    n = 24
+    for s in range(n):
+        acc += run(100 + s)
+    rel = ((acc / n).mean() - ref.mean()).abs().item() / ref.mean().abs().item()
+    assert rel <= 0.15, rel      # the 1 / (1 - p) scales are applied (a missing one: -25 % per site; ReLU keeps it from being exact)
+    zero_frac = (h1 == 0).float().mean().item()
+    assert zero_frac >= 0.25 - 0.01                                     # at least the read-out's own dropout site
