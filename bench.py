@@ -45,7 +45,7 @@ CONFIGS = {
     "C2": dict(kind="bond", n_mols=10_000, d_h=300, depth=3, precision="bf16", gen="mol", d_v=72, d_e=14, pool=3,
                scaling="weak", desc="10000 synthetic mols/GPU (~25 atoms), BondMessagePassing h=300 depth=3 + MeanAggregation"),
     "C3": dict(kind="bond", n_mols=50_000, d_h=600, depth=6, precision="fp32", gen="mol", d_v=72, d_e=14, pool=1,
-               scaling="weak", desc="50000 synthetic mols/GPU (~25 atoms), BondMessagePassing h=600 depth=6 fp32 + MeanAggregation"),
+               scaling="weak", graph=False,      # ~100 GB of activations per step: no room for a graph's private pool beside it desc="50000 synthetic mols/GPU (~25 atoms), BondMessagePassing h=600 depth=6 fp32 + MeanAggregation"),
     "C4": dict(kind="atom", n_mols=10_000, d_h=300, depth=3, precision="bf16", gen="cgr", d_v=106, d_e=28, pool=2,
                scaling="weak", desc="10000 synthetic condensed reaction graphs/GPU (~80 atoms, d_v=106 d_e=28), "
                                     "AtomMessagePassing h=300 depth=3 + MeanAggregation"),
@@ -379,7 +379,7 @@ def main_gpu(args):
     value = mols_per_step / (ms_per_step * 1e-3)
     eager = {"value": value, "ms_per_step": ms_per_step, "gpu_launches": int(launches)}
     graph_info = {"used": False}
-    if not args.no_graph:
+    if not args.no_graph and cfg.get("graph", True):
         try:
             from chemprop_b200.graph import CudaGraphStep
 
@@ -421,7 +421,16 @@ def main_gpu(args):
                     p.grad = None
         except Exception as e:  # noqa: BLE001 -- the eager figures stand
             graph_info = {"used": False, "error": f"{type(e).__name__}: {e}"[:300]}
-            torch.cuda.synchronize()
+            try:
+                torch.cuda.synchronize()
+            except Exception:  # noqa: BLE001
+                pass
+        finally:
+            gstep = None            # release the graph and its private memory pool before the loader-driven phases
+            import gc
+
+            gc.collect()
+            torch.cuda.empty_cache()
 
     # ---- end to end through the loader: ids in (pinned host -> device), loss out ---------------------------------
     loss_host = torch.empty(2, dtype=torch.float32).pin_memory()

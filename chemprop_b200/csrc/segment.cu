@@ -363,10 +363,10 @@ __global__ void k_sum_act_bwd_v4(SumSrcs srcs, int64_t ldz, const TZ* __restrict
 
 // OUT[r, :] = bf16([X1[i1(r), 0:K1] || X2[i2(r), 0:K2] || 0 ...])  -- the A operand of the tensor-core
 // linear layers: torch.cat([V[src], E], 1) (mixins.py:9) and torch.cat((V, M), 1) (base.py:180)
-template <typename T1, typename T2>
+template <typename T1, typename T2, typename TO = __nv_bfloat16>
 __global__ void k_concat_bf16(const T1* __restrict__ X1, int64_t ld1, const int32_t* __restrict__ idx1, int K1,
                               const T2* __restrict__ X2, int64_t ld2, const int32_t* __restrict__ idx2, int K2,
-                              __nv_bfloat16* __restrict__ OUT, int64_t ldo, int width, int64_t R) {
+                              TO* __restrict__ OUT, int64_t ldo, int width, int64_t R) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
   if (r >= R) return;
   const int64_t r1 = idx1 ? (int64_t)idx1[r] : r;
@@ -375,17 +375,17 @@ __global__ void k_concat_bf16(const T1* __restrict__ X1, int64_t ld1, const int3
     float v = 0.f;
     if (c < K1) v = ld_as_float(X1 + r1 * ld1 + c);
     else if (c < K1 + K2) v = ld_as_float(X2 + r2 * ld2 + (c - K1));
-    OUT[r * ldo + c] = __float2bfloat16_rn(v);
+    st_from_float(OUT + r * ldo + c, v);
   }
 }
 
 // 4-wide variant: thread = one column quad of `rows_par` interleaved rows, so every lane of a warp stores
 // (rows are 18..24 quads wide: a lane-per-quad-of-one-row mapping would idle a quarter of the warp)
-template <typename T1, typename T2>
+template <typename T1, typename T2, typename TO = __nv_bfloat16>
 __global__ void __launch_bounds__(256)
 k_concat_bf16_v4(const T1* __restrict__ X1, int64_t ld1, const int32_t* __restrict__ idx1, int K1,
                  const T2* __restrict__ X2, int64_t ld2, const int32_t* __restrict__ idx2, int K2,
-                 __nv_bfloat16* __restrict__ OUT, int64_t ldo, int QW, int64_t R, int rows_per_block, int x1_vec) {
+                 TO* __restrict__ OUT, int64_t ldo, int QW, int64_t R, int rows_per_block, int x1_vec) {
   const int rows_par = blockDim.x / QW;
   const int rsub = threadIdx.x / QW;
   const int c4 = 4 * (threadIdx.x - rsub * QW);
@@ -435,6 +435,31 @@ extern "C" int dmpnn_concat_bf16(const void* X1, int x1_dtype, int64_t ld1, cons
                                                      (__nv_bfloat16*)OUT, ldo, (int)width, R);
     ))
   DMPNN_CHECK_LAUNCH("concat_bf16", 1);
+  return 0;
+}
+
+// f32 output: the [V[src] || E] / [N || sum E] operands of the fp32 tier's tensor-core GEMMs (dmpnn_linear_x3)
+extern "C" int dmpnn_concat_f32(const void* X1, int x1_dtype, int64_t ld1, const int32_t* idx1, int64_t K1,
+                                const void* X2, int x2_dtype, int64_t ld2, const int32_t* idx2, int64_t K2,
+                                float* OUT, int64_t ldo, int64_t width, int64_t R, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DMPNN_CHECK_ARG(R >= 0 && K1 > 0 && K2 >= 0 && width >= K1 + K2 && ldo >= width, "concat_f32: bad sizes");
+  if (R == 0) return 0;
+  DMPNN_CHECK_ARG(X1 && OUT && (K2 == 0 || X2), "concat_f32: null pointer");
+  if (K2 == 0) x2_dtype = x1_dtype;
+  dim3 block(32, 8), grid(ceil_div_i64(R, 8));
+  const bool vec = width % 4 == 0 && width / 4 <= 256 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(OUT) & 15) == 0;
+  DMPNN_DISPATCH_DTYPE(x1_dtype, T1,
+    DMPNN_DISPATCH_DTYPE(x2_dtype, T2,
+      if (vec)
+        k_concat_bf16_v4<T1, T2, float><<<ceil_div_i64(R, 64), 256, 0, st>>>(
+            (const T1*)X1, ld1, idx1, (int)K1, (const T2*)X2, ld2, idx2, (int)K2, OUT, ldo, (int)(width / 4), R,
+            64, vec4_ok<T1>(X1, ld1) ? 1 : 0);
+      else
+        k_concat_bf16<T1, T2, float><<<grid, block, 0, st>>>((const T1*)X1, ld1, idx1, (int)K1, (const T2*)X2, ld2, idx2, (int)K2,
+                                                            OUT, ldo, (int)width, R);
+    ))
+  DMPNN_CHECK_LAUNCH("concat_f32", 1);
   return 0;
 }
 

@@ -623,6 +623,17 @@ def dropout_keep_bits(rows: int, h: int, cfg: "MPConfig", like: Tensor) -> Tenso
     return bits
 
 
+def concat_f32(X1: Tensor, K1: int, out: Tensor, R: int, *, idx1: Tensor | None = None, X2: Tensor | None = None,
+               K2: int = 0, idx2: Tensor | None = None, width: int | None = None):
+    lib = _lib.load()
+    width = out.shape[1] if width is None else width
+    assert out.dtype == torch.float32
+    rc = lib.dmpnn_concat_f32(X1.data_ptr(), _dt(X1), _ld(X1), _ptr(idx1), K1,
+                              _ptr(X2), _dt(X2) if X2 is not None else F32, _ld(X2) if X2 is not None else 0,
+                              _ptr(idx2), K2, out.data_ptr(), _ld(out), width, R, _stream())
+    _lib.check(rc, "dmpnn_concat_f32")
+
+
 def bond_step_fused(H_prev: Tensor, H0: Tensor, H_next: Tensor, h: int, Wpk: Tensor, bias: Tensor | None,
                     lay: Layout, act: int, act_param: float, first_step: bool, M_out: Tensor | None = None,
                     drop_bits: Tensor | None = None, drop_scale: float = 1.0):
@@ -713,6 +724,15 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
         concat_bf16(V, d_v, X0, nE, idx1=lay.src_row, X2=E, K2=d_e, idx2=lay.perm)
         H0 = _empty_hidden(nE, hp, T, dev)
         linear_tc(X0, d_v + d_e, pack_weight_tc(Wi), h, H0, bias=bi, R=nE)
+    elif _x3_ok(cfg, h, d_v + h) and nE > 0:
+        # fp32 tier on the tensor cores: [V[src] || E] materialised once in f32 (zero-padded to a multiple of 4 columns),
+        # W_i as a 3xTF32 GEMM; the same operand serves the W_i gradient
+        X0 = None
+        kx4 = (d_v + d_e + 3) // 4 * 4
+        X0f = torch.empty((nE, kx4), dtype=torch.float32, device=dev)
+        concat_f32(V, d_v, X0f, nE, idx1=lay.src_row, X2=E, K2=d_e, idx2=lay.perm)
+        H0 = _hidden(nE, hp, T, dev)
+        linear_x3(X0f, kx4, pack_weight_x3(Wi), h, H0, bias=bi, R=nE, pad_to=hp)
     else:
         X0 = None
         H0 = _hidden(nE, hp, T, dev)
@@ -789,7 +809,7 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
             # H_v = tau(W_o([V || M_v]))   (base.py:180-182)
             Hv = torch.empty((nV, h), dtype=T, device=dev)
             linear_fwd(V, d_v, Wo, Hv, h, X2=Mv, K2=h, bias=bo, act=a, act_param=ap, R=nV, pad_to=h)
-    saved = dict(H0=H0, Hs=Hs, Ms=Ms, Hbars=Hbars, Mv=Mv, Hv=Hv, X0=X0, XO=XO, tc=tc, x3=x3)
+    saved = dict(H0=H0, Hs=Hs, Ms=Ms, Hbars=Hbars, Mv=Mv, Hv=Hv, X0=X0, XO=XO, tc=tc, x3=x3, X0f=locals().get("X0f"))
     return Hv, saved
 
 
@@ -892,6 +912,13 @@ def bond_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo:
             dH0b = torch.empty((nE, hp), dtype=T, device=dev)
             concat_bf16(dH0, h, dH0b, nE)                      # f32 accumulator -> bf16 operand
             wgrad_tc(dH0b, saved["X0"], nE, h, d_v + d_e, dWi)
+            if dbi is not None:
+                column_sum(dH0, nE, h, dbi)
+        elif x3 and saved.get("X0f") is not None:
+            X0f = saved["X0f"]
+            dWi4 = torch.empty((h, X0f.shape[1]), dtype=torch.float32, device=dev)
+            wgrad_x3(dH0, X0f, nE, h, X0f.shape[1], dWi4)
+            dWi.copy_(dWi4[:, : d_v + d_e])
             if dbi is not None:
                 column_sum(dH0, nE, h, dbi)
         else:

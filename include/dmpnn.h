@@ -301,6 +301,10 @@ int dmpnn_act_bwd(const void* G, int g_dtype, int64_t ldg, const int32_t* gidx,
 int dmpnn_concat_bf16(const void* X1, int x1_dtype, int64_t ld1, const int32_t* idx1, int64_t K1,
                       const void* X2, int x2_dtype, int64_t ld2, const int32_t* idx2, int64_t K2,
                       void* OUT, int64_t ldo, int64_t width, int64_t R, void* stream);
+/* the same gather-concatenate with an f32 result: the operands of the fp32 tier's tensor-core GEMMs (dmpnn_linear_x3) */
+int dmpnn_concat_f32(const void* X1, int x1_dtype, int64_t ld1, const int32_t* idx1, int64_t K1,
+                     const void* X2, int x2_dtype, int64_t ld2, const int32_t* idx2, int64_t K2,
+                     float* OUT, int64_t ldo, int64_t width, int64_t R, void* stream);
 int dmpnn_pack_weight_tc_bytes(int64_t N, int64_t K, size_t* bytes);
 int dmpnn_pack_weight_tc(const float* W, int64_t ldw, int64_t N, int64_t K, int transpose, void* Wpk, void* stream);
 int dmpnn_linear_tc_bf16(const void* A, int64_t lda, int64_t R, int64_t K, const void* Wpk, int64_t N,

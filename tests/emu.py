@@ -205,6 +205,24 @@ def concat_bf16(X1, K1, out, R, *, idx1=None, X2=None, K2=0, idx2=None, width=No
         out[:R, K1 + K2:width] = 0
 
 
+def dropout_keep_bits(rows, h, cfg, like):
+    """engine.dropout_keep_bits without the device generator: keep bits from torch's CPU RNG (or the test's mask_fn)."""
+    nj = (h + 15) // 16
+    if cfg.mask_fn is not None:
+        M = cfg.mask_fn(like)[:rows, : nj * 16].to(torch.int32)
+    else:
+        M = (torch.rand(rows, nj * 16) >= cfg.dropout_p).to(torch.int32)
+    w = (M.reshape(rows, nj, 16) << torch.arange(16, dtype=torch.int32)).sum(-1)
+    return w.to(torch.uint16).contiguous()
+
+
+def concat_f32(X1, K1, out, R, *, idx1=None, X2=None, K2=0, idx2=None, width=None):
+    width = out.shape[1] if width is None else width
+    out[:R, :K1 + K2] = _cat(X1, K1, idx1, X2, K2, idx2, R)
+    if width > K1 + K2:
+        out[:R, K1 + K2:width] = 0
+
+
 def linear_tc(A, K, Wpk, N, out, *, bias=None, res=None, act=ACT_NONE, act_param=0.0, R=None):
     R = out.shape[0] if R is None else R
     assert A.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and Wpk.shape == (N, K)
@@ -236,8 +254,10 @@ def pack_weight_x3(W, transpose=False):
 
 def linear_x3(A, K, Wpk, N, out, *, idx=None, bias=None, res=None, act=ACT_NONE, act_param=0.0, R=None, pad_to=None):
     R = out.shape[0] if R is None else R
-    assert A.dtype == torch.float32 and out.dtype == torch.float32 and Wpk.shape == (N, K) and K % 4 == 0
-    Y = _rows(A, idx, R, K) @ Wpk.t()
+    Kw = Wpk.shape[1]                  # the packed weight's own K; A may carry up to 3 zero padding columns beyond it
+    assert A.dtype == torch.float32 and out.dtype == torch.float32 and Wpk.shape[0] == N and K % 4 == 0 and 0 <= K - Kw < 4
+    assert K == Kw or float(_rows(A, idx, R, K)[:, Kw:].abs().max()) == 0.0
+    Y = _rows(A, idx, R, Kw) @ Wpk.t()
     if bias is not None:
         Y = Y + bias.float()
     if res is not None:
@@ -407,7 +427,7 @@ def patch_engine(monkeypatch):
     """Route engine.py's kernel wrappers to the emulations above (host-logic tests only)."""
     for name in ("linear_fwd", "linear_wgrad", "segment_sum", "segment_bcast", "bond_message", "rev_average", "act_bwd",
                  "build_layout", "pack_weight_tc", "pack_weight_bf16", "concat_bf16", "linear_tc", "wgrad_tc", "column_sum",
-                 "pack_weight_x3", "linear_x3", "wgrad_x3", "bn_train_fwd", "bn_bwd", "mse_loss",
+                 "pack_weight_x3", "linear_x3", "wgrad_x3", "bn_train_fwd", "bn_bwd", "mse_loss", "concat_f32", "dropout_keep_bits",
                  "bond_step_fused", "bond_step_bwd_fused", "bond_message_bwd_masked", "sum_act_bwd", "scale_mask_"):
         monkeypatch.setattr(engine, name, globals()[name])
     monkeypatch.setattr(engine, "_require_cuda", lambda *ts: None)

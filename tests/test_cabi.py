@@ -40,7 +40,7 @@ def test_binding_matches_header_prototypes():
         param = param.strip()
         if "*" in param:
             return "ptr"
-        if re.search(r"\b(int64_t|size_t)\b", param):
+        if re.search(r"\b(int64_t|uint64_t|size_t)\b", param):
             return "i64"
         if re.search(r"\bfloat\b", param):
             return "f32"
@@ -51,7 +51,7 @@ def test_binding_matches_header_prototypes():
     def kind_of_ctypes(t) -> str:
         if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or hasattr(t, "_type_") and isinstance(t._type_, type):
             return "ptr"
-        return {ctypes.c_int64: "i64", ctypes.c_size_t: "i64", ctypes.c_int: "i32", ctypes.c_float: "f32"}[t]
+        return {ctypes.c_int64: "i64", ctypes.c_uint64: "i64", ctypes.c_size_t: "i64", ctypes.c_int: "i32", ctypes.c_float: "f32"}[t]
 
     for name, params in protos.items():
         plist = [] if params.strip() in ("", "void") else [x for x in params.split(",")]

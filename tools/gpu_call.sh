@@ -57,6 +57,12 @@ for s in $STEPS; do
     bench_c5)
       timeout 900 python bench.py --config C5 --steps 3 --warmup 3 > "$OUT/bench_c5.json" 2> "$OUT/bench_c5.err"
       echo "bench C5 rc=$?"; cat "$OUT/bench_c5.json"; tail -5 "$OUT/bench_c5.err" ;;
+    variants)
+      for d in chemprop_b200/lib/variants/*/; do
+        tag=$(basename "$d")
+        echo "== variant $tag"
+        LD_LIBRARY_PATH="$d" timeout 120 ./tests/native/fused_step_harness 10000 300 1 2>&1 | tee "$OUT/variant_$tag.log" | tail -6
+      done ;;
     native)
       ./tests/native/fused_step_harness 10000 300 2 2>&1 | tee "$OUT/native_fused_step.log" ;;
     *) echo "unknown step $s" ;;
