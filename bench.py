@@ -45,7 +45,8 @@ CONFIGS = {
     "C2": dict(kind="bond", n_mols=10_000, d_h=300, depth=3, precision="bf16", gen="mol", d_v=72, d_e=14, pool=3,
                scaling="weak", desc="10000 synthetic mols/GPU (~25 atoms), BondMessagePassing h=300 depth=3 + MeanAggregation"),
     "C3": dict(kind="bond", n_mols=50_000, d_h=600, depth=6, precision="fp32", gen="mol", d_v=72, d_e=14, pool=1,
-               scaling="weak", graph=False,      # ~100 GB of activations per step: no room for a graph's private pool beside it desc="50000 synthetic mols/GPU (~25 atoms), BondMessagePassing h=600 depth=6 fp32 + MeanAggregation"),
+               scaling="weak", graph=False,      # ~100 GB of activations per step: no room for a graph's private pool beside it
+               desc="50000 synthetic mols/GPU (~25 atoms), BondMessagePassing h=600 depth=6 fp32 + MeanAggregation"),
     "C4": dict(kind="atom", n_mols=10_000, d_h=300, depth=3, precision="bf16", gen="cgr", d_v=106, d_e=28, pool=2,
                scaling="weak", desc="10000 synthetic condensed reaction graphs/GPU (~80 atoms, d_v=106 d_e=28), "
                                     "AtomMessagePassing h=300 depth=3 + MeanAggregation"),

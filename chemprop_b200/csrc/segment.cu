@@ -292,28 +292,52 @@ __global__ void k_bond_message_v4(const TX* __restrict__ X, int64_t ldx, const i
   }
 }
 
+// thread = one VW-element column chunk of several rows: `rows_par` rows side by side in a block (all lanes busy at h = 300:
+// 38 chunks x 6 rows of 256 threads), each thread walking its rows with FOUR rows' loads in flight (the row gather through
+// `gidx` and the two streams are latency-bound with one row per thread); 32-bit index arithmetic, no per-element division
 template <int VW, typename TG, typename TYA, typename TZ, typename TA>
-__global__ void k_act_bwd_v4(const TG* __restrict__ G, int64_t ldg, const int32_t* __restrict__ gidx,
-                             const TYA* __restrict__ Yact, int64_t ldy, int from_preact, int act, float ap,
-                             TZ* __restrict__ dZ, int64_t lddz, TA* __restrict__ ACC, int64_t ldacc, int64_t R, int Q) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R * Q) return;
-  const int64_t r = i / Q;
-  const int q = (int)(i - r * Q);
-  const int64_t gr = gidx ? (int64_t)gidx[r] : r;
-  float g[VW], y[VW], dz[VW];
-  ldv<VW>(G + gr * ldg + VW * q, g);
-  ldv<VW>(Yact + r * ldy + VW * q, y);
+__global__ void __launch_bounds__(256)
+k_act_bwd_v4(const TG* __restrict__ G, int64_t ldg, const int32_t* __restrict__ gidx,
+             const TYA* __restrict__ Yact, int64_t ldy, int from_preact, int act, float ap,
+             TZ* __restrict__ dZ, int64_t lddz, TA* __restrict__ ACC, int64_t ldacc, int64_t R, int Q, int rows_per_block) {
+  const int rows_par = blockDim.x / Q;
+  const int rsub = threadIdx.x / Q;
+  const int c = VW * (threadIdx.x - rsub * Q);
+  if (rsub >= rows_par) return;
+  const int64_t r_end = min(R, ((int64_t)blockIdx.x + 1) * rows_per_block);
+  int64_t r = (int64_t)blockIdx.x * rows_per_block + rsub;
+  auto finish = [&](int64_t rr, const float (&g)[VW], const float (&y)[VW]) {
+    float dz[VW];
 #pragma unroll
-  for (int k = 0; k < VW; ++k)
-    dz[k] = g[k] * (from_preact ? act_grad_from_pre(act, ap, y[k]) : act_grad_from_out(act, ap, y[k]));
-  if (dZ) stv<VW>(dZ + r * lddz + VW * q, dz);
-  if (ACC) {
-    float a[VW];
-    ldv<VW>(ACC + r * ldacc + VW * q, a);
+    for (int k = 0; k < VW; ++k)
+      dz[k] = g[k] * (from_preact ? act_grad_from_pre(act, ap, y[k]) : act_grad_from_out(act, ap, y[k]));
+    if (dZ) stv<VW>(dZ + rr * lddz + c, dz);
+    if (ACC) {
+      float a[VW];
+      ldv<VW>(ACC + rr * ldacc + c, a);
 #pragma unroll
-    for (int k = 0; k < VW; ++k) a[k] += dz[k];
-    stv<VW>(ACC + r * ldacc + VW * q, a);
+      for (int k = 0; k < VW; ++k) a[k] += dz[k];
+      stv<VW>(ACC + rr * ldacc + c, a);
+    }
+  };
+  for (; r + 3 * rows_par < r_end; r += 4 * rows_par) {
+    float g[4][VW], y[4][VW];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t rr = r + u * rows_par;
+      const int64_t gr = gidx ? (int64_t)__ldg(gidx + rr) : rr;
+      ldv<VW>(G + gr * ldg + c, g[u]);
+      ldv<VW>(Yact + rr * ldy + c, y[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) finish(r + u * rows_par, g[u], y[u]);
+  }
+  for (; r < r_end; r += rows_par) {
+    float g[VW], y[VW];
+    const int64_t gr = gidx ? (int64_t)__ldg(gidx + r) : r;
+    ldv<VW>(G + gr * ldg + c, g);
+    ldv<VW>(Yact + r * ldy + c, y);
+    finish(r, g, y);
   }
 }
 
@@ -579,17 +603,18 @@ extern "C" int dmpnn_act_bwd(const void* G, int g_dtype, int64_t ldg, const int3
     DMPNN_DISPATCH_DTYPE(y_dtype, TYA,
       DMPNN_DISPATCH_DTYPE(dz_dtype, TZ,
         DMPNN_DISPATCH_DTYPE(acc_dtype, TA,
-          if (C % 4 == 0 && vec4_ok<TG>(G, ldg) && vec4_ok<TYA>(Yact, ldy) && vec4_ok<TZ>(dZ, dZ ? lddz : 4) &&
+          constexpr int kActBwdRows = 96;     // rows per block of the row-interleaved kernels
+          if (C % 4 == 0 && C / 4 <= 256 && vec4_ok<TG>(G, ldg) && vec4_ok<TYA>(Yact, ldy) && vec4_ok<TZ>(dZ, dZ ? lddz : 4) &&
               vec4_ok<TA>(ACC, ACC ? ldacc : 4)) {
             if (C % 8 == 0 && vec8_ok<TG>(G, ldg) && vec8_ok<TYA>(Yact, ldy) && vec8_ok<TZ>(dZ, dZ ? lddz : 8) &&
                 vec8_ok<TA>(ACC, ACC ? ldacc : 8))
-              k_act_bwd_v4<8, TG, TYA, TZ, TA><<<ceil_div_i64(R * (C / 8), 256), 256, 0, st>>>(
+              k_act_bwd_v4<8, TG, TYA, TZ, TA><<<ceil_div_i64(R, kActBwdRows), 256, 0, st>>>(
                   (const TG*)G, ldg, gidx, (const TYA*)Yact, ldy, from_preact, act, act_param, (TZ*)dZ, lddz, (TA*)ACC, ldacc,
-                  R, (int)(C / 8));
+                  R, (int)(C / 8), kActBwdRows);
             else
-              k_act_bwd_v4<4, TG, TYA, TZ, TA><<<ceil_div_i64(R * (C / 4), 256), 256, 0, st>>>(
+              k_act_bwd_v4<4, TG, TYA, TZ, TA><<<ceil_div_i64(R, kActBwdRows), 256, 0, st>>>(
                   (const TG*)G, ldg, gidx, (const TYA*)Yact, ldy, from_preact, act, act_param, (TZ*)dZ, lddz, (TA*)ACC, ldacc,
-                  R, (int)(C / 4));
+                  R, (int)(C / 4), kActBwdRows);
           } else
             k_act_bwd<TG, TYA, TZ, TA><<<grid, block, 0, st>>>((const TG*)G, ldg, gidx, (const TYA*)Yact, ldy,
                                                               from_preact, act, act_param, (TZ*)dZ, lddz, (TA*)ACC,

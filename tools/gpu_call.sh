@@ -63,6 +63,9 @@ for s in $STEPS; do
         echo "== variant $tag"
         LD_LIBRARY_PATH="$d" timeout 120 ./tests/native/fused_step_harness 10000 300 1 2>&1 | tee "$OUT/variant_$tag.log" | tail -6
       done ;;
+    trace)
+      timeout 300 python tools/trace_step.py > "$OUT/trace_block0.log" 2>&1; echo "trace rc=$?"; cat "$OUT/trace_block0.log"
+      DMPNN_TRACE_BLOCK=77 timeout 300 python tools/trace_step.py > "$OUT/trace_block77.log" 2>&1 ;;
     native)
       ./tests/native/fused_step_harness 10000 300 2 2>&1 | tee "$OUT/native_fused_step.log" ;;
     *) echo "unknown step $s" ;;
