@@ -317,9 +317,7 @@ def main_gpu(args):
                                world=world if strong else 1, drop_last=True, pack_tiles=not args.no_pack)
 
     def batches():
-        while True:
-            for b in loader:
-                yield b
+        return loader.stream()          # epoch after epoch, plans prefetched across the epoch boundaries
 
     first_ids = np.arange(n_mols, dtype=np.int64)
     resident = ds.batch(first_ids if args.no_pack else ds.packed_order(first_ids))

@@ -196,13 +196,18 @@ class PackedMolGraphDataset:
         ne = self._edge_ptr_h[ids + 1] - self._edge_ptr_h[ids]
         return ids[tile_packing_order(na, ne)]
 
+    def plan(self, ids):
+        """The host half of `batch(ids)`: ids, output offsets and the layout meta words (O(len(ids)), pure host work, safe to
+        run on a loader thread ahead of time); hand the result to `batch(ids, plan=...)`."""
+        return self._plan(ids)
+
     def batch(self, ids, pin_memory: bool = False, transfer_dtype: torch.dtype | None = None,
-              buffer: HostBatchBuffer | None = None, n_threads: int = 0) -> BatchMolGraph:
+              buffer: HostBatchBuffer | None = None, n_threads: int = 0, plan=None) -> BatchMolGraph:
         """The BatchMolGraph of molecules `ids` (in that order; repeats allowed), on this data set's device.
         Host data sets: `buffer` = reusable staging memory to gather into (see HostBatchBuffer); its `compact` flag
         then decides whether the bf16 / int32 transfer copy is produced; `n_threads` host threads share the copy (0 =
-        automatic: one per 2048 molecules, at most 8)."""
-        plan, n, Vt, Et, meta = self._plan(ids)
+        automatic: one per 2048 molecules, at most 8).  `plan`: the result of `plan(ids)` computed earlier."""
+        plan, n, Vt, Et, meta = self._plan(ids) if plan is None else plan
         lib = _lib.load()
         if self.device.type == "cuda":
             if transfer_dtype is not None:

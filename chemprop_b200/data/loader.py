@@ -92,11 +92,11 @@ class PackedBatchLoader:
             order = torch.randperm(len(self.dataset)).numpy()
         return epoch_shard(order, self.rank, self.world)
 
-    def batches_of(self, order: np.ndarray) -> list[np.ndarray]:
+    def batches_of(self, order: np.ndarray, pack: bool | None = None) -> list[np.ndarray]:
         out = [order[i:i + self.batch_size] for i in range(0, order.shape[0], self.batch_size)]
         if out and self.drop_last and out[-1].shape[0] < self.batch_size:
             out.pop()
-        if self.pack_tiles:      # same molecules per batch, ordered for full tiles; `LoadedBatch.ids` reports the order
+        if self.pack_tiles if pack is None else pack:   # same molecules per batch, ordered for full tiles; `LoadedBatch.ids` reports the order
             out = [self.dataset.packed_order(ids) for ids in out]
         return out
 
@@ -109,13 +109,65 @@ class PackedBatchLoader:
             out[k] = t
         return out
 
-    def __iter__(self) -> Iterator[LoadedBatch]:
-        chunks = self.batches_of(self.epoch_order())
+    def _resident_batches(self, epochs: int | None) -> Iterator[LoadedBatch]:
+        """Resident data set: the batch is gathered on the device (one launch), but its HOST half -- the tile-packing order of
+        the molecules (~1.6 ms per 10 k molecules) and the plan (ids, output offsets, meta words) -- runs on a producer
+        thread `prefetch` batches ahead (across epoch boundaries when `epochs` is None or > 1), so that the training loop's
+        thread only uploads the plan and launches."""
         ds = self.dataset
-        if ds.device.type == "cuda":                                # resident data set: gather on the device
-            for ids in chunks:
-                yield LoadedBatch(ds.batch(ids), ids, self._extras(ids))
+        q: queue.Queue = queue.Queue(maxsize=self.prefetch)
+        stop = threading.Event()
+
+        def produce_plans():
+            try:
+                e = 0
+                while (epochs is None or e < epochs) and not stop.is_set():
+                    for ids in self.batches_of(self.epoch_order(), pack=False):
+                        if stop.is_set():
+                            return
+                        ids = ds.packed_order(ids) if self.pack_tiles else ids
+                        item = (ids, ds.plan(ids))
+                        while not stop.is_set():
+                            try:
+                                q.put(item, timeout=0.1)
+                                break
+                            except queue.Full:
+                                pass
+                    e += 1
+                q.put(None)
+            except BaseException as ex:  # noqa: BLE001 -- handed to the consumer
+                q.put(ex)
+
+        th = threading.Thread(target=produce_plans, daemon=True, name="packed-batch-planner")
+        th.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                ids, plan = item
+                yield LoadedBatch(ds.batch(ids, plan=plan), ids, self._extras(ids))
+        finally:
+            stop.set()
+            th.join(timeout=5)
+
+    def stream(self) -> Iterator[LoadedBatch]:
+        """Batches for ever, epoch after epoch (the sampler reshuffles at every epoch boundary), without draining the
+        prefetch pipeline between epochs.  `for batch in loader` is one epoch."""
+        if self.dataset.device.type == "cuda":
+            yield from self._resident_batches(epochs=None)
+        else:
+            while True:
+                yield from iter(self)
+
+    def __iter__(self) -> Iterator[LoadedBatch]:
+        ds = self.dataset
+        if ds.device.type == "cuda":
+            yield from self._resident_batches(epochs=1)
             return
+        chunks = self.batches_of(self.epoch_order())
         to_cuda = self.device is not None and self.device.type == "cuda"
         compact = self.transfer_dtype is not None
         ring = [HostBatchBuffer(ds.d_v, ds.d_e, pin_memory=to_cuda, compact=compact) for _ in range(self.prefetch)]

@@ -179,6 +179,27 @@ def test_loader_feeds_the_gpu_with_the_batches_of_its_ids(resident):
     assert n == 1200
 
 
+def test_resident_loader_stream_crosses_epochs_without_draining():
+    """PackedBatchLoader.stream(): batches for ever, plans prefetched on the planner thread across epoch boundaries; every
+    epoch is a permutation of the data set, and every batch is the collate of its ids."""
+    from chemprop_b200.data import BatchMolGraph, PackedBatchLoader, PackedMolGraphDataset, make_molecules
+
+    mgs = make_molecules(500, seed=31, min_atoms=1)
+    ds = PackedMolGraphDataset.from_molgraphs(mgs).to("cuda")
+    loader = PackedBatchLoader(ds, batch_size=100, shuffle=True, seed=3)
+    seen = []
+    for i, b in enumerate(loader.stream()):
+        ref = BatchMolGraph([mgs[j] for j in b.ids])
+        assert torch.equal(b.bmg.V.cpu(), ref.V) and torch.equal(b.bmg.edge_index.cpu(), ref.edge_index)
+        assert b.bmg._meta_host == ref._meta_host
+        seen.append(np.sort(b.ids))
+        if i == 14:
+            break
+    for e in range(3):                                   # three complete epochs of five batches
+        assert np.array_equal(np.sort(np.concatenate(seen[5 * e:5 * e + 5])), np.arange(500))
+    assert not np.array_equal(np.concatenate(seen[:5]), np.concatenate(seen[5:10]))
+
+
 @pytest.mark.parametrize("name", golden_names(mab=True))
 def test_mab_modules_match_reference_golden(name):
     """MABBond / MABAtomMessagePassing through the real kernels: vertex embeddings, per-edge embeddings in the caller's

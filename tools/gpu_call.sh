@@ -66,6 +66,16 @@ for s in $STEPS; do
     trace)
       timeout 300 python tools/trace_step.py > "$OUT/trace_block0.log" 2>&1; echo "trace rc=$?"; cat "$OUT/trace_block0.log"
       DMPNN_TRACE_BLOCK=77 timeout 300 python tools/trace_step.py > "$OUT/trace_block77.log" 2>&1 ;;
+    bench_n2)
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        bench.py --gpus 2 --steps 10 --warmup 3 > "$OUT/bench_n2.json" 2> "$OUT/bench_n2.err"
+      echo "bench N=2 rc=$?"; cat "$OUT/bench_n2.json"; tail -8 "$OUT/bench_n2.err"
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
+        bench.py --config C5 --gpus 2 --steps 3 --warmup 3 > "$OUT/bench_c5_n2.json" 2> "$OUT/bench_c5_n2.err"
+      echo "bench C5 N=2 rc=$?"; cat "$OUT/bench_c5_n2.json"; tail -8 "$OUT/bench_c5_n2.err" ;;
+    bench_ref)
+      timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"
+      echo "bench reference rc=$?"; cat "$OUT/bench_ref.json"; tail -5 "$OUT/bench_ref.err" ;;
     native)
       ./tests/native/fused_step_harness 10000 300 2 2>&1 | tee "$OUT/native_fused_step.log" ;;
     *) echo "unknown step $s" ;;
