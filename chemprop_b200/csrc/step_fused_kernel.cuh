@@ -203,8 +203,12 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
           const uint32_t st = ws % kWStages, use = ws / kWStages;
           mbar_wait(bar(B_WFREE + st), (use & 1) ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(bar(B_WFULL + st), bytes);
-            bulk_load(sW + st * kWStageBytes, src, bytes, bar(B_WFULL + st));
+            if (p.exp_flags & 4096) {              // timing experiment: no W stream at all (stale shared memory, wrong results)
+              mbar_arrive(bar(B_WFULL + st));
+            } else {
+              mbar_expect_tx(bar(B_WFULL + st), bytes);
+              bulk_load(sW + st * kWStageBytes, src, bytes, bar(B_WFULL + st));
+            }
           }
           __syncwarp();
         }
@@ -544,7 +548,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       uint32_t left = (1u << p.nslab) - 1u;           // slabs this thread still has to release
       const int npass = (p.nslab + kWHalfSlabs - 1) / kWHalfSlabs;
       int cur_pass = 0;                               // k pass being written; earlier ones are published by this thread
-      mbar_wait(bar(B_ATFREE + 0), (it & 1) ^ 1);    // tensor core is done with the first k pass of the previous tile
+      if (!(p.exp_flags & 8192)) mbar_wait(bar(B_ATFREE + 0), (it & 1) ^ 1);    // tensor core is done with the first k pass of the previous tile
       tc_fence_after();
       for (int j = shalf; j < nj; j += 2) {
         const int pj = (j >> 2) / kWHalfSlabs;
@@ -553,7 +557,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
           tc_fence_before();
           for (int q = cur_pass; q < pj; ++q) mbar_arrive(bar(B_AREADY + q));
           cur_pass = pj;
-          mbar_wait(bar(B_ATFREE + pj), (it & 1) ^ 1);
+          if (!(p.exp_flags & 8192)) mbar_wait(bar(B_ATFREE + pj), (it & 1) ^ 1);   // 8192: timing experiment, as if A were double-buffered
           tc_fence_after();
         }
         if ((j >> 2) != cur_slab) {                   // entering a new 64-column slab of the H tile

@@ -76,6 +76,13 @@ for s in $STEPS; do
     bench_ref)
       timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"
       echo "bench reference rc=$?"; cat "$OUT/bench_ref.json"; tail -5 "$OUT/bench_ref.err" ;;
+    exps)
+      for e in 0 4096 8192 12288; do
+        echo "== DMPNN_EXP=$e"
+        DMPNN_EXP=$e timeout 120 ./tests/native/fused_step_harness 10000 300 1 2>&1 | tee "$OUT/exp_$e.log" | tail -3
+      done ;;
+    prof_e2e)
+      timeout 300 python tools/profile_e2e.py 30 > "$OUT/profile_e2e.log" 2>&1; echo "profile_e2e rc=$?"; head -60 "$OUT/profile_e2e.log" ;;
     native)
       ./tests/native/fused_step_harness 10000 300 2 2>&1 | tee "$OUT/native_fused_step.log" ;;
     *) echo "unknown step $s" ;;
