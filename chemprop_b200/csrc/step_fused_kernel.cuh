@@ -122,7 +122,9 @@ template <int ACT, bool FIRST, bool HAS_BIAS, int MODE, bool FAR, bool DROP>
 __global__ void __launch_bounds__(kThreads, 1)
 k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ CUtensorMap tmapH0, Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment as an OFFSET from the shared-memory symbol (not through a uintptr_t round trip): the compiler keeps
+  // the address space, so the row-pointer / rev() table look-ups of the message warps are LDS instead of generic LD.E
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t sA = sbase + kOffA, sW = sbase + kOffW, sH = sbase + kOffH, sBar = sbase + kOffBar;
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
@@ -170,10 +172,12 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer: H_prev tile -> shared memory (single buffer) =====================
     int it = 0;
+    int row_carry = (int)blockIdx.x < n_items ? __ldg(p.tile_row_ptr + blockIdx.x) : 0;   // the next tile's first row, loaded a tile ahead
     for (int t = blockIdx.x; t < n_items; t += gridDim.x, ++it) {
-      const int row0 = __ldg(p.tile_row_ptr + t);
+      const int row0 = row_carry;
       const int t2 = t + gridDim.x;
       const int row2 = (t2 < n_items && !(p.exp_flags & 2048)) ? __ldg(p.tile_row_ptr + t2) : -1;
+      if (t2 < n_items) row_carry = (p.exp_flags & 2048) ? __ldg(p.tile_row_ptr + t2) : row2;
       // slab s of this tile is loaded as soon as the message warps have left slab s of the previous tile: the load
       // of the leading slabs overlaps the gather of the trailing ones (one shared-memory tile, no exposed latency)
       for (int s = 0; s < p.nslab; ++s) {
@@ -467,26 +471,43 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         s_revl[tS] = (int16_t)(tS < nr ? __ldg(p.rev_row + row0 + tS) - row0 : tS);
       }
     }
+    // scalars of the tile after the current one (see the metadata pipeline below)
+    int nx_row0 = 0, nx_atom0 = 0, nx_natoms = 0, nx_nr = 0;
+    bool nx_far = false;
+    if (t + (int)gridDim.x < n_items) {
+      const int t1 = t + gridDim.x;
+      nx_row0 = __ldg(p.tile_row_ptr + t1);
+      nx_nr = __ldg(p.tile_row_ptr + t1 + 1) - nx_row0;
+      nx_atom0 = __ldg(p.tile_atom_ptr + t1);
+      nx_natoms = __ldg(p.tile_atom_ptr + t1 + 1) - nx_atom0;
+      nx_far = FAR && p.work_flag != nullptr && __ldg(p.work_flag + t1) != 0;
+      if (nx_far) nx_natoms = 0;
+    }
     for (; t < n_items; t += gridDim.x, ++it) {
       const int b = it & 1;
       const int32_t* rp = s_rowptr + b * 132;
       const int16_t* rvl = s_revl + b * 128;
-      // prefetch next tile's rowptr slice into a register
+      // Metadata pipeline, two tiles deep: the SCALARS of the next tile (row / atom offsets: first-level loads) were loaded
+      // one iteration ago, so the dependent second-level loads (its row-pointer slice and rev() rows) issue here without
+      // waiting for them; the scalars of the tile after that are requested now.  (One-deep, the address dependency stalled
+      // every message warp for an L2 round trip at the top of every tile.)
       const int tn = t + gridDim.x;
-      int row0n = 0, atom0n = 0, natomsn = 0, rpn = 0;
-      bool farn = false;
-      if (tn < n_items) {
-        row0n = __ldg(p.tile_row_ptr + tn);
-        atom0n = __ldg(p.tile_atom_ptr + tn);
-        natomsn = __ldg(p.tile_atom_ptr + tn + 1) - atom0n;
-        farn = FAR && p.work_flag != nullptr && __ldg(p.work_flag + tn) != 0;
-        if (farn) natomsn = 0;
-        if (tS <= natomsn) rpn = __ldg(p.rowptr + atom0n + tS) - row0n;
-      }
+      const int row0n = nx_row0, atom0n = nx_atom0, natomsn = nx_natoms, nrn = nx_nr;
+      const bool farn = nx_far;
+      int rpn = 0;
+      if (tn < n_items && tS <= natomsn) rpn = __ldg(p.rowptr + atom0n + tS) - row0n;
       int rvn = tS;
-      if (kNeedRev && tn < n_items && tS < 128) {
-        const int nrn = __ldg(p.tile_row_ptr + tn + 1) - row0n;
-        if (tS < nrn) rvn = __ldg(p.rev_row + row0n + tS) - row0n;
+      if (kNeedRev && tn < n_items && tS < 128 && tS < nrn) rvn = __ldg(p.rev_row + row0n + tS) - row0n;
+      {
+        const int tnn = tn + gridDim.x;
+        if (tnn < n_items) {
+          nx_row0 = __ldg(p.tile_row_ptr + tnn);
+          nx_nr = __ldg(p.tile_row_ptr + tnn + 1) - nx_row0;
+          nx_atom0 = __ldg(p.tile_atom_ptr + tnn);
+          nx_natoms = __ldg(p.tile_atom_ptr + tnn + 1) - nx_atom0;
+          nx_far = FAR && p.work_flag != nullptr && __ldg(p.work_flag + tnn) != 0;
+          if (nx_far) nx_natoms = 0;
+        }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");   // rp[] and rvl[] of this tile are complete
       // Forward: A row r is the message of edge r ITSELF = sum over the in-edges of src(r) other than rev(r), i.e. the

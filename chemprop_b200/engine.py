@@ -50,7 +50,15 @@ class _StepTimer:
         return False
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device.  Called once per kernel launch (~60 per training step):
+    the raw accessors cost ~0.3 us, `torch.cuda.current_stream().cuda_stream` ~15 us (0.45 ms of host time per step)."""
+    if _raw_stream is not None and _raw_device is not None:
+        return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream
 
 
