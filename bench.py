@@ -19,7 +19,7 @@ Prints ONE JSON line (rank 0):
  e2e           same metric through the public loader API (`PackedBatchLoader` over a `PackedMolGraphDataset` resident in
                HBM): every step the host draws the batch's molecule ids, uploads ids + offsets from pinned memory (24 B per
                molecule), the batch is assembled by one gather launch, and the step's loss is copied back and read by the host
- e2e_host_batch  (C2) the same step fed with a complete host batch per step (bf16 features + int32 indices, 57 MB H2D)
+ e2e_host_batch  (C2, N = 1) the same step fed with a complete host batch per step (bf16 features + int32 indices, 57 MB H2D)
  roofline      the dominant kernel: algorithmic bytes or flops / its CUDA-event duration vs the measured peak
  cpu_baseline  the oracle port (the reference's own op sequence on torch CPU) on the host cores, bounded sample
 
@@ -465,7 +465,7 @@ def main_gpu(args):
 
     # ---- (C2) end to end from complete host batches: 57 MB of features + indices per step ------------------------
     e2e_host = None
-    if name == "C2" and not strong and not args.no_host_batch:
+    if name == "C2" and not strong and not args.no_host_batch and world == 1:
         mgs = gen_mols(cfg, n_mols, seed=1 + rank)
         if not args.no_pack:
             mgs = [mgs[i] for i in tile_packing_order_of(mgs)]

@@ -267,10 +267,15 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
     // ===================== TMA producer: H_0 slabs -> staging buffers (two per epilogue group) ==========
     uint32_t cnt[2] = {0u, 0u};   // slabs handed to each group so far
     int it = 0;
+    // first rows of this tile and of the next, loaded one and two tiles ahead: nothing below waits for a load it just issued
+    int row_c = (int)blockIdx.x < n_items ? __ldg(p.tile_row_ptr + blockIdx.x) : 0;
+    int row_n = (int)(blockIdx.x + gridDim.x) < n_items ? __ldg(p.tile_row_ptr + blockIdx.x + gridDim.x) : -1;
     for (int t = blockIdx.x; MODE != MODE_BWD_COPY && t < n_items; t += gridDim.x, ++it) {
-      const int row0 = __ldg(p.tile_row_ptr + t);
+      const int row0 = row_c;
       const int tn = t + gridDim.x;
-      const int rown = (tn < n_items && !(p.exp_flags & 2048)) ? __ldg(p.tile_row_ptr + tn) : -1;
+      const int rown = (tn < n_items && !(p.exp_flags & 2048)) ? row_n : -1;
+      row_c = row_n;
+      row_n = (tn + (int)gridDim.x < n_items) ? __ldg(p.tile_row_ptr + tn + gridDim.x) : -1;
       if (rown >= 0 && elect_one())
         for (int s = 0; s < p.nslab; ++s) tma_prefetch_2d(&tmapH0, s * 64, rown);
       __syncwarp();

@@ -786,13 +786,18 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
         Hprev, first = Hn, False
     if tc:
         # [V || M_v] assembled once in bf16 (torch.cat of base.py:180), M_v written in place by the segment sum
-        ko = (d_v + h + 15) // 16 * 16
-        XO = torch.empty((max(nV, 1), ko), dtype=T, device=dev)   # columns >= d_v+h are clipped by the TMA descriptor
+        hc = (h + 15) // 16 * 16       # zero columns up to pad16(h): 16-byte stores in the segment sum
+        ko = (d_v + hc + 1 + 15) // 16 * 16
+        XO = torch.empty((max(nV, 1), ko), dtype=T, device=dev)   # columns beyond the K a GEMM asks for are clipped by its TMA descriptor
         concat_bf16(V, d_v, XO, nV, width=d_v)
         Mv = XO[:, d_v:d_v + h]
-        hc = (h + 15) // 16 * 16       # zero columns up to pad16(h) when the row has room: 16-byte stores in the sum
-        segment_sum(Hprev, lay.rowptr, nV, h, Mv, act=(a if first else ACT_NONE), act_param=ap,
-                    pad_to=(hc if d_v + hc <= ko else h))
+        segment_sum(Hprev, lay.rowptr, nV, h, Mv, act=(a if first else ACT_NONE), act_param=ap, pad_to=hc)
+        ones_col = None
+        if for_backward and bo is not None and d_v + hc + 1 <= 448:
+            # a column of ones after [V || M_v || 0-pad]: the W_o weight-gradient GEMM over K = d_v + pad16(h) + 1 then delivers
+            # the bias gradient (the column sums of dY) as its last column -- no separate column-sum pass over V x h
+            ones_col = d_v + hc
+            XO[:, ones_col].fill_(1.0)
         Hvp = torch.empty((max(nV, 1), pad_hidden(h)), dtype=T, device=dev)
         linear_tc(XO, d_v + h, pack_weight_tc(Wo), h, Hvp, bias=bo, act=a, act_param=ap, R=nV)
         if cfg.dropout_p > 0:
@@ -817,7 +822,8 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
             # H_v = tau(W_o([V || M_v]))   (base.py:180-182)
             Hv = torch.empty((nV, h), dtype=T, device=dev)
             linear_fwd(V, d_v, Wo, Hv, h, X2=Mv, K2=h, bias=bo, act=a, act_param=ap, R=nV, pad_to=h)
-    saved = dict(H0=H0, Hs=Hs, Ms=Ms, Hbars=Hbars, Mv=Mv, Hv=Hv, X0=X0, XO=XO, tc=tc, x3=x3, X0f=locals().get("X0f"))
+    saved = dict(H0=H0, Hs=Hs, Ms=Ms, Hbars=Hbars, Mv=Mv, Hv=Hv, X0=X0, XO=XO, tc=tc, x3=x3, X0f=locals().get("X0f"),
+                 ones_col=locals().get("ones_col"))
     return Hv, saved
 
 
@@ -968,9 +974,15 @@ def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
     s_e = s_drop if cfg.depth > 1 else 1.0            # site on H^{T-1} (base.py:139); H^0 = tau(H_0) has none
     dY = _empty_hidden(nV, hp, T, dev)
     act_bwd(gHv, Hv, nV, h, act=a, act_param=ap, dZ=dY)      # dY / s_v
-    wgrad_tc(dY, saved["XO"], nV, h, d_v + h, dWo)
-    if dbo is not None:
-        column_sum(dY, nV, h, dbo)
+    oc = saved.get("ones_col")
+    if dbo is not None and oc is not None:
+        dWo_ext = torch.empty((h, oc + 1), **f32)            # [dW_o | 0 | db_o]: the ones column of XO (bond_forward)
+        wgrad_tc(dY, saved["XO"], nV, h, oc + 1, dWo_ext)
+        dWo, dbo = dWo_ext[:, : d_v + h], dWo_ext[:, oc]
+    else:
+        wgrad_tc(dY, saved["XO"], nV, h, d_v + h, dWo)
+        if dbo is not None:
+            column_sum(dY, nV, h, dbo)
     if s_v != 1.0:
         dWo.mul_(s_v)
         if dbo is not None:
