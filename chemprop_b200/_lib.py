@@ -63,6 +63,7 @@ SIGNATURES = {
     "dmpnn_linear_tc_bf16": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _f32, _vp, _i64, _vp]),
     "dmpnn_wgrad_tc_workspace_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
     "dmpnn_wgrad_tc_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _vp, _vp]),
+    "dmpnn_wgrad_tc_multi_bf16": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _vp, _vp]),
     "dmpnn_column_sum": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _vp, _i32, _vp, _vp]),
     "dmpnn_set_trace_buffer": (C.c_int, [_vp, _i64]),
     "dmpnn_pack_weight_bf16_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),

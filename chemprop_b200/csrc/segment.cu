@@ -341,6 +341,57 @@ k_act_bwd_v4(const TG* __restrict__ G, int64_t ldg, const int32_t* __restrict__ 
   }
 }
 
+// ReLU, all-bf16, no accumulator: dZ[r] = G[gidx ? gidx[r] : r] masked by [Y[r] > 0] -- the two instances every bf16 training
+// step runs (atom rows after the read-out, edge rows with the atom -> edge broadcast).  Nothing is converted: the mask is
+// taken on the packed pairs (`__hgt2_mask`: 0xFFFF per half where y > 0, false for NaN like the scalar test) and ANDed
+// into the gradient bits, so a thread keeps U rows of NB-byte chunks in flight in 2 * U * NB / 4 registers.  (The generic
+// kernel above spends ~200 instructions per warp and row on its run-time activation switch and conversions: 262 us for
+// the 0.76 GB of the bench's edge instance, profiles/r2_glue_ncu.md.)
+template <int NB> struct BytesVec;
+template <> struct BytesVec<8> { using type = uint2; };
+template <> struct BytesVec<16> { using type = uint4; };
+__device__ __forceinline__ uint32_t relu_mask_bits(uint32_t g, uint32_t y) {
+  __nv_bfloat162 y2;
+  memcpy(&y2, &y, 4);
+  return g & __hgt2_mask(y2, __float2bfloat162_rn(0.f));
+}
+__device__ __forceinline__ uint2 relu_mask_bits(uint2 g, uint2 y) { return make_uint2(relu_mask_bits(g.x, y.x), relu_mask_bits(g.y, y.y)); }
+__device__ __forceinline__ uint4 relu_mask_bits(uint4 g, uint4 y) {
+  return make_uint4(relu_mask_bits(g.x, y.x), relu_mask_bits(g.y, y.y), relu_mask_bits(g.z, y.z), relu_mask_bits(g.w, y.w));
+}
+template <int NB, int U>
+__global__ void __launch_bounds__(256)
+k_act_bwd_relu_bf16(const __nv_bfloat16* __restrict__ G, int64_t ldg, const int32_t* __restrict__ gidx,
+                    const __nv_bfloat16* __restrict__ Y, int64_t ldy, __nv_bfloat16* __restrict__ dZ, int64_t lddz,
+                    int64_t R, int Q, int rows_per_block) {
+  using V = typename BytesVec<NB>::type;
+  const int rows_par = blockDim.x / Q;
+  const int rsub = threadIdx.x / Q;
+  const int c = (NB / 2) * (threadIdx.x - rsub * Q);
+  if (rsub >= rows_par) return;
+  const int64_t r_end = min(R, ((int64_t)blockIdx.x + 1) * rows_per_block);
+  int64_t r = (int64_t)blockIdx.x * rows_per_block + rsub;
+  for (; r + (U - 1) * rows_par < r_end; r += U * rows_par) {
+    int64_t gr[U];
+    V g[U], y[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) gr[u] = gidx ? (int64_t)__ldg(gidx + r + u * rows_par) : r + u * rows_par;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      g[u] = __ldg(reinterpret_cast<const V*>(G + gr[u] * ldg + c));
+      y[u] = __ldcs(reinterpret_cast<const V*>(Y + (r + u * rows_par) * ldy + c));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) *reinterpret_cast<V*>(dZ + (r + u * rows_par) * lddz + c) = relu_mask_bits(g[u], y[u]);
+  }
+  for (; r < r_end; r += rows_par) {
+    const int64_t gr = gidx ? (int64_t)__ldg(gidx + r) : r;
+    const V g = __ldg(reinterpret_cast<const V*>(G + gr * ldg + c));
+    const V y = __ldcs(reinterpret_cast<const V*>(Y + r * ldy + c));
+    *reinterpret_cast<V*>(dZ + r * lddz + c) = relu_mask_bits(g, y);
+  }
+}
+
 template <typename TX, typename TO>
 __global__ void k_rev_average_v4(const TX* __restrict__ X, int64_t ldx, const int32_t* __restrict__ rev_row, int64_t R,
                                  int Q, int act, float ap, TO* __restrict__ OUT, int64_t ldo) {
@@ -417,9 +468,14 @@ k_concat_bf16_v4(const T1* __restrict__ X1, int64_t ld1, const int32_t* __restri
   const int64_t r_end = min(R, ((int64_t)blockIdx.x + 1) * rows_per_block);
   for (int64_t r = (int64_t)blockIdx.x * rows_per_block + rsub; r < r_end; r += rows_par) {
     float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (c4 + 4 <= K1 && x1_vec) {
-      const int64_t r1 = idx1 ? (int64_t)idx1[r] : r;
-      ld4(X1 + r1 * ld1 + c4, v);
+    if (c4 + 4 <= K1) {               // quad inside the first operand: one row index, no per-element tests
+      const int64_t r1 = idx1 ? (int64_t)__ldg(idx1 + r) : r;
+      const T1* s1 = X1 + r1 * ld1 + c4;
+      if (x1_vec) ld4(s1, v);
+      else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = ld_as_float(s1 + i);
+      }
     } else if (c4 < K1 + K2) {
       const int64_t r1 = idx1 ? (int64_t)idx1[r] : r;
       const int64_t r2 = (K2 > 0 && idx2) ? (int64_t)idx2[r] : r;
@@ -598,6 +654,21 @@ extern "C" int dmpnn_act_bwd(const void* G, int g_dtype, int64_t ldg, const int3
   if (R == 0) return 0;
   if (!dZ) dz_dtype = g_dtype;
   if (!ACC) acc_dtype = g_dtype;
+  if (act == DMPNN_ACT_RELU && !ACC && g_dtype == DMPNN_BF16 && y_dtype == DMPNN_BF16 && dz_dtype == DMPNN_BF16 && C % 4 == 0 &&
+      C / 4 <= 256 && vec4_ok<__nv_bfloat16>(G, ldg) && vec4_ok<__nv_bfloat16>(Yact, ldy) && vec4_ok<__nv_bfloat16>(dZ, lddz)) {
+    constexpr int U = 8;
+    const bool wide = C % 8 == 0 && vec8_ok<__nv_bfloat16>(G, ldg) && vec8_ok<__nv_bfloat16>(Yact, ldy) && vec8_ok<__nv_bfloat16>(dZ, lddz);
+    const int Q = (int)(wide ? C / 8 : C / 4);
+    const int rpb = 2 * U * (256 / Q);           // two full passes of U interleaved rows per thread
+    if (wide)
+      k_act_bwd_relu_bf16<16, U><<<ceil_div_i64(R, rpb), 256, 0, st>>>((const __nv_bfloat16*)G, ldg, gidx, (const __nv_bfloat16*)Yact,
+                                                                        ldy, (__nv_bfloat16*)dZ, lddz, R, Q, rpb);
+    else
+      k_act_bwd_relu_bf16<8, U><<<ceil_div_i64(R, rpb), 256, 0, st>>>((const __nv_bfloat16*)G, ldg, gidx, (const __nv_bfloat16*)Yact,
+                                                                       ldy, (__nv_bfloat16*)dZ, lddz, R, Q, rpb);
+    DMPNN_CHECK_LAUNCH("act_bwd", 1);
+    return 0;
+  }
   dim3 block(64, 4), grid(ceil_div_i64(R, 4), ceil_div_i64(C, 64));
   DMPNN_DISPATCH_DTYPE(g_dtype, TG,
     DMPNN_DISPATCH_DTYPE(y_dtype, TYA,

@@ -11,6 +11,9 @@
 //     warp 2  TMEM allocator
 //     warps 4-7  after the last block: TMEM -> f32 partial[cta][128][Kpad] in global memory
 //   a second kernel adds the partials of each mt in fixed order (deterministic) into dW.
+// Up to three dY TERMS may share one launch (dW = sum_t dY_t^T X): the X boxes of a stage are loaded once and every term
+// accumulates into the same TMEM tile -- the W_i gradient of the bf16 mirror, whose dH_0 is a sum of per-step terms that
+// is never formed (engine.bond_backward_tc), reads X_0 once instead of once per term.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -40,7 +43,7 @@ enum { B_FULL = 0, B_EMPTY = 3, B_ACCFULL = 6 };
 struct Params {
   float* partial;       // [gridDim.x][128][Kpad]
   int64_t R;
-  int N, Kx, Kpad, nxb, n_mt, slots, n_blocks;
+  int N, Kx, Kpad, nxb, n_mt, slots, n_blocks, n_terms;
 };
 
 // MN-major SWIZZLE_128B operand: rows (K index) at 128 B pitch, 8-row groups 1024 B apart (SBO),
@@ -58,7 +61,8 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16_mn(int M, int N) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-k_wgrad_tc(const __grid_constant__ CUtensorMap tmapY, const __grid_constant__ CUtensorMap tmapX, Params p) {
+k_wgrad_tc(const __grid_constant__ CUtensorMap tmapY, const __grid_constant__ CUtensorMap tmapY1,
+           const __grid_constant__ CUtensorMap tmapY2, const __grid_constant__ CUtensorMap tmapX, Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -81,7 +85,9 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmapY, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const uint32_t stage_tx = (uint32_t)(2 + p.nxb) * kBoxBytes;
+  const int nt = p.n_terms;
+  const uint32_t stage_tx = (uint32_t)(2 * nt + p.nxb) * kBoxBytes;
+  const uint32_t x_off = (uint32_t)(2 * nt) * kBoxBytes;      // a stage = [2 boxes per term | X boxes]
 
   if (warp == 0) {
     uint32_t ks = 0;
@@ -91,10 +97,13 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmapY, const __grid_constant__ CU
       if (elect_one()) {
         const uint32_t base = sbase + st * kStageBytes;
         mbar_expect_tx(bar(B_FULL + st), stage_tx);
-        tma_load_2d(base, &tmapY, bar(B_FULL + st), mt * 128, blk * kRowsPerStage);
-        tma_load_2d(base + kBoxBytes, &tmapY, bar(B_FULL + st), mt * 128 + 64, blk * kRowsPerStage);
+        for (int t = 0; t < nt; ++t) {
+          const CUtensorMap* my = t == 0 ? &tmapY : (t == 1 ? &tmapY1 : &tmapY2);
+          tma_load_2d(base + (2 * t) * kBoxBytes, my, bar(B_FULL + st), mt * 128, blk * kRowsPerStage);
+          tma_load_2d(base + (2 * t + 1) * kBoxBytes, my, bar(B_FULL + st), mt * 128 + 64, blk * kRowsPerStage);
+        }
         for (int xb = 0; xb < p.nxb; ++xb)
-          tma_load_2d(base + (2 + xb) * kBoxBytes, &tmapX, bar(B_FULL + st), xb * 64, blk * kRowsPerStage);
+          tma_load_2d(base + x_off + xb * kBoxBytes, &tmapX, bar(B_FULL + st), xb * 64, blk * kRowsPerStage);
       }
       __syncwarp();
     }
@@ -111,13 +120,14 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmapY, const __grid_constant__ CU
       tc_fence_after();
       const uint32_t base = sbase + st * kStageBytes;
       if (elect_one()) {
-        for (int kk = 0; kk < kRowsPerStage / 16; ++kk) {
-          const uint32_t acc = (ks > 0 || kk > 0) ? 1u : 0u;
-          const uint64_t adesc = umma_desc_mn_sw128(base + kk * 2048, kBoxBytes);
-          umma_bf16(tmem_base, adesc, umma_desc_mn_sw128(base + 2 * kBoxBytes + kk * 2048, kBoxBytes), idesc0, acc);
-          if (n1 > 0)
-            umma_bf16(tmem_base + 256u, adesc, umma_desc_mn_sw128(base + 6 * kBoxBytes + kk * 2048, kBoxBytes), idesc1, acc);
-        }
+        for (int t = 0; t < nt; ++t)
+          for (int kk = 0; kk < kRowsPerStage / 16; ++kk) {
+            const uint32_t acc = (ks > 0 || kk > 0 || t > 0) ? 1u : 0u;
+            const uint64_t adesc = umma_desc_mn_sw128(base + (2 * t) * kBoxBytes + kk * 2048, kBoxBytes);
+            umma_bf16(tmem_base, adesc, umma_desc_mn_sw128(base + x_off + kk * 2048, kBoxBytes), idesc0, acc);
+            if (n1 > 0)
+              umma_bf16(tmem_base + 256u, adesc, umma_desc_mn_sw128(base + x_off + 4 * kBoxBytes + kk * 2048, kBoxBytes), idesc1, acc);
+          }
         umma_commit(bar(B_EMPTY + st));
       }
       __syncwarp();
@@ -157,15 +167,33 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmapY, const __grid_constant__ CU
 }
 
 // dW[n, k] (+)= sum_slot partial[slot * n_mt + n/128][n % 128][k]
-__global__ void k_wgrad_reduce(const float* __restrict__ partial, int slots, int n_mt, int Kpad, int N, int Kx,
-                               float* __restrict__ dW, int64_t lddw, int accumulate) {
+// block = 128 k lanes x 4 slot groups: group g sums slots g, g+4, ... (independent loads, four in flight per thread), the four
+// group sums are combined in a fixed order through shared memory -- deterministic, and the ~50 serial loads per output of
+// the one-thread-per-output version (9-27 us per call, six calls per step) become ~12.
+__global__ void __launch_bounds__(512) k_wgrad_reduce(const float* __restrict__ partial, int slots, int n_mt, int Kpad, int N, int Kx,
+                                                      float* __restrict__ dW, int64_t lddw, int accumulate) {
+  __shared__ float part[4][128];
   const int n = blockIdx.x;
   const int mt = n >> 7, nl = n & 127;
-  for (int k = threadIdx.x; k < Kx; k += blockDim.x) {
-    float s = 0.f;
-    for (int sl = 0; sl < slots; ++sl) s += partial[((size_t)(sl * n_mt + mt) * 128 + nl) * Kpad + k];
+  const int kx = threadIdx.x & 127, g = threadIdx.x >> 7;
+  const int k = blockIdx.y * 128 + kx;
+  float s0 = 0.f, s1 = 0.f;
+  if (k < Kx) {
+    const float* src = partial + ((size_t)mt * 128 + nl) * Kpad + k;
+    const size_t step = (size_t)n_mt * 128 * Kpad;
+    int sl = g;
+    for (; sl + 4 < slots; sl += 8) {
+      s0 += src[(size_t)sl * step];
+      s1 += src[(size_t)(sl + 4) * step];
+    }
+    if (sl < slots) s0 += src[(size_t)sl * step];
+  }
+  part[g][kx] = s0 + s1;
+  __syncthreads();
+  if (g == 0 && k < Kx) {
+    const float t = (part[0][kx] + part[1][kx]) + (part[2][kx] + part[3][kx]);
     float* o = dW + (int64_t)n * lddw + k;
-    *o = accumulate ? (*o + s) : s;
+    *o = accumulate ? (*o + t) : t;
   }
 }
 
@@ -227,24 +255,27 @@ extern "C" int dmpnn_wgrad_tc_workspace_bytes(int64_t N, int64_t Kx, size_t* byt
   return 0;
 }
 
-extern "C" int dmpnn_wgrad_tc_bf16(const void* dY, int64_t lddy, const void* X, int64_t ldx, int64_t R, int64_t N,
-                                   int64_t Kx, float* dW, int64_t lddw, int accumulate, void* workspace,
-                                   void* stream_) {
+extern "C" int dmpnn_wgrad_tc_multi_bf16(const void* const* dYs, int n_terms, int64_t lddy, const void* X, int64_t ldx, int64_t R,
+                                         int64_t N, int64_t Kx, float* dW, int64_t lddw, int accumulate, void* workspace,
+                                         void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   DMPNN_CHECK_ARG(R >= 0 && N > 0 && N <= 384 && Kx > 0 && Kx <= 64 * kMaxXBoxes, "wgrad_tc: unsupported sizes N=%lld K=%lld",
                   (long long)N, (long long)Kx);
-  DMPNN_CHECK_ARG(dW && workspace, "wgrad_tc: null pointer");
-  DMPNN_CHECK_ARG(R == 0 || (dY && X), "wgrad_tc: null operand");
-  DMPNN_CHECK_ARG(lddy % 8 == 0 && ldx % 8 == 0 && lddy >= N && ldx >= Kx, "wgrad_tc: lddy/ldx must be multiples of 8");
-  DMPNN_CHECK_ARG(R == 0 || ((reinterpret_cast<uintptr_t>(dY) & 15) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0),
-                  "wgrad_tc: operands must be 16-byte aligned");
+  DMPNN_CHECK_ARG(dW && workspace && dYs, "wgrad_tc: null pointer");
   Geom g = geom(N, Kx);
+  DMPNN_CHECK_ARG(n_terms >= 1 && n_terms <= 3 && 2 * n_terms + g.nxb <= 2 + kMaxXBoxes,
+                  "wgrad_tc: %d terms x K=%lld do not fit a stage (2 * terms + ceil(K / 64) <= 9)", n_terms, (long long)Kx);
+  DMPNN_CHECK_ARG(lddy % 8 == 0 && ldx % 8 == 0 && lddy >= N && ldx >= Kx, "wgrad_tc: lddy/ldx must be multiples of 8");
+  for (int t = 0; t < n_terms; ++t)
+    DMPNN_CHECK_ARG(R == 0 || (dYs[t] && (reinterpret_cast<uintptr_t>(dYs[t]) & 15) == 0), "wgrad_tc: dY operands must be 16-byte aligned");
+  DMPNN_CHECK_ARG(R == 0 || (X && (reinterpret_cast<uintptr_t>(X) & 15) == 0), "wgrad_tc: operands must be 16-byte aligned");
   if (R > 0) {
     EncodeTiledFn enc = get_encode_fn();
     DMPNN_CHECK_ARG(enc != nullptr, "wgrad_tc: cuTensorMapEncodeTiled not available from the driver");
-    CUtensorMap mY, mX;
-    DMPNN_CHECK_ARG(encode_map(enc, &mY, dY, N, R, lddy) && encode_map(enc, &mX, X, Kx, R, ldx),
-                    "wgrad_tc: cuTensorMapEncodeTiled failed");
+    CUtensorMap mY[3], mX;
+    for (int t = 0; t < 3; ++t)
+      DMPNN_CHECK_ARG(encode_map(enc, &mY[t], dYs[t < n_terms ? t : 0], N, R, lddy), "wgrad_tc: cuTensorMapEncodeTiled failed");
+    DMPNN_CHECK_ARG(encode_map(enc, &mX, X, Kx, R, ldx), "wgrad_tc: cuTensorMapEncodeTiled failed");
     Params p;
     p.partial = (float*)workspace;
     p.R = R;
@@ -255,17 +286,26 @@ extern "C" int dmpnn_wgrad_tc_bf16(const void* dY, int64_t lddy, const void* X, 
     p.n_mt = g.n_mt;
     p.slots = g.slots;
     p.n_blocks = (int)((R + kRowsPerStage - 1) / kRowsPerStage);
+    p.n_terms = n_terms;
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc);
       DMPNN_CHECK_ARG(e == cudaSuccess, "wgrad_tc: cannot configure %d B dynamic smem: %s", kSmemAlloc, cudaGetErrorString(e));
       attr_set = true;
     }
-    k_wgrad_tc<<<g.grid, kThreads, kSmemAlloc, st>>>(mY, mX, p);
+    k_wgrad_tc<<<g.grid, kThreads, kSmemAlloc, st>>>(mY[0], mY[1], mY[2], mX, p);
   } else {
     cudaMemsetAsync(workspace, 0, (size_t)g.grid * 128 * g.Kpad * sizeof(float), st);
   }
-  k_wgrad_reduce<<<(int)N, 128, 0, st>>>((const float*)workspace, g.slots, g.n_mt, g.Kpad, (int)N, (int)Kx, dW, lddw, accumulate);
+  k_wgrad_reduce<<<dim3((unsigned)N, (unsigned)((Kx + 127) / 128)), 512, 0, st>>>((const float*)workspace, g.slots, g.n_mt, g.Kpad, (int)N, (int)Kx, dW, lddw, accumulate);
   DMPNN_CHECK_LAUNCH("wgrad_tc", 2);
   return 0;
+}
+
+extern "C" int dmpnn_wgrad_tc_bf16(const void* dY, int64_t lddy, const void* X, int64_t ldx, int64_t R, int64_t N,
+                                   int64_t Kx, float* dW, int64_t lddw, int accumulate, void* workspace,
+                                   void* stream_) {
+  DMPNN_CHECK_ARG(R == 0 || dY, "wgrad_tc: null operand");
+  const void* terms[1] = {dY};
+  return dmpnn_wgrad_tc_multi_bf16(terms, 1, lddy, X, ldx, R, N, Kx, dW, lddw, accumulate, workspace, stream_);
 }

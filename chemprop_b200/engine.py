@@ -480,6 +480,24 @@ def wgrad_tc(dY: Tensor, X: Tensor, R: int, N: int, K: int, dW: Tensor, *, accum
     _lib.check(rc, "dmpnn_wgrad_tc_bf16")
 
 
+def wgrad_tc_multi(dYs: list, X: Tensor, R: int, N: int, K: int, dW: Tensor, *, accumulate: bool = False):
+    """dW[n, :K] (+)= sum_t sum_r dY_t[r, n] X[r, :K]: up to three terms per launch share the X stream; longer lists are
+    issued in groups, accumulating."""
+    lib = _lib.load()
+    nxb = ((K + 15) // 16 * 16 + 63) // 64             # X boxes of a stage (csrc/wgrad_tc.cu: 2 * terms + nxb <= 9)
+    per = max(1, min(3, (9 - nxb) // 2))
+    n = C.c_size_t(0)
+    _lib.check(lib.dmpnn_wgrad_tc_workspace_bytes(N, K, C.byref(n)), "dmpnn_wgrad_tc_workspace_bytes")
+    ws = torch.empty(n.value, dtype=torch.uint8, device=dW.device)
+    for i in range(0, len(dYs), per):
+        grp = dYs[i:i + per]
+        assert all(t.dtype == torch.bfloat16 and _ld(t) == _ld(grp[0]) for t in grp) and X.dtype == torch.bfloat16
+        arr = (C.c_void_p * len(grp))(*[t.data_ptr() for t in grp])
+        rc = lib.dmpnn_wgrad_tc_multi_bf16(C.cast(arr, C.c_void_p), len(grp), _ld(grp[0]), X.data_ptr(), _ld(X), R, N, K,
+                                           dW.data_ptr(), dW.stride(0), 1 if (accumulate or i > 0) else 0, ws.data_ptr(), _stream())
+        _lib.check(rc, "dmpnn_wgrad_tc_multi_bf16")
+
+
 # ---- fp32-accurate tensor-core GEMMs (3xTF32, csrc/gemm_x3.cu) -------------------------------------------------
 X3_ENABLED = os.environ.get("DMPNN_X3", "1") != "0"          # DMPNN_X3=0: A/B switch (fp32 tier on the SIMT f32 GEMMs)
 
@@ -1056,9 +1074,9 @@ def bond_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
                 bond_message_bwd_masked(dM, Hin, lay, h, dZ, act=a, act_param=ap)
                 dZs.append(dZ)
         if dH0_terms is not None:
-            for i, P in enumerate(dH0_terms):
-                wgrad_tc(P, saved["X0"], nE, h, d_v + d_e, dWi, accumulate=i > 0)
-                if dbi is not None:
+            wgrad_tc_multi(dH0_terms, saved["X0"], nE, h, d_v + d_e, dWi)     # X_0 read once for all terms
+            if dbi is not None:
+                for i, P in enumerate(dH0_terms):
                     column_sum(P, nE, h, dbi, accumulate=i > 0)
             return dWi, dbi, dWh, dbh, dWo, dbo
         if not fused_sum:
@@ -1299,9 +1317,9 @@ def atom_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
     dH0l = _empty_hidden(nV, hp, T, dev)
     act_bwd(dHa, H0, nV, hc, act=a, act_param=ap, from_preact=True, dZ=dH0l)
     terms.append(dH0l)
-    for i, P in enumerate(terms):           # dH_0 = sum_t dZ^t + dHa^0 * tau'(H_0), contracted term by term
-        wgrad_tc(P, Xv, nV, h, d_v, dWi, accumulate=i > 0)
-        if dbi is not None:
+    wgrad_tc_multi(terms, Xv, nV, h, d_v, dWi)       # dH_0 = sum_t dZ^t + dHa^0 * tau'(H_0), contracted term by term
+    if dbi is not None:
+        for i, P in enumerate(terms):
             column_sum(P, nV, h, dbi, accumulate=i > 0)
     return dWi, dbi, dWh, dbh, dWo, dbo
 

@@ -334,6 +334,11 @@ int dmpnn_bond_step_bwd_fused_bf16(const void* dZ, const void* Yact, void* dOut,
 int dmpnn_wgrad_tc_workspace_bytes(int64_t N, int64_t K, size_t* bytes);
 int dmpnn_wgrad_tc_bf16(const void* dY, int64_t lddy, const void* X, int64_t ldx, int64_t R, int64_t N, int64_t K,
                         float* dW, int64_t lddw, int accumulate, void* workspace, void* stream);
+/* The same with up to three dY terms sharing the launch:  dW (+)= sum_t dY_t^T X  (all terms R x N with one ld; X is read
+ * once per stage).  2 * n_terms + ceil(K / 64) <= 9.  Used for the W_i gradient (mixins.py:8-9 under autograd), whose
+ * upstream gradient dH_0 = sum_t dZ^t + dH^0 tau'(H_0) is a sum the mirror never forms. */
+int dmpnn_wgrad_tc_multi_bf16(const void* const* dYs, int n_terms, int64_t lddy, const void* X, int64_t ldx, int64_t R,
+                              int64_t N, int64_t K, float* dW, int64_t lddw, int accumulate, void* workspace, void* stream);
 /* Column sums (bias gradient): out[n] (+)= sum_r Y[r, n].  Workspace: dmpnn_linear_wgrad_workspace_bytes(R, N, 1). */
 int dmpnn_column_sum(const void* Y, int y_dtype, int64_t ldy, int64_t R, int64_t N, float* out, int accumulate,
                      void* workspace, void* stream);

@@ -246,6 +246,11 @@ def wgrad_tc(dY, X, R, N, K, dW, *, accumulate=False):
         dW[:N, :K] = upd
 
 
+def wgrad_tc_multi(dYs, X, R, N, K, dW, *, accumulate=False):
+    for i, dY in enumerate(dYs):
+        wgrad_tc(dY, X, R, N, K, dW, accumulate=accumulate or i > 0)
+
+
 def pack_weight_x3(W, transpose=False):
     """fp32-accurate tier: the 'packed' weight of the emulation is B[n][k] in f32 (the hi / lo split is exact to 2^-22)"""
     W = W.detach().float()
@@ -426,7 +431,7 @@ def segments_of(batch, n_seg=None):
 def patch_engine(monkeypatch):
     """Route engine.py's kernel wrappers to the emulations above (host-logic tests only)."""
     for name in ("linear_fwd", "linear_wgrad", "segment_sum", "segment_bcast", "bond_message", "rev_average", "act_bwd",
-                 "build_layout", "pack_weight_tc", "pack_weight_bf16", "concat_bf16", "linear_tc", "wgrad_tc", "column_sum",
+                 "build_layout", "pack_weight_tc", "pack_weight_bf16", "concat_bf16", "linear_tc", "wgrad_tc", "wgrad_tc_multi", "column_sum",
                  "pack_weight_x3", "linear_x3", "wgrad_x3", "bn_train_fwd", "bn_bwd", "mse_loss", "concat_f32", "dropout_keep_bits",
                  "bond_step_fused", "bond_step_bwd_fused", "bond_message_bwd_masked", "sum_act_bwd", "scale_mask_"):
         monkeypatch.setattr(engine, name, globals()[name])

@@ -95,6 +95,64 @@ def test_wgrad_tc_vs_torch(R, N, K, lddy, ldx):
     assert (dW.double() - 2 * ref).abs().max().item() <= 4e-4 * scale * max(1.0, (R / 1000) ** 0.5)
 
 
+@pytest.mark.parametrize("R,N,K,lddy,ldx,n_terms", [
+    (5000, 300, 147, 304, 160, 3), (3000, 300, 300, 320, 320, 2), (2500, 300, 372, 320, 384, 3), (130, 64, 64, 64, 64, 3),
+    (200000, 300, 147, 304, 152, 3), (700, 300, 133, 304, 136, 5),
+])
+def test_wgrad_tc_multi_term(R, N, K, lddy, ldx, n_terms):
+    """dW = sum_t dY_t^T X with the terms sharing the X stream (dmpnn_wgrad_tc_multi_bf16): equals the sum of the
+    single-term results up to f32 summation order; term lists longer than a stage holds are issued in groups."""
+    from chemprop_b200.engine import wgrad_tc_multi
+
+    g = torch.Generator(device="cuda").manual_seed(R + K + n_terms)
+    dYs = []
+    for _ in range(n_terms):
+        dY = torch.full((R, lddy), 3.0, dtype=torch.bfloat16, device="cuda")
+        dY[:, :N] = torch.randn(R, N, device="cuda", generator=g).bfloat16()
+        dYs.append(dY)
+    X = torch.full((R, ldx), -2.0, dtype=torch.bfloat16, device="cuda")
+    X[:, :K] = torch.randn(R, K, device="cuda", generator=g).bfloat16()
+    ref = sum(dY[:, :N].double().t() @ X[:, :K].double() for dY in dYs)
+    dW = torch.full((N, K), 0.5, device="cuda")
+    wgrad_tc_multi(dYs, X, R, N, K, dW)
+    torch.cuda.synchronize()
+    scale = max(1.0, float(ref.abs().max()))
+    tol = 2e-4 * scale * max(1.0, (n_terms * R / 1000) ** 0.5)
+    assert (dW.double() - ref).abs().max().item() <= tol
+    wgrad_tc_multi(dYs, X, R, N, K, dW, accumulate=True)
+    assert (dW.double() - 2 * ref).abs().max().item() <= 2 * tol
+    dW2 = torch.empty_like(dW)
+    wgrad_tc_multi(dYs, X, R, N, K, dW2)
+    wgrad_tc_multi(dYs, X, R, N, K, dW)
+    assert torch.equal(dW, dW2)                      # deterministic
+
+
+@pytest.mark.parametrize("R,C,ld,gather", [(5000, 304, 304, True), (4097, 300, 304, False), (333, 64, 64, True), (7, 300, 320, True),
+                                           (100000, 304, 304, True)])
+def test_act_bwd_relu_bf16_fast_path(R, C, ld, gather):
+    """All-bf16 ReLU instance of dmpnn_act_bwd (packed-pair mask kernel): dZ[r] = G[gidx[r]] where Y[r] > 0, else 0 --
+    bit-exact, including y = 0, y = -0 and NaN (no gradient)."""
+    from chemprop_b200.engine import ACT_RELU, act_bwd
+
+    g = torch.Generator(device="cuda").manual_seed(R + C)
+    nG = R // 2 + 1 if gather else R
+    G = torch.randn(nG, ld, device="cuda", generator=g).bfloat16()
+    Y = torch.randn(R, ld, device="cuda", generator=g).bfloat16()
+    Y[::7, ::3] = 0.0
+    Y[1::7, 1::3] = -0.0
+    Y[2::11, 2::5] = float("nan")
+    gidx = torch.randint(0, nG, (R,), device="cuda", dtype=torch.int32, generator=g) if gather else None
+    dZ = torch.full((R, ld), 9.0, dtype=torch.bfloat16, device="cuda")
+    act_bwd(G, Y, R, C, act=ACT_RELU, gidx=gidx, dZ=dZ)
+    Gr = G[gidx.long()] if gather else G
+    ref = torch.where(Y[:, :C] > 0, Gr[:, :C], torch.zeros((), dtype=torch.bfloat16, device="cuda"))
+    assert torch.equal(dZ[:, :C], ref)
+    assert bool((dZ[:, C:] == 9.0).all())                                 # nothing written beyond C
+    dZ2 = torch.empty_like(dZ)
+    act_bwd(G, Y, R, C, act=ACT_RELU, gidx=gidx, dZ=dZ2, from_preact=True)
+    assert torch.equal(dZ2[:, :C], ref)
+
+
 def test_column_sum():
     from chemprop_b200.engine import column_sum
 

@@ -29,6 +29,11 @@ for s in $STEPS; do
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bond_step_fused -s 12 -c 4 \
         -o "$OUT/fused_step" -f python bench.py --steps 1 --warmup 3 --no-cpu --no-dataset > "$OUT/ncu_fused.log" 2>&1
       echo "ncu fused rc=$?" ;;
+    ncu_glue)
+      timeout 900 ncu --set full --clock-control none --import-source on \
+        -k "regex:k_act_bwd_v4|k_segment_sum_flat8|k_concat_bf16_v4|k_wgrad_reduce|k_segment_sum_v4|k_segment_bcast|k_tiles_chunk" -s 27 -c 10 \
+        -o "$OUT/glue" -f python bench.py --steps 1 --warmup 3 --no-cpu --no-dataset > "$OUT/ncu_glue.log" 2>&1
+      echo "ncu glue rc=$?" ;;
     ncu_gemm)
       timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_linear_tc|k_wgrad_tc" -s 18 -c 6 \
         -o "$OUT/gemm" -f python bench.py --steps 1 --warmup 3 --no-cpu --no-dataset > "$OUT/ncu_gemm.log" 2>&1
