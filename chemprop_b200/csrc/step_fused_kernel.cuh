@@ -14,7 +14,11 @@ namespace fused {
 constexpr int kTileM = 128;
 constexpr int kSlabBytes = kTileM * 128;        // one 64-column K slab of a 128-row tile: 16 KB
 constexpr int kMaxSlabs = 5;                    // hp <= 320
-constexpr int kABufBytes = kMaxSlabs * kSlabBytes;
+#ifndef DMPNN_ASLOTS
+#define DMPNN_ASLOTS 5
+#endif
+constexpr int kASlots = DMPNN_ASLOTS;           // shared-memory slots of the raw H tile's 64-column slabs (ring when < kMaxSlabs)
+constexpr int kABufBytes = kASlots * kSlabBytes;
 constexpr int kChunkN = 80;                     // W stage / accumulator chunk = 80 output features (5 x 16)
 constexpr int kMaxChunks = 4;
 // A W stage = an 80-column chunk x up to kWHalfSlabs k slabs; the A tile is handed over in k passes of that many slabs.
@@ -36,6 +40,41 @@ constexpr int kWStageBytes = kWHalfSlabs * kChunkN * 128;   // 30 KB
 #ifndef DMPNN_WSTAGES
 #define DMPNN_WSTAGES (DMPNN_H0_DIRECT ? 4 : 2)
 #endif
+//   DMPNN_MMA_ORDER  order of the (accumulator chunk, k pass) stages in the MMA warp's in-order stream.  The accumulator is
+//                    single-buffered: chunk c of tile k+1 waits for the epilogue of tile k to drain chunk c, and the A tile
+//                    (TMEM) is single-buffered too: the message warps of tile k+2 wait for the last reader of each k half.
+//                    0 = pass-major (first k pass over all chunks, then the second) -- the product.  The LAST chunk's first
+//                        pass (freed when the previous epilogue ENDS) stands in front of the FIRST chunk's second pass, so an
+//                        epilogue starts ~1.5 us after the previous one has ended (profiles/r2_trace_block0.log: period
+//                        5.3 us = 3.8 us epilogue + that hand-over); but the first pass runs under the message phase;
+//                    1 = chunk-major: no hand-over gap, but every k half of A stays busy until the last chunk is done and
+//                        the message warps start late: 214-226 us against 189-195 (profiles/r2_fused_step_variants.log);
+//                    2 = pass-major over all chunks but the last, then the last chunk: 216 us -- the second pass of chunks
+//                        0..n-2 waits for the whole A tile, and the last chunk's first pass (the A half's last reader) queues
+//                        behind it.
+//                    Neither reordering helps while A and the accumulator are single-buffered (TMEM: 304 + 152 of 512
+//                    columns); a deeper W ring (timing-only builds with 3 / 4 stages) changes nothing either.
+#ifndef DMPNN_MMA_ORDER
+#define DMPNN_MMA_ORDER 0
+#endif
+constexpr int kMmaOrder = DMPNN_MMA_ORDER;
+// Timing experiments compiled in only with -DDMPNN_EXPERIMENTS=1 (tools/build_variants.sh; DMPNN_EXP selects at run time; results
+// are wrong by construction): 16384 epilogue skips tcgen05.ld, 32768 epilogue skips its global stores, 65536 message warps
+// skip their shared-memory gathers, 131072 message warps skip tcgen05.st, 262144 the MMA warp issues no MMA (commits only).
+#ifndef DMPNN_EXPERIMENTS
+#define DMPNN_EXPERIMENTS 0
+#endif
+constexpr bool kExp = DMPNN_EXPERIMENTS != 0;
+// stage q of a tile -> (chunk, k pass); the W producer and the MMA warp walk the same sequence
+__device__ __forceinline__ void mma_stage(int q, int nchunks, int npass, int& c, int& half) {
+  if (kMmaOrder == 0) { half = q / nchunks; c = q - half * nchunks; }
+  else if (kMmaOrder == 1) { c = q / npass; half = q - c * npass; }
+  else {
+    const int nb = (nchunks - 1) * npass;
+    if (q < nb) { half = q / (nchunks - 1); c = q - half * (nchunks - 1); }
+    else { c = nchunks - 1; half = q - nb; }
+  }
+}
 constexpr bool kH0Direct = DMPNN_H0_DIRECT != 0;
 constexpr int kWStages = DMPNN_WSTAGES;
 constexpr int kHStages = kH0Direct ? 0 : 4;     // H_0 staging slabs (16 KB each): two per epilogue group
@@ -185,7 +224,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         if (elect_one()) {
           if (s == 0) trace_ev(p, it, 0);
           mbar_expect_tx(bar(B_AFULL + s), kSlabBytes);
-          tma_load_2d(sA + s * kSlabBytes, &tmapH, bar(B_AFULL + s), s * 64, row0);
+          tma_load_2d(sA + (s % kASlots) * kSlabBytes, &tmapH, bar(B_AFULL + s), s * 64, row0);
         }
         __syncwarp();
       }
@@ -197,10 +236,14 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
     // ===================== TMA producer: W_h stages (pre-packed smem images) =====================
     // a stage = the W_h rows of one 80-column output chunk for k slabs {0,1,2} or {3,4} (contiguous in the image)
     uint32_t ws = 0;
+    const int npass = (p.nslab + kWHalfSlabs - 1) / kWHalfSlabs;
     for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
-      for (int s0 = 0; s0 < p.nslab; s0 += kWHalfSlabs) {         // k half (outer) ...
-        const int ns = min(kWHalfSlabs, p.nslab - s0);
-        for (int c = 0; c < p.nchunks; ++c, ++ws) {               // ... x 80-column output chunk (inner)
+      {
+        for (int q = 0; q < p.nchunks * npass; ++q, ++ws) {        // stage order = the MMA warp's (mma_stage)
+          int c, half;
+          mma_stage(q, p.nchunks, npass, c, half);
+          const int s0 = half * kWHalfSlabs;
+          const int ns = min(kWHalfSlabs, p.nslab - s0);
           const int nc = min(kChunkN, p.hp - c * kChunkN);
           const uint8_t* src = p.Wpk + (size_t)c * kChunkN * p.nslab * 128 + (size_t)s0 * nc * 128;
           const uint32_t bytes = (uint32_t)(ns * nc * 128);
@@ -223,15 +266,23 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
     // D[128 x hp] (TMEM cols 0..) += A (TMEM cols kTmemAOff.., written by the message warps) . W_h^T (smem ring)
     uint32_t ws = 0;
     int it = 0;
+    const int npass = (p.nslab + kWHalfSlabs - 1) / kWHalfSlabs;
     for (int t = blockIdx.x; t < n_items; t += gridDim.x, ++it) {
-      int half = 0;
-      for (int s0 = 0; s0 < p.nslab; s0 += kWHalfSlabs, ++half) {     // pass over one k half of the A tile
-        const int ns = min(kWHalfSlabs, p.nslab - s0);
-        const bool last_pass = s0 + ns >= p.nslab;
-        mbar_wait(bar(B_AREADY + half), it & 1);                       // the message warps have written this half
-        if (half == 0 && lane == 0) trace_ev(p, it, 3);
-        tc_fence_after();
-        for (int c = 0; c < p.nchunks; ++c, ++ws) {
+      {
+        uint32_t a_waited = 0;                                           // k halves of this tile's A already waited for
+        for (int q = 0; q < p.nchunks * npass; ++q, ++ws) {
+          int c, half;                                                   // half = k pass over one half of the A tile
+          mma_stage(q, p.nchunks, npass, c, half);
+          const int s0 = half * kWHalfSlabs;
+          const int ns = min(kWHalfSlabs, p.nslab - s0);
+          const bool last_pass = s0 + ns >= p.nslab;
+          const bool last_chunk = c == p.nchunks - 1;
+          if (!((a_waited >> half) & 1u)) {
+            a_waited |= 1u << half;
+            mbar_wait(bar(B_AREADY + half), it & 1);                     // the message warps have written this half
+            if (half == 0 && lane == 0) trace_ev(p, it, 3);
+            tc_fence_after();
+          }
           const int nc = min(kChunkN, p.hp - c * kChunkN);
           const uint32_t idesc = umma_idesc_bf16(kTileM, nc);
           const uint32_t d_tmem = tmem_base + (uint32_t)(c * kChunkN);
@@ -250,16 +301,16 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
               const uint64_t bdesc = umma_desc_sw128(sW + st * kWStageBytes + (uint32_t)(si * nc * 128));
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)   // k step = 16 bf16 = 8 TMEM columns of A = 32 B of each W row
-                if (kk < ks)
+                if (kk < ks && !(kExp && (p.exp_flags & 262144)))
                   umma_bf16_ts(d_tmem, a_tmem + (uint32_t)(8 * kk), bdesc + (uint64_t)(2 * kk), idesc, (s > 0 || kk > 0) ? 1u : 0u);
             }
             umma_commit(bar(B_WFREE + st));
             if (last_pass) umma_commit(bar(B_ACCFULL + c));
+            // this k half of the A tile may be overwritten once its last reader (the last chunk's pass over it) is done
+            if (last_chunk) umma_commit(bar(B_ATFREE + half));
           }
           __syncwarp();
         }
-        if (elect_one()) umma_commit(bar(B_ATFREE + half));            // this k half of the A tile may be overwritten
-        __syncwarp();
       }
       if (lane == 0) trace_ev(p, it, 5);
     }
@@ -362,6 +413,10 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
             cready = c;
           }
           uint32_t v[16];
+          if (kExp && (p.exp_flags & 16384)) {
+#pragma unroll
+            for (int qq = 0; qq < 16; ++qq) v[qq] = 0u;
+          } else
           tmem_ld16(taddr + j * 16, v);
           uint4 h0 = make_uint4(0, 0, 0, 0), h1 = make_uint4(0, 0, 0, 0);
           if constexpr (kH0Direct) {
@@ -430,7 +485,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
             if constexpr (ACT == DMPNN_ACT_RELU) o[qq] = act_word<ACT>(pack_bf2(z0, z1), 0.f);  // max after rounding == rounding after max
             else o[qq] = pack_bf2(act_t<ACT>(p.act_param, z0), act_t<ACT>(p.act_param, z1));
           }
-          if (rvalid) st_global_256(orow + j * 16, o);
+          if (rvalid && !(kExp && (p.exp_flags & 32768))) st_global_256(orow + j * 16, o);
           // release accumulator chunk c once this group has read its last column block of it
           const int jn = (jj + 1 < njj) ? j + 1 : 4 * (s + kEpiGroups);   // next block this group will read
           if (jn >= nj || jn / 5 != c) {
@@ -592,7 +647,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
           mbar_wait(bar(B_AFULL + cur_slab), it & 1);
           if (tS == 0 && cur_slab == 0) trace_ev(p, it, 1);
         }
-        const uint32_t sbase = sA + (uint32_t)(j >> 2) * kSlabBytes;
+        const uint32_t sbase = sA + (uint32_t)((j >> 2) % kASlots) * kSlabBytes;
         const int c0 = 2 * (j & 3);
         uint32_t o[8];
         if (d <= 4) {
@@ -602,7 +657,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
             // predicated: an absent sibling costs no shared-memory wavefront (tau(0) = 0 for every activation)
             u[k][0] = make_uint4(0, 0, 0, 0);
             u[k][1] = make_uint4(0, 0, 0, 0);
-            if (sval[k]) {
+            if (sval[k] && !(kExp && (p.exp_flags & 65536))) {
               if (FAR && far) {
                 const uint4* gp = reinterpret_cast<const uint4*>(fsrc[k] + j * 16);
                 u[k][0] = g_load<ACT, FIRST>(gp, p.act_param);
@@ -648,7 +703,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
 #pragma unroll
           for (int q = 0; q < 8; ++q) o[q] = pack_bf2(acc[2 * q], acc[2 * q + 1]);
         }
-        tmem_st8(at_base + (uint32_t)(j * 8), o);
+        if (!(kExp && (p.exp_flags & 131072))) tmem_st8(at_base + (uint32_t)(j * 8), o);
         if constexpr (kCanEmit) {
           // forward: A row r is M[r] (mixins.py:11-18); backward: A row r is ((S.P) dZ)[r].  One 32-byte
           // sector per thread and block (STG.256), consumed by the W_h weight-gradient GEMM.

@@ -82,9 +82,11 @@ for s in $STEPS; do
       timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"
       echo "bench reference rc=$?"; cat "$OUT/bench_ref.json"; tail -5 "$OUT/bench_ref.err" ;;
     exps)
-      for e in 0 4096 8192 12288; do
+      # timing experiments of the fused depth step: the library built with -DDMPNN_EXPERIMENTS=1 (tools/build_variants.sh -> variants/exp)
+      L=chemprop_b200/lib/variants/exp
+      for e in ${DMPNN_EXPS:-0 4096 8192 16384 32768 49152 65536 131072 196608 262144}; do
         echo "== DMPNN_EXP=$e"
-        DMPNN_EXP=$e timeout 120 ./tests/native/fused_step_harness 10000 300 1 2>&1 | tee "$OUT/exp_$e.log" | tail -3
+        LD_LIBRARY_PATH=$L DMPNN_EXP=$e timeout 120 ./tests/native/fused_step_harness 10000 300 1 2>&1 | tee "$OUT/exp_$e.log" | tail -3
       done ;;
     prof_e2e)
       timeout 300 python tools/profile_e2e.py 30 > "$OUT/profile_e2e.log" 2>&1; echo "profile_e2e rc=$?"; head -60 "$OUT/profile_e2e.log" ;;
