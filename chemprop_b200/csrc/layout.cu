@@ -232,17 +232,36 @@ __global__ void k_tiles_chunk(const int32_t* __restrict__ mol_atom_ptr, const in
     s_nxt[t0] = lo;
   }
   __syncthreads();
+  // thread 0 only follows the chain (one dependent shared-memory load per tile, ~420 hops per chunk); the per-tile row /
+  // atom counts and their maxima are taken by the whole block afterwards (they were part of the serial walk: 28 us per
+  // step at the bench size, profiles/r2_glue_ncu.md)
+  __shared__ int32_t s_start[kTileChunk + 1];
+  __shared__ int s_cnt;
   if (threadIdx.x == 0) {
-    int32_t* out = seg_tiles + (int64_t)blockIdx.x * kTileChunk;
-    int cnt = 0, max_rows = 0, max_atoms = 0;
-    for (int t0 = 0; t0 < n;) {
-      const int i = s_nxt[t0];
-      out[cnt++] = (int32_t)(base + t0);
-      const int rows = s_rw[i] - s_rw[t0], atoms = s_at[i] - s_at[t0];
-      max_rows = rows > max_rows ? rows : max_rows;
-      max_atoms = atoms > max_atoms ? atoms : max_atoms;
-      t0 = i;
-    }
+    int cnt = 0;
+    for (int t0 = 0; t0 < n; t0 = s_nxt[t0]) s_start[cnt++] = t0;
+    s_start[cnt] = n;
+    s_cnt = cnt;
+  }
+  __syncthreads();
+  const int cnt = s_cnt;
+  int32_t* out = seg_tiles + (int64_t)blockIdx.x * kTileChunk;
+  int max_rows = 0, max_atoms = 0;
+  for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+    const int t0 = s_start[k], i = s_start[k + 1];
+    out[k] = (int32_t)(base + t0);
+    max_rows = max(max_rows, s_rw[i] - s_rw[t0]);
+    max_atoms = max(max_atoms, s_at[i] - s_at[t0]);
+  }
+  __shared__ int s_mr[8], s_ma[8];
+  for (int o = 16; o > 0; o >>= 1) {
+    max_rows = max(max_rows, __shfl_down_sync(0xffffffffu, max_rows, o));
+    max_atoms = max(max_atoms, __shfl_down_sync(0xffffffffu, max_atoms, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_mr[threadIdx.x >> 5] = max_rows; s_ma[threadIdx.x >> 5] = max_atoms; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { max_rows = max(max_rows, s_mr[w]); max_atoms = max(max_atoms, s_ma[w]); }
     seg_info[blockIdx.x * 4 + 0] = cnt;
     seg_info[blockIdx.x * 4 + 1] = max_rows;
     seg_info[blockIdx.x * 4 + 2] = max_atoms;
