@@ -551,6 +551,14 @@ def main_gpu(args):
                     "frac_of_x3_ceiling": ach / (pk["bf16"] / 6.0),
                     "hbm_bound": {"algorithmic_bytes": alg_b, "achieved_gbs": alg_b / (dur_ms * 1e-3) / 1e9, "peak_gbs": pk["hbm"],
                                   "frac": alg_b / (dur_ms * 1e-3) / 1e9 / pk["hbm"]}}
+    elif "atom_fused" in by_tag:
+        dur_ms = statistics.mean(by_tag["atom_fused"])
+        alg = 3 * V_atoms * h * s + 4 * E_rows + 4 * V_atoms          # H_prev, H_0', H_next rows + neighbour table + row pointers
+        ach = alg / (dur_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
+                    "kernel": "k_bond_step_fused<ATOM>: atom depth step t>=2 (neighbour gather + W_h GEMM + H_0' + tau, one launch)",
+                    "launch_ms": dur_ms, "algorithmic_bytes": alg, "peak_source": pk["src"],
+                    "first_step_ms": statistics.mean(by_tag.get("atom_fused_first", [float("nan")]))}
     elif "atom_step" in by_tag:
         dur_ms = statistics.mean(by_tag["atom_step"])
         alg = 3 * V_atoms * h * s
@@ -588,7 +596,7 @@ def main_gpu(args):
         "data": "synthetic", "config": config,
         "details": {"atoms_per_batch": V_atoms, "directed_edges_per_batch": E_rows, "precision": precision,
                     "tensor_core_fp32": bool(precision == "fp32" and engine.X3_ENABLED and not args.no_fused),
-                    "fused_depth_step": "fused" in by_tag, "micro_batches_per_step_per_rank": micro_per_step,
+                    "fused_depth_step": ("fused" in by_tag or "atom_fused" in by_tag), "micro_batches_per_step_per_rank": micro_per_step,
                     "molecule_order": ("loader tile packing (best-fit decreasing on edge counts, dmpnn_tile_pack_order)"
                                        if not args.no_pack else "sampler order"),
                     "tiles": n_tiles, "tile_fill": (E_rows / (128.0 * n_tiles)) if n_tiles else None,

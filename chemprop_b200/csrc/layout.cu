@@ -208,7 +208,7 @@ __global__ void k_mol_ptr(const int64_t* __restrict__ batch, int64_t V, int64_t 
 constexpr int kTileChunk = 1024;
 
 __global__ void k_tiles_chunk(const int32_t* __restrict__ mol_atom_ptr, const int32_t* __restrict__ mol_row_ptr,
-                              int64_t B, int32_t* __restrict__ seg_tiles /*[n_chunks][kTileChunk]*/,
+                              int64_t B, int row_limit, int atom_limit, int32_t* __restrict__ seg_tiles /*[n_chunks][kTileChunk]*/,
                               int32_t* __restrict__ seg_info /*[n_chunks][4]: count, max_rows, max_atoms*/) {
   __shared__ int32_t s_at[kTileChunk + 1];
   __shared__ int32_t s_rw[kTileChunk + 1];
@@ -223,7 +223,7 @@ __global__ void k_tiles_chunk(const int32_t* __restrict__ mol_atom_ptr, const in
   // are monotone in the closing index, so each thread finds it by bisection; thread 0 then only follows the chain.
   __shared__ int32_t s_nxt[kTileChunk];
   for (int t0 = threadIdx.x; t0 < n; t0 += blockDim.x) {
-    const int32_t rlim = s_rw[t0] + kTileRows, alim = s_at[t0] + kTileAtoms;
+    const int32_t rlim = s_rw[t0] + row_limit, alim = s_at[t0] + atom_limit;
     int lo = t0 + 1, hi = n;               // smallest i in [t0+1, n) with s_rw[i+1] > rlim or s_at[i+1] > alim, else n
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
@@ -317,9 +317,57 @@ __global__ void k_tiles_gather(const int32_t* __restrict__ seg_tiles, const int3
   }
 }
 
+// the same packing with caller-given limits, tile starts only (dmpnn_tiles_build: the ATOM tiles of the fused atom step)
+__global__ void k_tiles_gather_plain(const int32_t* __restrict__ seg_tiles, const int32_t* __restrict__ seg_info, int n_chunks,
+                                     const int32_t* __restrict__ mol_atom_ptr, const int32_t* __restrict__ mol_row_ptr, int64_t B,
+                                     int32_t* tile_row_ptr, int32_t* tile_atom_ptr, int32_t* info) {
+  __shared__ int32_t s_tot, s_mr, s_ma;
+  int off = 0;
+  for (int c = 0; c < n_chunks; ++c) {             // n_chunks = B / 1024: a handful
+    const int cnt = seg_info[c * 4];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int32_t m = seg_tiles[(int64_t)c * kTileChunk + i];
+      tile_row_ptr[off + i] = mol_row_ptr[m];
+      tile_atom_ptr[off + i] = mol_atom_ptr[m];
+    }
+    off += cnt;
+  }
+  if (threadIdx.x == 0) {
+    int mr = 0, ma = 0;
+    for (int c = 0; c < n_chunks; ++c) { mr = max(mr, seg_info[c * 4 + 1]); ma = max(ma, seg_info[c * 4 + 2]); }
+    tile_row_ptr[off] = mol_row_ptr[B];
+    tile_atom_ptr[off] = mol_atom_ptr[B];
+    info[0] = off; info[1] = mr; info[2] = ma; info[3] = 0;
+  }
+  (void)s_tot; (void)s_mr; (void)s_ma;
+}
+
 }  // namespace dmpnn
 
 using namespace dmpnn;
+
+extern "C" int dmpnn_tiles_workspace_bytes(int64_t B, size_t* bytes) {
+  DMPNN_CHECK_ARG(B >= 0 && bytes, "tiles_workspace_bytes: bad args");
+  const int64_t n_chunks = (B + kTileChunk - 1) / kTileChunk;
+  *bytes = (size_t)(n_chunks > 0 ? n_chunks : 1) * (kTileChunk + 4) * sizeof(int32_t);
+  return 0;
+}
+
+extern "C" int dmpnn_tiles_build(const int32_t* mol_atom_ptr, const int32_t* mol_row_ptr, int64_t B, int row_limit,
+                                 int atom_limit, int32_t* tile_row_ptr, int32_t* tile_atom_ptr, int32_t* info,
+                                 void* workspace, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  DMPNN_CHECK_ARG(B >= 0 && row_limit > 0 && atom_limit > 0 && mol_atom_ptr && mol_row_ptr && tile_row_ptr && tile_atom_ptr &&
+                      info && workspace, "tiles_build: bad args");
+  const int n_chunks = (int)((B + kTileChunk - 1) / kTileChunk);
+  int32_t* seg_tiles = (int32_t*)workspace;
+  int32_t* seg_info = seg_tiles + (size_t)(n_chunks > 0 ? n_chunks : 1) * kTileChunk;
+  if (n_chunks > 0) k_tiles_chunk<<<n_chunks, 256, 0, st>>>(mol_atom_ptr, mol_row_ptr, B, row_limit, atom_limit, seg_tiles, seg_info);
+  k_tiles_gather_plain<<<1, 1024, 0, st>>>(seg_tiles, seg_info, n_chunks, mol_atom_ptr, mol_row_ptr, B, tile_row_ptr, tile_atom_ptr,
+                                           info);
+  DMPNN_CHECK_LAUNCH("tiles_build", 2);
+  return 0;
+}
 
 extern "C" int dmpnn_layout_workspace_bytes(int64_t V, int64_t E, int64_t B, size_t* bytes) {
   DMPNN_CHECK_ARG(V >= 0 && E >= 0 && B >= 0 && bytes, "layout_workspace_bytes: bad args");
@@ -360,7 +408,7 @@ extern "C" int dmpnn_layout_build(const int64_t* edge_index, const int64_t* rev_
   if (E > 0) k_rev_rows<<<ceil_div_i64(E, T), T, 0, st>>>(rev_edge_index, E, perm, inv_perm, rev_row);
   k_mol_ptr<<<ceil_div_i64(V + 1, T), T, 0, st>>>(batch, V, B, rowptr, mol_atom_ptr, mol_row_ptr);
   const int n_chunks = (int)((B + kTileChunk - 1) / kTileChunk);
-  if (n_chunks > 0) k_tiles_chunk<<<n_chunks, 256, 0, st>>>(mol_atom_ptr, mol_row_ptr, B, ws.seg_tiles, ws.seg_info);
+  if (n_chunks > 0) k_tiles_chunk<<<n_chunks, 256, 0, st>>>(mol_atom_ptr, mol_row_ptr, B, kTileRows, kTileAtoms, ws.seg_tiles, ws.seg_info);
   k_tiles_gather<<<1, 1024, 0, st>>>(ws.seg_tiles, ws.seg_info, n_chunks, mol_atom_ptr, mol_row_ptr, B, tile_mol_ptr,
                                      tile_row_ptr, tile_atom_ptr, meta, ws.viol);
   DMPNN_CHECK_LAUNCH("layout_build", 11);

@@ -122,10 +122,12 @@ static int launch_step(const char* what, const void* H_prev, const void* H_0, vo
                        const int32_t* tile_row_ptr, const int32_t* tile_atom_ptr, int64_t n_tiles, int act, float act_param,
                        int first_step, int mode, void* gather_out, const void* add0, const void* add1,
                        const int8_t* work_flag, const int32_t* n_work_dev, const int32_t* dst_row, const uint16_t* drop_bits,
-                       float drop_scale, cudaStream_t st) {
+                       float drop_scale, cudaStream_t st, const int32_t* nbr_row = nullptr) {
+  const bool atom = nbr_row != nullptr;     // atom-granular step: rows are atoms, tile_row_ptr / tile_atom_ptr = atom / edge offsets
   DMPNN_CHECK_ARG(drop_bits == nullptr || mode == MODE_FWD, "%s: keep bits apply to the forward step", what);
-  DMPNN_CHECK_ARG((work_flag == nullptr) == (n_work_dev == nullptr) && (work_flag == nullptr || dst_row != nullptr),
+  DMPNN_CHECK_ARG(atom || ((work_flag == nullptr) == (n_work_dev == nullptr) && (work_flag == nullptr || dst_row != nullptr)),
                   "%s: work_flag, n_work_dev and dst_row come together (dmpnn_work_table_build)", what);
+  DMPNN_CHECK_ARG(!atom || (work_flag == nullptr && drop_bits == nullptr), "%s: no windows / keep bits in the atom step", what);
   DMPNN_CHECK_ARG((add0 == nullptr && add1 == nullptr) || (mode == MODE_BWD_LAST && add0 != nullptr),
                   "%s: addends need y_is_preact (and add0 before add1)", what);
   DMPNN_CHECK_ARG(((reinterpret_cast<uintptr_t>(add0) | reinterpret_cast<uintptr_t>(add1)) & 15) == 0,
@@ -135,7 +137,7 @@ static int launch_step(const char* what, const void* H_prev, const void* H_0, vo
                   "%s: the gathered operand can only be written by the first forward step", what);
   DMPNN_CHECK_ARG(gather_out == nullptr || ((reinterpret_cast<uintptr_t>(gather_out) & 31) == 0 && ld % 16 == 0),
                   "%s: gather output needs a 32-byte aligned base and ld %% 16 == 0", what);
-  DMPNN_CHECK_ARG(H_prev && H_next && Wpk && rowptr && rev_row && tile_row_ptr && tile_atom_ptr && (H_0 || mode == MODE_BWD_COPY),
+  DMPNN_CHECK_ARG(H_prev && H_next && Wpk && rowptr && (rev_row || atom) && tile_row_ptr && tile_atom_ptr && (H_0 || mode == MODE_BWD_COPY),
                   "%s: null pointer", what);
   DMPNN_CHECK_ARG(h > 0 && h <= kMaxHp, "%s: h=%lld unsupported (max %d)", what, (long long)h, kMaxHp);
   const int hp = (int)((h + 15) / 16 * 16);
@@ -172,6 +174,7 @@ static int launch_step(const char* what, const void* H_prev, const void* H_0, vo
   p.n_work_dev = n_work_dev;
   p.dst_row = dst_row;
   p.Hprev = (const __nv_bfloat16*)H_prev;
+  p.nbr_row = nbr_row;
   p.drop_bits = drop_bits;
   p.drop_scale = drop_scale;
   p.n_tiles = (int)n_tiles;
@@ -199,10 +202,13 @@ static int launch_step(const char* what, const void* H_prev, const void* H_0, vo
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int grid = (work_flag != nullptr || n_tiles >= sm_count) ? sm_count : (int)n_tiles;
+  const int grid = (work_flag != nullptr || n_work_dev != nullptr || n_tiles >= sm_count) ? sm_count : (int)n_tiles;
   const bool far = work_flag != nullptr;
   cudaError_t e;
-  if (mode == MODE_FWD)
+  if (atom)
+    e = mode == MODE_FWD ? dispatch_fwd<false, true>(act, first_step != 0, bias != nullptr, false, grid, st, mH, mH0, p)
+                         : dispatch_bwd<false, true>(mode, act, grid, st, mH, mH0, p);
+  else if (mode == MODE_FWD)
     e = far ? dispatch_fwd<true>(act, first_step != 0, bias != nullptr, drop_bits != nullptr, grid, st, mH, mH0, p)
             : dispatch_fwd<false>(act, first_step != 0, bias != nullptr, drop_bits != nullptr, grid, st, mH, mH0, p);
   else
@@ -235,4 +241,29 @@ extern "C" int dmpnn_bond_step_bwd_fused_bf16(const void* dZ, const void* Yact, 
                      tile_atom_ptr, n_tiles, act, act_param, 0,
                      Yact ? (y_is_preact ? MODE_BWD_LAST : MODE_BWD_MASK) : MODE_BWD_COPY, G_out, add0, add1, work_flag,
                      n_work_dev, dst_row, nullptr, 1.f, (cudaStream_t)stream_);
+}
+
+// ---- atom-granular step (AtomMessagePassing restated on atoms; ATOM instantiations of the same kernel) -------------------
+extern "C" int dmpnn_atom_step_fused_bf16(const void* H_prev, const void* H_0, void* H_next, int64_t ld, int64_t n_rows_alloc,
+                                          int64_t h, const void* Wpk, const float* bias, const int32_t* rowptr,
+                                          const int32_t* nbr_row, const int32_t* tile_atom_ptr, const int32_t* tile_edge_ptr,
+                                          const int32_t* n_tiles_dev, int64_t n_tiles_max, int act, float act_param,
+                                          int first_step, void* N_out, void* stream_) {
+  DMPNN_CHECK_ARG(nbr_row && n_tiles_dev, "atom_step_fused: null pointer");
+  return launch_step("atom_step_fused", H_prev, H_0, H_next, ld, n_rows_alloc, h, Wpk, bias, rowptr, nullptr, tile_atom_ptr,
+                     tile_edge_ptr, n_tiles_max, act, act_param, first_step, MODE_FWD, N_out, nullptr, nullptr, nullptr, n_tiles_dev,
+                     nullptr, nullptr, 1.f, (cudaStream_t)stream_, nbr_row);
+}
+
+extern "C" int dmpnn_atom_step_bwd_fused_bf16(const void* dZ, const void* Yact, void* dOut, int64_t ld, int64_t n_rows_alloc,
+                                              int64_t h, const void* WpkT, const int32_t* rowptr, const int32_t* nbr_row,
+                                              const int32_t* tile_atom_ptr, const int32_t* tile_edge_ptr,
+                                              const int32_t* n_tiles_dev, int64_t n_tiles_max, int act, float act_param,
+                                              int y_is_preact, const void* add0, const void* add1, void* G_out, void* stream_) {
+  DMPNN_CHECK_ARG(nbr_row && n_tiles_dev, "atom_step_bwd_fused: null pointer");
+  DMPNN_CHECK_ARG(!y_is_preact || Yact, "atom_step_bwd_fused: y_is_preact needs Yact");
+  return launch_step("atom_step_bwd_fused", dZ, Yact, dOut, ld, n_rows_alloc, h, WpkT, nullptr, rowptr, nullptr, tile_atom_ptr,
+                     tile_edge_ptr, n_tiles_max, act, act_param, 0,
+                     Yact ? (y_is_preact ? MODE_BWD_LAST : MODE_BWD_MASK) : MODE_BWD_COPY, G_out, add0, add1, nullptr, n_tiles_dev,
+                     nullptr, nullptr, 1.f, (cudaStream_t)stream_, nbr_row);
 }

@@ -102,6 +102,8 @@ struct Params {
   const int32_t* n_work_dev;     // nullable; number of work items when the work table is in use (device scalar)
   const int32_t* dst_row;        // destination atom of every row (needed by the non-local windows only)
   const __nv_bfloat16* Hprev;    // the H tile's matrix again, for the non-local windows' global gathers
+  const int32_t* nbr_row;        // ATOM kernels: source atom of every dst-sorted edge row (the layout's src_row); rows are
+                                 // ATOMS there, `tile_row_ptr` / `tile_atom_ptr` hold the atom / edge offsets of the atom tiles
   const uint16_t* drop_bits;     // nullable (forward): 16 keep bits per (row, 16-column block), dmpnn_dropout_bits
   float drop_scale;              // 1 / (1 - p)
   int n_tiles, h, hp, nslab, ksteps_last, nchunks;
@@ -122,7 +124,9 @@ constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kOffRowptr = kOffTmem + 16;                    // int32 [2][132]
 constexpr int kOffRevl = kOffRowptr + 2 * 132 * 4;           // int16 [2][128]: tile-local rev() (backward mode)
 constexpr int kOffBias = kOffRevl + 2 * 128 * 2;             // float [304]
-constexpr int kSmemBytes = kOffBias + kMaxHp * 4;
+constexpr int kNbCap = 1024;                                 // ATOM kernels: staged neighbour entries per tile (else global look-ups)
+constexpr int kOffNb = kOffBias + kMaxHp * 4;                // int16 [2][kNbCap]: tile-local neighbour rows of the atom tile
+constexpr int kSmemBytes = kOffNb + 2 * kNbCap * 2;
 constexpr int kSmemAlloc = kSmemBytes + 1024;
 static_assert(kOffH % 1024 == 0, "staging slabs must be 1024-byte aligned for SWIZZLE_128B");
 static_assert(kSmemAlloc <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
@@ -157,7 +161,11 @@ enum { MODE_FWD = 0, MODE_BWD_MASK = 1, MODE_BWD_COPY = 2, MODE_BWD_LAST = 3 };
 
 // FAR: the launch's work table may hold windows of molecules larger than a tile (global gathers); DROP: keep bits in the
 // forward epilogue.  Both are compile-time so that the common kernel (neither) carries none of their code.
-template <int ACT, bool FIRST, bool HAS_BIAS, int MODE, bool FAR, bool DROP>
+// ATOM: the atom-granular step of AtomMessagePassing (mixins.py:25-30 restated on atoms): rows are atoms, a
+// tile is a run of whole molecules with <= 128 atoms, and A row v = sum over the in-edges e of v of g(H[src(e)]) -- the neighbour
+// rows are read from the same TMA-loaded tile through a staged tile-local neighbour table; the adjacency is symmetric (every bond
+// is two directed edges), so the autograd mirror is the same gather applied to dZ.  Everything after the gather is shared.
+template <int ACT, bool FIRST, bool HAS_BIAS, int MODE, bool FAR, bool DROP, bool ATOM = false>
 __global__ void __launch_bounds__(kThreads, 1)
 k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_constant__ CUtensorMap tmapH0, Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -170,6 +178,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
   int32_t* s_rowptr = reinterpret_cast<int32_t*>(smem + kOffRowptr);
   int16_t* s_revl = reinterpret_cast<int16_t*>(smem + kOffRevl);
   float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
+  int16_t* s_nb = reinterpret_cast<int16_t*>(smem + kOffNb);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
 
@@ -514,20 +523,28 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
     const uint32_t at_base = tmem_base + kTmemAOff + ((uint32_t)(sq * 32) << 16);
     const int nj = p.hp >> 4;
     constexpr bool kCanEmit = FIRST || MODE != MODE_FWD;   // variants that may also write the gathered operand out
-    constexpr bool kNeedRev = true;    // every mode gathers through the tile-local rev() table
+    constexpr bool kNeedRev = !ATOM;   // every bond mode gathers through the tile-local rev() table
     int it = 0;
     int t = blockIdx.x;
-    int row0 = 0, atom0 = 0, natoms = 0;
+    // ATOM kernels: `atom0` / `natoms` are the first EDGE row and the edge count of the atom tile (its CSR slice), rows are atoms
+    int row0 = 0, atom0 = 0, natoms = 0, nr = 0;
     bool far = false;                        // this work item is a window of a multi-window molecule
     if (t < n_items) {
       row0 = __ldg(p.tile_row_ptr + t);
+      nr = __ldg(p.tile_row_ptr + t + 1) - row0;
       atom0 = __ldg(p.tile_atom_ptr + t);
       natoms = __ldg(p.tile_atom_ptr + t + 1) - atom0;
       far = FAR && p.work_flag != nullptr && __ldg(p.work_flag + t) != 0;
       if (far) natoms = 0;
-      if (tS <= natoms) s_rowptr[tS] = __ldg(p.rowptr + atom0 + tS) - row0;
+      if (ATOM) {
+        if (tS <= nr) s_rowptr[tS] = __ldg(p.rowptr + row0 + tS) - atom0;
+#pragma unroll
+        for (int k = 0; k < kNbCap / 256; ++k) {
+          const int i = tS + 256 * k;
+          if (i < natoms) s_nb[i] = (int16_t)(__ldg(p.nbr_row + atom0 + i) - row0);
+        }
+      } else if (tS <= natoms) s_rowptr[tS] = __ldg(p.rowptr + atom0 + tS) - row0;
       if (kNeedRev && tS < 128) {
-        const int nr = __ldg(p.tile_row_ptr + t + 1) - row0;
         s_revl[tS] = (int16_t)(tS < nr ? __ldg(p.rev_row + row0 + tS) - row0 : tS);
       }
     }
@@ -547,6 +564,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       const int b = it & 1;
       const int32_t* rp = s_rowptr + b * 132;
       const int16_t* rvl = s_revl + b * 128;
+      const int16_t* nbl = s_nb + b * kNbCap;
       // Metadata pipeline, two tiles deep: the SCALARS of the next tile (row / atom offsets: first-level loads) were loaded
       // one iteration ago, so the dependent second-level loads (its row-pointer slice and rev() rows) issue here without
       // waiting for them; the scalars of the tile after that are requested now.  (One-deep, the address dependency stalled
@@ -555,7 +573,15 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       const int row0n = nx_row0, atom0n = nx_atom0, natomsn = nx_natoms, nrn = nx_nr;
       const bool farn = nx_far;
       int rpn = 0;
-      if (tn < n_items && tS <= natomsn) rpn = __ldg(p.rowptr + atom0n + tS) - row0n;
+      int nbn[kNbCap / 256];
+      if (ATOM) {
+        if (tn < n_items && tS <= nrn) rpn = __ldg(p.rowptr + row0n + tS) - atom0n;
+#pragma unroll
+        for (int k = 0; k < kNbCap / 256; ++k) {
+          const int i = tS + 256 * k;
+          nbn[k] = (tn < n_items && i < natomsn) ? __ldg(p.nbr_row + atom0n + i) - row0n : 0;
+        }
+      } else if (tn < n_items && tS <= natomsn) rpn = __ldg(p.rowptr + atom0n + tS) - row0n;
       int rvn = tS;
       if (kNeedRev && tn < n_items && tS < 128 && tS < nrn) rvn = __ldg(p.rev_row + row0n + tS) - row0n;
       {
@@ -577,8 +603,10 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       // window, so everything is looked up in ABSOLUTE rows (rev_row / dst_row / rowptr) and gathered from global memory
       // (L2 hits: the molecule's other windows are in flight on neighbouring CTAs); the shared-memory tile is not read.
       const int wrows = (FAR && far) ? (__ldg(p.tile_row_ptr + t + 1) - row0) : 0;
-      const bool rin = (FAR && far) ? (r < wrows) : (r < rp[natoms]);
-      int rs = (MODE == MODE_FWD && rin && !(FAR && far)) ? (int)rvl[r] : r;
+      const bool rin = ATOM ? (r < nr) : ((FAR && far) ? (r < wrows) : (r < rp[natoms]));
+      int rs = (!ATOM && MODE == MODE_FWD && rin && !(FAR && far)) ? (int)rvl[r] : r;
+      // ATOM: neighbour k of row r = tile-local row nbl[rp[r] + k]; tiles with more edges than the staged table read the global one
+      auto nb_at = [&](int i) -> int { return (natoms <= kNbCap) ? (int)nbl[i] : (int)(__ldg(p.nbr_row + atom0 + i) - row0); };
       // segment (atom) of row rs: largest a with rp[a] <= rs
       int g0 = 0, d = 0;
       const __nv_bfloat16* fsrc[3] = {p.Hprev, p.Hprev, p.Hprev};   // far: the (<= 3) sibling rows in global memory
@@ -589,6 +617,8 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         const int v = __ldg(p.dst_row + rsa);
         g0a = __ldg(p.rowptr + v);
         d = __ldg(p.rowptr + v + 1) - g0a;
+      } else if (ATOM) {
+        if (rin) { g0 = rp[r]; d = rp[r + 1] - g0; }
       } else if (rin) {
         int lo = 0, hi = natoms;          // invariant: rp[lo] <= rs < rp[hi]
         while (hi - lo > 1) {
@@ -598,15 +628,17 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         g0 = rp[lo];
         d = rp[lo + 1] - g0;
       }
-      // up to three siblings (in-degree <= 4); slot k is row g0+k, skipping rs itself
+      // up to three siblings (in-degree <= 4); slot k is row g0+k, skipping rs itself.  ATOM: up to three neighbours, all of them
+      const int nsib = ATOM ? d : d - 1;  // rows summed into A row r
       uint32_t soff[3];
       int sxr[3];
       bool sval[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         int x = g0 + k;
-        if (x >= rs) ++x;
-        sval[k] = (k < d - 1) && d <= 4;
+        if (!ATOM && x >= rs) ++x;
+        sval[k] = (k < nsib) && nsib <= 3;
+        if (ATOM) x = sval[k] ? nb_at(x) : r;
         if (FAR && far) {
           int xa = g0a + k;
           if (xa >= rsa) ++xa;
@@ -617,7 +649,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
           x = r;
         }
         if (!sval[k]) x = r;               // harmless in-bounds address for the predicated-off slot
-        if (MODE != MODE_FWD && !(FAR && far)) x = rvl[x];  // autograd mirror: the sibling contributes the row of its reverse edge
+        if (!ATOM && MODE != MODE_FWD && !(FAR && far)) x = rvl[x];  // autograd mirror: the sibling contributes the row of its reverse edge
         soff[k] = (uint32_t)((x >> 3) * 1024 + (x & 7) * 128);
         sxr[k] = x & 7;
       }
@@ -650,7 +682,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         const uint32_t sbase = sA + (uint32_t)((j >> 2) % kASlots) * kSlabBytes;
         const int c0 = 2 * (j & 3);
         uint32_t o[8];
-        if (d <= 4) {
+        if (nsib <= 3) {
           uint4 u[3][2];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
@@ -684,7 +716,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
 #pragma unroll
           for (int q = 0; q < 16; ++q) acc[q] = 0.f;
           for (int xx = ((FAR && far) ? g0a : g0); xx < ((FAR && far) ? g0a : g0) + d; ++xx) {
-            if (xx == ((FAR && far) ? rsa : rs)) continue;
+            if (!ATOM && xx == ((FAR && far) ? rsa : rs)) continue;
             uint4 u0, u1;
             if (FAR && far) {
               const int xa = (MODE != MODE_FWD) ? __ldg(p.rev_row + xx) : xx;
@@ -692,7 +724,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
               u0 = g_load<ACT, FIRST>(gp, p.act_param);
               u1 = g_load<ACT, FIRST>(gp + 1, p.act_param);
             } else {
-              const int x = (MODE != MODE_FWD) ? (int)rvl[xx] : xx;
+              const int x = ATOM ? nb_at(xx) : ((MODE != MODE_FWD) ? (int)rvl[xx] : xx);
               u0 = s_load<ACT, FIRST>(sbase + sw128_off(x, c0), p.act_param);
               u1 = s_load<ACT, FIRST>(sbase + sw128_off(x, c0 + 1), p.act_param);
             }
@@ -718,9 +750,16 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       for (int q = cur_pass; q < npass; ++q) mbar_arrive(bar(B_AREADY + q));   // every thread arrives once per pass
       if (tS == 0) trace_ev(p, it, 2);
       // publish the next tile's rowptr slice (other buffer; readers of it finished a tile ago)
-      if (tn < n_items && tS <= natomsn) s_rowptr[(b ^ 1) * 132 + tS] = rpn;
+      if (ATOM) {
+        if (tn < n_items && tS <= nrn) s_rowptr[(b ^ 1) * 132 + tS] = rpn;
+#pragma unroll
+        for (int k = 0; k < kNbCap / 256; ++k) {
+          const int i = tS + 256 * k;
+          if (tn < n_items && i < natomsn) s_nb[(b ^ 1) * kNbCap + i] = (int16_t)nbn[k];
+        }
+      } else if (tn < n_items && tS <= natomsn) s_rowptr[(b ^ 1) * 132 + tS] = rpn;
       if (kNeedRev && tn < n_items && tS < 128) s_revl[(b ^ 1) * 128 + tS] = (int16_t)rvn;
-      row0 = row0n; atom0 = atom0n; natoms = natomsn; far = farn;
+      row0 = row0n; atom0 = atom0n; natoms = natomsn; far = farn; nr = nrn;
     }
   }
 
@@ -733,29 +772,32 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
 }
 
 
-template <int ACT, bool FIRST, bool HAS_BIAS, int MODE, bool FAR, bool DROP>
+template <int ACT, bool FIRST, bool HAS_BIAS, int MODE, bool FAR, bool DROP, bool ATOM = false>
 static cudaError_t launch_variant(int grid, cudaStream_t st, const CUtensorMap& mH, const CUtensorMap& mH0, const Params& p) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_bond_step_fused<ACT, FIRST, HAS_BIAS, MODE, FAR, DROP>,
+    cudaError_t e = cudaFuncSetAttribute(k_bond_step_fused<ACT, FIRST, HAS_BIAS, MODE, FAR, DROP, ATOM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_bond_step_fused<ACT, FIRST, HAS_BIAS, MODE, FAR, DROP><<<grid, kThreads, kSmemAlloc, st>>>(mH, mH0, p);
+  k_bond_step_fused<ACT, FIRST, HAS_BIAS, MODE, FAR, DROP, ATOM><<<grid, kThreads, kSmemAlloc, st>>>(mH, mH0, p);
   return cudaSuccess;
 }
 
 // forward step: every fused activation x first x bias; dropout (keep bits) is a ReLU-only feature (engine.dropout_fused_ok)
-template <bool FAR>
+template <bool FAR, bool ATOM = false>
 cudaError_t dispatch_fwd(int act, bool first, bool bias, bool drop, int grid, cudaStream_t st, const CUtensorMap& mH,
                          const CUtensorMap& mH0, const Params& p) {
 #define DMPNN_FB(A, D)                                                                                              \
-  (first ? (bias ? launch_variant<A, true, true, MODE_FWD, FAR, D>(grid, st, mH, mH0, p)                             \
-                 : launch_variant<A, true, false, MODE_FWD, FAR, D>(grid, st, mH, mH0, p))                            \
-         : (bias ? launch_variant<A, false, true, MODE_FWD, FAR, D>(grid, st, mH, mH0, p)                            \
-                 : launch_variant<A, false, false, MODE_FWD, FAR, D>(grid, st, mH, mH0, p)))
-  if (drop) return act == DMPNN_ACT_RELU ? DMPNN_FB(DMPNN_ACT_RELU, true) : cudaErrorInvalidValue;
+  (first ? (bias ? launch_variant<A, true, true, MODE_FWD, FAR, D, ATOM>(grid, st, mH, mH0, p)                             \
+                 : launch_variant<A, true, false, MODE_FWD, FAR, D, ATOM>(grid, st, mH, mH0, p))                            \
+         : (bias ? launch_variant<A, false, true, MODE_FWD, FAR, D, ATOM>(grid, st, mH, mH0, p)                            \
+                 : launch_variant<A, false, false, MODE_FWD, FAR, D, ATOM>(grid, st, mH, mH0, p)))
+  if (drop) {
+    if constexpr (ATOM) return cudaErrorInvalidValue;
+    else return act == DMPNN_ACT_RELU ? DMPNN_FB(DMPNN_ACT_RELU, true) : cudaErrorInvalidValue;
+  }
   switch (act) {
     case DMPNN_ACT_NONE: return DMPNN_FB(DMPNN_ACT_NONE, false);
     case DMPNN_ACT_RELU: return DMPNN_FB(DMPNN_ACT_RELU, false);
@@ -767,13 +809,13 @@ cudaError_t dispatch_fwd(int act, bool first, bool bias, bool drop, int grid, cu
   return cudaErrorInvalidValue;
 }
 
-template <bool FAR>
+template <bool FAR, bool ATOM = false>
 cudaError_t dispatch_bwd(int mode, int act, int grid, cudaStream_t st, const CUtensorMap& mH, const CUtensorMap& mH0,
                          const Params& p) {
-  if (mode == MODE_BWD_COPY) return launch_variant<DMPNN_ACT_NONE, false, false, MODE_BWD_COPY, FAR, false>(grid, st, mH, mH0, p);
+  if (mode == MODE_BWD_COPY) return launch_variant<DMPNN_ACT_NONE, false, false, MODE_BWD_COPY, FAR, false, ATOM>(grid, st, mH, mH0, p);
 #define DMPNN_BM(A)                                                                                         \
-  (mode == MODE_BWD_LAST ? launch_variant<A, false, false, MODE_BWD_LAST, FAR, false>(grid, st, mH, mH0, p)   \
-                         : launch_variant<A, false, false, MODE_BWD_MASK, FAR, false>(grid, st, mH, mH0, p))
+  (mode == MODE_BWD_LAST ? launch_variant<A, false, false, MODE_BWD_LAST, FAR, false, ATOM>(grid, st, mH, mH0, p)   \
+                         : launch_variant<A, false, false, MODE_BWD_MASK, FAR, false, ATOM>(grid, st, mH, mH0, p))
   switch (act) {
     case DMPNN_ACT_NONE: return DMPNN_BM(DMPNN_ACT_NONE);
     case DMPNN_ACT_RELU: return DMPNN_BM(DMPNN_ACT_RELU);
@@ -785,7 +827,9 @@ cudaError_t dispatch_bwd(int mode, int act, int grid, cudaStream_t st, const CUt
   return cudaErrorInvalidValue;
 }
 
-// explicit instantiations live in step_fused_{fwd,bwd,far_fwd,far_bwd}.cu
+// explicit instantiations live in step_fused_{fwd,bwd,far_fwd,far_bwd,atom_fwd,atom_bwd}.cu
+extern template cudaError_t dispatch_fwd<false, true>(int, bool, bool, bool, int, cudaStream_t, const CUtensorMap&, const CUtensorMap&, const Params&);
+extern template cudaError_t dispatch_bwd<false, true>(int, int, int, cudaStream_t, const CUtensorMap&, const CUtensorMap&, const Params&);
 extern template cudaError_t dispatch_fwd<false>(int, bool, bool, bool, int, cudaStream_t, const CUtensorMap&, const CUtensorMap&, const Params&);
 extern template cudaError_t dispatch_fwd<true>(int, bool, bool, bool, int, cudaStream_t, const CUtensorMap&, const CUtensorMap&, const Params&);
 extern template cudaError_t dispatch_bwd<false>(int, int, int, cudaStream_t, const CUtensorMap&, const CUtensorMap&, const Params&);

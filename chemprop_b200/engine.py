@@ -114,6 +114,7 @@ class Layout:
     meta: Tensor
     _meta_host: list | None = None
     _work: tuple | None = None
+    _atom_work: tuple | None = None
 
     def _host(self):
         if self._meta_host is None:
@@ -729,6 +730,69 @@ def bond_step_bwd_fused(dZ: Tensor, Yact: Tensor | None, dOut: Tensor, h: int, W
     _lib.check(rc, "dmpnn_bond_step_bwd_fused_bf16")
 
 
+# ---- atom-granular fused step (AtomMessagePassing; the ATOM instantiations of the fused kernel) ------------------------
+ATOM_FUSED_ENABLED = os.environ.get("DMPNN_ATOM_FUSED", "1") != "0"      # DMPNN_ATOM_FUSED=0: A/B switch (gather + GEMM launches)
+ATOM_TILE_ATOMS, ATOM_TILE_EDGES = 128, 1024
+
+
+def atom_tables(lay: Layout):
+    """(tile_atom_ptr, tile_edge_ptr, n_tiles_dev, n_tiles_max) of the ATOM tiles of a batch: runs of whole molecules with
+    <= 128 atoms (and <= 1024 edge rows, what the kernel's staged neighbour table holds), built once per batch on the device
+    (dmpnn_tiles_build; the kernel reads the tile count from device memory: no host read-back)."""
+    if lay._atom_work is None:
+        lib = _lib.load()
+        dev = lay.rowptr.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        ta = torch.empty(lay.B + 2, **i32)
+        te = torch.empty(lay.B + 2, **i32)
+        info = torch.zeros(4, **i32)
+        n = C.c_size_t(0)
+        _lib.check(lib.dmpnn_tiles_workspace_bytes(lay.B, C.byref(n)), "dmpnn_tiles_workspace_bytes")
+        ws = torch.empty(max(n.value, 16), dtype=torch.uint8, device=dev)
+        _lib.check(lib.dmpnn_tiles_build(lay.mol_atom_ptr.data_ptr(), lay.mol_row_ptr.data_ptr(), lay.B, ATOM_TILE_EDGES,
+                                         ATOM_TILE_ATOMS, te.data_ptr(), ta.data_ptr(), info.data_ptr(), ws.data_ptr(), _stream()),
+                   "dmpnn_tiles_build")
+        lay._atom_work = (ta, te, info, max(lay.B, 1))
+    return lay._atom_work
+
+
+def _atom_fused_ok(cfg: MPConfig, lay: Layout, h: int, d_v: int, d_e: int) -> bool:
+    """The fused atom step applies: bf16 tier on the tensor-core kernels, directed, depth > 1, no training dropout, and every
+    molecule of the batch has <= 128 atoms (an atom tile is a run of whole molecules: max_tile_atoms of the layout exceeds
+    128 only for a single oversized molecule)."""
+    ok = (ATOM_FUSED_ENABLED and cfg.depth > 1 and not cfg.undirected and cfg.dropout_p == 0 and lay.V > 0 and lay.E > 0
+          and _atom_tc_ok(cfg, h, d_v, d_e) and lay.max_tile_atoms <= ATOM_TILE_ATOMS)
+    if not ok and ATOM_FUSED_ENABLED and cfg.depth > 1 and lay.E > 0 and _atom_tc_ok(cfg, h, d_v, d_e):
+        _warn_once("atom_unfused", "chemprop_b200: this batch leaves the fused atom depth step (" +
+                   ("undirected=True" if cfg.undirected else "training dropout" if cfg.dropout_p > 0 else
+                    "a molecule with more than 128 atoms") + "): neighbour sum and GEMM run as separate launches")
+    return ok
+
+
+def atom_step_fused(H_prev: Tensor, H0: Tensor, H_next: Tensor, h: int, Wpk: Tensor, bias: Tensor | None, lay: Layout,
+                    act: int, act_param: float, first_step: bool, N_out: Tensor | None = None):
+    """H_next[v] = act(H0[v] + bias + W . sum_{e in in(v)} g(H_prev[src(e)])) in one launch (dmpnn_atom_step_fused_bf16)."""
+    lib = _lib.load()
+    ta, te, info, nmax = atom_tables(lay)
+    rc = lib.dmpnn_atom_step_fused_bf16(
+        H_prev.data_ptr(), H0.data_ptr(), H_next.data_ptr(), _ld(H0), H0.shape[0], h, Wpk.data_ptr(), _ptr(bias),
+        lay.rowptr.data_ptr(), lay.src_row.data_ptr(), ta.data_ptr(), te.data_ptr(), info.data_ptr(), nmax, act,
+        float(act_param), 1 if first_step else 0, _ptr(N_out), _stream())
+    _lib.check(rc, "dmpnn_atom_step_fused_bf16")
+
+
+def atom_step_bwd_fused(dZ: Tensor, Yact: Tensor | None, dOut: Tensor, h: int, WpkT: Tensor, lay: Layout, act: int,
+                        act_param: float, G_out: Tensor | None = None, y_is_preact: bool = False):
+    """dOut[v] = ((sum_{e in in(v)} dZ[src(e)]) . W) [* act'(Yact[v])]; G_out also receives the gathered operand."""
+    lib = _lib.load()
+    ta, te, info, nmax = atom_tables(lay)
+    rc = lib.dmpnn_atom_step_bwd_fused_bf16(
+        dZ.data_ptr(), _ptr(Yact), dOut.data_ptr(), _ld(dZ), dZ.shape[0], h, WpkT.data_ptr(), lay.rowptr.data_ptr(),
+        lay.src_row.data_ptr(), ta.data_ptr(), te.data_ptr(), info.data_ptr(), nmax, act, float(act_param),
+        1 if y_is_preact else 0, None, None, _ptr(G_out), _stream())
+    _lib.check(rc, "dmpnn_atom_step_bwd_fused_bf16")
+
+
 def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, bh, Wo: Tensor, bo,
                  cfg: MPConfig, for_backward: bool = False):
     """BondMessagePassing.forward up to W_o (chemprop/nn/message_passing/base.py:196-212 with
@@ -1329,6 +1393,121 @@ def atom_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
     return dWi, dbi, dWh, dbh, dWo, dbo
 
 
+def atom_forward_fused(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, bh, Wo: Tensor, bo, cfg: MPConfig):
+    """bf16 tier of atom_forward with ONE launch per depth step (dmpnn_atom_step_fused_bf16).  The reference's update
+    (base.py:135-141) on atoms is tau(H_0 + b_h + W_h . [N^t || SE]) with N^t the neighbour sum of the previous state and SE the
+    loop-invariant sum of the incoming bond features: W_h[:, h:] . SE + b_h is added to H_0 ONCE (a K = d_e GEMM with H_0 as
+    the residual of its epilogue), which gives the step the bond step's shape  tau(H_0' + W_h[:, :h] . N^t)  -- gather, GEMM
+    and epilogue in the fused kernel, with the gathered operand of the first step saved for the W_h gradient."""
+    dev = V.device
+    h = Wi.shape[0]
+    hp = pad_hidden(h)
+    hc = (h + 15) // 16 * 16
+    d_v, d_e = V.shape[1], E.shape[1]
+    T = cfg.hidden_dtype
+    nV = lay.V
+    a, ap = cfg.act, cfg.act_param
+    rows = max(nV, 1)
+    kv = (d_v + 15) // 16 * 16
+    Xv = torch.empty((rows, kv), dtype=T, device=dev)
+    concat_bf16(V, d_v, Xv, nV, width=kv)
+    H0 = _empty_hidden(nV, hp, T, dev)
+    linear_tc(Xv, d_v, pack_weight_tc(Wi), h, H0, bias=bi, R=nV)                              # mixins.py:22-23
+    SEb, H0p, step_bias = None, H0, bh
+    if d_e > 0:                                                                               # loop-invariant bond term
+        SE = torch.zeros((rows, d_e), dtype=torch.float32, device=dev)
+        segment_sum(E, lay.rowptr, nV, d_e, SE, idx=lay.perm)
+        ke = (d_e + 15) // 16 * 16
+        SEb = torch.empty((rows, ke), dtype=T, device=dev)
+        concat_bf16(SE, d_e, SEb, nV, width=ke)
+        H0p = _empty_hidden(nV, hp, T, dev)                                                   # H_0 + b_h + W_h[:, h:] . SE
+        linear_tc(SEb, d_e, pack_weight_tc(Wh[:, h:]), h, H0p, bias=bh, res=H0, R=nV)
+        step_bias = None
+    Whpk = pack_weight_bf16(Wh[:, :h].contiguous())
+    Hs, N1 = [], None
+    Hprev, first = H0, True
+    for _ in range(1, cfg.depth):
+        Hn = _empty_hidden(nV, hp, T, dev)
+        if first:
+            N1 = _empty_hidden(nV, hp, T, dev)
+        with _StepTimer("atom_fused_first" if first else "atom_fused"):
+            atom_step_fused(Hprev, H0p, Hn, h, Whpk, step_bias, lay, a, ap, first, N_out=N1 if first else None)
+        Hs.append(Hn)
+        Hprev, first = Hn, False
+    ko = (d_v + h + 15) // 16 * 16
+    XO = torch.empty((rows, ko), dtype=T, device=dev)
+    concat_bf16(V, d_v, XO, nV, width=d_v)
+    segment_sum(Hprev, lay.rowptr, nV, h, XO[:, d_v:d_v + h], idx=lay.src_row, act=ACT_NONE, act_param=ap,
+                pad_to=(hc if d_v + hc <= ko else h))                                         # base.py:208-211
+    Hvp = torch.empty((rows, hp), dtype=T, device=dev)
+    linear_tc(XO, d_v + h, pack_weight_tc(Wo), h, Hvp, bias=bo, act=a, act_param=ap, R=nV)    # base.py:180-182
+    Hv = Hvp[:nV, :h]
+    return Hv, dict(H0=H0, Hs=Hs, N1=N1, SEb=SEb, XO=XO, Xv=Xv, Hv=Hv, tc=True, fused=True)
+
+
+def atom_backward_fused(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo: Tensor, cfg: MPConfig,
+                        saved: dict, gHv: Tensor, need_bias):
+    """Autograd mirror of atom_forward_fused.  With A the (symmetric) atom adjacency, N^t = A H^{t-1}:
+    dH^{t-1} = ((A dZ^t) . W_h[:, :h]) * tau'(H^{t-1}) -- the mirror mode of the fused kernel, whose gathered operand
+    G^t = A dZ^t is also the left factor of the step's weight gradient (dZ^T . N^t = G^T . H^{t-1}); t = 1 uses the N^1 the
+    forward saved.  dW_h[:, h:] = (sum_t dZ^t)^T . SE and dW_i = (sum_t dZ^t + dH^0 tau'(H_0))^T . V as multi-term GEMMs."""
+    dev = V.device
+    h = Wi.shape[0]
+    hp = pad_hidden(h)
+    hc = (h + 15) // 16 * 16
+    d_v, d_e = V.shape[1], E.shape[1]
+    T = cfg.hidden_dtype
+    nV = lay.V
+    a, ap = cfg.act, cfg.act_param
+    H0, Hs, N1, SEb, XO, Xv, Hv = (saved[k] for k in ("H0", "Hs", "N1", "SEb", "XO", "Xv", "Hv"))
+    f32 = dict(dtype=torch.float32, device=dev)
+    dWi = torch.empty_like(Wi, dtype=torch.float32)
+    dWh = torch.empty_like(Wh, dtype=torch.float32)
+    dWo = torch.empty_like(Wo, dtype=torch.float32)
+    dbi = torch.zeros(h, **f32) if need_bias[0] else None
+    dbh = torch.zeros(h, **f32) if need_bias[1] else None
+    dbo = torch.zeros(h, **f32) if need_bias[2] else None
+    if gHv.stride(1) != 1:
+        gHv = gHv.contiguous()
+    dY = _empty_hidden(nV, hp, T, dev)
+    act_bwd(gHv, Hv, nV, h, act=a, act_param=ap, dZ=dY)
+    wgrad_tc(dY, XO, nV, h, d_v + h, dWo)
+    if dbo is not None:
+        column_sum(dY, nV, h, dbo)
+    dMv = _empty_hidden(nV, hp, T, dev)
+    linear_tc(dY, h, pack_weight_tc(Wo[:, d_v:], transpose=True), h, dMv, R=nV)
+    dHa = _empty_hidden(nV, hp, T, dev)                      # d(Ha^{T-1}) = A dM_v   (rev is an involution)
+    segment_sum(dMv, lay.rowptr, nV, h, dHa, idx=lay.src_row, pad_to=hc)
+    dZ = _empty_hidden(nV, hp, T, dev)
+    act_bwd(dHa, Hs[-1], nV, hc, act=a, act_param=ap, dZ=dZ)                                  # dZ^{T-1}
+    WhT = pack_weight_bf16(Wh[:, :h].t().contiguous())
+    dWhN = dWh[:, :h]
+    terms, wrote = [dZ], False
+    dH0l = _empty_hidden(nV, hp, T, dev)
+    for t in range(cfg.depth - 1, 0, -1):
+        if dbh is not None:
+            column_sum(dZ, nV, h, dbh, accumulate=True)
+        if t == 1:
+            wgrad_tc(dZ, N1, nV, h, h, dWhN, accumulate=wrote)
+            atom_step_bwd_fused(dZ, H0, dH0l, h, WhT, lay, a, ap, y_is_preact=True)           # dH^0 * tau'(H_0)
+        else:
+            Hin = Hs[t - 2]
+            dZn = _empty_hidden(nV, hp, T, dev)
+            G = _empty_hidden(nV, hp, T, dev)
+            atom_step_bwd_fused(dZ, Hin, dZn, h, WhT, lay, a, ap, G_out=G)
+            wgrad_tc(G, Hin, nV, h, h, dWhN, accumulate=wrote)
+            dZ = dZn
+            terms.append(dZ)
+        wrote = True
+    if d_e > 0:
+        wgrad_tc_multi(terms, SEb, nV, h, d_e, dWh[:, h:])
+    wgrad_tc_multi(terms + [dH0l], Xv, nV, h, d_v, dWi)
+    if dbi is not None:
+        for i, P in enumerate(terms + [dH0l]):
+            column_sum(P, nV, h, dbi, accumulate=i > 0)
+    return dWi, dbi, dWh, dbh, dWo, dbo
+
+
 class AtomMPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, V, E, Wi, bi, Wh, bh, Wo, bo, lay, cfg):
@@ -1341,6 +1520,8 @@ class AtomMPFunction(torch.autograd.Function):
         bh_ = None if bh is None else bh.detach().contiguous().float()
         bo_ = None if bo is None else bo.detach().contiguous().float()
         fwd = atom_forward_tc if (_atom_tc_ok(cfg, Wi_.shape[0], V.shape[1], E.shape[1]) and lay.V > 0) else atom_forward
+        if fwd is atom_forward_tc and _atom_fused_ok(cfg, lay, Wi_.shape[0], V.shape[1], E.shape[1]):
+            fwd = atom_forward_fused
         Hv, saved = fwd(lay, V, E, Wi_, bi_, Wh_, bh_, Wo_, bo_, cfg)
         # `Hv` is the tensor autograd turns into this node's output: keeping THAT object in ctx.saved would be a reference
         # cycle (node -> saved -> Hv -> grad_fn = node) and the step's activations would live until Python's cyclic GC
@@ -1357,7 +1538,7 @@ class AtomMPFunction(torch.autograd.Function):
     def backward(ctx, gHv):
         V, E = ctx.VE
         Wi, Wh, Wo = ctx.W
-        bwd = atom_backward_tc if ctx.saved.get("tc") else atom_backward
+        bwd = atom_backward_fused if ctx.saved.get("fused") else atom_backward_tc if ctx.saved.get("tc") else atom_backward
         dWi, dbi, dWh, dbh, dWo, dbo = bwd(ctx.lay, V, E, Wi, Wh, Wo, ctx.cfg, ctx.saved, gHv, ctx.has_bias)
         # ctx.saved stays until autograd frees the node: a second backward (retain_graph=True) works like torch's own
         d0, d1, d2 = ctx.wdtypes

@@ -328,6 +328,35 @@ int dmpnn_bond_step_bwd_fused_bf16(const void* dZ, const void* Yact, void* dOut,
                                    void* G_out, const int8_t* work_flag, const int32_t* n_work_dev, const int32_t* dst_row,
                                    void* stream);
 
+/* Molecule-aligned tiles with caller-given limits (the packing rule of dmpnn_layout_build: greedy, restarted every 1024
+ * molecules): tile_row_ptr / tile_atom_ptr [<= B + 1] receive the first edge row / first atom of every tile plus the end
+ * sentinel, info[0..2] = tile count, max rows (edges) and max atoms of a tile.  Used for the ATOM tiles (<= 128 atoms) of
+ * dmpnn_atom_step_fused_bf16.  Workspace from dmpnn_tiles_workspace_bytes; stream-ordered, no host sync. */
+int dmpnn_tiles_workspace_bytes(int64_t B, size_t* bytes);
+int dmpnn_tiles_build(const int32_t* mol_atom_ptr, const int32_t* mol_row_ptr, int64_t B, int row_limit, int atom_limit,
+                      int32_t* tile_row_ptr, int32_t* tile_atom_ptr, int32_t* info, void* workspace, void* stream);
+
+/* Atom-granular fused depth step -- AtomMessagePassing (chemprop/nn/message_passing/mixins.py:25-30 + base.py:135-141)
+ * restated on atoms (the reference's edge state H[e] depends only on src(e)):
+ *   H_next[v] = act( H_0[v] + bias + W . sum_{e in in(v)} g(H_prev[src(e)]) ),   g = act on the first step, identity after,
+ * one launch: neighbour gather from the TMA-loaded atom tile + tcgen05 GEMM + epilogue, the kernel of
+ * dmpnn_bond_step_fused_bf16 with its ATOM gather.  The loop-invariant bond term W_h[:, h:] . sum_in E of the reference's
+ * update is folded into H_0 by the caller (engine.atom_forward_fused).  rowptr: dst-sorted CSR over atoms; nbr_row: source
+ * atom of every edge row; tile_atom_ptr / tile_edge_ptr: first atom / first edge row of every atom tile (dmpnn_tiles_build
+ * with atom_limit = 128) and *n_tiles_dev tiles (device scalar; n_tiles_max only sizes the checks).  Every molecule must
+ * have <= 128 atoms.  N_out (first step only): the gathered operand, for the W_h gradient.  The mirror:
+ *   dOut[v] = ( (sum_{e in in(v)} dZ[src(e)]) . W ) * act'(Yact[v])      (the adjacency is symmetric)
+ * with the modes of dmpnn_bond_step_bwd_fused_bf16 (Yact null: no mask; y_is_preact + addends: the last step). */
+int dmpnn_atom_step_fused_bf16(const void* H_prev, const void* H_0, void* H_next, int64_t ld, int64_t n_rows_alloc, int64_t h,
+                               const void* Wpk, const float* bias, const int32_t* rowptr, const int32_t* nbr_row,
+                               const int32_t* tile_atom_ptr, const int32_t* tile_edge_ptr, const int32_t* n_tiles_dev,
+                               int64_t n_tiles_max, int act, float act_param, int first_step, void* N_out, void* stream);
+int dmpnn_atom_step_bwd_fused_bf16(const void* dZ, const void* Yact, void* dOut, int64_t ld, int64_t n_rows_alloc, int64_t h,
+                                   const void* WpkT, const int32_t* rowptr, const int32_t* nbr_row,
+                                   const int32_t* tile_atom_ptr, const int32_t* tile_edge_ptr, const int32_t* n_tiles_dev,
+                                   int64_t n_tiles_max, int act, float act_param, int y_is_preact, const void* add0,
+                                   const void* add1, void* G_out, void* stream);
+
 /* Tensor-core weight gradient (bf16 operands, f32 accumulate, deterministic two-pass reduction):
  *   dW[n, 0:K] (+)= sum_r dY[r, n] * X[r, 0:K]      dY: R x N (ld lddy), X: R x K (ld ldx), both bf16 row-major
  * N <= 384, K <= 448; lddy, ldx multiples of 8.  Workspace from dmpnn_wgrad_tc_workspace_bytes. */

@@ -395,6 +395,64 @@ def bond_step_bwd_fused(dZ, Yact, dOut, h, WpkT, lay, act, act_param, G_out=None
         G_out[: lay.E, h:(h + 15) // 16 * 16] = 0
 
 
+def atom_tables(lay):
+    """engine.atom_tables: the emulated atom step needs no tile tables"""
+    return None
+
+
+def _neighbour_sum_packed(f, lay):
+    """The ATOM gather of the fused kernel, rounding for rounding: A row v = sum over the in-edges e of v of f[src(e)], added in
+    slot order as packed bf16 (`__hadd2(__hadd2(a0, a1), a2)`, an absent neighbour is +0) for in-degree <= 3 and in f32 with one
+    rounding otherwise.  `f` is bf16-valued f32 [V, C]."""
+    V = lay.V
+    rowptr, src = lay.rowptr.long(), lay.src_row.long()
+    g0 = rowptr[:V]
+    d = rowptr[1:V + 1] - g0
+    r = torch.arange(V)
+    vals = []
+    for k in range(3):
+        ok = (k < d) & (d <= 3)
+        x = torch.where(ok, src[torch.clamp(g0 + k, max=max(lay.E - 1, 0))], r)
+        vals.append(f[x] * ok.unsqueeze(1).to(f.dtype))
+    small = _bf(_bf(vals[0] + vals[1]) + vals[2])
+    big = d > 3
+    if bool(big.any()):
+        s = torch.zeros((V, f.shape[1])).index_add_(0, lay.dst_row.long(), f[src])
+        small = torch.where(big.unsqueeze(1), _bf(s), small)
+    return small
+
+
+def atom_step_fused(H_prev, H0, H_next, h, Wpk, bias, lay, act, act_param, first_step, N_out=None):
+    """H_next[v] = tau(H0[v] + b + W . N[v]),  N = neighbour sum of g(H_prev), g = tau on the first step (include/dmpnn.h)."""
+    V = lay.V
+    f = _act(H_prev.float()[:V, :h], act if first_step else ACT_NONE, act_param)
+    if first_step:
+        f = _bf(f)
+    N = _neighbour_sum_packed(f, lay)
+    Z = N @ Wpk.t() + H0[:V, :h].float()
+    if bias is not None:
+        Z = Z + bias.float()
+    H_next[:V, :h] = _act(Z, act, act_param).to(H_next.dtype)
+    H_next[:V, h:(h + 15) // 16 * 16] = 0
+    if N_out is not None:
+        N_out[:V, :h] = N.to(N_out.dtype)
+        N_out[:V, h:(h + 15) // 16 * 16] = 0
+
+
+def atom_step_bwd_fused(dZ, Yact, dOut, h, WpkT, lay, act, act_param, G_out=None, y_is_preact=False):
+    """dOut = (A dZ) . W [* tau'(Yact)];  G_out = A dZ   (WpkT holds B = W^T of A . B^T)."""
+    V = lay.V
+    G = _neighbour_sum_packed(dZ.float()[:V, :h], lay)
+    D = G @ WpkT.t()
+    if Yact is not None:
+        D = D * _dact(Yact[:V, :h].float(), act, act_param, y_is_preact)
+    dOut[:V, :h] = D.to(dOut.dtype)
+    dOut[:V, h:(h + 15) // 16 * 16] = 0
+    if G_out is not None:
+        G_out[:V, :h] = G.to(G_out.dtype)
+        G_out[:V, h:(h + 15) // 16 * 16] = 0
+
+
 def bond_message_bwd_masked(dM, Yact, lay, Ccols, out, *, act, act_param=0.0):
     if lay.E == 0:
         return
@@ -433,7 +491,8 @@ def patch_engine(monkeypatch):
     for name in ("linear_fwd", "linear_wgrad", "segment_sum", "segment_bcast", "bond_message", "rev_average", "act_bwd",
                  "build_layout", "pack_weight_tc", "pack_weight_bf16", "concat_bf16", "linear_tc", "wgrad_tc", "wgrad_tc_multi", "column_sum",
                  "pack_weight_x3", "linear_x3", "wgrad_x3", "bn_train_fwd", "bn_bwd", "mse_loss", "concat_f32", "dropout_keep_bits",
-                 "bond_step_fused", "bond_step_bwd_fused", "bond_message_bwd_masked", "sum_act_bwd", "scale_mask_"):
+                 "bond_step_fused", "bond_step_bwd_fused", "bond_message_bwd_masked", "sum_act_bwd", "scale_mask_",
+                 "atom_step_fused", "atom_step_bwd_fused", "atom_tables"):
         monkeypatch.setattr(engine, name, globals()[name])
     monkeypatch.setattr(engine, "_require_cuda", lambda *ts: None)
     monkeypatch.setattr(engine, "_fused_available", lambda: True)

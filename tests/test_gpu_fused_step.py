@@ -245,3 +245,114 @@ def test_fused_backward_step_molecules_larger_than_a_tile():
     G = ((A[dst] - X).bfloat16().float() @ W.bfloat16().float()) * (Hp[:, :h].float() > 0).float()
     assert torch.isfinite(out.float()).all()
     torch.testing.assert_close(out[:, :h].float(), G.bfloat16().float(), rtol=2 ** -6, atol=2e-2)
+
+
+# ---- atom-granular step (ATOM instantiations of the same kernel: dmpnn_atom_step_fused_bf16) ---------------------------
+def _atom_setup(n_mols, h, seed, cgr=False, mean_atoms=25.0):
+    from chemprop_b200.data import BatchMolGraph, make_cgr_graphs, make_molecules
+    from chemprop_b200.engine import get_layout, pad_hidden
+
+    mgs = make_cgr_graphs(n_mols, seed=seed) if cgr else make_molecules(n_mols, seed=seed, shuffle_edges=True, min_atoms=1,
+                                                                         mean_atoms=mean_atoms)
+    bmg = BatchMolGraph(mgs)
+    bmg.to("cuda")
+    lay = get_layout(bmg)
+    hp = pad_hidden(h)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    H0 = torch.zeros(lay.V, hp, dtype=torch.bfloat16, device="cuda")
+    H0[:, :h] = (torch.randn(lay.V, h, device="cuda", generator=g) * 0.7).bfloat16()
+    Hp = torch.zeros_like(H0)
+    Hp[:, :h] = torch.relu(torch.randn(lay.V, h, device="cuda", generator=g)).bfloat16()
+    W = torch.randn(h, h, device="cuda", generator=g) / h ** 0.5
+    b = torch.randn(h, device="cuda", generator=g) * 0.1
+    return lay, H0, Hp, W, b, hp
+
+
+def _neighbour_sum(lay, X):
+    """sum over the in-edges e of v of X[src(e)] (f32)"""
+    return torch.zeros(lay.V, X.shape[1], device=X.device).index_add_(0, lay.dst_row.long(), X[lay.src_row.long()])
+
+
+@pytest.mark.parametrize("h,first,act,bias,cgr", [
+    (300, False, "relu", False, False), (300, True, "relu", False, False), (300, False, "tanh", True, True),
+    (64, False, "relu", True, False), (128, True, "tanh", False, True), (304, False, "relu", False, True),
+    (16, True, "relu", True, False),
+])
+def test_atom_fused_step_vs_torch_reference(h, first, act, bias, cgr):
+    """H_next[v] = tau(H_0[v] + b + W . sum_{e in in(v)} g(H[src e])): the ATOM gather (tile-local neighbour table, packed-bf16
+    sums for in-degree <= 3, f32 beyond) + the shared GEMM / epilogue, against torch with the kernel's rounding points."""
+    from chemprop_b200 import _lib
+    from chemprop_b200.engine import atom_step_fused, pack_weight_bf16
+
+    lay, H0, Hp, W, b, hp = _atom_setup(90 if cgr else 700, h, seed=h + int(first), cgr=cgr)
+    assert lay.max_tile_atoms <= 128
+    tau = {"relu": torch.relu, "tanh": torch.tanh}[act]
+    code = {"relu": _lib.ACT_RELU, "tanh": _lib.ACT_TANH}[act]
+    Hin = H0 if first else Hp
+    Hn = torch.full_like(H0, float("nan"))
+    Hn[:, h:] = 0
+    N1 = torch.full_like(H0, float("nan")) if first else None
+    atom_step_fused(Hin, H0, Hn, h, pack_weight_bf16(W), b if bias else None, lay, code, 0.0, first, N_out=N1)
+    torch.cuda.synchronize()
+    X = Hin[:, :h].float()
+    if first:
+        X = tau(X).bfloat16().float()
+    N = _neighbour_sum(lay, X).bfloat16().float()
+    ref = tau(N @ W.bfloat16().float().t() + H0[:, :h].float() + (b if bias else 0.0)).bfloat16().float()
+    assert torch.isfinite(Hn.float()).all(), "rows/columns left unwritten"
+    assert hp == h or float(Hn[:, h:].float().abs().max()) == 0.0
+    if first:
+        torch.testing.assert_close(N1[:, :h].float(), N, rtol=2 ** -6, atol=2e-2)
+    torch.testing.assert_close(Hn[:, :h].float(), ref, rtol=2 ** -6, atol=2e-2)
+
+
+@pytest.mark.parametrize("mode", ["mask", "copy", "last"])
+@pytest.mark.parametrize("cgr", [False, True])
+def test_atom_fused_backward_step(mode, cgr):
+    """Mirror: dOut = ((A dZ) . W) [* tau'(Y)], G_out = A dZ, with A the symmetric atom adjacency."""
+    from chemprop_b200 import _lib
+    from chemprop_b200.engine import atom_step_bwd_fused, pack_weight_bf16
+
+    h = 300
+    lay, Ypre, Yact, W, _, hp = _atom_setup(80 if cgr else 600, h, seed=11, cgr=cgr)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dZ = torch.zeros_like(Ypre)
+    dZ[:, :h] = torch.randn(lay.V, h, device="cuda", generator=g).bfloat16()
+    dOut = torch.full_like(Ypre, float("nan"))
+    dOut[:, h:] = 0
+    G = torch.full_like(Ypre, float("nan"))
+    Y = None if mode == "copy" else (Ypre if mode == "last" else Yact)
+    atom_step_bwd_fused(dZ, Y, dOut, h, pack_weight_bf16(W.t().contiguous()), lay, _lib.ACT_RELU, 0.0, G_out=G,
+                        y_is_preact=(mode == "last"))
+    torch.cuda.synchronize()
+    Gref = _neighbour_sum(lay, dZ[:, :h].float()).bfloat16().float()
+    D = Gref @ W.bfloat16().float()
+    if Y is not None:
+        D = D * (Y[:, :h].float() > 0).float()
+    torch.testing.assert_close(G[:, :h].float(), Gref, rtol=2 ** -6, atol=2e-2)
+    torch.testing.assert_close(dOut[:, :h].float(), D.bfloat16().float(), rtol=2 ** -6, atol=3e-2)
+
+
+def test_atom_tiles_cover_the_batch():
+    """dmpnn_tiles_build with the atom limits: tiles are runs of whole molecules, <= 128 atoms each, covering every atom once;
+    the greedy rule (restarted every 1024 molecules) checked against a host walk."""
+    from chemprop_b200.engine import atom_tables
+
+    lay, *_ = _atom_setup(2500, 64, seed=3, mean_atoms=30.0)
+    ta, te, info, _ = atom_tables(lay)
+    n = int(info[0])
+    ta, te = ta[: n + 1].cpu().numpy(), te[: n + 1].cpu().numpy()
+    mol_a, mol_r = lay.mol_atom_ptr.cpu().numpy(), lay.mol_row_ptr.cpu().numpy()
+    exp_a, B, m = [], lay.B, 0
+    while m < B:
+        stop = min(B, (m // 1024 + 1) * 1024)
+        j = m + 1
+        while j < stop and mol_a[j + 1] - mol_a[m] <= 128 and mol_r[j + 1] - mol_r[m] <= 1024:
+            j += 1
+        exp_a.append(mol_a[m])
+        m = j
+    exp_a.append(mol_a[B])
+    assert ta.tolist() == exp_a
+    assert ta[0] == 0 and ta[-1] == lay.V and te[-1] == lay.E and int(info[2]) <= 128
+    rowptr = lay.rowptr.cpu().numpy()
+    assert (te == rowptr[ta]).all()

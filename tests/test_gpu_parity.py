@@ -399,6 +399,9 @@ def test_cgr_dims_vs_oracle(kind, precision):
     if kind == "bond" and precision == "bf16":
         # ~170 directed edges per graph: every molecule is larger than a 128-row tile and still runs on the fused kernel
         assert engine.get_layout(bmg).max_tile_rows > 128 and tags == {"fused_first", "fused"}, tags
+    if kind == "atom" and precision == "bf16":
+        # ~80-atom graphs: every depth step of the atom path is one launch of the fused kernel's ATOM instantiation
+        assert tags == {"atom_fused_first", "atom_fused"}, tags
     a = MeanAggregation()(H, bmg.batch)
     a.float().square().sum().backward()
     tol = FP32_ATOL if precision == "fp32" else BF16_ATOL * max(1.0, H_ref.detach().abs().max().item())

@@ -11,7 +11,7 @@ build_one() {   # tag, -D flags...
   tag=$1; shift
   d=chemprop_b200/lib/variants/$tag
   mkdir -p "$d"
-  for f in step_fused step_fused_fwd step_fused_bwd step_fused_far_fwd step_fused_far_bwd; do
+  for f in step_fused step_fused_fwd step_fused_bwd step_fused_far_fwd step_fused_far_bwd step_fused_atom_fwd step_fused_atom_bwd; do
     nvcc $FLAGS "$@" -c chemprop_b200/csrc/$f.cu -o "$d/$f.o" &
   done
   wait
