@@ -637,7 +637,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
       for (int k = 0; k < 3; ++k) {
         int x = g0 + k;
         if (!ATOM && x >= rs) ++x;
-        sval[k] = (k < nsib) && nsib <= 3;
+        sval[k] = (k < nsib) && nsib <= (ATOM ? 4 : 3);
         if (ATOM) x = sval[k] ? nb_at(x) : r;
         if (FAR && far) {
           int xa = g0a + k;
@@ -652,6 +652,17 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         if (!ATOM && MODE != MODE_FWD && !(FAR && far)) x = rvl[x];  // autograd mirror: the sibling contributes the row of its reverse edge
         soff[k] = (uint32_t)((x >> 3) * 1024 + (x & 7) * 128);
         sxr[k] = x & 7;
+      }
+      // ATOM: a fourth neighbour (sp3 centres) is added after the first three, into the same registers -- without it nearly every
+      // warp holds one degree-4 atom and would run the f32 loop below next to the packed path
+      uint32_t soff3 = 0;
+      int sxr3 = 0;
+      bool sval3 = false;
+      if (ATOM && rin && d == 4) {
+        const int x3 = nb_at(g0 + 3);
+        sval3 = true;
+        soff3 = (uint32_t)((x3 >> 3) * 1024 + (x3 & 7) * 128);
+        sxr3 = x3 & 7;
       }
       __nv_bfloat16* gout = nullptr;
       if constexpr (kCanEmit) {
@@ -682,7 +693,7 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
         const uint32_t sbase = sA + (uint32_t)((j >> 2) % kASlots) * kSlabBytes;
         const int c0 = 2 * (j & 3);
         uint32_t o[8];
-        if (nsib <= 3) {
+        if (nsib <= (ATOM ? 4 : 3)) {
           uint4 u[3][2];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
@@ -710,6 +721,13 @@ k_bond_step_fused(const __grid_constant__ CUtensorMap tmapH, const __grid_consta
               const bf2 a0 = u2b(w0[q]), a1 = u2b(w1[q]), a2 = u2b(w2[q]);
               o[4 * hh + q] = b2u(__hadd2(__hadd2(a0, a1), a2));   // x + 0 is exact: <= 2 roundings for d <= 4
             }
+          }
+          if (ATOM && sval3) {
+            const uint4 v0 = s_load<ACT, FIRST>(sbase + soff3 + (uint32_t)((c0 ^ sxr3) << 4), p.act_param);
+            const uint4 v1 = s_load<ACT, FIRST>(sbase + soff3 + (uint32_t)(((c0 + 1) ^ sxr3) << 4), p.act_param);
+            const uint32_t w3[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = b2u(__hadd2(u2b(o[q]), u2b(w3[q])));
           }
         } else {
           float acc[16];

@@ -402,20 +402,20 @@ def atom_tables(lay):
 
 def _neighbour_sum_packed(f, lay):
     """The ATOM gather of the fused kernel, rounding for rounding: A row v = sum over the in-edges e of v of f[src(e)], added in
-    slot order as packed bf16 (`__hadd2(__hadd2(a0, a1), a2)`, an absent neighbour is +0) for in-degree <= 3 and in f32 with one
-    rounding otherwise.  `f` is bf16-valued f32 [V, C]."""
+    slot order as packed bf16 (`__hadd2(__hadd2(__hadd2(a0, a1), a2), a3)`, an absent neighbour is +0) for in-degree <= 4 and in f32
+    with one rounding otherwise.  `f` is bf16-valued f32 [V, C]."""
     V = lay.V
     rowptr, src = lay.rowptr.long(), lay.src_row.long()
     g0 = rowptr[:V]
     d = rowptr[1:V + 1] - g0
     r = torch.arange(V)
     vals = []
-    for k in range(3):
-        ok = (k < d) & (d <= 3)
+    for k in range(4):
+        ok = (k < d) & (d <= 4)
         x = torch.where(ok, src[torch.clamp(g0 + k, max=max(lay.E - 1, 0))], r)
         vals.append(f[x] * ok.unsqueeze(1).to(f.dtype))
-    small = _bf(_bf(vals[0] + vals[1]) + vals[2])
-    big = d > 3
+    small = _bf(_bf(_bf(vals[0] + vals[1]) + vals[2]) + vals[3])
+    big = d > 4
     if bool(big.any()):
         s = torch.zeros((V, f.shape[1])).index_add_(0, lay.dst_row.long(), f[src])
         small = torch.where(big.unsqueeze(1), _bf(s), small)

@@ -25,6 +25,10 @@ for s in $STEPS; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file "$OUT/launches.csv" \
         python bench.py --steps 2 --warmup 3 --no-cpu --no-dataset > "$OUT/bench_under_ncu.log" 2>&1
       echo "ncu launches rc=$?" ;;
+    launches_c4)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file "$OUT/launches_c4.csv" \
+        python bench.py --config C4 --steps 2 --warmup 3 --no-cpu --no-graph > "$OUT/bench_c4_under_ncu.log" 2>&1
+      echo "ncu launches C4 rc=$?" ;;
     ncu_fused)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bond_step_fused -s 12 -c 4 \
         -o "$OUT/fused_step" -f python bench.py --steps 1 --warmup 3 --no-cpu --no-dataset > "$OUT/ncu_fused.log" 2>&1
