@@ -1285,6 +1285,25 @@ def atom_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo:
     return dWi, dbi, dWh, dbh, dWo, dbo
 
 
+def _readout_pad(d_v: int, h: int) -> int:
+    """Column at which M_v starts inside the read-out operand [V || M_v]: d_v rounded up to 8 columns (16-byte aligned bf16 rows
+    for the vectorised segment sum that writes M_v in place; d_v = 106 of the reaction graphs left it on the scalar kernel:
+    1.2 ms per step at C4), unless that would exceed the GEMM's K limit."""
+    dvp = (d_v + 7) // 8 * 8
+    return dvp if dvp + h <= 448 else d_v
+
+
+def _wo_padded(Wo: Tensor, d_v: int, dvp: int) -> Tensor:
+    """W_o with zero columns for the padding between V and M_v"""
+    if dvp == d_v:
+        return Wo
+    return torch.cat([Wo[:, :d_v], Wo.new_zeros((Wo.shape[0], dvp - d_v)), Wo[:, d_v:]], 1)
+
+
+def _wo_unpadded(dWo_p: Tensor, d_v: int, dvp: int) -> Tensor:
+    return dWo_p if dvp == d_v else torch.cat([dWo_p[:, :d_v], dWo_p[:, dvp:]], 1)
+
+
 def _atom_tc_ok(cfg: MPConfig, h: int, d_v: int, d_e: int) -> bool:
     return _tc_ok(cfg, h, d_v, h + d_e, d_v + h) and h % 4 == 0
 
@@ -1326,15 +1345,16 @@ def atom_forward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tenso
         Hs.append(Hn)
         XAs.append(XA)
         Hprev, first = Hn, False
-    ko = (d_v + h + 15) // 16 * 16
+    dvp = _readout_pad(d_v, h)
+    ko = (dvp + h + 15) // 16 * 16
     XO = torch.empty((rows, ko), dtype=T, device=dev)
-    concat_bf16(V, d_v, XO, nV, width=d_v)
-    segment_sum(Hprev, lay.rowptr, nV, h, XO[:, d_v:d_v + h], idx=lay.src_row, act=(a if first else ACT_NONE),
-                act_param=ap, pad_to=(hc if d_v + hc <= ko else h))                           # base.py:208-211
+    concat_bf16(V, d_v, XO, nV, width=dvp)
+    segment_sum(Hprev, lay.rowptr, nV, h, XO[:, dvp:dvp + h], idx=lay.src_row, act=(a if first else ACT_NONE),
+                act_param=ap, pad_to=(hc if dvp + hc <= ko else h))                           # base.py:208-211
     Hvp = torch.empty((rows, hp), dtype=T, device=dev)
-    linear_tc(XO, d_v + h, pack_weight_tc(Wo), h, Hvp, bias=bo, act=a, act_param=ap, R=nV)    # base.py:180-182
+    linear_tc(XO, dvp + h, pack_weight_tc(_wo_padded(Wo, d_v, dvp)), h, Hvp, bias=bo, act=a, act_param=ap, R=nV)    # base.py:180-182
     Hv = Hvp[:nV, :h]
-    return Hv, dict(H0=H0, Hs=Hs, XAs=XAs, XO=XO, Xv=Xv, Hv=Hv, tc=True)
+    return Hv, dict(H0=H0, Hs=Hs, XAs=XAs, XO=XO, Xv=Xv, Hv=Hv, tc=True, dvp=dvp)
 
 
 def atom_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo: Tensor, cfg: MPConfig,
@@ -1362,7 +1382,13 @@ def atom_backward_tc(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, 
         gHv = gHv.contiguous()
     dY = _empty_hidden(nV, hp, T, dev)
     act_bwd(gHv, Hv, nV, h, act=a, act_param=ap, dZ=dY)
-    wgrad_tc(dY, XO, nV, h, d_v + h, dWo)
+    dvp = saved.get("dvp", d_v)
+    if dvp == d_v:
+        wgrad_tc(dY, XO, nV, h, d_v + h, dWo)
+    else:
+        dWo_p = torch.empty((h, dvp + h), dtype=torch.float32, device=dev)
+        wgrad_tc(dY, XO, nV, h, dvp + h, dWo_p)
+        dWo = _wo_unpadded(dWo_p, d_v, dvp)
     if dbo is not None:
         column_sum(dY, nV, h, dbo)
     dMv = _empty_hidden(nV, hp, T, dev)
@@ -1434,15 +1460,16 @@ def atom_forward_fused(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Te
             atom_step_fused(Hprev, H0p, Hn, h, Whpk, step_bias, lay, a, ap, first, N_out=N1 if first else None)
         Hs.append(Hn)
         Hprev, first = Hn, False
-    ko = (d_v + h + 15) // 16 * 16
+    dvp = _readout_pad(d_v, h)
+    ko = (dvp + h + 15) // 16 * 16
     XO = torch.empty((rows, ko), dtype=T, device=dev)
-    concat_bf16(V, d_v, XO, nV, width=d_v)
-    segment_sum(Hprev, lay.rowptr, nV, h, XO[:, d_v:d_v + h], idx=lay.src_row, act=ACT_NONE, act_param=ap,
-                pad_to=(hc if d_v + hc <= ko else h))                                         # base.py:208-211
+    concat_bf16(V, d_v, XO, nV, width=dvp)
+    segment_sum(Hprev, lay.rowptr, nV, h, XO[:, dvp:dvp + h], idx=lay.src_row, act=ACT_NONE, act_param=ap,
+                pad_to=(hc if dvp + hc <= ko else h))                                         # base.py:208-211
     Hvp = torch.empty((rows, hp), dtype=T, device=dev)
-    linear_tc(XO, d_v + h, pack_weight_tc(Wo), h, Hvp, bias=bo, act=a, act_param=ap, R=nV)    # base.py:180-182
+    linear_tc(XO, dvp + h, pack_weight_tc(_wo_padded(Wo, d_v, dvp)), h, Hvp, bias=bo, act=a, act_param=ap, R=nV)    # base.py:180-182
     Hv = Hvp[:nV, :h]
-    return Hv, dict(H0=H0, Hs=Hs, N1=N1, SEb=SEb, XO=XO, Xv=Xv, Hv=Hv, tc=True, fused=True)
+    return Hv, dict(H0=H0, Hs=Hs, N1=N1, SEb=SEb, XO=XO, Xv=Xv, Hv=Hv, tc=True, fused=True, dvp=dvp)
 
 
 def atom_backward_fused(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo: Tensor, cfg: MPConfig,
@@ -1471,7 +1498,13 @@ def atom_backward_fused(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tenso
         gHv = gHv.contiguous()
     dY = _empty_hidden(nV, hp, T, dev)
     act_bwd(gHv, Hv, nV, h, act=a, act_param=ap, dZ=dY)
-    wgrad_tc(dY, XO, nV, h, d_v + h, dWo)
+    dvp = saved.get("dvp", d_v)
+    if dvp == d_v:
+        wgrad_tc(dY, XO, nV, h, d_v + h, dWo)
+    else:
+        dWo_p = torch.empty((h, dvp + h), dtype=torch.float32, device=dev)
+        wgrad_tc(dY, XO, nV, h, dvp + h, dWo_p)
+        dWo = _wo_unpadded(dWo_p, d_v, dvp)
     if dbo is not None:
         column_sum(dY, nV, h, dbo)
     dMv = _empty_hidden(nV, hp, T, dev)
