@@ -1507,12 +1507,10 @@ def atom_backward_fused(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tenso
         dWo = _wo_unpadded(dWo_p, d_v, dvp)
     if dbo is not None:
         column_sum(dY, nV, h, dbo)
-    dMv = _empty_hidden(nV, hp, T, dev)
-    linear_tc(dY, h, pack_weight_tc(Wo[:, d_v:], transpose=True), h, dMv, R=nV)
-    dHa = _empty_hidden(nV, hp, T, dev)                      # d(Ha^{T-1}) = A dM_v   (rev is an involution)
-    segment_sum(dMv, lay.rowptr, nV, h, dHa, idx=lay.src_row, pad_to=hc)
+    # dZ^{T-1} = (A (dY . W_o[:, d_v:])) * tau'(H^{T-1}) = ((A dY) . W_o[:, d_v:]) * tau'(H^{T-1}): the read-out GEMM, the
+    # neighbour gather of its result and the tau' pass are ONE mirror launch of the fused kernel on dY (three launches before)
     dZ = _empty_hidden(nV, hp, T, dev)
-    act_bwd(dHa, Hs[-1], nV, hc, act=a, act_param=ap, dZ=dZ)                                  # dZ^{T-1}
+    atom_step_bwd_fused(dY, Hs[-1], dZ, h, pack_weight_bf16(Wo[:, d_v:].t().contiguous()), lay, a, ap)
     WhT = pack_weight_bf16(Wh[:, :h].t().contiguous())
     dWhN = dWh[:, :h]
     terms, wrote = [dZ], False
