@@ -29,6 +29,10 @@ for s in $STEPS; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file "$OUT/launches_c4.csv" \
         python bench.py --config C4 --steps 2 --warmup 3 --no-cpu --no-graph > "$OUT/bench_c4_under_ncu.log" 2>&1
       echo "ncu launches C4 rc=$?" ;;
+    ncu_fused_c4)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bond_step_fused -s 12 -c 4 \
+        -o "$OUT/atom_step" -f python bench.py --config C4 --steps 1 --warmup 3 --no-cpu > "$OUT/ncu_fused_c4.log" 2>&1
+      echo "ncu fused C4 rc=$?" ;;
     ncu_fused)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bond_step_fused -s 12 -c 4 \
         -o "$OUT/fused_step" -f python bench.py --steps 1 --warmup 3 --no-cpu --no-dataset > "$OUT/ncu_fused.log" 2>&1
