@@ -1434,8 +1434,11 @@ def atom_forward_fused(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Te
     nV = lay.V
     a, ap = cfg.act, cfg.act_param
     rows = max(nV, 1)
+    # [V || sum_in E] side by side in ONE bf16 operand (16-column blocks): W_i reads its first d_v columns, the H_0' GEMM the
+    # second block, and the mirror contracts the dZ^t terms with both in one weight-gradient launch
     kv = (d_v + 15) // 16 * 16
-    Xv = torch.empty((rows, kv), dtype=T, device=dev)
+    ke = (d_e + 15) // 16 * 16 if d_e > 0 else 0
+    Xv = torch.empty((rows, kv + ke), dtype=T, device=dev)
     concat_bf16(V, d_v, Xv, nV, width=kv)
     H0 = _empty_hidden(nV, hp, T, dev)
     linear_tc(Xv, d_v, pack_weight_tc(Wi), h, H0, bias=bi, R=nV)                              # mixins.py:22-23
@@ -1443,8 +1446,7 @@ def atom_forward_fused(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Te
     if d_e > 0:                                                                               # loop-invariant bond term
         SE = torch.zeros((rows, d_e), dtype=torch.float32, device=dev)
         segment_sum(E, lay.rowptr, nV, d_e, SE, idx=lay.perm)
-        ke = (d_e + 15) // 16 * 16
-        SEb = torch.empty((rows, ke), dtype=T, device=dev)
+        SEb = Xv[:, kv:kv + ke]
         concat_bf16(SE, d_e, SEb, nV, width=ke)
         H0p = _empty_hidden(nV, hp, T, dev)                                                   # H_0 + b_h + W_h[:, h:] . SE
         linear_tc(SEb, d_e, pack_weight_tc(Wh[:, h:]), h, H0p, bias=bh, res=H0, R=nV)
@@ -1531,8 +1533,15 @@ def atom_backward_fused(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tenso
             terms.append(dZ)
         wrote = True
     if d_e > 0:
-        wgrad_tc_multi(terms, SEb, nV, h, d_e, dWh[:, h:])
-    wgrad_tc_multi(terms + [dH0l], Xv, nV, h, d_v, dWi)
+        # one pass over the dZ^t terms for both [V || sum_in E] blocks of Xv, then the dH^0 term for the V block alone
+        kv = (d_v + 15) // 16 * 16
+        dWx = torch.empty((h, kv + d_e), **f32)
+        wgrad_tc_multi(terms, Xv, nV, h, kv + d_e, dWx)
+        wgrad_tc(dH0l, Xv, nV, h, d_v, dWx[:, :d_v], accumulate=True)
+        dWi = dWx[:, :d_v]
+        dWh[:, h:].copy_(dWx[:, kv:kv + d_e])
+    else:
+        wgrad_tc_multi(terms + [dH0l], Xv, nV, h, d_v, dWi)
     if dbi is not None:
         for i, P in enumerate(terms + [dH0l]):
             column_sum(P, nV, h, dbi, accumulate=i > 0)
