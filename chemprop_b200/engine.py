@@ -1463,15 +1463,18 @@ def atom_forward_fused(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Te
         Hs.append(Hn)
         Hprev, first = Hn, False
     dvp = _readout_pad(d_v, h)
-    ko = (dvp + h + 15) // 16 * 16
+    ones_col = dvp + hc if (bo is not None and dvp + hc + 1 <= 448) else None   # see bond_forward: db_o rides on dW_o's GEMM
+    ko = (dvp + hc + 1 + 15) // 16 * 16 if ones_col is not None else (dvp + h + 15) // 16 * 16
     XO = torch.empty((rows, ko), dtype=T, device=dev)
     concat_bf16(V, d_v, XO, nV, width=dvp)
     segment_sum(Hprev, lay.rowptr, nV, h, XO[:, dvp:dvp + h], idx=lay.src_row, act=ACT_NONE, act_param=ap,
                 pad_to=(hc if dvp + hc <= ko else h))                                         # base.py:208-211
+    if ones_col is not None:
+        XO[:, ones_col].fill_(1.0)
     Hvp = torch.empty((rows, hp), dtype=T, device=dev)
     linear_tc(XO, dvp + h, pack_weight_tc(_wo_padded(Wo, d_v, dvp)), h, Hvp, bias=bo, act=a, act_param=ap, R=nV)    # base.py:180-182
     Hv = Hvp[:nV, :h]
-    return Hv, dict(H0=H0, Hs=Hs, N1=N1, SEb=SEb, XO=XO, Xv=Xv, Hv=Hv, tc=True, fused=True, dvp=dvp)
+    return Hv, dict(H0=H0, Hs=Hs, N1=N1, SEb=SEb, XO=XO, Xv=Xv, Hv=Hv, tc=True, fused=True, dvp=dvp, ones_col=ones_col)
 
 
 def atom_backward_fused(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo: Tensor, cfg: MPConfig,
@@ -1501,14 +1504,20 @@ def atom_backward_fused(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tenso
     dY = _empty_hidden(nV, hp, T, dev)
     act_bwd(gHv, Hv, nV, h, act=a, act_param=ap, dZ=dY)
     dvp = saved.get("dvp", d_v)
-    if dvp == d_v:
-        wgrad_tc(dY, XO, nV, h, d_v + h, dWo)
+    oc = saved.get("ones_col")
+    if dbo is not None and oc is not None:
+        dWo_p = torch.empty((h, oc + 1), dtype=torch.float32, device=dev)      # [dW_o (padded) | 0 | db_o]
+        wgrad_tc(dY, XO, nV, h, oc + 1, dWo_p)
+        dWo, dbo = _wo_unpadded(dWo_p[:, :dvp + h], d_v, dvp), dWo_p[:, oc]
     else:
-        dWo_p = torch.empty((h, dvp + h), dtype=torch.float32, device=dev)
-        wgrad_tc(dY, XO, nV, h, dvp + h, dWo_p)
-        dWo = _wo_unpadded(dWo_p, d_v, dvp)
-    if dbo is not None:
-        column_sum(dY, nV, h, dbo)
+        if dvp == d_v:
+            wgrad_tc(dY, XO, nV, h, d_v + h, dWo)
+        else:
+            dWo_p = torch.empty((h, dvp + h), dtype=torch.float32, device=dev)
+            wgrad_tc(dY, XO, nV, h, dvp + h, dWo_p)
+            dWo = _wo_unpadded(dWo_p, d_v, dvp)
+        if dbo is not None:
+            column_sum(dY, nV, h, dbo)
     # dZ^{T-1} = (A (dY . W_o[:, d_v:])) * tau'(H^{T-1}) = ((A dY) . W_o[:, d_v:]) * tau'(H^{T-1}): the read-out GEMM, the
     # neighbour gather of its result and the tau' pass are ONE mirror launch of the fused kernel on dY (three launches before)
     dZ = _empty_hidden(nV, hp, T, dev)
