@@ -284,3 +284,52 @@ def test_training_loop_through_the_loader_overfits(precision, dropout, monkeypat
             tot += loss.item()
         epoch_loss.append(tot / len(loader))
     assert epoch_loss[-1] < 0.1 * epoch_loss[0] and epoch_loss[-1] < 0.01, (epoch_loss[0], epoch_loss[-1])
+
+
+@pytest.mark.parametrize("depth,d_e,bias", [(3, 28, False), (2, 28, True), (4, 0, True), (3, 14, True)])
+def test_atom_bf16_tier_runs_on_the_fused_atom_step(depth, d_e, bias, monkeypatch):
+    """AtomMessagePassing, bf16 tier: every depth step is ONE call of the fused atom step (forward: depth - 1; mirror: depth - 1
+    step launches + the read-out launch on dY), the loop-invariant bond term is folded into H_0' (no bias left for the step when
+    d_e > 0), and the result matches the oracle at the tier's tolerance; a molecule with more than 128 atoms sends the batch to the
+    two-launch step with a one-time warning."""
+    from chemprop_b200 import engine
+    from chemprop_b200.data import BatchMolGraph, make_cgr_graphs, make_molecules
+    from chemprop_b200.nn import AtomMessagePassing
+    from oracle import restatement as R
+
+    emu.patch_engine(monkeypatch)
+    calls = []
+    f0, b0 = engine.atom_step_fused, engine.atom_step_bwd_fused
+    monkeypatch.setattr(engine, "atom_step_fused", lambda *a, **k: (calls.append(("f", a[5] is not None, a[9])), f0(*a, **k))[1])
+    monkeypatch.setattr(engine, "atom_step_bwd_fused", lambda *a, **k: (calls.append(("b",)), b0(*a, **k))[1])
+    torch.manual_seed(depth + d_e)
+    mgs = make_cgr_graphs(5, seed=depth, d_v=106, d_e=d_e) if d_e else make_molecules(9, seed=depth, d_v=106, d_e=14, min_atoms=1)
+    if d_e == 0:                                                         # bond-feature-less graphs: no term to fold into H_0'
+        mgs = [type(m)(V=m.V, E=m.E[:, :0], edge_index=m.edge_index, rev_edge_index=m.rev_edge_index) for m in mgs]
+    bmg = BatchMolGraph(mgs)
+    mp = AtomMessagePassing(d_v=106, d_e=d_e, d_h=48, depth=depth, bias=bias, precision="bf16")
+    H = mp(bmg)
+    H.float().square().sum().backward()
+    fwd = [c for c in calls if c[0] == "f"]
+    assert len(fwd) == depth - 1 and [c[2] for c in fwd] == [True] + [False] * (depth - 2)          # first_step flags
+    assert all(c[1] == (bias and d_e == 0) for c in fwd)                 # the step carries b_h only when nothing folded it into H_0'
+    assert len([c for c in calls if c[0] == "b"]) == depth               # read-out launch + depth - 1 mirror steps
+    P = {k: v.detach().double().requires_grad_(True) for k, v in mp.state_dict().items()}
+    Hr = R.message_passing_forward("atom", bmg.V.double(), bmg.E.double(), bmg.edge_index, bmg.rev_edge_index, P["W_i.weight"],
+                                   P.get("W_i.bias"), P["W_h.weight"], P.get("W_h.bias"), P["W_o.weight"], P["W_o.bias"], depth)
+    Hr.square().sum().backward()
+    assert float((H.detach().double() - Hr.detach()).abs().max()) <= 1e-2 * max(1.0, float(Hr.detach().abs().max()))
+    for k, p in mp.named_parameters():
+        ref = P[k].grad
+        assert float((p.grad.double() - ref).abs().max()) <= 6e-2 * max(1e-6, float(ref.abs().max())), k
+
+    calls.clear()
+    engine._WARNED.discard("atom_unfused")
+    bigs = make_molecules(2, seed=1, mean_atoms=150.0, std_atoms=1.0, min_atoms=140, max_atoms=160, d_v=106, d_e=max(d_e, 1)) \
+        + make_molecules(3, seed=2, d_v=106, d_e=max(d_e, 1))
+    if d_e == 0:
+        bigs = [type(m)(V=m.V, E=m.E[:, :0], edge_index=m.edge_index, rev_edge_index=m.rev_edge_index) for m in bigs]
+    big = BatchMolGraph(bigs)
+    with pytest.warns(RuntimeWarning, match="fused atom depth step"):
+        mp(big)
+    assert not calls
