@@ -333,3 +333,29 @@ def test_atom_bf16_tier_runs_on_the_fused_atom_step(depth, d_e, bias, monkeypatc
     with pytest.warns(RuntimeWarning, match="fused atom depth step"):
         mp(big)
     assert not calls
+
+
+@pytest.mark.parametrize("kind,precision", [("bond", "fp32"), ("bond", "bf16"), ("atom", "bf16"), ("atom", "fp32")])
+def test_second_backward_and_feature_gradients(kind, precision, monkeypatch):
+    """The autograd node keeps its saved tensors: a second backward with `retain_graph=True` reproduces the first one's
+    gradients exactly (torch's own behaviour; round 1 dropped them after the first backward).  And features that require grad are
+    refused loudly -- the hand-written mirror produces parameter gradients only, a silent `None` would be wrong."""
+    from chemprop_b200._lib import DmpnnError
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.nn import AtomMessagePassing, BondMessagePassing
+
+    emu.patch_engine(monkeypatch)
+    torch.manual_seed(3)
+    bmg = BatchMolGraph(make_molecules(12, seed=4))
+    mp = (BondMessagePassing if kind == "bond" else AtomMessagePassing)(d_h=32, depth=3, precision=precision)
+    loss = mp(bmg).float().square().sum()
+    loss.backward(retain_graph=True)
+    first = {k: p.grad.clone() for k, p in mp.named_parameters()}
+    mp.zero_grad(set_to_none=True)
+    loss.backward()
+    for k, p in mp.named_parameters():
+        assert torch.equal(p.grad, first[k]), k
+    bmg2 = BatchMolGraph(make_molecules(3, seed=5))
+    bmg2.V = bmg2.V.clone().requires_grad_(True)
+    with pytest.raises(DmpnnError, match="require grad"):
+        mp(bmg2)
