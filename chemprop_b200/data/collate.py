@@ -89,7 +89,8 @@ def tile_packing_order_of(mgs: Sequence[MolGraph]) -> np.ndarray:
 
 class BatchMolGraph:
     # the three index tensors sit behind properties: replacing one drops the cached device layout and host meta
-    __slots__ = ("V", "E", "_edge_index", "_rev_edge_index", "_batch", "_size", "_layout", "_xfer", "_meta_host")
+    # (`__weakref__`: chemprop_b200.graph.CudaGraphStep remembers the last batch it loaded without keeping it alive)
+    __slots__ = ("V", "E", "_edge_index", "_rev_edge_index", "_batch", "_size", "_layout", "_xfer", "_meta_host", "__weakref__")
 
     def _index_property(name):  # noqa: N805
         def get(self):
@@ -236,7 +237,8 @@ class BatchMolGraph:
         # the index layout stays valid for the copy.
         new = object.__new__(type(self))
         for s in self.__slots__:
-            setattr(new, s, getattr(self, s))
+            if s != "__weakref__":
+                setattr(new, s, getattr(self, s))
         return new
 
 

@@ -118,6 +118,15 @@ class PackedBatchLoader:
         q: queue.Queue = queue.Queue(maxsize=self.prefetch)
         stop = threading.Event()
 
+        def put(item):
+            # the queue is bounded: never block for good on a consumer that has gone away (early `break`, exception)
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    return
+                except queue.Full:
+                    pass
+
         def produce_plans():
             try:
                 e = 0
@@ -126,17 +135,11 @@ class PackedBatchLoader:
                         if stop.is_set():
                             return
                         ids = ds.packed_order(ids) if self.pack_tiles else ids
-                        item = (ids, ds.plan(ids))
-                        while not stop.is_set():
-                            try:
-                                q.put(item, timeout=0.1)
-                                break
-                            except queue.Full:
-                                pass
+                        put((ids, ds.plan(ids)))
                     e += 1
-                q.put(None)
+                put(None)
             except BaseException as ex:  # noqa: BLE001 -- handed to the consumer
-                q.put(ex)
+                put(ex)
 
         th = threading.Thread(target=produce_plans, daemon=True, name="packed-batch-planner")
         th.start()

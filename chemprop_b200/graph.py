@@ -15,6 +15,7 @@ batches, or a resident batch as in bench.py) therefore replay one graph for the 
 """
 from __future__ import annotations
 
+import weakref
 from collections import OrderedDict
 from typing import Callable
 
@@ -32,7 +33,7 @@ def batch_signature(bmg: BatchMolGraph) -> tuple:
 
 
 class _Captured:
-    __slots__ = ("graph", "bmg", "out", "last", "launches")
+    __slots__ = ("graph", "bmg", "out", "last", "last_ref", "launches")
 
 
 class CudaGraphStep:
@@ -74,7 +75,7 @@ class CudaGraphStep:
         cap = _Captured()
         cap.graph = torch.cuda.CUDAGraph()
         cap.bmg = static
-        cap.last = None
+        cap.last = cap.last_ref = None
         static._layout = None
         kw = {} if self._pool is None else {"pool": self._pool}
         from . import _lib
@@ -89,11 +90,18 @@ class CudaGraphStep:
         return cap
 
     def load(self, cap: _Captured, bmg: BatchMolGraph):
-        # the very same (unmodified) batch object as last time -- a resident batch replayed step after step: nothing to copy
-        stamp = (id(bmg),) + tuple(t._version for t in (bmg.V, bmg.E, bmg.edge_index, bmg.rev_edge_index, bmg.batch))
-        if cap.last == stamp:
+        # The very same (unmodified) batch object as last time -- a resident batch replayed step after step: nothing to copy.
+        # "Same" = the object itself (held through a weak reference: an `id()` is reused as soon as a batch is freed, and a
+        # fresh batch's tensors are all at version 0), the same storage and no in-place change torch knows of.  Tensors that
+        # are rewritten through raw pointers behind torch's back are not seen: pass such a batch as a new object.
+        ts = (bmg.V, bmg.E, bmg.edge_index, bmg.rev_edge_index, bmg.batch)
+        stamp = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
+        if cap.last_ref is not None and cap.last_ref() is bmg and cap.last == stamp:
             return
-        cap.last = stamp
+        try:
+            cap.last_ref, cap.last = weakref.ref(bmg), stamp
+        except TypeError:                                  # a batch type without weak references: copied every time
+            cap.last_ref = cap.last = None
         s = cap.bmg
         s.V.copy_(bmg.V, non_blocking=True)
         s.E.copy_(bmg.E, non_blocking=True)

@@ -359,3 +359,41 @@ def test_second_backward_and_feature_gradients(kind, precision, monkeypatch):
     bmg2.V = bmg2.V.clone().requires_grad_(True)
     with pytest.raises(DmpnnError, match="require grad"):
         mp(bmg2)
+
+
+def test_graph_step_reloads_a_new_batch_object_even_at_a_reused_address():
+    """`CudaGraphStep.load` skips the copy into the graph's static inputs only for the very same, unmodified batch OBJECT.
+    Batches of a fixed-signature loader are new objects whose `id()` is routinely the one of the batch just freed and whose
+    tensors are all at version 0: an id / version stamp alone replayed stale inputs (host-only check of that logic)."""
+    import gc
+
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.graph import CudaGraphStep, _Captured
+
+    mgs = make_molecules(6, seed=3)
+    static = BatchMolGraph(mgs)
+    static.V.zero_()
+    cap = _Captured()
+    cap.bmg, cap.last, cap.last_ref = static, None, None
+    step = CudaGraphStep(lambda b: None)
+
+    b1 = BatchMolGraph(mgs)
+    step.load(cap, b1)
+    assert torch.equal(static.V, b1.V)
+    static.V.fill_(-1.0)
+    step.load(cap, b1)                                   # same object, untouched: nothing copied
+    assert bool((static.V == -1.0).all())
+    b1.V.mul_(2.0)                                       # in-place change torch knows of: copied again
+    step.load(cap, b1)
+    assert torch.equal(static.V, b1.V)
+
+    seen = set()
+    for k in range(64):                                  # new objects, many of them at the address of the one just freed
+        b = BatchMolGraph(mgs)
+        b.V.fill_(float(k))
+        seen.add(id(b))
+        step.load(cap, b)
+        assert bool((static.V == float(k)).all())
+        del b
+        gc.collect()
+    assert len(seen) < 64                                # the allocator did hand out a reused id at least once

@@ -136,3 +136,32 @@ def test_tile_packing_keeps_batch_membership_and_fills_tiles():
     assert np.array_equal(np.sort(o), np.arange(4)) and o[0] == 0          # the oversized one sits alone, first
     with pytest.raises(ValueError):
         tile_packing_order([1, 2], [1])
+
+
+def test_plan_prefetch_thread_of_the_resident_path(data):
+    """The resident data set's loader path (`_resident_batches`: plans made `prefetch` batches ahead on a thread, batches
+    assembled by the consumer) driven over the HOST data set, where `batch(ids, plan=...)` takes the same plan: same batches as
+    the host path, epoch boundaries crossed by `epochs=None`, and a consumer that leaves early (bounded queue full, producer
+    already past its last batch) neither hangs nor leaves the thread behind."""
+    import threading
+
+    mgs, ds = data
+    a = PackedBatchLoader(ds, batch_size=32, shuffle=True, seed=8, prefetch=2)
+    b = PackedBatchLoader(ds, batch_size=32, shuffle=True, seed=8, prefetch=2)
+    host = [x.ids for x in a] + [x.ids for x in a]
+    it = b._resident_batches(epochs=None)                       # two epochs and a bit, without a drain in between
+    got = [next(it) for _ in range(len(host) + 2)]
+    for x in got:
+        _check_batch(x, mgs)
+    assert all(np.array_equal(x.ids, y) for x, y in zip(got, host))
+    it.close()
+
+    c = PackedBatchLoader(ds, batch_size=64, shuffle=False, prefetch=2)          # 4 batches: the queue (2) fills up at once
+    it = c._resident_batches(epochs=1)
+    first = next(it)
+    _check_batch(first, mgs)
+    time.sleep(0.3)                                             # producer: all plans made, blocked on the full queue
+    t0 = time.perf_counter()
+    it.close()                                                  # the consumer goes away
+    assert time.perf_counter() - t0 < 2.0
+    assert not [t for t in threading.enumerate() if t.name == "packed-batch-planner" and t.is_alive()]
