@@ -239,7 +239,8 @@ def get_layout(bmg) -> Layout:
         pass
     # let Aggregation.forward(H, bmg.batch) find the molecule offsets without a device sync
     try:
-        bmg.batch._dmpnn_seg = (lay.mol_atom_ptr, bmg.batch.to(torch.int32), lay.B)
+        bt = bmg.batch
+        bt._dmpnn_seg, bt._dmpnn_seg_v = (lay.mol_atom_ptr, bt.to(torch.int32), lay.B), bt._version
     except Exception:
         pass
     return lay
@@ -249,8 +250,9 @@ def segments_of(batch: Tensor, n_seg: int | None = None):
     """(ptr int32 [B+1], seg_of_row int32 [V], B) for a sorted int64 `batch` (agg.py:74-75).  `n_seg`: the segment count
     is given by the caller (nn/ffn.py:123 sizes by the constraints' rows): trailing segments without rows come out empty
     (`ptr[s] == ptr[s+1]`), an index >= n_seg is an error."""
-    seg = getattr(batch, "_dmpnn_seg", None)
-    if seg is not None and seg[0].device == batch.device and (n_seg is None or seg[2] == n_seg):
+    seg = getattr(batch, "_dmpnn_seg", None)          # attached by get_layout / an earlier call; void after an in-place change
+    if (seg is not None and getattr(batch, "_dmpnn_seg_v", None) == batch._version and seg[0].device == batch.device
+            and (n_seg is None or seg[2] == n_seg)):
         return seg
     _require_cuda(batch)
     lib = _lib.load()
@@ -272,7 +274,7 @@ def segments_of(batch: Tensor, n_seg: int | None = None):
     seg = (ptr, bc.to(torch.int32), B)
     if n_seg is None:
         try:
-            batch._dmpnn_seg = seg
+            batch._dmpnn_seg, batch._dmpnn_seg_v = seg, batch._version
         except Exception:
             pass
     return seg

@@ -192,12 +192,18 @@ class EngineBatchNorm1d(nn.BatchNorm1d):
     """nn.BatchNorm1d (same parameters / buffers); training mode runs dmpnn_bn_train_fwd / dmpnn_bn_bwd."""
 
     def forward(self, x: Tensor) -> Tensor:
-        if not self.training or not x.is_cuda:
+        # torch's own path where the kernel has no equivalent: eval mode, CPU tensors, no running statistics, and
+        # momentum=None (cumulative average: the factor 1 / num_batches_tracked is host state, a sync per step)
+        if not self.training or not x.is_cuda or self.running_mean is None or self.momentum is None:
             return super().forward(x)
+        if x.dim() != 2:
+            raise ValueError(f"expected a 2D input (molecules x features), got {x.dim()}D")
+        if x.shape[0] <= 1:                       # as torch: the batch variance of one row is undefined (the reference's
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(x.shape)}")  # loader drops such a batch, dataloader.py:77-86)
         if self.num_batches_tracked is not None:
             self.num_batches_tracked.add_(1)
-        mom = 0.1 if self.momentum is None else self.momentum
-        return BatchNormTrainFunction.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, mom)
+        return BatchNormTrainFunction.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
+                                            self.momentum)
 
 
 class EngineMPNN(nn.Module):

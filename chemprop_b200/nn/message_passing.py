@@ -17,7 +17,7 @@ import torch
 from torch import Tensor, nn
 
 from .. import _lib, composed
-from ..engine import AtomMPFunction, BondMPFunction, MPConfig, dropout_fused_ok, get_layout
+from ..engine import AtomMPFunction, BondMPFunction, MPConfig, _warn_once, dropout_fused_ok, get_layout
 from ..exceptions import InvalidShapeError
 
 try:                                   # custom-op registration for torch.export (inference); optional
@@ -147,6 +147,14 @@ class _MessagePassingBase(nn.Module):
         lay = get_layout(bmg)
         out_dtype = self.output_dtype or (torch.bfloat16 if self.precision == "bf16" else torch.float32)
         if self.uses_composed_tier(lay):
+            if self.precision == "bf16":
+                # no silent cliff: this tier keeps f32 hidden states and runs its GEMMs on the f32 FMA pipes
+                why = (f"activation {type(self.tau).__name__}" if not is_fused_activation(self.tau) else
+                       "undirected AtomMessagePassing" if (self.undirected and type(self)._kind == 1) else
+                       "training-mode dropout outside the fused ReLU path")
+                _warn_once("composed_bf16", f"chemprop_b200: precision='bf16' requested, but this configuration ({why}) runs on "
+                           "the composed tier: f32 hidden states, one kernel per reference op, no tensor-core depth step "
+                           "(expect several times the step time of the fused bf16 tier)")
             H = type(self)._composed_forward(self, bmg, lay)          # computed in f32 on this tier
         else:
             cfg = self._config()

@@ -475,7 +475,7 @@ def sum_act_bwd(Zs, G, Ypre, out, R, Ccols, *, act, act_param=0.0):
 def segments_of(batch, n_seg=None):
     """engine.segments_of for a bare sorted `batch` (dmpnn_sorted_index_to_ptr): (ptr int32 [B + 1], seg_of_row int32, B)."""
     seg = getattr(batch, "_dmpnn_seg", None)
-    if seg is not None and (n_seg is None or seg[2] == n_seg):
+    if seg is not None and getattr(batch, "_dmpnn_seg_v", None) == batch._version and (n_seg is None or seg[2] == n_seg):
         return seg
     b = batch.numpy()
     assert np.all(np.diff(b) >= 0)

@@ -397,3 +397,25 @@ def test_graph_step_reloads_a_new_batch_object_even_at_a_reused_address():
         del b
         gc.collect()
     assert len(seen) < 64                                # the allocator did hand out a reused id at least once
+
+
+def test_cached_segment_tables_do_not_outlive_an_in_place_change_of_batch(monkeypatch):
+    """`get_layout` leaves the molecule offsets on `bmg.batch` so that `Aggregation.forward(H, bmg.batch)` needs no device
+    read-back; the attachment carries the tensor's version and is void once `batch` has been changed in place."""
+    from chemprop_b200 import engine
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.nn import BondMessagePassing, SumAggregation
+
+    emu.patch_engine(monkeypatch)
+    bmg = BatchMolGraph(make_molecules(5, seed=2))
+    mp = BondMessagePassing(d_h=16, depth=2)
+    H = mp(bmg).detach()
+    assert getattr(bmg.batch, "_dmpnn_seg", None) is not None
+    agg = SumAggregation()
+    out5 = agg(H, bmg.batch)
+    assert out5.shape[0] == 5
+    merged = bmg.batch
+    merged.clamp_(max=1)                                   # molecules 1..4 become one segment; the cache must not be used
+    out2 = agg(H, merged)
+    assert out2.shape[0] == 2
+    assert torch.allclose(out2[1], out5[1:].sum(0), atol=1e-5) and torch.allclose(out2[0], out5[0], atol=1e-6)
