@@ -175,12 +175,40 @@ def gen_mols(cfg: dict, n: int, seed: int):
 # CPU arm: the oracle port (the reference's op sequence on torch CPU), all useful host threads
 # ------------------------------------------------------------------------------------------------
 def cpu_step_fn(cfg: dict, n_mols: int, seed: int):
-    from oracle import restatement as R
-
+    """One fwd+bwd step of the path on the host cores, and what ran it: the UNMODIFIED reference's own modules
+    (`chemprop.nn.{Bond,Atom}MessagePassing` + `MeanAggregation` on a `chemprop.data.BatchMolGraph`, imported from the
+    reference tree through oracle/ref_shim.py) where that tree is reachable -- i.e. in the build container -- and otherwise
+    (the GPU box: the tree does not travel) the oracle restatement of the same op sequence.  -> (step, kind)"""
     torch.manual_seed(seed)
     mgs = gen_mols(cfg, n_mols, seed)
-    V, E, ei, rev, batch = (torch.from_numpy(x) for x in R.collate(mgs))
     h, d_v, d_e = cfg["d_h"], cfg["d_v"], cfg["d_e"]
+    try:
+        from oracle.ref_shim import import_reference, reference_available
+
+        if os.environ.get("DMPNN_BENCH_CPU_KIND", "") != "port" and reference_available():
+            import_reference()
+            import chemprop.nn as ref_nn
+            from chemprop.data import BatchMolGraph as RefBMG
+            from chemprop.data.molgraph import MolGraph as RefMG
+
+            cls = ref_nn.BondMessagePassing if cfg["kind"] == "bond" else ref_nn.AtomMessagePassing
+            mp = cls(d_v=d_v, d_e=d_e, d_h=h, depth=cfg["depth"])
+            agg = ref_nn.MeanAggregation()
+            bmg = RefBMG([RefMG(*m) for m in mgs])
+
+            def step_ref():
+                mp.zero_grad(set_to_none=True)
+                loss = agg(mp(bmg), bmg.batch).square().mean()
+                loss.backward()
+                return loss.item()
+
+            return step_ref, "reference"
+    except Exception as e:  # noqa: BLE001 -- the port below is always available
+        print(f"[bench] reference modules not usable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+
+    from oracle import restatement as R
+
+    V, E, ei, rev, batch = (torch.from_numpy(x) for x in R.collate(mgs))
     lin = lambda o, i: torch.nn.Linear(i, o).weight.detach().requires_grad_(True)  # noqa: E731
     if cfg["kind"] == "bond":
         Wi, Wh = lin(h, d_v + d_e), lin(h, h)
@@ -197,14 +225,14 @@ def cpu_step_fn(cfg: dict, n_mols: int, seed: int):
         loss.backward()
         return loss.item()
 
-    return step
+    return step, "port"
 
 
 def run_cpu(cfg: dict, n_mols: int, steps: int, warmup: int):
     """torch's CPU scatter / index kernels stop scaling (and regress) well before 128 threads, so the thread count is
     probed (8, 16, 32, all cores: one step each on a small sample) and the fastest is used for the timed steps."""
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    probe = cpu_step_fn(cfg, min(n_mols, 500), seed=1)
+    probe, _ = cpu_step_fn(cfg, min(n_mols, 500), seed=1)
     best_t, best_dt = ncpu, float("inf")
     for nt in sorted({min(8, ncpu), min(16, ncpu), min(32, ncpu), ncpu}):
         torch.set_num_threads(nt)
@@ -215,14 +243,14 @@ def run_cpu(cfg: dict, n_mols: int, steps: int, warmup: int):
         if dt < best_dt:
             best_t, best_dt = nt, dt
     torch.set_num_threads(best_t)
-    step = cpu_step_fn(cfg, n_mols, seed=1)
+    step, kind = cpu_step_fn(cfg, n_mols, seed=1)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return n_mols / dt, dt, best_t, ncpu
+    return n_mols / dt, dt, best_t, ncpu, kind
 
 
 def main_reference(args):
@@ -233,17 +261,19 @@ def main_reference(args):
     world = args.gpus
     # the full batch of the configuration per step, unless that cannot finish in minutes (C3 / C5 per-step batches)
     per_step = cfg["n_mols"] if name == "C2" else {"C3": 1_000, "C4": 1_500, "C5": 10_000}[name]
-    v, dt, cores, ncpu = run_cpu(cfg, per_step, args.steps, args.warmup)
+    v, dt, cores, ncpu, kind = run_cpu(cfg, per_step, args.steps, args.warmup)
+    what = ("the unmodified reference's modules (imported from its source tree)" if kind == "reference" else
+            "oracle restatement of the reference's op sequence")
     full = per_step == cfg["n_mols"]
     line = {
         "impl": "reference", "metric": f"molecules/sec fwd+bwd (h={cfg['d_h']} d={cfg['depth']})", "value": v,
         "unit": "molecules/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(name, cfg, world),
-        "cpu_baseline": {"value": v, "unit": "molecules/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": v, "unit": "molecules/s", "cores": cores, "kind": kind,
                          "sample": (f"{per_step} molecules per step" + (" = the configuration's full per-GPU batch" if full else
                                     f" (bounded sample of the {cfg['n_mols']}-molecule batch)") +
-                                    f" x {args.steps} steps, oracle restatement on torch CPU, {cores} threads "
+                                    f" x {args.steps} steps, {what} on torch CPU, {cores} threads "
                                     f"(fastest of 8/16/32/{ncpu})")},
         "e2e": {"value": v, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -583,10 +613,11 @@ def main_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         sample = 1000 if cfg["d_h"] <= 300 and cfg["gen"] == "mol" else 300
-        v, dt, cores, ncpu = run_cpu(cfg, sample, 3, 1)
-        cpu = {"value": v, "unit": "molecules/s", "cores": cores, "kind": "port",
-               "sample": f"{sample} molecules x 3 steps (1 warm-up), oracle restatement on torch CPU, {cores} threads "
-                         f"(fastest of 8/16/32/{ncpu})"}
+        v, dt, cores, ncpu, kind = run_cpu(cfg, sample, 3, 1)
+        cpu = {"value": v, "unit": "molecules/s", "cores": cores, "kind": kind,
+               "sample": f"{sample} molecules x 3 steps (1 warm-up), "
+                         + ("the reference's own modules" if kind == "reference" else "oracle restatement") +
+                         f" on torch CPU, {cores} threads (fastest of 8/16/32/{ncpu})"}
 
     config = workload_config(name, cfg, world)
     line = {

@@ -10,10 +10,12 @@ the D-MPNN hot path is exercised afterwards, and that arithmetic is plain ``torc
 * ``chemprop/nn/agg.py:65-113``                    (Mean / Sum / Norm aggregation)
 * ``chemprop/data/collate.py:37-62``               (BatchMolGraph collate)
 
-``/root/reference`` does not exist on the GPU box, so nothing here may be used by `-m gpu`
-tests, ``bench.py`` or ``smoke()``; it is used by ``oracle/make_golden.py`` (run here, output
-committed under ``tests/golden/``) and by the CPU tests that pin ``oracle/restatement.py``
-against the real reference when the reference tree is reachable.
+``/root/reference`` does not exist on the GPU box, so nothing that runs there (`-m gpu` tests,
+``smoke()``, ``bench.py``'s GPU arm) may depend on it; it is used by ``oracle/make_golden.py`` (run
+here, output committed under ``tests/golden/``), by the CPU tests that pin
+``oracle/restatement.py`` against the real reference when the reference tree is reachable, and by
+``bench.py``'s CPU arm (``cpu_baseline`` / ``--impl reference``), which times the reference's own
+modules where `reference_available()` and the oracle port otherwise, and reports which (``kind``).
 """
 from __future__ import annotations
 

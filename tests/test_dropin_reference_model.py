@@ -228,3 +228,51 @@ def test_engine_constrainer_inside_the_reference_mol_atom_bond_mpnn(monkeypatch)
     torch.testing.assert_close(b, a, rtol=1e-4, atol=1e-5)
     sums = torch.zeros(7, 1).index_add_(0, bmg.batch, b)
     torch.testing.assert_close(sums, constraints[0], rtol=1e-4, atol=1e-4)
+
+
+def test_the_maintainer_side_subclass_of_integration_md_runs_as_written(monkeypatch):
+    """INTEGRATION.md section 2 shows the binding a chemprop maintainer would add: a subclass of the REFERENCE's
+    `BondMessagePassing` whose `forward` calls the engine.  The code block is taken from the document verbatim, executed,
+    and the resulting class -- reference constructor, reference parameters, reference BatchMolGraph -- is compared with the
+    reference module on the same weights (forward incl. the `V_d` branch, and every gradient)."""
+    import os
+    import re
+
+    from oracle.ref_shim import import_reference
+
+    import_reference()
+    import chemprop.nn as ref_nn
+    from chemprop.data import BatchMolGraph as RefBMG
+    from chemprop.data.molgraph import MolGraph as RefMG
+
+    from chemprop_b200.data import make_molecules
+
+    doc = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(# chemprop/nn/message_passing/fused\.py.*?)```", doc, re.S).group(1)
+    ns = {"torch": torch}
+    exec(compile(block, "INTEGRATION.md#fused.py", "exec"), ns)              # noqa: S102 -- our own document
+    Fused = ns["FusedBondMessagePassing"]
+    assert issubclass(Fused, ref_nn.BondMessagePassing)
+
+    emu.patch_engine(monkeypatch)
+    torch.manual_seed(1)
+    mgs = make_molecules(12, seed=5, mean_atoms=8, std_atoms=3, min_atoms=1)
+    bmg = RefBMG([RefMG(*m) for m in mgs])
+    V_d = torch.randn(bmg.V.shape[0], 3)
+    kw = dict(d_h=32, depth=3, bias=True, activation="elu", d_vd=3)
+    ref = ref_nn.BondMessagePassing(**kw)
+    fused = Fused(**kw)
+    fused.precision = "fp32"                                                # the sketch's class attribute: bf16 by default
+    fused.load_state_dict(ref.state_dict())
+    G = torch.randn(bmg.V.shape[0], ref.output_dim)
+    res = []
+    for m in (ref, fused):
+        m.zero_grad()
+        H = m(bmg, V_d)
+        (H * G).sum().backward()
+        res.append((H.detach(), {k: p.grad.clone() for k, p in m.named_parameters()}))
+    torch.testing.assert_close(res[1][0], res[0][0], rtol=1e-4, atol=1e-5)
+    assert set(res[0][1]) == set(res[1][1])
+    for k in res[0][1]:
+        torch.testing.assert_close(res[1][1][k], res[0][1][k], rtol=2e-3, atol=2e-5, msg=k)
+    torch.testing.assert_close(fused(bmg), ref(bmg), rtol=1e-4, atol=1e-5)  # without descriptors
