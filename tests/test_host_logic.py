@@ -419,3 +419,17 @@ def test_cached_segment_tables_do_not_outlive_an_in_place_change_of_batch(monkey
     out2 = agg(H, merged)
     assert out2.shape[0] == 2
     assert torch.allclose(out2[1], out5[1:].sum(0), atol=1e-5) and torch.allclose(out2[0], out5[0], atol=1e-6)
+
+
+@pytest.mark.parametrize("oracle", [True, False])
+@pytest.mark.parametrize("kind,gen_kw", [("bond", dict(seed=4)), ("atom", dict(seed=6, cgr=True))])
+def test_full_size_property_checks_through_emulation(kind, gen_kw, oracle, monkeypatch):
+    """tests/util.full_size_checks (the oracle bound plus reproducibility, exact linearity of the mirror, checksum of
+    checksums and molecule-order invariance; run at BASELINE sizes on the GPU) exercised here at a small size over the
+    emulated kernel wrappers, so that the checks themselves are known to be sound before they meet hardware."""
+    from tests.util import full_size_checks
+
+    emu.patch_engine(monkeypatch)
+    out = full_size_checks(kind, 60 if kind == "bond" else 12, "cpu", gen_kw=gen_kw, grad_tol=0.2,   # tiny batch: kink noise
+                           oracle=oracle)
+    assert out["rows"] > 0 and (("err_H" in out and out["err_H"] > 0) if oracle else "err_H" not in out)

@@ -395,3 +395,114 @@ def check_mpnn_head(device: str, rtol: float = 2e-4, atol: float = 2e-6, graph: 
     model.eval()
     with torch.no_grad():
         np.testing.assert_allclose(model(bmg).cpu().numpy(), g["preds_eval"], rtol=rtol, atol=1e-5)
+
+
+def full_size_checks(kind: str, n_mols: int, device: str, gen_kw: dict | None = None, module_kw: dict | None = None,
+                     tile_tags: set | None = None, grad_tol: float = 6e-2, oracle: bool = True) -> dict:
+    """The benchmarked tier (bf16, fused depth step) on ONE batch of a BASELINE configuration's size, held to
+      (1) the oracle (f32 CPU restatement) -- hidden states, aggregates and every weight gradient -- at the bounds of the
+          medium-size parity tests;
+    and to the size-independent properties of the path:
+      (2) reproducibility: the same batch twice gives bit-identical outputs and gradients (no float atomics anywhere);
+      (3) linearity of the hand-written mirror in the upstream gradient: doubling it doubles every weight gradient EXACTLY
+          (a power of two commutes with every rounding on the way);
+      (4) a checksum of checksums: the column sums of the per-molecule sums equal the column sums of the atom states;
+      (5) molecule-order invariance: the loader's tile-packing order and the sampler's order give the same per-molecule
+          aggregates (molecules never interact: chemprop/data/collate.py:48-56).
+    Used on the GPU (tests/test_gpu_zzz_full_size.py) and, at a small size through the emulated kernel wrappers, on the CPU
+    (tests/test_host_logic.py) so that the checks themselves are exercised without hardware.  Returns the measured figures."""
+    from chemprop_b200 import engine
+    from chemprop_b200.data import BatchMolGraph, make_cgr_graphs, make_molecules, tile_packing_order_of
+    from chemprop_b200.nn import AtomMessagePassing, BondMessagePassing, MeanAggregation, SumAggregation
+    from oracle import restatement as R
+
+    torch.manual_seed(0)
+    gen_kw = dict(gen_kw or {})
+    cgr = gen_kw.pop("cgr", False)
+    mgs = (make_cgr_graphs if cgr else make_molecules)(n_mols, **gen_kw)
+    order = tile_packing_order_of(mgs)
+    packed = [mgs[i] for i in order]
+    d_v, d_e = mgs[0].V.shape[1], mgs[0].E.shape[1]
+    cls = BondMessagePassing if kind == "bond" else AtomMessagePassing
+    kw = dict(d_v=d_v, d_e=d_e, d_h=300, depth=3, precision="bf16")
+    kw.update(module_kw or {})
+    mp = cls(**kw)
+    host = BatchMolGraph(packed)
+    P = {k: v.detach().clone().requires_grad_(True) for k, v in mp.state_dict().items()}
+    if oracle:
+        H_ref = R.message_passing_forward(kind, host.V, host.E, host.edge_index, host.rev_edge_index, P["W_i.weight"],
+                                          P.get("W_i.bias"), P["W_h.weight"], P.get("W_h.bias"), P["W_o.weight"], P["W_o.bias"],
+                                          kw["depth"])
+        a_ref = R.aggregate(H_ref, host.batch, "mean")
+        G = a_ref.detach().clone() / n_mols   # the upstream gradient of 0.5 * mean-over-molecules |agg|^2, held fixed (see (3))
+        (a_ref * G).sum().backward()
+        H_ref, a_ref = H_ref.detach(), a_ref.detach()
+    else:                                     # properties only (sizes the CPU oracle needs minutes for)
+        G = torch.randn(n_mols, kw["d_h"]) / n_mols
+
+    mp = mp.to(device)
+    Gd = G.to(device)
+
+    def run(batch_mgs, scale=1.0):
+        bmg = BatchMolGraph(batch_mgs)
+        bmg.to(device)
+        mp.zero_grad(set_to_none=True)
+        engine.STEP_EVENTS = [] if str(device) != "cpu" else None          # CUDA events: which depth-step kernels ran
+        try:
+            H = mp(bmg)
+            tags = {t for t, _, _ in (engine.STEP_EVENTS or [])}
+        finally:
+            engine.STEP_EVENTS = None
+        a = MeanAggregation()(H, bmg.batch)
+        s = SumAggregation()(H, bmg.batch)
+        return bmg, H, a, s, tags
+
+    bmg, H, a, s, tags = run(packed)
+    if tile_tags is not None and str(device) != "cpu":
+        assert tags == tile_tags, tags                                      # the fused kernel ran every depth step
+    (a * Gd).sum().backward()
+    grads = {k: p.grad.detach().clone() for k, p in mp.named_parameters()}
+    out = {"tiles": bmg._meta_host[0], "rows": int(bmg.E.shape[0]), "atoms": int(bmg.V.shape[0])}
+
+    # (1) the oracle
+    scale = 1.0
+    if oracle:
+        scale = max(1.0, H_ref.abs().max().item())
+        out["err_H"] = (H.detach().float().cpu() - H_ref).abs().max().item()
+        out["err_agg"] = (a.detach().float().cpu() - a_ref).abs().max().item()
+        assert out["err_H"] <= 1e-2 * scale and out["err_agg"] <= 1e-2 * scale, out
+        out["err_grad"] = {}
+        for k, g in grads.items():
+            ref = P[k].grad
+            out["err_grad"][k] = ((g.float().cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+            assert out["err_grad"][k] <= grad_tol, (k, out["err_grad"][k])   # bf16 storage flips ReLU derivatives near zero:
+                                                                              # noise that averages out with the batch size
+    else:
+        scale = max(1.0, H.detach().float().abs().max().item())
+
+    # (2) reproducibility, bit for bit
+    _, H2, a2, s2, _ = run(packed)
+    (a2 * Gd).sum().backward()
+    assert torch.equal(H2, H) and torch.equal(a2, a) and torch.equal(s2, s)
+    for k, p in mp.named_parameters():
+        assert torch.equal(p.grad, grads[k]), ("not reproducible", k)
+
+    # (3) linearity of the mirror: upstream gradient x 2 -> every weight gradient x 2, exactly
+    _, H3, a3, _, _ = run(packed)
+    (a3 * (2.0 * Gd)).sum().backward()
+    for k, p in mp.named_parameters():
+        assert torch.equal(p.grad, 2.0 * grads[k]), ("mirror not linear in the upstream gradient", k)
+
+    # (4) checksum of checksums (f32 sums in different orders: relative to the sum of magnitudes)
+    Hf = H.detach().float()
+    lhs, rhs = s.detach().float().sum(0).cpu(), Hf.sum(0).cpu()
+    mag = Hf.abs().sum(0).cpu().clamp_min(1e-6)
+    out["checksum_rel"] = ((lhs - rhs).abs() / mag).max().item()
+    assert out["checksum_rel"] <= 1e-4, out["checksum_rel"]
+
+    # (5) molecule order: molecule order[j] sits at position j of the packed batch
+    _, _, a_plain, _, _ = run(mgs)
+    idx = torch.as_tensor(np.asarray(order), dtype=torch.long, device=a_plain.device)
+    out["order_diff"] = (a_plain.detach().float()[idx] - a.detach().float()).abs().max().item()
+    assert out["order_diff"] <= 1e-2 * scale, out["order_diff"]
+    return out
