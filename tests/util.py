@@ -419,7 +419,8 @@ def full_size_checks(kind: str, n_mols: int, device: str, gen_kw: dict | None = 
     torch.manual_seed(0)
     gen_kw = dict(gen_kw or {})
     cgr = gen_kw.pop("cgr", False)
-    mgs = (make_cgr_graphs if cgr else make_molecules)(n_mols, **gen_kw)
+    pool = gen_kw.pop("pool", n_mols)         # bench.py draws its resident batch as the first n_mols molecules of a larger pool
+    mgs = (make_cgr_graphs if cgr else make_molecules)(pool, **gen_kw)[:n_mols]
     order = tile_packing_order_of(mgs)
     packed = [mgs[i] for i in order]
     d_v, d_e = mgs[0].V.shape[1], mgs[0].E.shape[1]
@@ -430,12 +431,17 @@ def full_size_checks(kind: str, n_mols: int, device: str, gen_kw: dict | None = 
     host = BatchMolGraph(packed)
     P = {k: v.detach().clone().requires_grad_(True) for k, v in mp.state_dict().items()}
     if oracle:
-        H_ref = R.message_passing_forward(kind, host.V, host.E, host.edge_index, host.rev_edge_index, P["W_i.weight"],
-                                          P.get("W_i.bias"), P["W_h.weight"], P.get("W_h.bias"), P["W_o.weight"], P["W_o.bias"],
-                                          kw["depth"])
-        a_ref = R.aggregate(H_ref, host.batch, "mean")
-        G = a_ref.detach().clone() / n_mols   # the upstream gradient of 0.5 * mean-over-molecules |agg|^2, held fixed (see (3))
-        (a_ref * G).sum().backward()
+        nt = torch.get_num_threads()
+        torch.set_num_threads(min(nt, 16))    # torch's CPU scatter / index kernels regress beyond a few dozen threads (bench.py)
+        try:
+            H_ref = R.message_passing_forward(kind, host.V, host.E, host.edge_index, host.rev_edge_index, P["W_i.weight"],
+                                              P.get("W_i.bias"), P["W_h.weight"], P.get("W_h.bias"), P["W_o.weight"],
+                                              P["W_o.bias"], kw["depth"])
+            a_ref = R.aggregate(H_ref, host.batch, "mean")
+            G = a_ref.detach().clone() / n_mols   # upstream gradient of 0.5 * mean-over-molecules |agg|^2, held fixed (see (3))
+            (a_ref * G).sum().backward()
+        finally:
+            torch.set_num_threads(nt)
         H_ref, a_ref = H_ref.detach(), a_ref.detach()
     else:                                     # properties only (sizes the CPU oracle needs minutes for)
         G = torch.randn(n_mols, kw["d_h"]) / n_mols

@@ -18,7 +18,7 @@ with pytest.MonkeyPatch.context() as m:
     emu.patch_engine(m)
     t0 = time.time()
     if kind == "bond":
-        out = full_size_checks("bond", 10000, "cpu", gen_kw=dict(seed=1, mean_atoms=25.0), grad_tol=1.0)
+        out = full_size_checks("bond", 10000, "cpu", gen_kw=dict(seed=1, mean_atoms=25.0, pool=30000), grad_tol=1.0)
     else:
         out = full_size_checks("atom", 10000, "cpu", gen_kw=dict(seed=1, cgr=True), grad_tol=1.0)
     print(kind, f"{time.time() - t0:.0f} s", out)
