@@ -132,3 +132,23 @@ def test_collate_empty_edges():
     rng = np.random.default_rng(0)
     bmg = BatchMolGraph([make_molecule(rng, 1) for _ in range(4)])
     assert bmg.E.shape == (0, 14) and bmg.edge_index.shape == (2, 0) and bmg.batch.tolist() == [0, 1, 2, 3]
+
+
+def test_integration_md_ctypes_stub_matches_the_binding():
+    """INTEGRATION.md section 3 shows the ctypes stub a host language would write for the fused depth step: its argument
+    list must be the one `_lib.SIGNATURES` (checked symbol for symbol against include/dmpnn.h above) binds."""
+    import ctypes as C
+    import os
+    import re
+
+    from chemprop_b200 import _lib
+
+    doc = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    m = re.search(r"lib\.dmpnn_bond_step_fused_bf16\.argtypes = (.*?)\nrc = ", doc, re.S)
+    assert m, "the stub is gone from INTEGRATION.md"
+    argtypes = eval(m.group(1).replace("\\\n", " "), {"C": C})       # noqa: S307 -- our own document
+    res, args = _lib.SIGNATURES["dmpnn_bond_step_fused_bf16"]
+    assert res is C.c_int and list(argtypes) == list(args)
+    call = re.search(r"rc = lib\.dmpnn_bond_step_fused_bf16\((.*?)\)\nif rc", doc, re.S).group(1)
+    n_args = len([a for a in re.sub(r"#.*", "", call).replace("\n", " ").split(",") if a.strip()])
+    assert n_args == len(args), (n_args, len(args))
