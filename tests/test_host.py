@@ -200,3 +200,39 @@ def test_batchmolgraph_pickles_with_its_staging_copy_and_meta_words():
     c = pickle.loads(pickle.dumps(b))
     assert len(c) == 5 and torch.equal(c.edge_index, b.edge_index) and torch.equal(c.V, b.V)
     assert c._meta_host == b._meta_host and c._xfer is not None and c._layout is None
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No silent fallback: without libdmpnn_sm100.so every entry into the engine raises, naming the build command."""
+    from chemprop_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libdmpnn_sm100.so")
+    with pytest.raises(DmpnnError, match="chemprop_b200.build.*no CPU / PyTorch fallback"):
+        _lib.load()
+    with pytest.raises(DmpnnError, match="not found"):
+        BatchMolGraph(make_molecules(2, seed=0), use_extension=False)          # the host collate is a library call too
+
+
+def test_product_path_never_imports_the_oracle_or_the_reference():
+    """oracle/ is test infrastructure: nothing under chemprop_b200/ may import it (or chemprop, or tests) -- checked on the
+    syntax trees, so that comments and docstrings citing the oracle do not count."""
+    import ast
+    import pathlib
+
+    root = pathlib.Path(__file__).resolve().parents[1] / "chemprop_b200"
+    banned = {"oracle", "tests"}
+    optional = {"chemprop"}                       # only integrate.py may import the reference, inside a function, on request
+    for path in sorted(root.rglob("*.py")):
+        tree = ast.parse(path.read_text(), filename=str(path))
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.level == 0 and node.module:
+                names = [node.module]
+            for n in names:
+                top = n.split(".")[0]
+                assert top not in banned, (str(path), n)
+                if top in optional:
+                    assert path.name == "integrate.py", (str(path), n)
