@@ -236,3 +236,26 @@ def test_product_path_never_imports_the_oracle_or_the_reference():
                 assert top not in banned, (str(path), n)
                 if top in optional:
                     assert path.name == "integrate.py", (str(path), n)
+
+
+def test_collate_batch_in_dataloader_worker_processes():
+    """The reference runs `collate_batch` in CPU-only DataLoader worker processes (chemprop/data/dataloader.py:88-96,
+    `num_workers`): the batch object crosses a process boundary by pickle and must arrive whole -- tensors, size and the
+    host-computed layout meta words (without them the training step would fall back to a device read-back)."""
+    import pickle
+
+    from chemprop_b200.data.collate import Datum
+
+    mgs = make_molecules(12, seed=2)
+    data = [Datum(m, None, None, np.array([float(i)], dtype=np.float32), 1.0, None, None) for i, m in enumerate(mgs)]
+    direct = [collate_batch(data[:6]), collate_batch(data[6:])]
+    dl = torch.utils.data.DataLoader(data, batch_size=6, collate_fn=collate_batch, num_workers=2)
+    got = list(dl)
+    assert len(got) == 2
+    for a, b in zip(got, direct):
+        for k in ("V", "E", "edge_index", "rev_edge_index", "batch"):
+            assert torch.equal(getattr(a.bmg, k), getattr(b.bmg, k)), k
+        assert len(a.bmg) == len(b.bmg) == 6 and a.bmg._meta_host == b.bmg._meta_host is not None
+        assert torch.equal(a.Y, b.Y) and torch.equal(a.w, b.w)
+    c = pickle.loads(pickle.dumps(direct[0].bmg))
+    assert c._meta_host == direct[0].bmg._meta_host and c._layout is None and torch.equal(c.E, direct[0].bmg.E)
