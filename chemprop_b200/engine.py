@@ -833,6 +833,9 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
     Wpk = pack_weight_bf16(Wh) if use_fused else None
     x3 = _x3_ok(cfg, h, d_v + h)          # fp32 tier: W_h / W_o GEMMs as 3xTF32 on the tensor cores (f32-accurate)
     Wh_x3 = pack_weight_x3(Wh) if (x3 and cfg.depth > 1 and nE > 0) else None
+    # bf16 tier off the fused kernel (undirected=True): the W_h GEMM still runs on the tensor cores (k_linear_tc, H_0 residual,
+    # bias and tau in its epilogue -- the form AtomMessagePassing's unfused step uses), not on the f32 FMA pipes
+    Wh_tc = pack_weight_tc(Wh) if (tc and not use_fused and cfg.depth > 1 and nE > 0) else None
     for _ in range(1, cfg.depth):
         if use_fused:
             Hn = _empty_hidden(nE, hp, T, dev)
@@ -861,6 +864,8 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
                 if Wh_x3 is not None:
                     with _StepTimer("x3_gemm"):
                         linear_x3(M, h, Wh_x3, h, Hn, bias=bh, res=H0, act=a, act_param=ap, R=nE, pad_to=hp)
+                elif Wh_tc is not None:
+                    linear_tc(M, h, Wh_tc, h, Hn, bias=bh, res=H0, act=a, act_param=ap, R=nE)
                 else:
                     linear_fwd(M, h, Wh, Hn, h, bias=bh, res=H0, act=a, act_param=ap, R=nE, pad_to=hp)  # base.py:135-141
             Ms.append(M)

@@ -433,3 +433,39 @@ def test_full_size_property_checks_through_emulation(kind, gen_kw, oracle, monke
     out = full_size_checks(kind, 60 if kind == "bond" else 12, "cpu", gen_kw=gen_kw, grad_tol=0.2,   # tiny batch: kink noise
                            oracle=oracle)
     assert out["rows"] > 0 and (("err_H" in out and out["err_H"] > 0) if oracle else "err_H" not in out)
+
+
+@pytest.mark.parametrize("depth,bias,act", [(3, False, "relu"), (4, True, "tanh")])
+def test_undirected_bf16_tier_keeps_every_gemm_on_the_tensor_core_kernels(depth, bias, act, monkeypatch):
+    """BondMessagePassing(undirected=True, precision="bf16") leaves the fused depth step (base.py:202-203 averages H with its
+    reverse before the message), but not the tensor cores: W_i, every W_h step (H_0 residual, bias and tau in the GEMM's
+    epilogue) and W_o run on dmpnn_linear_tc_bf16 -- no call of the f32 FMA GEMM in the forward -- and the result matches the
+    oracle at the tier's tolerance."""
+    from chemprop_b200 import engine
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.nn import BondMessagePassing
+    from oracle import restatement as R
+
+    emu.patch_engine(monkeypatch)
+    calls = []
+    tc0, simt0 = engine.linear_tc, engine.linear_fwd
+    monkeypatch.setattr(engine, "linear_tc", lambda *a, **k: (calls.append(("tc", k.get("res") is not None)), tc0(*a, **k))[1])
+    monkeypatch.setattr(engine, "linear_fwd", lambda *a, **k: (calls.append(("simt",)), simt0(*a, **k))[1])
+    torch.manual_seed(depth)
+    bmg = BatchMolGraph(make_molecules(14, seed=depth, shuffle_edges=True))
+    mp = BondMessagePassing(d_h=64, depth=depth, bias=bias, activation=act, undirected=True, precision="bf16")
+    H = mp(bmg)
+    fwd = list(calls)
+    assert ("simt",) not in fwd, fwd
+    assert fwd.count(("tc", True)) == depth - 1 and fwd.count(("tc", False)) == 2          # W_h steps; W_i and W_o
+    H.float().square().sum().backward()
+    assert ("simt",) not in calls                                                        # the generic mirror's GEMMs too
+    P = {k: v.detach().double().requires_grad_(True) for k, v in mp.state_dict().items()}
+    Hr = R.message_passing_forward("bond", bmg.V.double(), bmg.E.double(), bmg.edge_index, bmg.rev_edge_index, P["W_i.weight"],
+                                   P.get("W_i.bias"), P["W_h.weight"], P.get("W_h.bias"), P["W_o.weight"], P["W_o.bias"], depth,
+                                   act, undirected=True)
+    Hr.square().sum().backward()
+    assert float((H.detach().double() - Hr.detach()).abs().max()) <= 1e-2 * max(1.0, float(Hr.detach().abs().max()))
+    for k, p in mp.named_parameters():
+        ref = P[k].grad
+        assert float((p.grad.double() - ref).abs().max()) <= 6e-2 * max(1e-6, float(ref.abs().max())), k
