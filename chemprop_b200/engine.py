@@ -683,8 +683,13 @@ def h_is_mult4(Wh: Tensor) -> bool:
 
 def _tc_ok(cfg: MPConfig, h: int, *Ks: int) -> bool:
     """Tensor-core linear kernels apply: bf16 tier, fused kernels enabled, sizes inside the kernel limits."""
-    return (cfg.fused and cfg.hidden_dtype == torch.bfloat16 and h <= 304 and all(k <= 448 for k in Ks)
-            and _fused_available())
+    ok = (cfg.fused and cfg.hidden_dtype == torch.bfloat16 and h <= 304 and all(k <= 448 for k in Ks)
+          and _fused_available())
+    if not ok and cfg.fused and cfg.hidden_dtype == torch.bfloat16 and _fused_available():
+        _warn_once("tc_limits", f"chemprop_b200: precision='bf16' with d_h = {h}, GEMM inner dimensions {tuple(Ks)}: outside the "
+                   "tensor-core kernels' limits (d_h <= 304, d_v + d_e and d_v + d_h <= 448); the linear layers run on the f32 "
+                   "FMA pipes with bf16 storage (the fp32 tier's 3xTF32 tensor-core GEMMs take d_h up to 4096)")
+    return ok
 
 
 def _empty_hidden(rows: int, hp: int, dtype, dev) -> Tensor:
