@@ -52,8 +52,16 @@ class GatherLinear(torch.autograd.Function):
         K2 = 0 if X2c is None else X2c.shape[1]
         N = Wc.shape[0]
         out = _buf(R, N, Wc)
-        if R > 0:
+        # a plain (ungathered, single-source) product -- the W_h GEMM of every depth step, 2 E h^2 flop -- runs f32-accurate on
+        # the tensor cores (3xTF32, csrc/gemm_x3.cu) when its dimensions allow 16-byte rows; gathered / two-source operands
+        # (W_i, W_o) stay on the f32 FMA kernel, which reads them in place
+        x3 = (idx1 is None and X2c is None and R > 0 and K1 % 4 == 0 and N % 4 == 0 and 0 < K1 <= 4096 and 0 < N <= 4096
+              and K.X3_ENABLED and K._fused_available())
+        if x3:
+            K.linear_x3(X1c, K1, K.pack_weight_x3(Wc), N, out, bias=bc, res=resc, R=R, pad_to=N)
+        elif R > 0:
             K.linear_fwd(X1c, K1, Wc, out, N, idx1=idx1, X2=X2c, K2=K2, idx2=idx2, bias=bc, res=resc, R=R, pad_to=N)
+        ctx.x3 = x3
         ctx.args = (X1c, idx1, X2c, idx2, Wc, K1, K2, N, R)
         ctx.wdtype = W.dtype
         ctx.bdtype = None if b is None else b.dtype
@@ -68,7 +76,11 @@ class GatherLinear(torch.autograd.Function):
         if need_w or need_b:
             dW = torch.zeros_like(Wc)
             db = torch.zeros(N, dtype=torch.float32, device=Wc.device) if need_b else None
-            if R > 0:
+            if ctx.x3:
+                K.wgrad_x3(dY, X1c, R, N, K1, dW)
+                if db is not None:
+                    K.column_sum(dY, R, N, db)
+            elif R > 0:
                 K.linear_wgrad(dY, X1c, K1, dW, N, idx1=idx1, X2=X2c, K2=K2, idx2=idx2, dbias=db, R=R)
             dW = dW.to(ctx.wdtype)
             db = None if db is None else db.to(ctx.bdtype)
@@ -76,7 +88,9 @@ class GatherLinear(torch.autograd.Function):
             if idx1 is not None:
                 raise K.DmpnnError("GatherLinear: no gradient through a gathered operand")
             dX1 = _buf(R, K1, Wc)
-            if R > 0:
+            if ctx.x3:
+                K.linear_x3(dY, N, K.pack_weight_x3(Wc, transpose=True), K1, dX1, R=R, pad_to=K1)
+            elif R > 0:
                 K.linear_fwd(dY, N, Wc[:, :K1].t().contiguous(), dX1, K1, R=R, pad_to=K1)
         if need_x2:
             if idx2 is not None:

@@ -148,12 +148,13 @@ class _MessagePassingBase(nn.Module):
         out_dtype = self.output_dtype or (torch.bfloat16 if self.precision == "bf16" else torch.float32)
         if self.uses_composed_tier(lay):
             if self.precision == "bf16":
-                # no silent cliff: this tier keeps f32 hidden states and runs its GEMMs on the f32 FMA pipes
+                # no silent cliff: this tier keeps f32 hidden states; its W_h GEMMs run as 3xTF32 on the tensor cores (a sixth
+                # of the bf16 rate), W_i / W_o on the f32 FMA pipes, and every reference op is a launch of its own
                 why = (f"activation {type(self.tau).__name__}" if not is_fused_activation(self.tau) else
                        "undirected AtomMessagePassing" if (self.undirected and type(self)._kind == 1) else
                        "training-mode dropout outside the fused ReLU path")
                 _warn_once("composed_bf16", f"chemprop_b200: precision='bf16' requested, but this configuration ({why}) runs on "
-                           "the composed tier: f32 hidden states, one kernel per reference op, no tensor-core depth step "
+                           "the composed tier: f32 hidden states, one kernel per reference op, no fused depth step "
                            "(expect several times the step time of the fused bf16 tier)")
             H = type(self)._composed_forward(self, bmg, lay)          # computed in f32 on this tier
         else:

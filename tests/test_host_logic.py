@@ -469,3 +469,40 @@ def test_undirected_bf16_tier_keeps_every_gemm_on_the_tensor_core_kernels(depth,
     for k, p in mp.named_parameters():
         ref = P[k].grad
         assert float((p.grad.double() - ref).abs().max()) <= 6e-2 * max(1e-6, float(ref.abs().max())), k
+
+
+@pytest.mark.parametrize("d_h,expect_x3", [(64, True), (62, False)])
+def test_composed_tier_runs_its_plain_gemms_on_the_x3_tensor_core_kernels(d_h, expect_x3, monkeypatch):
+    """Composed tier (here: PReLU): the W_h GEMM of every depth step -- an ungathered single-source product -- and its two
+    mirror GEMMs go to the f32-accurate tensor-core kernels (dmpnn_linear_x3 / dmpnn_wgrad_x3) when d_h is a multiple of 4;
+    otherwise, and for the gathered two-source W_i / W_o operands, the f32 FMA kernel runs.  Same results either way."""
+    from chemprop_b200 import engine
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.nn import BondMessagePassing
+    from oracle import restatement as R
+
+    emu.patch_engine(monkeypatch)
+    calls = []
+    for name in ("linear_x3", "wgrad_x3", "linear_fwd", "linear_wgrad"):
+        f0 = getattr(engine, name)
+        monkeypatch.setattr(engine, name, lambda *a, _f=f0, _n=name, **k: (calls.append(_n), _f(*a, **k))[1])
+    torch.manual_seed(3)
+    bmg = BatchMolGraph(make_molecules(10, seed=3))
+    depth = 3
+    mp = BondMessagePassing(d_h=d_h, depth=depth, bias=True, activation="prelu")
+    assert mp.uses_composed_tier()
+    H = mp(bmg)
+    assert calls.count("linear_x3") == ((depth - 1) if expect_x3 else 0)
+    assert calls.count("linear_fwd") == (2 if expect_x3 else depth + 1)                  # W_i and W_o (+ W_h steps without x3)
+    H.square().sum().backward()
+    assert calls.count("wgrad_x3") == ((depth - 1) if expect_x3 else 0)
+    assert calls.count("linear_x3") == (2 * (depth - 1) if expect_x3 else 0)             # + dX = dY . W_h per step
+    P = {k: v.detach().double().requires_grad_(True) for k, v in mp.state_dict().items()}
+    Hr = R.message_passing_forward("bond", bmg.V.double(), bmg.E.double(), bmg.edge_index, bmg.rev_edge_index, P["W_i.weight"],
+                                   P["W_i.bias"], P["W_h.weight"], P["W_h.bias"], P["W_o.weight"], P["W_o.bias"], depth, "prelu",
+                                   prelu_weight=P["tau.weight"])
+    Hr.square().sum().backward()
+    assert float((H.detach().double() - Hr.detach()).abs().max()) <= 1e-5
+    for k, p in mp.named_parameters():
+        ref = P[k].grad
+        assert float((p.grad.double() - ref).abs().max()) <= 1e-5 * max(1e-6, float(ref.abs().max())), k   # f32 sums vs f64
