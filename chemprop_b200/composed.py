@@ -56,6 +56,7 @@ class GatherLinear(torch.autograd.Function):
         # the tensor cores (3xTF32, csrc/gemm_x3.cu) when its dimensions allow 16-byte rows; gathered / two-source operands
         # (W_i, W_o) stay on the f32 FMA kernel, which reads them in place
         x3 = (idx1 is None and X2c is None and R > 0 and K1 % 4 == 0 and N % 4 == 0 and 0 < K1 <= 4096 and 0 < N <= 4096
+              and X1c.data_ptr() % 16 == 0 and (resc is None or resc.data_ptr() % 16 == 0)
               and K.X3_ENABLED and K._fused_available())
         if x3:
             K.linear_x3(X1c, K1, K.pack_weight_x3(Wc), N, out, bias=bc, res=resc, R=R, pad_to=N)
