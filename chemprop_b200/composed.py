@@ -73,11 +73,12 @@ class GatherLinear(torch.autograd.Function):
         X1c, idx1, X2c, idx2, Wc, K1, K2, N, R = ctx.args
         need_x1, _, need_x2, _, need_w, need_b, need_res, _ = ctx.needs_input_grad
         dY = _c(dY)
+        x3 = ctx.x3 and dY.data_ptr() % 16 == 0
         dX1 = dX2 = dW = db = None
         if need_w or need_b:
             dW = torch.zeros_like(Wc)
             db = torch.zeros(N, dtype=torch.float32, device=Wc.device) if need_b else None
-            if ctx.x3:
+            if x3:
                 K.wgrad_x3(dY, X1c, R, N, K1, dW)
                 if db is not None:
                     K.column_sum(dY, R, N, db)
@@ -89,7 +90,7 @@ class GatherLinear(torch.autograd.Function):
             if idx1 is not None:
                 raise K.DmpnnError("GatherLinear: no gradient through a gathered operand")
             dX1 = _buf(R, K1, Wc)
-            if ctx.x3:
+            if x3:
                 K.linear_x3(dY, N, K.pack_weight_x3(Wc, transpose=True), K1, dX1, R=R, pad_to=K1)
             elif R > 0:
                 K.linear_fwd(dY, N, Wc[:, :K1].t().contiguous(), dX1, K1, R=R, pad_to=K1)
