@@ -396,14 +396,15 @@ def _hidden(rows: int, hp: int, dtype, dev) -> Tensor:
 
 
 def _fused_step_ok(cfg: MPConfig, lay: Layout, h: int) -> bool:
-    """The fused tcgen05 depth step applies: bf16 tier, directed bonds, h <= 304.  Molecules of any size: those with more
-    than 128 directed edges run as 128-row windows of the same kernel (Layout.step_tables)."""
-    ok = (cfg.fused and cfg.hidden_dtype == torch.bfloat16 and not cfg.undirected and h <= 304 and lay.E > 0
+    """The fused tcgen05 depth step applies: bf16 tier, h <= 304.  Molecules of any size: those with more than 128 directed
+    edges run as 128-row windows of the same kernel (Layout.step_tables).  `undirected=True` (base.py:202-203) runs on it too:
+    the reverse-edge average is a prologue pass that produces the step's input (bond_forward)."""
+    ok = (cfg.fused and cfg.hidden_dtype == torch.bfloat16 and h <= 304 and lay.E > 0 and (not cfg.undirected or h % 4 == 0)
           and _fused_available())
     if not ok and cfg.fused and cfg.hidden_dtype == torch.bfloat16 and lay.E > 0:
         _warn_once("unfused", "chemprop_b200: this batch leaves the fused depth-step kernel (" +
-                   ("undirected=True" if cfg.undirected else f"d_h = {h} > 304" if h > 304 else "kernel unavailable") +
-                   "): the depth loop runs as separate message + GEMM launches")
+                   (f"d_h = {h} > 304" if h > 304 else "undirected=True with d_h % 4 != 0" if cfg.undirected else
+                    "kernel unavailable") + "): the depth loop runs as separate message + GEMM launches")
     return ok
 
 
@@ -844,13 +845,23 @@ def bond_forward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, bi, Wh: Tensor, 
     for _ in range(1, cfg.depth):
         if use_fused:
             Hn = _empty_hidden(nE, hp, T, dev)
+            src_in, first_in = Hprev, first
+            if cfg.undirected:
+                # H~ = (H + H[rev]) / 2 (base.py:202-203) as a prologue pass; the first step's tau(H_0) is applied by it, so the
+                # fused step always sees an activation.  H~^{t-1} is kept: it is the right factor of this step's W_h
+                # gradient (dZ^T . M^t = ((S.P) dZ)^T . H~^{t-1}, bond_backward).  Zero-filled: the step's TMA boxes read
+                # the padding columns up to the 64-column slab edge
+                Hbar = _hidden(nE, hp, T, dev)
+                rev_average(Hprev, lay, h, Hbar, act=(a if first else ACT_NONE), act_param=ap)
+                Hbars.append(Hbar)
+                src_in, first_in = Hbar, False
             # training: the first step also stores M^1 (it is tau(H_0)-gathered, which no later kernel can rebuild
             # from a stored activation); the later steps' W_h gradients use (S.P) dZ from the backward kernel instead
-            M1 = _empty_hidden(nE, hp, T, dev) if (first and for_backward) else None
+            M1 = _empty_hidden(nE, hp, T, dev) if (first_in and for_backward) else None
             # base.py:139 (training-mode dropout): keep bits from Philox, applied in the step's epilogue -- no pass over E x h
             bits = dropout_keep_bits(nE, h, cfg, Hn) if cfg.dropout_p > 0 else None
             with _StepTimer("fused_first" if first else "fused"):
-                bond_step_fused(Hprev, H0, Hn, h, Wpk, bh, lay, a, ap, first, M_out=M1, drop_bits=bits,
+                bond_step_fused(src_in, H0, Hn, h, Wpk, bh, lay, a, ap, first_in, M_out=M1, drop_bits=bits,
                                 drop_scale=1.0 / (1.0 - cfg.dropout_p) if bits is not None else 1.0)
             Ms.append(M1)
         else:
@@ -973,6 +984,7 @@ def bond_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo:
         else:
             WhT = None if (tc or x3) else Wh.t().contiguous()
             WhT_pk = pack_weight_tc(Wh, transpose=True) if tc else None
+            WhT_f = None                                   # W_h^T packed for the fused mirror (undirected fused steps)
             WhT_x3 = pack_weight_x3(Wh, transpose=True) if x3 else None
             dZ = _hidden(nE, hp, T, dev)
             act_bwd(dMv, Hs[-1], nE, h, act=a, act_param=ap, gidx=lay.dst_row, dZ=dZ, acc=dH0)
@@ -981,9 +993,33 @@ def bond_backward(lay: Layout, V: Tensor, E: Tensor, Wi: Tensor, Wh: Tensor, Wo:
                 first = t == 1
                 Hin = H0 if first else Hs[t - 2]
                 M = Ms[t - 1]
+                if M is None and cfg.undirected and tc and _fused_step_ok(cfg, lay, h):
+                    # undirected step that ran on the fused kernel: its mirror on the fused kernel too.
+                    # dH~^{t-1} = (S.P)(dZ . W_h) = ((S.P) dZ) . W_h, unmasked; the gathered operand G = (S.P) dZ is the left
+                    # factor of the W_h gradient (dZ^T . M^t = G^T . H~^{t-1}, H~^{t-1} saved by the forward's prologue);
+                    # then the adjoint of the average (self-adjoint) and tau' as in the generic mirror
+                    if WhT_f is None:
+                        WhT_f = pack_weight_bf16(Wh.t().contiguous())
+                    if dbh is not None:
+                        column_sum(dZ, nE, h, dbh, accumulate=True)
+                    G = _empty_hidden(nE, hp, T, dev)
+                    dHbar = _empty_hidden(nE, hp, T, dev)
+                    bond_step_bwd_fused(dZ, None, dHbar, h, WhT_f, lay, a, ap, G_out=G)
+                    wgrad_tc(G, Hbars[t - 1], nE, h, h, dWh, accumulate=True)
+                    dHin = _hidden(nE, hp, T, dev)
+                    rev_average(dHbar, lay, h, dHin)
+                    if first:
+                        act_bwd(dHin, H0, nE, h, act=a, act_param=ap, from_preact=True, acc=dH0)
+                    else:
+                        dZ = _hidden(nE, hp, T, dev)
+                        act_bwd(dHin, Hin, nE, h, act=a, act_param=ap, dZ=dZ, acc=dH0)
+                    continue
                 if M is None:  # fused forward did not materialise M^t: recompute it
                     M = _hidden(nE, hp, T, dev)
-                    bond_message(Hin, lay, h, M, act=(a if first else ACT_NONE), act_param=ap)
+                    if cfg.undirected:
+                        bond_message(Hbars[t - 1], lay, h, M)
+                    else:
+                        bond_message(Hin, lay, h, M, act=(a if first else ACT_NONE), act_param=ap)
                 if tc:
                     wgrad_tc(dZ, M, nE, h, h, dWh, accumulate=True)
                     if dbh is not None:

@@ -70,8 +70,8 @@ def test_monolithic_bf16_tier_through_emulation(name, fused, monkeypatch):
     mp = build_engine_module(g, "cpu", "bf16", fused)
     mp, bmg, H, aggs = _run(g, mp)
     cfg = g["config"]
-    expect_fused = (fused and cfg["kind"] == "bond" and cfg["depth"] > 1 and not cfg.get("undirected") and g["E"].shape[0] > 0
-                    and cfg["d_h"] % 4 == 0)      # molecules larger than a 128-row tile stay on the fused kernel too
+    expect_fused = (fused and cfg["kind"] == "bond" and cfg["depth"] > 1 and g["E"].shape[0] > 0
+                    and cfg["d_h"] % 4 == 0)      # molecules larger than a 128-row tile and undirected=True stay on the fused kernel too
     assert (calls["fwd"], calls["bwd"]) == ((cfg["depth"] - 1,) * 2 if expect_fused else (0, 0)), calls
     assert H.dtype == (torch.float32 if "V_d" in g else torch.bfloat16)      # W_d (torch, f32) follows the engine's part
     np.testing.assert_allclose(H.detach().float().numpy(), g["H_v"], rtol=0, atol=1e-2)
@@ -435,31 +435,39 @@ def test_full_size_property_checks_through_emulation(kind, gen_kw, oracle, monke
     assert out["rows"] > 0 and (("err_H" in out and out["err_H"] > 0) if oracle else "err_H" not in out)
 
 
-@pytest.mark.parametrize("depth,bias,act", [(3, False, "relu"), (4, True, "tanh")])
-def test_undirected_bf16_tier_keeps_every_gemm_on_the_tensor_core_kernels(depth, bias, act, monkeypatch):
-    """BondMessagePassing(undirected=True, precision="bf16") leaves the fused depth step (base.py:202-203 averages H with its
-    reverse before the message), but not the tensor cores: W_i, every W_h step (H_0 residual, bias and tau in the GEMM's
-    epilogue) and W_o run on dmpnn_linear_tc_bf16 -- no call of the f32 FMA GEMM in the forward -- and the result matches the
-    oracle at the tier's tolerance."""
+@pytest.mark.parametrize("depth,bias,act,d_h", [(3, False, "relu", 64), (4, True, "tanh", 64), (3, True, "relu", 62)])
+def test_undirected_bf16_tier_runs_on_the_fused_step(depth, bias, act, d_h, monkeypatch):
+    """BondMessagePassing(undirected=True, precision="bf16") (base.py:202-203 averages H with its reverse before the message):
+    the average is a prologue pass (dmpnn_rev_average, applying the first step's tau) and every depth step -- forward and
+    mirror -- is ONE launch of the fused kernel on the averaged state; the W_h gradient contracts the mirror's gathered operand
+    with the saved averaged state.  With d_h % 4 != 0 the step runs as message + dmpnn_linear_tc_bf16 (H_0 residual, bias and
+    tau in the GEMM's epilogue).  Either way no GEMM of the tier touches the f32 FMA kernel, and the result matches the oracle
+    at the tier's tolerance."""
     from chemprop_b200 import engine
     from chemprop_b200.data import BatchMolGraph, make_molecules
     from chemprop_b200.nn import BondMessagePassing
     from oracle import restatement as R
 
     emu.patch_engine(monkeypatch)
+    engine._WARNED.discard("unfused")
     calls = []
-    tc0, simt0 = engine.linear_tc, engine.linear_fwd
-    monkeypatch.setattr(engine, "linear_tc", lambda *a, **k: (calls.append(("tc", k.get("res") is not None)), tc0(*a, **k))[1])
-    monkeypatch.setattr(engine, "linear_fwd", lambda *a, **k: (calls.append(("simt",)), simt0(*a, **k))[1])
+    for name, tag in (("linear_tc", "tc"), ("linear_fwd", "simt"), ("linear_wgrad", "simt"), ("bond_step_fused", "fused"),
+                      ("bond_step_bwd_fused", "fused_bwd"), ("rev_average", "avg")):
+        f0 = getattr(engine, name)
+        monkeypatch.setattr(engine, name, lambda *a, _f=f0, _t=tag, **k: (
+            calls.append((_t, k.get("res") is not None) if _t == "tc" else (_t,)), _f(*a, **k))[1])
     torch.manual_seed(depth)
     bmg = BatchMolGraph(make_molecules(14, seed=depth, shuffle_edges=True))
-    mp = BondMessagePassing(d_h=64, depth=depth, bias=bias, activation=act, undirected=True, precision="bf16")
+    mp = BondMessagePassing(d_h=d_h, depth=depth, bias=bias, activation=act, undirected=True, precision="bf16")
     H = mp(bmg)
     fwd = list(calls)
+    fused = d_h % 4 == 0
     assert ("simt",) not in fwd, fwd
-    assert fwd.count(("tc", True)) == depth - 1 and fwd.count(("tc", False)) == 2          # W_h steps; W_i and W_o
+    assert fwd.count(("fused",)) == (depth - 1 if fused else 0) and fwd.count(("avg",)) == depth - 1
+    assert fwd.count(("tc", True)) == (0 if fused else depth - 1) and fwd.count(("tc", False)) == 2     # W_h steps; W_i and W_o
     H.float().square().sum().backward()
-    assert ("simt",) not in calls                                                        # the generic mirror's GEMMs too
+    assert ("simt",) not in calls                                                        # the mirror's GEMMs too
+    assert calls.count(("fused_bwd",)) == (depth - 1 if fused else 0) and calls.count(("avg",)) == 2 * (depth - 1)
     P = {k: v.detach().double().requires_grad_(True) for k, v in mp.state_dict().items()}
     Hr = R.message_passing_forward("bond", bmg.V.double(), bmg.E.double(), bmg.edge_index, bmg.rev_edge_index, P["W_i.weight"],
                                    P.get("W_i.bias"), P["W_h.weight"], P.get("W_h.bias"), P["W_o.weight"], P["W_o.bias"], depth,
