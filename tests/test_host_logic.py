@@ -514,3 +514,61 @@ def test_composed_tier_runs_its_plain_gemms_on_the_x3_tensor_core_kernels(d_h, e
     for k, p in mp.named_parameters():
         ref = P[k].grad
         assert float((p.grad.double() - ref).abs().max()) <= 1e-5 * max(1e-6, float(ref.abs().max())), k   # f32 sums vs f64
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_randomised_bf16_bond_configurations_fused_vs_unfused_vs_oracle(seed, monkeypatch):
+    """bf16 tier of BondMessagePassing over random configurations (directed / undirected, depth 1-5, bias, the four fused
+    activations) and batch shapes (edgeless, 1-atom molecules, a molecule of more than 128 directed edges, shuffled edge order):
+    the path on the fused depth step and the path with `fused=False` (separate message / GEMM kernels, generic mirror) are two
+    host-side compositions of the same arithmetic -- they must agree closely, and both sit within the tier's bound of the f64
+    oracle.  Smooth activations carry the tight gradient bound; with ReLU-like kinks bf16 storage flips derivatives near zero."""
+    from chemprop_b200.data import BatchMolGraph, make_molecule, make_molecules
+    from chemprop_b200.nn import BondMessagePassing, MeanAggregation
+    from oracle import restatement as R
+
+    emu.patch_engine(monkeypatch)
+    rng = np.random.default_rng(7000 + seed)
+    act = ("relu", "leakyrelu", "tanh", "elu")[int(rng.integers(4))]
+    depth, bias, undirected = int(rng.integers(1, 6)), bool(rng.integers(2)), bool(seed % 2)
+    d_h = int(rng.choice([16, 48, 64, 100]))
+    shape = int(rng.integers(4))
+    if shape == 0:
+        mgs = [make_molecule(rng, 1, 72, 14) for _ in range(3)]
+    elif shape == 1:
+        mgs = make_molecules(9, seed=seed, mean_atoms=8, std_atoms=4, min_atoms=1, shuffle_edges=True)
+    elif shape == 2:
+        mgs = [make_molecule(rng, 3, 72, 14), make_molecule(rng, 80, 72, 14), make_molecule(rng, 1, 72, 14)]
+    else:
+        mgs = make_molecules(12, seed=seed, mean_atoms=20)
+    torch.manual_seed(seed)
+    mp = BondMessagePassing(d_h=d_h, bias=bias, depth=depth, activation=act, undirected=undirected, precision="bf16")
+    bmg = BatchMolGraph(mgs)
+    P = {k: v.detach().double().requires_grad_(True) for k, v in mp.state_dict().items()}
+    H_ref = R.message_passing_forward("bond", bmg.V.double(), bmg.E.double(), bmg.edge_index, bmg.rev_edge_index,
+                                      P["W_i.weight"], P.get("W_i.bias"), P["W_h.weight"], P.get("W_h.bias"),
+                                      P["W_o.weight"], P["W_o.bias"], depth, act, undirected)
+    G = torch.from_numpy(rng.normal(size=(len(mgs), d_h)))
+    (R.aggregate(H_ref, bmg.batch, "mean", n_mols=len(mgs)) * G).sum().backward()
+    runs = {}
+    for fused in (True, False):
+        mp.fused = fused
+        mp.zero_grad(set_to_none=True)
+        b = BatchMolGraph(mgs)
+        H = mp(b)
+        (MeanAggregation()(H, b.batch) * G.float()).sum().backward()
+        runs[fused] = (H.detach().double(), {k: (torch.zeros_like(P[k]) if p.grad is None else p.grad.double())
+                                             for k, p in mp.named_parameters()})
+    scale = max(1.0, float(H_ref.detach().abs().max()))
+    smooth = act in ("tanh", "elu")
+    for fused, (H, grads) in runs.items():
+        assert float((H - H_ref.detach()).abs().max()) <= 1e-2 * scale, (fused, act, depth, undirected, shape)
+        for k, g in grads.items():
+            ref = torch.zeros_like(P[k]) if P[k].grad is None else P[k].grad
+            lim = 3e-2 if smooth else 0.5
+            assert float((g - ref).abs().max()) <= lim * max(1e-3, float(ref.abs().max())), (fused, k, act, depth, undirected, shape)
+    assert float((runs[True][0] - runs[False][0]).abs().max()) <= 1.6e-2 * scale
+    if smooth:
+        for k in runs[True][1]:
+            a, b_ = runs[True][1][k], runs[False][1][k]
+            assert float((a - b_).abs().max()) <= 3e-2 * max(1e-3, float(b_.abs().max())), (k, act, depth, undirected, shape)
