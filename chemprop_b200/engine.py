@@ -395,11 +395,14 @@ def _hidden(rows: int, hp: int, dtype, dev) -> Tensor:
     return torch.zeros((max(rows, 1), hp), dtype=dtype, device=dev)
 
 
+UNDIRECTED_FUSED = os.environ.get("DMPNN_UNDIRECTED_FUSED", "1") != "0"   # DMPNN_UNDIRECTED_FUSED=0: A/B switch (message + GEMM launches)
+
+
 def _fused_step_ok(cfg: MPConfig, lay: Layout, h: int) -> bool:
     """The fused tcgen05 depth step applies: bf16 tier, h <= 304.  Molecules of any size: those with more than 128 directed
     edges run as 128-row windows of the same kernel (Layout.step_tables).  `undirected=True` (base.py:202-203) runs on it too:
     the reverse-edge average is a prologue pass that produces the step's input (bond_forward)."""
-    ok = (cfg.fused and cfg.hidden_dtype == torch.bfloat16 and h <= 304 and lay.E > 0 and (not cfg.undirected or h % 4 == 0)
+    ok = (cfg.fused and cfg.hidden_dtype == torch.bfloat16 and h <= 304 and lay.E > 0 and (not cfg.undirected or (UNDIRECTED_FUSED and h % 4 == 0))
           and _fused_available())
     if not ok and cfg.fused and cfg.hidden_dtype == torch.bfloat16 and lay.E > 0:
         _warn_once("unfused", "chemprop_b200: this batch leaves the fused depth-step kernel (" +
