@@ -276,3 +276,42 @@ def test_the_maintainer_side_subclass_of_integration_md_runs_as_written(monkeypa
     for k in res[0][1]:
         torch.testing.assert_close(res[1][1][k], res[0][1][k], rtol=2e-3, atol=2e-5, msg=k)
     torch.testing.assert_close(fused(bmg), ref(bmg), rtol=1e-4, atol=1e-5)  # without descriptors
+
+
+@pytest.mark.parametrize("ref_agg", [False, True])
+def test_bf16_engine_module_inside_the_reference_mpnn(ref_agg, monkeypatch):
+    """precision="bf16" inside the unmodified reference MPNN (its f32 BatchNorm / FFN follow): with the engine's aggregation
+    (which always returns f32) as is; with the REFERENCE's aggregation -- a scatter on whatever dtype it is given -- through
+    `output_dtype=torch.float32`.  Predictions within the bf16 tier's tolerance of the all-reference model."""
+    from oracle.ref_shim import import_reference
+
+    import_reference()
+    import chemprop.nn as ref_nn
+    from chemprop.data import BatchMolGraph as RefBMG
+    from chemprop.data.molgraph import MolGraph as RefMG
+    from chemprop.models import MPNN
+
+    import chemprop_b200.nn as ours
+    from chemprop_b200.data import make_molecules
+
+    emu.patch_engine(monkeypatch)
+    torch.manual_seed(0)
+    bmg = RefBMG([RefMG(*m) for m in make_molecules(16, seed=7, mean_atoms=9, std_atoms=3, min_atoms=1)])
+    kw = dict(d_h=64, depth=3)
+    ref = MPNN(ref_nn.BondMessagePassing(**kw), ref_nn.MeanAggregation(), ref_nn.RegressionFFN(input_dim=64), batch_norm=False)
+    our_mp = ours.BondMessagePassing(precision="bf16", output_dtype=torch.float32 if ref_agg else None, **kw)
+    agg = ref_nn.MeanAggregation() if ref_agg else ours.MeanAggregation()
+    drop = MPNN(our_mp, agg, copy.deepcopy(ref.predictor), batch_norm=False)
+    drop.load_state_dict(ref.state_dict())
+    for m in (ref, drop):
+        m.eval()
+    with torch.no_grad():
+        Z_ref, Z = ref.fingerprint(bmg), drop.fingerprint(bmg)
+        assert Z.dtype == torch.float32
+        assert float((Z - Z_ref).abs().max()) <= 1e-2
+        torch.testing.assert_close(drop(bmg), ref(bmg), rtol=0, atol=2e-2)
+    drop.train()
+    targets = torch.zeros(16, 1)
+    loss = torch.nn.functional.mse_loss(drop.predictor.train_step(drop.fingerprint(bmg)), targets)
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in drop.parameters())
