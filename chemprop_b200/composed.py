@@ -40,6 +40,29 @@ def _c(t: Tensor | None) -> Tensor | None:
     return t if t.is_contiguous() else t.contiguous()
 
 
+# First use of the 3xTF32 kernels from this tier in a process: the same product is also run on the f32 FMA kernel and
+# compared (one device sync, once).  This composition was written after the round's last hardware run; until it has been seen
+# to agree on the device at hand it does not get to decide a result.  A mismatch disables it (loudly) for the process.
+_X3_STATE = {"ok": None}        # None: not checked yet; True / False: verdict
+
+
+def _x3_first_use_check(out_x3: Tensor, X1c: Tensor, K1: int, Wc: Tensor, N: int, bc, resc, R: int) -> Tensor:
+    ref = _buf(R, N, Wc)
+    K.linear_fwd(X1c, K1, Wc, ref, N, bias=bc, res=resc, R=R, pad_to=N)
+    err = (out_x3 - ref).abs().max()
+    scale = ref.abs().max().clamp_min(1e-6)
+    ok = bool((torch.isfinite(err) & (err <= 1e-4 * scale)).item())
+    _X3_STATE["ok"] = ok
+    if not ok:
+        import warnings
+
+        warnings.warn("chemprop_b200: the composed tier's 3xTF32 GEMM disagrees with the f32 FMA kernel on this device "
+                      f"(max |diff| = {float(err):.3e} at scale {float(scale):.3e}); it stays disabled for this process and "
+                      "the f32 FMA result is used -- please report this", RuntimeWarning, stacklevel=3)
+        return ref
+    return out_x3
+
+
 class GatherLinear(torch.autograd.Function):
     """Y[r] = [X1[i1(r)] || X2[i2(r)]] . W^T + b + res[r]   (r < R)  -- dmpnn_linear_fwd.
     Covers W_i (mixins.py:8-9, :22-23), W_h with the H_0 residual (base.py:136-138) and W_o (base.py:180).
@@ -57,9 +80,14 @@ class GatherLinear(torch.autograd.Function):
         # (W_i, W_o) stay on the f32 FMA kernel, which reads them in place
         x3 = (idx1 is None and X2c is None and R > 0 and K1 % 4 == 0 and N % 4 == 0 and 0 < K1 <= 4096 and 0 < N <= 4096
               and X1c.data_ptr() % 16 == 0 and (resc is None or resc.data_ptr() % 16 == 0)
-              and K.X3_ENABLED and K._fused_available())
+              and K.X3_ENABLED and K._fused_available() and _X3_STATE["ok"] is not False)
+        if x3 and _X3_STATE["ok"] is None and X1c.is_cuda and torch.cuda.is_current_stream_capturing():
+            x3 = False                                  # the first-use check synchronises: not inside a graph capture
         if x3:
             K.linear_x3(X1c, K1, K.pack_weight_x3(Wc), N, out, bias=bc, res=resc, R=R, pad_to=N)
+            if _X3_STATE["ok"] is None:
+                out = _x3_first_use_check(out, X1c, K1, Wc, N, bc, resc, R)
+                x3 = bool(_X3_STATE["ok"])
         elif R > 0:
             K.linear_fwd(X1c, K1, Wc, out, N, idx1=idx1, X2=X2c, K2=K2, idx2=idx2, bias=bc, res=resc, R=R, pad_to=N)
         ctx.x3 = x3
@@ -73,7 +101,7 @@ class GatherLinear(torch.autograd.Function):
         X1c, idx1, X2c, idx2, Wc, K1, K2, N, R = ctx.args
         need_x1, _, need_x2, _, need_w, need_b, need_res, _ = ctx.needs_input_grad
         dY = _c(dY)
-        x3 = ctx.x3 and dY.data_ptr() % 16 == 0
+        x3 = ctx.x3 and dY.data_ptr() % 16 == 0 and _X3_STATE["ok"] is True
         dX1 = dX2 = dW = db = None
         if need_w or need_b:
             dW = torch.zeros_like(Wc)

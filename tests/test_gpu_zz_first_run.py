@@ -65,6 +65,21 @@ def test_composed_under_bf16_precision_setting(name):
     np.testing.assert_allclose(aggs["mean"].detach().float().cpu().numpy(), g["agg_mean"], rtol=0, atol=BF16_ATOL)
 
 
+def test_composed_x3_first_use_check_verdict():
+    """The composed tier cross-checks its first 3xTF32 product against the f32 FMA kernel and falls back (with a warning) on a
+    disagreement, so the tests above cannot fail because of it -- THIS test is where a disagreement on the device shows."""
+    from chemprop_b200 import composed, engine
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.nn import BondMessagePassing
+
+    bmg = BatchMolGraph(make_molecules(40, seed=2))
+    bmg.to("cuda")
+    mp = BondMessagePassing(d_h=300, depth=3, activation="prelu").cuda()
+    mp(bmg).square().mean().backward()
+    if engine.X3_ENABLED:
+        assert composed._X3_STATE["ok"] is True, composed._X3_STATE
+
+
 @pytest.mark.parametrize("kind,undirected,act", [("bond", False, "relu"), ("bond", True, "tanh"), ("atom", False, "elu"),
                                                  ("atom", True, "prelu")])
 def test_training_dropout_mask_for_mask(kind, undirected, act):

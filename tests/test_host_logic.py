@@ -489,7 +489,10 @@ def test_composed_tier_runs_its_plain_gemms_on_the_x3_tensor_core_kernels(d_h, e
     from chemprop_b200.nn import BondMessagePassing
     from oracle import restatement as R
 
+    from chemprop_b200 import composed
+
     emu.patch_engine(monkeypatch)
+    monkeypatch.setitem(composed._X3_STATE, "ok", True)              # the first-use check has its own test below
     calls = []
     for name in ("linear_x3", "wgrad_x3", "linear_fwd", "linear_wgrad"):
         f0 = getattr(engine, name)
@@ -572,3 +575,48 @@ def test_randomised_bf16_bond_configurations_fused_vs_unfused_vs_oracle(seed, mo
         for k in runs[True][1]:
             a, b_ = runs[True][1][k], runs[False][1][k]
             assert float((a - b_).abs().max()) <= 3e-2 * max(1e-3, float(b_.abs().max())), (k, act, depth, undirected, shape)
+
+
+@pytest.mark.parametrize("broken", [False, True])
+def test_composed_tier_checks_its_x3_gemm_on_first_use(broken, monkeypatch):
+    """The composed tier's first 3xTF32 product in a process is cross-checked against the f32 FMA kernel (one extra launch and
+    one sync, once).  Agreement: x3 from then on.  Disagreement (here: a kernel that returns garbage): a RuntimeWarning, x3
+    off for the process, and the results -- this call's included -- come from the FMA kernel, so they are still right."""
+    from chemprop_b200 import composed, engine
+    from chemprop_b200.data import BatchMolGraph, make_molecules
+    from chemprop_b200.nn import BondMessagePassing
+    from oracle import restatement as R
+
+    emu.patch_engine(monkeypatch)
+    monkeypatch.setitem(composed._X3_STATE, "ok", None)
+    calls = []
+    good = engine.linear_x3
+
+    def x3(*a, **k):
+        calls.append("x3")
+        good(*a, **k)
+        if broken:
+            a[4].mul_(1.5)                                           # `out`: a wrong product
+
+    simt0 = engine.linear_fwd
+    monkeypatch.setattr(engine, "linear_x3", x3)
+    monkeypatch.setattr(engine, "linear_fwd", lambda *a, **k: (calls.append("simt"), simt0(*a, **k))[1])
+    torch.manual_seed(1)
+    bmg = BatchMolGraph(make_molecules(8, seed=1))
+    mp = BondMessagePassing(d_h=32, depth=3, activation="selu")
+    if broken:
+        with pytest.warns(RuntimeWarning, match="3xTF32 GEMM disagrees"):
+            H = mp(bmg)
+        assert composed._X3_STATE["ok"] is False and calls.count("x3") == 1        # tried once, never again
+    else:
+        H = mp(bmg)
+        assert composed._X3_STATE["ok"] is True and calls.count("x3") == 2 and calls.count("simt") == 3   # W_i, check, W_o
+    H.square().sum().backward()
+    P = {k: v.detach().double().requires_grad_(True) for k, v in mp.state_dict().items()}
+    Hr = R.message_passing_forward("bond", bmg.V.double(), bmg.E.double(), bmg.edge_index, bmg.rev_edge_index, P["W_i.weight"],
+                                   None, P["W_h.weight"], None, P["W_o.weight"], P["W_o.bias"], 3, "selu")
+    Hr.square().sum().backward()
+    assert float((H.detach().double() - Hr.detach()).abs().max()) <= 1e-5
+    for k, p in mp.named_parameters():
+        ref = P[k].grad
+        assert float((p.grad.double() - ref).abs().max()) <= 1e-5 * max(1e-6, float(ref.abs().max())), k
