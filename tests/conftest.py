@@ -51,7 +51,9 @@ def _gpu_rank(item) -> int:
         return len(_GPU_ORDER) + 3         # the one test a disagreement of the composed tier's x3 GEMM would fail: very last
     if path in _LATE_FILES:
         return len(_GPU_ORDER) + 2
-    if any(name.startswith(p) for p in _LATE_NAMES) or name in _LATE_IDS:
+    if name in _LATE_IDS:
+        return len(_GPU_ORDER) + 4         # a single test: nothing can hide behind it
+    if any(name.startswith(p) for p in _LATE_NAMES):
         return len(_GPU_ORDER) + 1
     for rank, (fname, prefixes) in enumerate(_GPU_ORDER):
         if path == fname and any(name.startswith(p) for p in prefixes):
